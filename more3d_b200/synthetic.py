@@ -1,0 +1,96 @@
+"""Seeded synthetic open-terrain clouds.
+
+All inputs are generated on the host in fp64 with ``numpy.random.Generator(PCG64(seed))``:
+xy ~ U(0, L)^2 with L = sqrt(N / density); z = 7-octave sin*cos relief + N(0, noise^2) + one
+Gaussian bump/pit per 50 m x 50 m block; finally x, y are centred and z is shifted by -1000 m so
+that the coordinate origin ("scanner") sits above the tile -- ``Curvature_Kernel`` orients normals
+toward the origin (reference DM_saliency.py:131-135).
+"""
+import numpy as np
+
+DENSITY = 40.0  # points / m^2
+
+
+def terrain(n, seed, density=DENSITY, noise=0.02, boulders=0, extent=None):
+    """Return an (n, 3) float64 C-order terrain cloud.
+
+    ``boulders`` > 0 adds that many steep 0.5 m hemispherical bumps per 50 m block (the "stress
+    tile" of SURVEY.md §8d that exercises the dn branch of the saliency processor).
+    ``extent`` = (Lx, Ly) overrides the square footprint (used for multi-GPU strips).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if extent is None:
+        L = float(np.sqrt(n / density))
+        Lx = Ly = L
+    else:
+        Lx, Ly = map(float, extent)
+    x = rng.random(n) * Lx
+    y = rng.random(n) * Ly
+    z = np.zeros(n)
+    for o in range(7):
+        f = float(2 ** o)
+        z += 2.0 * 2.0 ** (-0.8 * o) * np.sin(f * x / 40.0 + o) * np.cos(f * y / 37.0 + 2 * o)
+    z += rng.normal(0.0, noise, n)
+
+    # embedded entities: one Gaussian bump / pit per 50 m block, centre kept >= 10 m from the
+    # block border so a point is only influenced by the entity of its own block.
+    B = 50.0
+    nbx = max(1, int(np.ceil(Lx / B)))
+    nby = max(1, int(np.ceil(Ly / B)))
+    erng = np.random.Generator(np.random.PCG64(seed + 7919))
+    cx = (np.arange(nbx)[:, None] * B + 10.0 + 30.0 * erng.random((nbx, nby)))
+    cy = (np.arange(nby)[None, :] * B + 10.0 + 30.0 * erng.random((nbx, nby)))
+    amp = 0.4 * np.where(erng.random((nbx, nby)) < 0.5, -1.0, 1.0)
+    sig = 1.0 + erng.random((nbx, nby))
+    bx = np.minimum((x / B).astype(np.int64), nbx - 1)
+    by = np.minimum((y / B).astype(np.int64), nby - 1)
+    d2 = (x - cx[bx, by]) ** 2 + (y - cy[bx, by]) ** 2
+    z += amp[bx, by] * np.exp(-0.5 * d2 / sig[bx, by] ** 2)
+
+    if boulders:
+        R = 0.5
+        for _ in range(int(boulders)):
+            ox = (np.arange(nbx)[:, None] * B + 2.0 + 46.0 * erng.random((nbx, nby)))
+            oy = (np.arange(nby)[None, :] * B + 2.0 + 46.0 * erng.random((nbx, nby)))
+            d2 = (x - ox[bx, by]) ** 2 + (y - oy[bx, by]) ** 2
+            z += np.sqrt(np.maximum(R * R - d2, 0.0))
+
+    pts = np.empty((n, 3), dtype=np.float64)
+    pts[:, 0] = x - 0.5 * Lx
+    pts[:, 1] = y - 0.5 * Ly
+    pts[:, 2] = z - 1000.0
+    return pts
+
+
+def lattice(nx, ny, nz, spacing=1.0):
+    """Integer lattice: exact radius ties (SURVEY.md §8c known-answer test)."""
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1)
+    return np.ascontiguousarray(g.reshape(-1, 3).astype(np.float64) * spacing)
+
+
+def plane(n, seed, normal=(0.0, 0.0, 1.0), extent=10.0, z0=-1000.0):
+    """Random points on an exact plane through (0,0,z0) (K = 0, dn = dk = 0 known answers)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nrm = np.asarray(normal, dtype=np.float64)
+    nrm = nrm / np.linalg.norm(nrm)
+    a = np.cross(nrm, [1.0, 0.0, 0.0])
+    if np.linalg.norm(a) < 1e-6:
+        a = np.cross(nrm, [0.0, 1.0, 0.0])
+    a /= np.linalg.norm(a)
+    b = np.cross(nrm, a)
+    uv = (rng.random((n, 2)) - 0.5) * extent
+    pts = uv[:, :1] * a[None, :] + uv[:, 1:] * b[None, :]
+    pts[:, 2] += z0
+    return np.ascontiguousarray(pts)
+
+
+def sphere_cap(n, seed, radius=50.0, cap=0.2):
+    """Points on the top cap of a sphere centred at the origin-shifted location (0, 0, -1000 - R)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u = rng.random(n)
+    cos_t = 1.0 - u * (1.0 - np.cos(cap))
+    sin_t = np.sqrt(1.0 - cos_t ** 2)
+    ph = rng.random(n) * 2 * np.pi
+    pts = np.stack([radius * sin_t * np.cos(ph), radius * sin_t * np.sin(ph),
+                    radius * cos_t - radius - 1000.0], -1)
+    return np.ascontiguousarray(pts)

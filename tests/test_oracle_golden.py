@@ -1,0 +1,121 @@
+"""CPU: the oracle restatement (oracle/ref_path.py) against golden vectors produced by executing
+the reference verbatim (tools/make_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_path as rp
+
+SAL_CASES = ["terrain_r05", "terrain_r10", "rough_r05", "boulders_r075"]
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def nbr_lists(g):
+    off, idx = g["nbr_off"], g["nbr_idx"]
+    return [idx[off[i]:off[i + 1]].astype(np.int64) for i in range(len(off) - 1)]
+
+
+@pytest.mark.parametrize("name", SAL_CASES)
+def test_radius_sets_match_reference(golden_dir, name):
+    g = load(golden_dir, name)
+    pts, r = g["points"], float(g["radius"])
+    tree = rp.build_tree(pts)
+    got = rp.query_radius(tree, pts, r)
+    want = nbr_lists(g)
+    for a, b in zip(got, want):
+        assert np.array_equal(np.sort(a), b)
+    # the pure accept rule == the ball tree (bulk-accept / prune shortcuts never change a set)
+    bf = rp.query_radius_bruteforce(pts, pts[:200], r)
+    for a, b in zip(bf, want[:200]):
+        assert np.array_equal(np.sort(a), b)
+
+
+@pytest.mark.parametrize("name", SAL_CASES)
+def test_curvature_kernel_bit_exact(golden_dir, name):
+    g = load(golden_dir, name)
+    K, cnt, nrm = rp.curvature_kernel(g["points"], g["normals_in"], nbr_lists(g), float(g["alpha"]),
+                                      float(g["roughness"]), int(g["min_points"]))
+    assert np.array_equal(cnt, g["pcount"])
+    assert np.array_equal(nrm, g["normals"], equal_nan=True)
+    # same expressions up to summation association -> a few ulp of f32
+    np.testing.assert_allclose(K, g["K"], rtol=1e-6, atol=0)
+    assert np.array_equal(K != 0, g["K"] != 0)
+
+
+@pytest.mark.parametrize("name", SAL_CASES)
+def test_saliency_kernel(golden_dir, name):
+    g = load(golden_dir, name)
+    dk, dn = rp.saliency_kernel(g["points"], g["normals"], g["K"], nbr_lists(g), float(g["rho"]),
+                                float(g["sigma_n"]), float(g["sigma_k"]), float(g["alpha"]),
+                                int(g["min_points"]))
+    np.testing.assert_allclose(dk, g["dk"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(dn, g["dn"], rtol=1e-6, atol=0)
+
+
+def test_lattice_ties_included(golden_dir):
+    g = load(golden_dir, "lattice_r5")
+    pts, q = g["points"], g["queries"]
+    want = nbr_lists(g)
+    got = rp.query_radius_bruteforce(pts, q, 5.0)
+    ties = 0
+    for a, b, qq in zip(got, want, q):
+        assert np.array_equal(a, b)
+        d2 = ((pts[b] - qq) ** 2).sum(1)
+        ties += int((d2 == 25.0).sum())
+    assert ties > 1000          # exact ties exist and are INCLUDED (<=)
+    tree = rp.build_tree(pts)
+    assert np.array_equal(np.sort(rp.query_radius(tree, pts[100], 5.0)), g["single"])
+    ki, kd = rp.query_knn(tree, q[:50] + 0.25, 5, return_distnaces=True)
+    assert np.array_equal(ki, g["knn_i"]) and np.array_equal(kd, g["knn_d"])
+
+
+def test_lod_cells_match_reference_wrapper(golden_dir):
+    g = load(golden_dir, "balltree_6k")
+    tree = rp.build_tree(g["points"], 40)
+    _, idx_array, nodes, _ = tree.get_arrays()
+    assert np.array_equal(idx_array, g["idx_array"])
+    assert np.array_equal(nodes["radius"], g["radius"])
+    n = int(g["numberOfNodes"])
+    # heap layout == the reference's O(n^2) hierarchy reconstruction
+    left = np.where(g["is_leaf"] == 1, -1, 2 * np.arange(n) + 1)
+    assert np.array_equal(left, g["left"])
+    parent = np.where(np.arange(n) == 0, -1, (np.arange(n) - 1) // 2)
+    assert np.array_equal(parent, g["parent"])
+    for lod in (1.0, 2.0, 5.0):
+        assert np.array_equal(rp.lod_cells(tree, lod), g["cells_%g" % lod])
+
+
+def test_known_answers_plane_and_blend():
+    from more3d_b200 import synthetic
+    pts = synthetic.plane(1500, 3, normal=(0.1, -0.2, 1.0))
+    tree = rp.build_tree(pts)
+    nb = rp.query_radius(tree, pts, 0.8)
+    nrm, ratio = rp.pca_normals(pts, nb)
+    ok = np.array([len(j) >= 3 for j in nb])
+    n0 = np.array([0.1, -0.2, 1.0]) / np.linalg.norm([0.1, -0.2, 1.0])
+    assert np.all(np.abs(np.abs(nrm[ok] @ n0) - 1) < 1e-12)
+    assert np.all(ratio[ok] < 1e-12)
+    K, cnt, nrm2 = rp.curvature_kernel(pts, nrm, nb, 0.05, 0.02, 4)
+    assert np.all(K == 0)
+    dk, dn = rp.saliency_kernel(pts, nrm2, K, nb, 0.8 / np.sqrt(2))
+    assert np.all(dk == 0) and np.all(dn == 0)
+    sal, mm = rp.saliency_blend(np.array([0, 1, 2], np.float32), np.array([1, 1, 3], np.float32), 0.25)
+    # (x - min)/(max - min) + min, reference DM_saliency.py:577-580
+    assert np.allclose(sal, 0.75 * np.array([1, 1, 2.0]) + 0.25 * np.array([0, .5, 1]))
+
+
+def test_otsu_and_voxel_restatements():
+    rng = np.random.Generator(np.random.PCG64(1))
+    v = np.concatenate([rng.normal(0.2, 0.05, 5000), rng.normal(0.8, 0.05, 3000)])
+    t = rp.otsu_threshold(v)
+    assert 0.35 < t < 0.65
+    pts = rng.random((2000, 3)) * 4
+    means, keys = rp.voxel_downsample(pts, 1.0)
+    k = rp.voxel_keys(pts, 1.0)
+    assert len(means) == len(np.unique(k, axis=0))
+    j = np.nonzero(np.all(k == keys[3], axis=1))[0]
+    assert np.allclose(means[3], pts[j].mean(0))
