@@ -1,0 +1,112 @@
+/*
+ * more3d_b200 -- C-ABI of the B200 (sm_100a) per-point neighbourhood-feature path of MorE3D.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point
+ * cites the reference routine it replaces (paths relative to TUW-GEO/MorE3D).  Conventions:
+ *   - every function returns int: 0 = ok, < 0 = error (see MORE3D_E_*); it never throws or aborts;
+ *     more3d_last_error() returns a thread-local message for the last failure.
+ *   - pointers are DEVICE pointers unless the parameter name ends in _h (host memory).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Work is enqueued
+ *     on that stream; functions that return a host scalar (counts, sizes) synchronise it.
+ *   - the caller allocates every output; opaque handles (more3d_grid*) are owned by the library.
+ *   - per-point arrays are in the ORIGINAL point order of the cloud the grid was built from.
+ *   - one grid per GPU/stream user; functions are not re-entrant on the same grid.
+ */
+#ifndef MORE3D_B200_H
+#define MORE3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MORE3D_OK 0
+#define MORE3D_E_INVALID (-1)  /* bad argument */
+#define MORE3D_E_CUDA (-2)     /* CUDA runtime error (message in more3d_last_error) */
+#define MORE3D_E_NOMEM (-3)    /* device allocation failed */
+#define MORE3D_E_RANGE (-4)    /* size exceeds an implementation limit */
+
+typedef struct more3d_grid more3d_grid;
+
+int more3d_version(void);
+const char* more3d_last_error(void);
+
+/* ---- spatial index --------------------------------------------------------------------------
+ * Replaces BallTreePointSet.__init__ -> sklearn BallTree build (Downsampling/BallTreePointSet.py:19-53).
+ * Uniform xy-column grid: fp64 cell keys -> LSD radix sort -> column-start table -> sorted
+ * (x, y, z, original index) records.  `cell` is the column width; a query of radius r scans a
+ * stencil of ceil(r / cell) columns either side.  xyz: n*3 float64, row-major (x0 y0 z0 x1 ...). */
+int more3d_grid_create(const double* xyz, int64_t n, double cell, void* stream, more3d_grid** out);
+int more3d_grid_destroy(more3d_grid* g);
+/* info[0]=n, info[1]=nx, info[2]=ny (host ints); geom[0]=cell, geom[1]=origin_x, geom[2]=origin_y */
+int more3d_grid_info(const more3d_grid* g, int64_t* info_h, double* geom_h);
+/* sorted position -> original index, n x int32 (device) */
+int more3d_grid_order(const more3d_grid* g, int32_t* order, void* stream);
+
+/* ---- fixed-radius query -----------------------------------------------------------------------
+ * Replaces BallTreePointSet.queryRadius (BallTreePointSet.py:317-347 -> sklearn query_radius).
+ * Accept rule, bit-exact with the reference: fp64 ((dx*dx)+(dy*dy))+(dz*dz) <= r*r, no FMA
+ * (sklearn metrics/_dist_metrics.pxd.tp:39-49, neighbors/_binary_tree.pxi.tp:1951-1957).
+ * q == NULL means "the cloud itself" (nq must equal n); results are still in original order.
+ * Two-pass CSR: count -> (caller or more3d_offsets_from_counts) -> fill. */
+int more3d_radius_count(const more3d_grid* g, const double* q, int64_t nq, double r,
+                        int32_t* counts, void* stream);
+/* offsets[0..nq] = exclusive prefix sum of counts (int64); total_h (host, may be NULL) = offsets[nq]. */
+int more3d_offsets_from_counts(const int32_t* counts, int64_t nq, int64_t* offsets,
+                               int64_t* total_h, void* stream);
+/* idx_bytes = 4 (int32) or 8 (int64) original point indices; order inside a list is unspecified
+ * (the reference's is too: compare as sets). */
+int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t nq, double r,
+                       const int64_t* offsets, void* idx, int idx_bytes, void* stream);
+
+/* ---- k nearest neighbours ---------------------------------------------------------------------
+ * Replaces BallTreePointSet.query (BallTreePointSet.py:292-315) and the 2k-NN of
+ * levelsets_func.build_neighborhoods (levelsets_func.py:158-163).  Sorted by (distance, index);
+ * idx: nq*k int64, dist: nq*k float64 (may be NULL).  Distances are sqrt of the fp64 rule above.
+ * q == NULL -> self query.  Requires k <= MORE3D_MAX_K and k <= n. */
+#define MORE3D_MAX_K 64
+int more3d_knn(const more3d_grid* g, const double* q, int64_t nq, int k, int64_t* idx, double* dist,
+               void* stream);
+
+/* ---- neighbourhood moments: PCA normal, surface variation, non-parametric curvature -------------
+ * more3d_normals_pca: centroid-PCA normal (sign arbitrary) and lambda_min/sum(lambda) over the
+ * radius-r neighbourhood (self included); precondition of DM_nonparam_curvature (DM_saliency.py:329-330;
+ * open3d estimate_normals in downsample_compare.py:53-64).  Fewer than 3 neighbours -> NaN normal.
+ * normals: n*3 f64; lam_ratio: n f64 (may be NULL); counts: n int32 (may be NULL). */
+int more3d_normals_pca(const more3d_grid* g, double r, double* normals, double* lam_ratio,
+                       int32_t* counts, void* stream);
+/* Curvature_Kernel.process for every point (DM_saliency.py:88-157).  eps = norm.ppf(1-alpha/2)*roughness
+ * is computed by the caller with scipy exactly as the reference does (:99).  normals are read and, where
+ * n.(-p) < 0, flipped in place (:131-135).  K: n float32 (_nonparam_K, :381); pcount: n int32 (:382). */
+int more3d_nonparam_curvature(const more3d_grid* g, double r, double* normals_inout, double eps,
+                              int min_points, float* K, int32_t* pcount, void* stream);
+/* Both of the above in one neighbourhood pass (normals at the same radius as the curvature). */
+int more3d_normals_curvature(const more3d_grid* g, double r, double eps, int min_points,
+                             double* normals, double* lam_ratio, float* K, int32_t* pcount,
+                             void* stream);
+
+/* ---- dk / dn centre-surround differences ---------------------------------------------------------
+ * Saliency_Kernel.process for every point (DM_saliency.py:219-324).  chi2_table[df] =
+ * chi2.ppf(alpha, df) for df = 0..table_len-1, computed by the caller with scipy (:282); a
+ * neighbourhood with more active neighbours than table_len-1 returns MORE3D_E_RANGE.
+ * dk, dn: n float32 (_dk, _dn; :491-492).  minmax (may be NULL): 4 float32 {min_dk, max_dk, min_dn,
+ * max_dn} over this call's outputs, reduced on the device (the Histo pass of DM_saliency, :562-568). */
+int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
+                 double sigma_normal, double sigma_curvature, const double* chi2_table, int table_len,
+                 int min_points, float* dk, float* dn, float* minmax, void* stream);
+
+/* ---- DM_saliency: min-max normalise (+min, as written) and blend (DM_saliency.py:565-580) ---------
+ * minmax: 4 float32 on the device as produced by more3d_dk_dn / more3d_minmax4.
+ * sal: n float32.  sal_minmax (may be NULL): 2 float32 {min, max} of sal. */
+int more3d_minmax4(const float* dk, const float* dn, int64_t n, float* minmax, void* stream);
+int more3d_saliency_blend(const float* dk, const float* dn, int64_t n, const float* minmax,
+                          double curvature_weight, float* sal, float* sal_minmax, void* stream);
+/* 256-bin histogram of sal over [lo, hi] with numpy.histogram's binning; edges: 257 float64 from
+ * numpy.linspace (host computed, device resident).  hist: 256 int64 (zeroed by the call). */
+int more3d_histogram256(const float* v, int64_t n, const double* edges, int64_t* hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORE3D_B200_H */

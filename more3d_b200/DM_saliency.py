@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's saliency module (DM_saliency.py) on top of the B200 kernels.
+
+Same names, argument meaning and error behaviour as the reference:
+``Curvature_Kernel`` / ``Saliency_Kernel`` (``setArgs`` as DM_saliency.py:59, :182),
+``DM_nonparam_curvature`` (:326), ``DM_dk_dn`` (:419), ``DM_saliency`` (:539),
+``DM_saliency_stats`` (:585).  Where the reference takes the path of an OPALS ODM file, these take
+a :class:`PointCloudDM` (an in-memory, device-resident attribute table -- ODM is a proprietary
+format) or the path of an ``.npz`` written by ``PointCloudDM.save_as``.
+
+The OPALS per-point callback dispatch (``pyDM.ProcessorEx(dm, query, ...).run(kernel)``,
+DM_saliency.py:403-407) is kept as :class:`ProcessorEx`; ``run`` launches ONE bulk CUDA pass that
+evaluates ``kernel.process`` for every point instead of calling back into Python per point.
+Only ``shape='sphere'`` is in scope (the reference marks circle/cylinder "TODO: check if ... works").
+"""
+import datetime
+import re
+import sys
+
+import numpy as np
+import torch
+from scipy import stats
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .grid import UniformGrid, as_device_points, CELL_MARGIN
+
+
+class PointCloudDM:
+    """In-memory stand-in for ``pyDM.Datamanager``: xyz plus named per-point attribute columns,
+    resident in HBM.  Column names follow the reference layout (DM_saliency.py:377-384, 486-494)."""
+
+    FLOAT_COLS = ("_nonparam_K", "_dk", "_dn", "_normed_dk", "_normed_dn", "_saliency")
+
+    def __init__(self, xyz, normals=None, device=None):
+        self.xyz = as_device_points(xyz, device)
+        self.device = self.xyz.device
+        self.n = int(self.xyz.shape[0])
+        self.attrs = {}
+        self.normals = None if normals is None else as_device_points(normals, self.device).clone()
+        self._grids = {}
+        self._minmax = None
+
+    # -- ODM-like surface ---------------------------------------------------------------
+    @classmethod
+    def load(cls, path, *_):
+        try:
+            z = np.load(path)
+        except (OSError, ValueError) as e:
+            raise IOError(str(e))
+        dm = cls(z["xyz"], z["normals"] if "normals" in z else None)
+        for k in z.files:
+            if k not in ("xyz", "normals"):
+                dm.attrs[k] = torch.from_numpy(z[k]).to(dm.device)
+        return dm
+
+    def save(self):
+        """ODM persistence is a no-op for the in-memory table (DM_saliency.py:415, :527)."""
+        return self
+
+    def save_as(self, path):
+        out = {"xyz": self.xyz.cpu().numpy()}
+        if self.normals is not None:
+            out["normals"] = self.normals.cpu().numpy()
+        for k, v in self.attrs.items():
+            out[k] = v.cpu().numpy()
+        np.savez(path, **out)
+
+    def sizePoint(self):
+        return self.n
+
+    def get(self, name):
+        """Column as a host numpy array."""
+        if name in ("NormalX", "NormalY", "NormalZ"):
+            return self.normals[:, "XYZ".index(name[-1])].cpu().numpy()
+        return self.attrs[name].cpu().numpy()
+
+    # -- spatial index ------------------------------------------------------------------
+    def grid(self, radius):
+        """Uniform grid whose column width matches the query radius (built once per radius)."""
+        key = float(radius)
+        g = self._grids.get(key)
+        if g is None:
+            g = UniformGrid(self.xyz, key * CELL_MARGIN)
+            self._grids[key] = g
+        return g
+
+    def drop_grids(self):
+        for g in self._grids.values():
+            g.close()
+        self._grids = {}
+
+
+class QueryDescriptor:
+    """``pyDM.QueryDescriptor('sphere(r=0.5)')`` (DM_saliency.py:393-398)."""
+
+    def __init__(self, shape):
+        m = re.fullmatch(r"\s*sphere\(r=([^)]+)\)\s*", str(shape))
+        if not m:
+            raise NotImplementedError("only 'sphere(r=...)' queries are in scope, got %r" % (shape,))
+        self.radius = float(m.group(1))
+
+
+class ProcessorEx:
+    """``pyDM.ProcessorEx(dm, query, processFilter, processLayout, processLayoutReadOnly,
+    spatialFilter, spatialLayout, spatialLayoutReadOnly)`` (DM_saliency.py:403, :513-516)."""
+
+    def __init__(self, dm, query, processFilter=None, processLayout=None, processLayoutReadOnly=False,
+                 spatialFilter=None, spatialLayout=None, spatialLayoutReadOnly=False):
+        if processFilter is not None or spatialFilter is not None:
+            raise NotImplementedError("process/spatial filters are out of scope")
+        self.dm, self.query = dm, query
+
+    def run(self, kernel):
+        kernel.tileFilter()
+        kernel.process_all(self.dm, self.query.radius)
+        kernel.releaseLeaf()
+
+
+class _KernelPointEx:
+    def tileFilter(self):
+        return None
+
+    def releaseLeaf(self):
+        return
+
+    def leafChanged(self, leaf, *args, **kwargs):
+        return
+
+
+class Curvature_Kernel(_KernelPointEx):
+    """Non-parametric curvature processor (DM_saliency.py:40-157)."""
+    _roughness = None
+    _alpha = None
+    _minPoints_neighbourhood = None
+
+    def setArgs(self, alpha, roughness, min_points=4):
+        self._alpha = alpha
+        self._roughness = roughness
+        self._minPoints_neighbourhood = min_points
+
+    def epsilon(self):
+        return float(stats.norm.ppf(1 - self._alpha / 2) * self._roughness)   # DM_saliency.py:99
+
+    def process_all(self, dm, radius):
+        """``process(pt, neighbours)`` for every point of ``dm`` in one device pass.
+        Uses the normals stored in ``dm``; if there are none (the reference requires them,
+        DM_saliency.py:329-330) centroid-PCA normals at the same radius are computed in the same pass."""
+        g = dm.grid(radius)
+        if dm.normals is None:
+            normals, ratio, K, pcount = g.normals_curvature(radius, self.epsilon(), self._minPoints_neighbourhood)
+            dm.normals = normals
+            dm.attrs["_lam_ratio"] = ratio
+        else:
+            K, pcount = g.nonparam_curvature(radius, dm.normals, self.epsilon(), self._minPoints_neighbourhood)
+        dm.attrs["_nonparam_K"] = K
+        dm.attrs["_pcount"] = pcount
+        return True
+
+
+_CHI2_CACHE = {}
+
+
+def _chi2_table(alpha, length, device):
+    key = (float(alpha), int(length), str(device))
+    t = _CHI2_CACHE.get(key)
+    if t is None:
+        with np.errstate(all="ignore"):
+            host = stats.chi2.ppf(alpha, np.arange(length)).astype(np.float64)   # DM_saliency.py:282
+        t = torch.from_numpy(host).to(device)
+        _CHI2_CACHE[key] = t
+    return t
+
+
+class Saliency_Kernel(_KernelPointEx):
+    """dk / dn processor (DM_saliency.py:159-324)."""
+    _alpha = None
+    _sigma_curvature = None
+    _sigma_normal = None
+    _sigma_neighbourhood = None
+    _rho_neighbourhood = None
+    _minPoints_neighbourhood = None
+
+    def setArgs(self, rho_neighbourhood, sigma_neighbourhood, sigma_normal=0.01, sigma_curvature=0.1,
+                alpha=0.05, min_points=4):
+        self._alpha = alpha
+        self._sigma_curvature = sigma_curvature
+        self._sigma_normal = sigma_normal
+        self._sigma_neighbourhood = sigma_neighbourhood   # stored, unused -- as in the reference (:268-269)
+        self._rho_neighbourhood = rho_neighbourhood
+        self._minPoints_neighbourhood = min_points
+
+    def process_all(self, dm, radius):
+        if dm.normals is None or "_nonparam_K" not in dm.attrs:
+            raise ValueError("dk/dn needs normals and _nonparam_K (run DM_nonparam_curvature first)")
+        g = dm.grid(radius)
+        length = 1024
+        while True:
+            table = _chi2_table(self._alpha, length, dm.device)
+            try:
+                dk, dn, minmax = g.dk_dn(radius, dm.normals, dm.attrs["_nonparam_K"], self._rho_neighbourhood,
+                                         self._sigma_normal, self._sigma_curvature, table,
+                                         self._minPoints_neighbourhood)
+                break
+            except _lib.More3DError as e:
+                if "error -4" not in str(e) or length >= (1 << 22):
+                    raise
+                length *= 8
+        dm.attrs["_dk"] = dk
+        dm.attrs["_dn"] = dn
+        dm._minmax = minmax
+        return True
+
+
+def _open(inFile):
+    if isinstance(inFile, PointCloudDM):
+        return inFile
+    try:
+        return PointCloudDM.load(inFile, False, False)
+    except IOError as e:
+        print(e)
+        return None
+
+
+def _check_shape(shape, kwargs):
+    # sanity checks of DM_saliency.py:367-374 / :476-483
+    if "radius" not in kwargs:
+        print("must have radius for search")
+        sys.exit(1)
+    if shape == "cylinder":
+        if "zmin" not in kwargs or "zmax" not in kwargs:
+            print("for cylinder zmin and zmax must be defined for search")
+            sys.exit(1)
+    if shape != "sphere":
+        raise NotImplementedError("only shape='sphere' is in scope (reference: circle/cylinder are TODO)")
+    return "sphere(r=" + str(kwargs["radius"]) + ")"
+
+
+def DM_nonparam_curvature(inFile, shape, roughness=0.15, alpha=0.05, min_points=3, verbose=False, **kwargs):
+    """DM_saliency.py:326-417.  Returns the data manager."""
+    dm = _open(inFile)
+    if dm is None:
+        return
+    query = QueryDescriptor(_check_shape(shape, kwargs))
+    k = Curvature_Kernel()
+    k.setArgs(alpha=alpha, roughness=roughness, min_points=min_points)
+    start = datetime.datetime.now()
+    processor = ProcessorEx(dm, query, None, None, False, None, None, False)
+    processor.run(k)
+    if verbose:
+        torch.cuda.synchronize(dm.device)
+        print("Done. Non-parametric curvature computation took %.2f [s]"
+              % (datetime.datetime.now() - start).total_seconds())
+    dm.save()
+    return dm
+
+
+def DM_dk_dn(inFile, shape, rho_neighbourhood, sigma_neighbourhood, sigma_normal=0.01, sigma_curvature=0.1,
+             alpha=0.05, min_points=4, verbose=False, **kwargs):
+    """DM_saliency.py:419-527."""
+    dm = _open(inFile)
+    if dm is None:
+        return
+    query = QueryDescriptor(_check_shape(shape, kwargs))
+    s = Saliency_Kernel()
+    s.setArgs(rho_neighbourhood, sigma_neighbourhood, sigma_normal, sigma_curvature, alpha, min_points)
+    processor = ProcessorEx(dm, query, None, None, False, None, None, False)
+    start = datetime.datetime.now()
+    processor.run(s)
+    if verbose:
+        torch.cuda.synchronize(dm.device)
+        print("Done. dn and dk computation took %.2f [s]" % (datetime.datetime.now() - start).total_seconds())
+    dm.save()
+    return dm
+
+
+def DM_saliency(inFile, curvature_weight=.5, verbose=False, **kwargs):
+    """DM_saliency.py:539-583: Histo min/max of _dk/_dn, the two normalisations and the blend."""
+    dm = _open(inFile)
+    if dm is None:
+        return
+    lib = _lib.load()
+    dk, dn = dm.attrs["_dk"], dm.attrs["_dn"]
+    with torch.cuda.device(dm.device):
+        minmax = dm._minmax
+        if minmax is None:
+            minmax = torch.empty(4, dtype=torch.float32, device=dm.device)
+            check(lib.more3d_minmax4(ptr(dk), ptr(dn), dm.n, ptr(minmax), stream_ptr()))
+        sal = torch.empty(dm.n, dtype=torch.float32, device=dm.device)
+        smm = torch.empty(2, dtype=torch.float32, device=dm.device)
+        check(lib.more3d_saliency_blend(ptr(dk), ptr(dn), dm.n, ptr(minmax), float(curvature_weight),
+                                        ptr(sal), ptr(smm), stream_ptr()))
+    dm.attrs["_saliency"] = sal
+    dm.attrs["_saliency_minmax"] = smm
+    dm.attrs["_dkdn_minmax"] = minmax
+    if verbose:
+        mm = minmax.cpu().numpy()
+        print("diff_k {}, diff_n {}".format(float(mm[1]) - float(mm[0]), float(mm[3]) - float(mm[2])))
+    return dm
+
+
+def DM_saliency_stats(odm):
+    """DM_saliency.py:585-607: (min, max, mean, sigma) of ``_saliency``."""
+    dm = _open(odm)
+    if dm is None:
+        print("Unable to open ODM '" + str(odm) + "'")
+        sys.exit(1)
+    if "_saliency" not in dm.attrs:
+        print("no saliency values")
+        return 1
+    s = dm.attrs["_saliency"].double()
+    return (float(s.min()), float(s.max()), float(s.mean()), float(s.std(unbiased=False)))

@@ -1,0 +1,89 @@
+"""ctypes binding of libmore3d_b200.so (the C-ABI declared in include/more3d_b200.h).
+
+There is NO CPU fallback: if the shared library is missing and cannot be built, or no CUDA
+device is present, the product path raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmore3d_b200.so")
+
+_lib = None
+
+_vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
+
+# name -> argtypes; every function returns int except the two noted below
+SIGNATURES = {
+    "more3d_grid_create": [_vp, _i64, _f64, _vp, C.POINTER(_vp)],
+    "more3d_grid_destroy": [_vp],
+    "more3d_grid_info": [_vp, C.POINTER(_i64), C.POINTER(_f64)],
+    "more3d_grid_order": [_vp, _vp, _vp],
+    "more3d_radius_count": [_vp, _vp, _i64, _f64, _vp, _vp],
+    "more3d_offsets_from_counts": [_vp, _i64, _vp, C.POINTER(_i64), _vp],
+    "more3d_radius_fill": [_vp, _vp, _i64, _f64, _vp, _vp, _i32, _vp],
+    "more3d_knn": [_vp, _vp, _i64, _i32, _vp, _vp, _vp],
+    "more3d_normals_pca": [_vp, _f64, _vp, _vp, _vp, _vp],
+    "more3d_nonparam_curvature": [_vp, _f64, _vp, _f64, _i32, _vp, _vp, _vp],
+    "more3d_normals_curvature": [_vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "more3d_dk_dn": [_vp, _f64, _vp, _vp, _f64, _f64, _f64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "more3d_minmax4": [_vp, _vp, _i64, _vp, _vp],
+    "more3d_saliency_blend": [_vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp],
+    "more3d_histogram256": [_vp, _i64, _vp, _vp, _vp],
+}
+
+
+class More3DError(RuntimeError):
+    pass
+
+
+def load(build_if_needed=True):
+    """Load (building first when stale and nvcc is available) and return the ctypes library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_needed and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        from . import build as _build
+        try:
+            if _build.stale():
+                _build.build()
+        except Exception as e:  # stale lib + failed rebuild must not be silently used
+            raise More3DError("building libmore3d_b200.so failed: %s" % e)
+    if not os.path.exists(LIB_PATH):
+        raise More3DError("libmore3d_b200.so not found (run `python -m more3d_b200.build`); "
+                          "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.more3d_last_error.restype = C.c_char_p
+    lib.more3d_last_error.argtypes = []
+    lib.more3d_version.restype = C.c_int
+    lib.more3d_version.argtypes = []
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            continue  # reported by tests/test_abi.py; entry points may land incrementally
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().more3d_last_error().decode("utf-8", "replace")
+        raise More3DError("libmore3d_b200 error %d: %s" % (rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise More3DError("more3d_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")

@@ -1,0 +1,125 @@
+// Shared internals of libmore3d_b200 (sm_100a).  Not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/more3d_b200.h"
+
+namespace m3d {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: C-ABI functions return codes, never throw
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define M3D_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            m3d::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                   \
+                           cudaGetErrorString(_e));                                        \
+            return (_e == cudaErrorMemoryAllocation) ? MORE3D_E_NOMEM : MORE3D_E_CUDA;     \
+        }                                                                                  \
+    } while (0)
+
+#define M3D_CHECK_LAUNCH() M3D_CUDA(cudaGetLastError())
+
+#define M3D_TRY(expr)                  \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != MORE3D_OK) return _rc; \
+    } while (0)
+
+#define M3D_REQUIRE(cond, msg)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            m3d::set_error("invalid argument: %s", msg); \
+            return MORE3D_E_INVALID;                   \
+        }                                              \
+    } while (0)
+
+// stream-ordered scratch allocation
+template <typename T>
+static inline int dev_alloc(T** p, size_t count, cudaStream_t s) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    M3D_CUDA(cudaMallocAsync((void**)p, count * sizeof(T), s));
+    return MORE3D_OK;
+}
+static inline void dev_free(void* p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
+// Margin between the grid's column width and the largest radius one stencil step covers: rounding
+// in floor((x - ox) * inv_cell) is ~1e-13 relative, 2^-16 leaves orders of magnitude of slack.
+#define M3D_CELL_MARGIN (1.0 + 1.0 / 65536.0)
+
+// sorted point record: 32 B, two LDG.128
+struct __align__(32) PointRec {
+    double x, y, z;
+    long long idx;  // original index
+};
+
+// sorted feature record for the dk/dn pass: 64 B
+struct __align__(32) FeatRec {
+    double x, y, z;
+    double K;        // _nonparam_K (f32 value widened)
+    double nx, ny, nz;  // unit normal (n / ||n||), NaN if the point has no normal
+    long long flags;    // bit 0: coincident with an earlier point (np.unique drop), bit 1: raw normal was NaN
+};
+
+}  // namespace m3d
+
+struct more3d_grid {
+    int64_t n;
+    int nx, ny;
+    double cell, inv_cell, ox, oy;
+    int device;
+    uint32_t* order;        // n: sorted pos -> original index
+    m3d::PointRec* rec;     // n sorted records
+    uint32_t* col_start;    // nx*ny + 1
+    uint8_t* dup;           // n (sorted order): 1 if coincident with an earlier sorted point
+};
+
+namespace m3d {
+
+// sort.cu ------------------------------------------------------------------------------------
+// Stable LSD radix sort of (key, val) pairs, keys use bits [0, key_bits).  Results end in
+// keys_out/vals_out (which may not alias the inputs); inputs are clobbered (ping-pong).
+int radix_sort_pairs_u32(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
+                         int64_t n, int key_bits, uint32_t** keys_sorted, uint32_t** vals_sorted,
+                         cudaStream_t s);
+int radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
+                         int64_t n, int key_bits, uint64_t** keys_sorted, uint32_t** vals_sorted,
+                         cudaStream_t s);
+// exclusive prefix sums; out[n] = total (out has n+1 entries).  in and out may alias for u32.
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t s);
+int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s);
+
+// device helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ double dist2_rule(double dx, double dy, double dz) {
+    // ((dx*dx)+(dy*dy))+(dz*dz), round-to-nearest each step, never contracted to FMA:
+    // sklearn metrics/_dist_metrics.pxd.tp:44-49
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int cell_coord(double v, double o, double inv, int n) {
+    double f = floor((v - o) * inv);
+    // clamp far-away queries before the int conversion (ix +- stencil must not overflow int32)
+    f = fmin(fmax(f, -1.0e9), 1.0e9);
+    (void)n;
+    return (int)f;
+}
+
+// order-preserving float <-> uint mapping for atomic min/max
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+}  // namespace m3d

@@ -1,0 +1,407 @@
+// K4/K5/K6: fused neighbourhood moments -> PCA normal / surface variation / non-parametric
+// curvature, and the dk/dn centre-surround pass.
+// Replaces Curvature_Kernel.process (DM_saliency.py:88-157), Saliency_Kernel.process (:219-324) and the
+// normals precondition (DM_saliency.py:329-330).
+#include "gridview.cuh"
+
+namespace m3d {
+
+// ------------------------------------------------------------------------------------------
+// symmetric 3x3 eigen-solve: smallest eigenpair, closed form with a Jacobi fallback
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void jacobi3_min(double a00, double a01, double a02, double a11, double a12,
+                                         double a22, double& lmin, double v[3]) {
+    double A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double apq = A[p][q];
+                if (fabs(apq) < 1e-300) continue;
+                double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                double t = ((theta >= 0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    int m = 0;
+    if (A[1][1] < A[m][m]) m = 1;
+    if (A[2][2] < A[m][m]) m = 2;
+    lmin = A[m][m];
+    v[0] = V[0][m]; v[1] = V[1][m]; v[2] = V[2][m];
+}
+
+// Input: symmetric matrix (any scale).  Output: smallest eigenvalue (same scale) and unit eigenvector.
+__device__ __forceinline__ void sym3_min_eig(double a00, double a01, double a02, double a11, double a12,
+                                             double a22, double& lmin, double v[3]) {
+    double sc = fmax(fmax(fabs(a00), fabs(a11)), fmax(fabs(a22), fmax(fabs(a01), fmax(fabs(a02), fabs(a12)))));
+    if (!(sc > 0.0)) { lmin = 0.0; v[0] = 1.0; v[1] = 0.0; v[2] = 0.0; return; }
+    const double is = 1.0 / sc;
+    a00 *= is; a01 *= is; a02 *= is; a11 *= is; a12 *= is; a22 *= is;
+    const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+    const double q = (a00 + a11 + a22) * (1.0 / 3.0);
+    const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+    bool ok = false;
+    double lam = 0.0;
+    if (p2 > 0.0) {
+        // Smith's trigonometric solution of the characteristic cubic
+        const double p = sqrt(p2 * (1.0 / 6.0));
+        const double ip = 1.0 / p;
+        const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip;
+        const double c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
+        double hd = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) +
+                           c02 * (c01 * c12 - c11 * c02));
+        hd = fmin(fmax(hd, -1.0), 1.0);
+        const double phi = acos(hd) * (1.0 / 3.0);
+        lam = q + 2.0 * p * cos(phi + 2.0943951023931954923);  // + 2*pi/3 -> smallest root
+        // eigenvector = largest cross product of two rows of (A - lam I)
+        const double r0x = a00 - lam, r0y = a01, r0z = a02;
+        const double r1x = a01, r1y = a11 - lam, r1z = a12;
+        const double r2x = a02, r2y = a12, r2z = a22 - lam;
+        double cx0 = r0y * r1z - r0z * r1y, cy0 = r0z * r1x - r0x * r1z, cz0 = r0x * r1y - r0y * r1x;
+        double cx1 = r0y * r2z - r0z * r2y, cy1 = r0z * r2x - r0x * r2z, cz1 = r0x * r2y - r0y * r2x;
+        double cx2 = r1y * r2z - r1z * r2y, cy2 = r1z * r2x - r1x * r2z, cz2 = r1x * r2y - r1y * r2x;
+        double n0 = cx0 * cx0 + cy0 * cy0 + cz0 * cz0;
+        double n1 = cx1 * cx1 + cy1 * cy1 + cz1 * cz1;
+        double n2 = cx2 * cx2 + cy2 * cy2 + cz2 * cz2;
+        double bx = cx0, by = cy0, bz = cz0, bn = n0;
+        if (n1 > bn) { bx = cx1; by = cy1; bz = cz1; bn = n1; }
+        if (n2 > bn) { bx = cx2; by = cy2; bz = cz2; bn = n2; }
+        if (bn > 1e-22) {
+            const double in = 1.0 / sqrt(bn);
+            bx *= in; by *= in; bz *= in;
+            // Rayleigh quotient + residual check
+            const double wx = a00 * bx + a01 * by + a02 * bz;
+            const double wy = a01 * bx + a11 * by + a12 * bz;
+            const double wz = a02 * bx + a12 * by + a22 * bz;
+            const double rq = bx * wx + by * wy + bz * wz;
+            const double ex = wx - rq * bx, ey = wy - rq * by, ez = wz - rq * bz;
+            if (ex * ex + ey * ey + ez * ez < 1e-24) {
+                lam = rq; v[0] = bx; v[1] = by; v[2] = bz; ok = true;
+            }
+        }
+    }
+    if (!ok) jacobi3_min(a00, a01, a02, a11, a12, a22, lam, v);
+    lmin = lam * sc;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 + K5
+// ------------------------------------------------------------------------------------------
+enum { MODE_NORMALS = 0, MODE_CURV = 1, MODE_FUSED = 2 };
+
+struct CurvParams {
+    double r2;
+    double eps;
+    int min_points;
+    int s;
+};
+
+// One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
+// query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
+template <int MODE>
+__global__ void __launch_bounds__(256) moments_kernel(GridView g, CurvParams prm,
+                                                      double* __restrict__ normals,
+                                                      double* __restrict__ lam_ratio,
+                                                      float* __restrict__ Kout,
+                                                      int32_t* __restrict__ pcount) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const PointRec p = load_rec(g.rec, i);
+    const int64_t o = p.idx;
+    int m = 0;
+    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    for_each_candidate(g, p.x, p.y, prm.s, [&](int64_t j) {
+        const PointRec c = load_rec(g.rec, j);
+        const double dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
+        if (dist2_rule(dx, dy, dz) <= prm.r2) {
+            ++m;
+            sx += dx; sy += dy; sz += dz;
+            if (MODE != MODE_CURV) {
+                sxx += dx * dx; sxy += dx * dy; sxz += dx * dz;
+                syy += dy * dy; syz += dy * dz; szz += dz * dz;
+            }
+        }
+    });
+
+    double nx, ny, nz;
+    if (MODE == MODE_CURV) {
+        nx = normals[3 * o]; ny = normals[3 * o + 1]; nz = normals[3 * o + 2];
+    } else {
+        double ratio = 0.0;
+        if (m >= 3) {
+            const double im = 1.0 / (double)m;
+            const double cx = sx * im, cy = sy * im, cz = sz * im;
+            const double a00 = sxx * im - cx * cx, a01 = sxy * im - cx * cy, a02 = sxz * im - cx * cz;
+            const double a11 = syy * im - cy * cy, a12 = syz * im - cy * cz, a22 = szz * im - cz * cz;
+            double lmin, v[3];
+            sym3_min_eig(a00, a01, a02, a11, a12, a22, lmin, v);
+            nx = v[0]; ny = v[1]; nz = v[2];
+            const double tr = a00 + a11 + a22;
+            ratio = (tr > 0.0) ? fmax(lmin, 0.0) / tr : 0.0;
+        } else {
+            nx = ny = nz = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if (lam_ratio) lam_ratio[o] = ratio;
+        if (MODE == MODE_NORMALS) {
+            normals[3 * o] = nx; normals[3 * o + 1] = ny; normals[3 * o + 2] = nz;
+            if (pcount) pcount[o] = m;
+            return;
+        }
+    }
+
+    // ---- Curvature_Kernel.process ----
+    pcount[o] = m;                                                    // DM_saliency.py:102
+    float K = 0.0f;
+    bool flipped = false;
+    if (!isnan(nx) && m >= prm.min_points) {                          // :107-110, :120-123
+        // mean tangential offset, projector built from the un-flipped normal (sign invariant) :117,139-141
+        const double im = 1.0 / (double)m;
+        const double cx = sx * im, cy = sy * im, cz = sz * im;
+        const double nc = nx * cx + ny * cy + nz * cz;
+        const double tx = cx - nx * nc, ty = cy - ny * nc, tz = cz - nz * nc;
+        if (nx * (-p.x) + ny * (-p.y) + nz * (-p.z) < 0.0) {          // :131-135
+            nx = -nx; ny = -ny; nz = -nz; flipped = true;
+        }
+        if (!(sqrt(tx * tx + ty * ty + tz * tz) > 1.0)) {             // :142-144
+            // sum_i n.(p - q_i) / (m - 1) = -n.sum(d) / (m - 1)        :137-146
+            const double sum_proj = -(nx * sx + ny * sy + nz * sz) / (double)(m - 1);
+            if (!(fabs(sum_proj) < prm.eps)) K = (float)sum_proj;     // :149-153
+        }
+    }
+    Kout[o] = K;
+    if (MODE == MODE_FUSED || flipped) {
+        normals[3 * o] = nx; normals[3 * o + 1] = ny; normals[3 * o + 2] = nz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: dk/dn
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const double* __restrict__ normals,
+                                                         const float* __restrict__ K,
+                                                         FeatRec* __restrict__ feat) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const PointRec p = load_rec(g.rec, i);
+    const int64_t o = p.idx;
+    const double nx = normals[3 * o], ny = normals[3 * o + 1], nz = normals[3 * o + 2];
+    // n / ||n||, DM_saliency.py:258-259 (norm = sqrt of the sequential sum of squares)
+    const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
+    FeatRec f;
+    f.x = p.x; f.y = p.y; f.z = p.z;
+    f.K = (double)K[o];
+    f.nx = nx / nn; f.ny = ny / nn; f.nz = nz / nn;
+    f.flags = (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL);
+    feat[i] = f;
+}
+
+struct D4 { double x, y, z, w; };
+// half h (0/1) of a 64-B feature record as two LDG.128 through the read-only path
+__device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
+    const double2* p = reinterpret_cast<const double2*>(f) + 2 * h;
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    D4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+
+struct DkDnParams {
+    double r2, rho2, inv_rho2, sigma_n, sigma_k;
+    int min_points, s, table_len;
+};
+
+__global__ void __launch_bounds__(256) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                   DkDnParams prm, const double* __restrict__ chi2_table,
+                                                   float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                   unsigned* __restrict__ mm /* ordered min/max x4 */,
+                                                   int* __restrict__ err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float dkf = 0.0f, dnf = 0.0f;
+    const bool live = i < g.n;
+    if (live) {
+        const D4 pa = ld_d4(feat + i, 0), pb = ld_d4(feat + i, 1);   // (x y z K) (nx ny nz flags)
+        const double px = pa.x, py = pa.y, pz = pa.z, Kp = pa.w;
+        const double pnx = pb.x, pny = pb.y, pnz = pb.z;
+        const long long pflags = __double_as_longlong(pb.w);
+        int m = 0, mu = 0, nact = 0, zn = 0, zk = 0, zk100 = 0;
+        double s1n = 0, s2n = 0, s1k = 0, s2k = 0, wn = 0, wk = 0, wsum = 0;
+        for_each_candidate(g, px, py, prm.s, [&](int64_t j) {
+            const D4 qa = ld_d4(feat + j, 0);
+            const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);   // :256-257
+            if (d2 <= prm.r2) {
+                const D4 qb = ld_d4(feat + j, 1);
+                ++m;
+                if (!(__double_as_longlong(qb.w) & 1LL)) {                    // np.unique, :247
+                    ++mu;
+                    const double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);   // :261
+                    const double dk = Kp - qa.w;                              // :262
+                    double w = 0.0;                                           // :272-275
+                    if (d2 < prm.rho2) w = __dmul_rn(prm.inv_rho2, d2);
+                    else if (d2 > prm.rho2) w = __dadd_rn(__dmul_rn(-prm.inv_rho2, d2), 2.0);
+                    if (w < 0.0) w = 0.0;
+                    const bool act = w > 0.01;                                // :279
+                    s1n += dn; s2n += dn * dn;
+                    s1k += dk; s2k += dk * dk;
+                    const double adn = fabs(dn), adk = fabs(dk);
+                    if (act) {
+                        ++nact;
+                        zn += (adn < 0.016) ? 1 : 0;                          // :286
+                        zk += (adk <= 0.04) ? 1 : 0;                          // :287
+                        zk100 += (fabs(__dmul_rn(dk, 100.0)) <= 0.04) ? 1 : 0;  // :290
+                    }
+                    wn += adn * w; wk += dk * w; wsum += w;                   // :300, :316
+                }
+            }
+        });
+        if (!(pflags & 2LL) && m >= prm.min_points) {                         // :225-229, :240-244
+            if (nact >= prm.table_len) {
+                atomicExch(err, 1);
+            } else {
+                const double chi_t = chi2_table[nact];                        // :282
+                const double imu = 1.0 / (double)mu;
+                const double mn = s1n * imu, mk = s1k * imu;
+                const double std_n = sqrt(fmax(s2n * imu - mn * mn, 0.0));
+                const double std_k = sqrt(fmax(s2k * imu - mk * mk, 0.0));
+                // NaN propagates like numpy: fmax(NaN, 0) would hide it, so re-inject
+                const double sdn = isnan(s1n) ? s1n : std_n;
+                const double sdk = isnan(s1k) ? s1k : std_k;
+                const double chi_n = (double)(m - 1) * sdn / prm.sigma_n;     // :283
+                const double chi_k = (double)(m - 1) * sdk / prm.sigma_k;     // :284
+                if (zk == nact) zk = zk100;                                   // :289-290
+                const double lim = 0.6 * (double)nact;
+                double dn;
+                if (chi_n < chi_t) dn = 0.0;                                  // :292-300
+                else if ((double)zn > lim) dn = 0.0;
+                else dn = wn / wsum;
+                if (isnan(dn)) dn = 0.0;                                      // :303-308
+                else if (dn > 2.0) dn = 1.0;
+                double dk;
+                if (chi_k < chi_t) dk = 0.0;                                  // :309-316
+                else if ((double)zk > lim) dk = 0.0;
+                else dk = fabs(wk / wsum);
+                dkf = (float)dk; dnf = (float)dn;
+            }
+        }
+        const int64_t o = __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+        dk_out[o] = dkf;
+        dn_out[o] = dnf;
+    }
+    if (mm) {
+        // fused Histo min/max (DM_saliency.py:562-568): warp shuffle, then one atomic per warp
+        unsigned lo_k = live ? f32_ordered(dkf) : 0xffffffffu, hi_k = live ? f32_ordered(dkf) : 0u;
+        unsigned lo_n = live ? f32_ordered(dnf) : 0xffffffffu, hi_n = live ? f32_ordered(dnf) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo_k = min(lo_k, __shfl_xor_sync(0xffffffffu, lo_k, o));
+            hi_k = max(hi_k, __shfl_xor_sync(0xffffffffu, hi_k, o));
+            lo_n = min(lo_n, __shfl_xor_sync(0xffffffffu, lo_n, o));
+            hi_n = max(hi_n, __shfl_xor_sync(0xffffffffu, hi_n, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k);
+            atomicMin(mm + 2, lo_n); atomicMax(mm + 3, hi_n);
+        }
+    }
+}
+
+__global__ void minmax_init(unsigned* mm) {
+    if (threadIdx.x < 4) mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
+}
+__global__ void minmax_finish(const unsigned* mm, float* out) {
+    if (threadIdx.x < 4) out[threadIdx.x] = f32_unordered(mm[threadIdx.x]);
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+static int launch_moments(const more3d_grid* g, int mode, double r, double eps, int min_points,
+                          double* normals, double* lam_ratio, float* K, int32_t* pcount, cudaStream_t s) {
+    M3D_REQUIRE(g != nullptr, "grid is NULL");
+    M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
+    M3D_REQUIRE(normals != nullptr, "normals is NULL");
+    CurvParams prm;
+    prm.r2 = r * r; prm.eps = eps; prm.min_points = min_points; prm.s = stencil_halfwidth(g, r);
+    const unsigned nb = (unsigned)((g->n + 255) / 256);
+    GridView v = make_view(g);
+    if (mode == MODE_NORMALS)
+        moments_kernel<MODE_NORMALS><<<nb, 256, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount);
+    else if (mode == MODE_CURV)
+        moments_kernel<MODE_CURV><<<nb, 256, 0, s>>>(v, prm, normals, nullptr, K, pcount);
+    else
+        moments_kernel<MODE_FUSED><<<nb, 256, 0, s>>>(v, prm, normals, lam_ratio, K, pcount);
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_normals_pca(const more3d_grid* g, double r, double* normals, double* lam_ratio,
+                                  int32_t* counts, void* stream) {
+    return launch_moments(g, MODE_NORMALS, r, 0.0, 0, normals, lam_ratio, nullptr, counts, (cudaStream_t)stream);
+}
+
+extern "C" int more3d_nonparam_curvature(const more3d_grid* g, double r, double* normals_inout, double eps,
+                                         int min_points, float* K, int32_t* pcount, void* stream) {
+    M3D_REQUIRE(K != nullptr && pcount != nullptr, "K / pcount is NULL");
+    return launch_moments(g, MODE_CURV, r, eps, min_points, normals_inout, nullptr, K, pcount, (cudaStream_t)stream);
+}
+
+extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double eps, int min_points,
+                                        double* normals, double* lam_ratio, float* K, int32_t* pcount,
+                                        void* stream) {
+    M3D_REQUIRE(K != nullptr && pcount != nullptr, "K / pcount is NULL");
+    return launch_moments(g, MODE_FUSED, r, eps, min_points, normals, lam_ratio, K, pcount, (cudaStream_t)stream);
+}
+
+extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
+                            double sigma_normal, double sigma_curvature, const double* chi2_table,
+                            int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream) {
+    M3D_REQUIRE(g != nullptr, "grid is NULL");
+    M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
+    M3D_REQUIRE(normals && K && chi2_table && dk && dn, "NULL argument");
+    M3D_REQUIRE(table_len > 0, "chi2 table is empty");
+    cudaStream_t s = (cudaStream_t)stream;
+    FeatRec* feat = nullptr;
+    unsigned* mm = nullptr;
+    int* err = nullptr;
+    M3D_TRY(dev_alloc(&feat, (size_t)g->n, s));
+    M3D_TRY(dev_alloc(&mm, 4, s));
+    M3D_TRY(dev_alloc(&err, 1, s));
+    M3D_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+    const unsigned nb = (unsigned)((g->n + 255) / 256);
+    GridView v = make_view(g);
+    build_feat_kernel<<<nb, 256, 0, s>>>(v, normals, K, feat);
+    minmax_init<<<1, 32, 0, s>>>(mm);
+    DkDnParams prm;
+    prm.r2 = r * r; prm.rho2 = rho * rho; prm.inv_rho2 = 1.0 / (rho * rho);
+    prm.sigma_n = sigma_normal; prm.sigma_k = sigma_curvature;
+    prm.min_points = min_points; prm.s = stencil_halfwidth(g, r); prm.table_len = table_len;
+    dkdn_kernel<<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+    if (minmax) minmax_finish<<<1, 32, 0, s>>>(mm, minmax);
+    M3D_CHECK_LAUNCH();
+    int err_h = 0;
+    M3D_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    dev_free(feat, s); dev_free(mm, s); dev_free(err, s);
+    if (err_h) {
+        set_error("dk/dn: a neighbourhood has more active neighbours than chi2_table covers (table_len=%d)", table_len);
+        return MORE3D_E_RANGE;
+    }
+    return MORE3D_OK;
+}

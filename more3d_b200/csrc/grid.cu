@@ -1,0 +1,229 @@
+// Uniform xy-column grid: the spatial index that replaces the reference's ball tree
+// (Downsampling/BallTreePointSet.py:19-53 -> sklearn BallTree build).
+//
+// Layout in HBM after more3d_grid_create:
+//   rec[n]        sorted 32-B records (x, y, z, original index), order = (column key, original index)
+//   order[n]      sorted position -> original index (u32)
+//   col_start[]   nx*ny + 1 exclusive offsets; column (ix, iy) owns rec[col_start[iy*nx+ix] .. col_start[iy*nx+ix+1])
+//   dup[n]        1 if the sorted point coincides (bit-equal xyz) with an earlier sorted point
+// Columns are x-fastest, so the (2s+1) columns of one stencil row are ONE contiguous range of rec.
+#include "common.cuh"
+
+namespace m3d {
+
+constexpr int BB_THREADS = 256;
+
+__global__ void __launch_bounds__(BB_THREADS) bbox_partial(const double* __restrict__ xyz, int64_t n,
+                                                           double* __restrict__ part) {
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double x = xyz[3 * i], y = xyz[3 * i + 1];
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x);
+        mny = fmin(mny, y); mxy = fmax(mxy, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    __shared__ double sm[4][BB_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm[0][warp] = mnx; sm[1][warp] = mny; sm[2][warp] = mxx; sm[3][warp] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < BB_THREADS / 32; ++w) {
+            mnx = fmin(mnx, sm[0][w]); mny = fmin(mny, sm[1][w]);
+            mxx = fmax(mxx, sm[2][w]); mxy = fmax(mxy, sm[3][w]);
+        }
+        part[4 * blockIdx.x + 0] = mnx; part[4 * blockIdx.x + 1] = mny;
+        part[4 * blockIdx.x + 2] = mxx; part[4 * blockIdx.x + 3] = mxy;
+    }
+}
+
+__global__ void bbox_final(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = threadIdx.x; i < nparts; i += 32) {
+        mnx = fmin(mnx, part[4 * i]); mny = fmin(mny, part[4 * i + 1]);
+        mxx = fmax(mxx, part[4 * i + 2]); mxy = fmax(mxy, part[4 * i + 3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (threadIdx.x == 0) { out[0] = mnx; out[1] = mny; out[2] = mxx; out[3] = mxy; }
+}
+
+// K1: column key per point + column population (spread-address REDG)
+__global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz, int64_t n, double ox,
+                                                 double oy, double inv, int nx, int ny,
+                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                 uint32_t* __restrict__ col_count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ix = cell_coord(xyz[3 * i], ox, inv, nx);
+    int iy = cell_coord(xyz[3 * i + 1], oy, inv, ny);
+    ix = min(max(ix, 0), nx - 1);
+    iy = min(max(iy, 0), ny - 1);
+    uint32_t key = (uint32_t)iy * (uint32_t)nx + (uint32_t)ix;
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    atomicAdd(&col_count[key], 1u);
+}
+
+// K2 tail: gather the sorted records
+__global__ void __launch_bounds__(256) gather_records(const double* __restrict__ xyz,
+                                                      const uint32_t* __restrict__ order, int64_t n,
+                                                      PointRec* __restrict__ rec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o = order[i];
+    PointRec r;
+    r.x = xyz[3 * (int64_t)o];
+    r.y = xyz[3 * (int64_t)o + 1];
+    r.z = xyz[3 * (int64_t)o + 2];
+    r.idx = (long long)o;
+    rec[i] = r;
+}
+
+// coincident-point flags: the np.unique(axis=1) of Saliency_Kernel.process (DM_saliency.py:247)
+// keeps one representative of every set of bit-equal positions; coincident points share a column.
+__global__ void __launch_bounds__(256) dup_flags(const PointRec* __restrict__ rec,
+                                                 const uint32_t* __restrict__ col_start, int64_t n,
+                                                 double ox, double oy, double inv, int nx, int ny,
+                                                 uint8_t* __restrict__ dup) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PointRec p = rec[i];
+    int ix = min(max(cell_coord(p.x, ox, inv, nx), 0), nx - 1);
+    int iy = min(max(cell_coord(p.y, oy, inv, ny), 0), ny - 1);
+    uint32_t b = col_start[(size_t)iy * nx + ix];
+    uint8_t f = 0;
+    for (int64_t j = b; j < i; ++j) {
+        PointRec q = rec[j];
+        if (q.x == p.x && q.y == p.y && q.z == p.z) { f = 1; break; }
+    }
+    dup[i] = f;
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, void* stream,
+                                  more3d_grid** out) {
+    M3D_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    M3D_REQUIRE(n > 0 && xyz != nullptr, "empty cloud");
+    M3D_REQUIRE(cell > 0 && isfinite(cell), "cell must be > 0");
+    if (n >= ((int64_t)1 << 31)) {
+        set_error("n >= 2^31 points per grid not supported");
+        return MORE3D_E_RANGE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+
+    // bounding box (host needs it to size the table: one small sync per build)
+    const int nparts = 592;  // 4 CTAs per SM on 148 SMs
+    double* part = nullptr;
+    M3D_TRY(dev_alloc(&part, (size_t)4 * nparts + 4, s));
+    bbox_partial<<<nparts, BB_THREADS, 0, s>>>(xyz, n, part);
+    bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 4 * nparts);
+    M3D_CHECK_LAUNCH();
+    double bb[4];
+    M3D_CUDA(cudaMemcpyAsync(bb, part + 4 * nparts, sizeof(bb), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    dev_free(part, s);
+    if (!(isfinite(bb[0]) && isfinite(bb[1]) && isfinite(bb[2]) && isfinite(bb[3]))) {
+        set_error("non-finite coordinates in cloud");
+        return MORE3D_E_INVALID;
+    }
+
+    // widen the cell until the column table fits (stencils stay correct for any cell >= requested)
+    const double max_cols = 268435456.0;  // 2^28 columns = 1 GiB table
+    double c = cell;
+    double ex = bb[2] - bb[0], ey = bb[3] - bb[1];
+    for (int it = 0; it < 64; ++it) {
+        double cols = (floor(ex / c) + 3.0) * (floor(ey / c) + 3.0);
+        if (cols <= max_cols) break;
+        c *= 1.25;
+    }
+    more3d_grid* g = new more3d_grid();
+    g->n = n;
+    g->cell = c;
+    g->inv_cell = 1.0 / c;
+    g->ox = bb[0] - c;
+    g->oy = bb[1] - c;
+    g->nx = (int)floor(ex / c) + 3;
+    g->ny = (int)floor(ey / c) + 3;
+    cudaGetDevice(&g->device);
+    g->order = nullptr; g->rec = nullptr; g->col_start = nullptr; g->dup = nullptr;
+    const size_t ncols = (size_t)g->nx * g->ny;
+
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    int rc = MORE3D_OK;
+#define G_TRY(e) do { rc = (e); if (rc != MORE3D_OK) goto fail; } while (0)
+#define G_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); rc = (_e == cudaErrorMemoryAllocation) ? MORE3D_E_NOMEM : MORE3D_E_CUDA; goto fail; } } while (0)
+    {
+        G_CUDA(cudaMalloc((void**)&g->col_start, (ncols + 1) * sizeof(uint32_t)));
+        G_CUDA(cudaMalloc((void**)&g->order, (size_t)n * sizeof(uint32_t)));
+        G_CUDA(cudaMalloc((void**)&g->rec, (size_t)n * sizeof(PointRec)));
+        G_CUDA(cudaMalloc((void**)&g->dup, (size_t)n));
+        G_TRY(dev_alloc(&keys, (size_t)n, s));
+        G_TRY(dev_alloc(&vals, (size_t)n, s));
+        G_TRY(dev_alloc(&keys2, (size_t)n, s));
+        G_TRY(dev_alloc(&vals2, (size_t)n, s));
+        G_CUDA(cudaMemsetAsync(g->col_start, 0, (ncols + 1) * sizeof(uint32_t), s));
+        const unsigned nb = (unsigned)((n + 255) / 256);
+        cell_keys<<<nb, 256, 0, s>>>(xyz, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, keys, vals,
+                                     g->col_start);
+        G_CUDA(cudaGetLastError());
+        G_TRY(exclusive_scan_u32(g->col_start, g->col_start, (int64_t)ncols, s));
+        int bits = 1;
+        while (((size_t)1 << bits) < ncols) ++bits;
+        uint32_t *ks = nullptr, *vs = nullptr;
+        G_TRY(radix_sort_pairs_u32(keys, vals, keys2, vals2, n, bits, &ks, &vs, s));
+        G_CUDA(cudaMemcpyAsync(g->order, vs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec);
+        dup_flags<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny,
+                                     g->dup);
+        G_CUDA(cudaGetLastError());
+    }
+    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s);
+    *out = g;
+    return MORE3D_OK;
+fail:
+    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s);
+    more3d_grid_destroy(g);
+    return rc;
+#undef G_TRY
+#undef G_CUDA
+}
+
+extern "C" int more3d_grid_destroy(more3d_grid* g) {
+    if (!g) return MORE3D_OK;
+    cudaFree(g->order);
+    cudaFree(g->rec);
+    cudaFree(g->col_start);
+    cudaFree(g->dup);
+    delete g;
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_grid_info(const more3d_grid* g, int64_t* info_h, double* geom_h) {
+    M3D_REQUIRE(g != nullptr, "grid is NULL");
+    if (info_h) { info_h[0] = g->n; info_h[1] = g->nx; info_h[2] = g->ny; }
+    if (geom_h) { geom_h[0] = g->cell; geom_h[1] = g->ox; geom_h[2] = g->oy; }
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_grid_order(const more3d_grid* g, int32_t* order, void* stream) {
+    M3D_REQUIRE(g != nullptr && order != nullptr, "NULL argument");
+    M3D_CUDA(cudaMemcpyAsync(order, g->order, (size_t)g->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return MORE3D_OK;
+}

@@ -1,0 +1,115 @@
+// K3: fixed-radius neighbour query -> CSR (count, scan, fill).
+// Replaces BallTreePointSet.queryRadius (Downsampling/BallTreePointSet.py:317-347).
+#include "gridview.cuh"
+
+namespace m3d {
+
+// SELF: queries are the grid's own points, walked in sorted order (neighbouring threads share
+// stencil rows, so candidate loads are L1 broadcasts); results land at the ORIGINAL index.
+template <bool SELF>
+__global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const double* __restrict__ q,
+                                                           int64_t nq, double r2, int s,
+                                                           int32_t* __restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double px, py, pz;
+    int64_t out;
+    if (SELF) {
+        PointRec p = load_rec(g.rec, i);
+        px = p.x; py = p.y; pz = p.z; out = p.idx;
+    } else {
+        px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
+    }
+    int c = 0;
+    for_each_candidate(g, px, py, s, [&](int64_t j) {
+        PointRec c_ = load_rec(g.rec, j);
+        double d2 = dist2_rule(px - c_.x, py - c_.y, pz - c_.z);
+        c += (d2 <= r2) ? 1 : 0;
+    });
+    counts[out] = c;
+}
+
+template <bool SELF, typename IdxT>
+__global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const double* __restrict__ q,
+                                                          int64_t nq, double r2, int s,
+                                                          const int64_t* __restrict__ offsets,
+                                                          IdxT* __restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double px, py, pz;
+    int64_t out;
+    if (SELF) {
+        PointRec p = load_rec(g.rec, i);
+        px = p.x; py = p.y; pz = p.z; out = p.idx;
+    } else {
+        px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
+    }
+    int64_t w = offsets[out];
+    for_each_candidate(g, px, py, s, [&](int64_t j) {
+        PointRec c_ = load_rec(g.rec, j);
+        double d2 = dist2_rule(px - c_.x, py - c_.y, pz - c_.z);
+        if (d2 <= r2) idx[w++] = (IdxT)c_.idx;
+    });
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+static int check_query(const more3d_grid* g, const double* q, int64_t nq, double r) {
+    M3D_REQUIRE(g != nullptr, "grid is NULL");
+    M3D_REQUIRE(nq >= 0, "nq < 0");
+    M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
+    M3D_REQUIRE(q != nullptr || nq == g->n, "self query (q == NULL) needs nq == n");
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_radius_count(const more3d_grid* g, const double* q, int64_t nq, double r,
+                                   int32_t* counts, void* stream) {
+    M3D_TRY(check_query(g, q, nq, r));
+    if (nq == 0) return MORE3D_OK;
+    M3D_REQUIRE(counts != nullptr, "counts is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sw = stencil_halfwidth(g, r);
+    const unsigned nb = (unsigned)((nq + 255) / 256);
+    if (q)
+        radius_count_kernel<false><<<nb, 256, 0, s>>>(make_view(g), q, nq, r * r, sw, counts);
+    else
+        radius_count_kernel<true><<<nb, 256, 0, s>>>(make_view(g), nullptr, nq, r * r, sw, counts);
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_offsets_from_counts(const int32_t* counts, int64_t nq, int64_t* offsets,
+                                          int64_t* total_h, void* stream) {
+    M3D_REQUIRE(offsets != nullptr && (counts != nullptr || nq == 0), "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    M3D_TRY(exclusive_scan_i32_to_i64(counts, offsets, nq, s));
+    if (total_h) {
+        M3D_CUDA(cudaMemcpyAsync(total_h, offsets + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        M3D_CUDA(cudaStreamSynchronize(s));
+    }
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t nq, double r,
+                                  const int64_t* offsets, void* idx, int idx_bytes, void* stream) {
+    M3D_TRY(check_query(g, q, nq, r));
+    if (nq == 0) return MORE3D_OK;
+    M3D_REQUIRE(offsets != nullptr && idx != nullptr, "NULL argument");
+    M3D_REQUIRE(idx_bytes == 4 || idx_bytes == 8, "idx_bytes must be 4 or 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sw = stencil_halfwidth(g, r);
+    const unsigned nb = (unsigned)((nq + 255) / 256);
+    GridView v = make_view(g);
+    const double r2 = r * r;
+    if (q) {
+        if (idx_bytes == 4) radius_fill_kernel<false, int32_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, offsets, (int32_t*)idx);
+        else radius_fill_kernel<false, int64_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, offsets, (int64_t*)idx);
+    } else {
+        if (idx_bytes == 4) radius_fill_kernel<true, int32_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, offsets, (int32_t*)idx);
+        else radius_fill_kernel<true, int64_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, offsets, (int64_t*)idx);
+    }
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}

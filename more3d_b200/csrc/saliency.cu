@@ -1,0 +1,135 @@
+// K7: DM_saliency -- min/max (OPALS Histo), normalise (+min, as written) and blend (AddInfo),
+// and the 256-bin histogram that feeds Otsu (Downsample.py:54).
+// Replaces DM_saliency.py:562-580.
+#include "common.cuh"
+
+namespace m3d {
+
+__global__ void mm4_init(unsigned* mm, int n) {
+    if ((int)threadIdx.x < n) mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
+}
+__global__ void mm4_finish(const unsigned* mm, float* out, int n) {
+    if ((int)threadIdx.x < n) out[threadIdx.x] = f32_unordered(mm[threadIdx.x]);
+}
+
+__device__ __forceinline__ void warp_minmax_atomic(unsigned lo, unsigned hi, unsigned* mm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+
+__global__ void __launch_bounds__(256) minmax4_kernel(const float* __restrict__ dk,
+                                                      const float* __restrict__ dn, int64_t n,
+                                                      unsigned* __restrict__ mm) {
+    unsigned lk = 0xffffffffu, hk = 0u, ln = 0xffffffffu, hn = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned a = f32_ordered(dk[i]), b = f32_ordered(dn[i]);
+        lk = min(lk, a); hk = max(hk, a); ln = min(ln, b); hn = max(hn, b);
+    }
+    warp_minmax_atomic(lk, hk, mm);
+    warp_minmax_atomic(ln, hn, mm + 2);
+}
+
+// (x - min)/(max - min) + min evaluated in fp64 and stored as f32 ('(float)' AddInfo columns),
+// then (1-w)*ndn + w*ndk; no FMA contraction so the result is reproducible on the host.
+__global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk, const float* __restrict__ dn,
+                                                    int64_t n, const float* __restrict__ minmax, double cw,
+                                                    double nw, float* __restrict__ sal,
+                                                    unsigned* __restrict__ smm) {
+    const double min_k = (double)minmax[0], max_k = (double)minmax[1];
+    const double min_n = (double)minmax[2], max_n = (double)minmax[3];
+    const double diff_k = __dsub_rn(max_k, min_k), diff_n = __dsub_rn(max_n, min_n);   // :570-571
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float ndk = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)dk[i], min_k), diff_k), min_k);  // :577
+        const float ndn = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)dn[i], min_n), diff_n), min_n);  // :578
+        const float sv = (float)__dadd_rn(__dmul_rn(nw, (double)ndn), __dmul_rn(cw, (double)ndk));      // :579-580
+        sal[i] = sv;
+        const unsigned u = f32_ordered(sv);
+        lo = min(lo, u); hi = max(hi, u);
+    }
+    if (smm) warp_minmax_atomic(lo, hi, smm);
+}
+
+// numpy.histogram's uniform-bin path (numpy/lib/_histograms_impl.py): index from the scaled
+// offset, then the two edge fix-ups against the linspace edges.  CTA-private smem histogram,
+// match_any warp aggregation in front of the shared-memory atomics, one global atomic per bin per CTA.
+__global__ void __launch_bounds__(256) hist256_kernel(const float* __restrict__ v, int64_t n,
+                                                      const double* __restrict__ edges,
+                                                      unsigned long long* __restrict__ hist) {
+    __shared__ unsigned h[256];
+    __shared__ double e[257];
+    h[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 257; i += 256) e[i] = edges[i];
+    __syncthreads();
+    const double first = e[0], last = e[256];
+    const double denom = __dsub_rn(last, first);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = ((n + stride - 1) / stride) * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        int bin = -1;
+        if (i < n) {
+            const double a = (double)v[i];
+            if (a >= first && a <= last) {
+                double f = __dmul_rn(__ddiv_rn(__dsub_rn(a, first), denom), 256.0);
+                int b = (int)f;
+                if (b == 256) b = 255;
+                if (a < e[b]) b -= 1;
+                if (a >= e[b + 1] && b != 255) b += 1;
+                bin = b;
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&h[bin], __popc(peers));
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+extern "C" int more3d_minmax4(const float* dk, const float* dn, int64_t n, float* minmax, void* stream) {
+    M3D_REQUIRE(dk && dn && minmax && n > 0, "NULL / empty argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* mm = nullptr;
+    M3D_TRY(dev_alloc(&mm, 4, s));
+    mm4_init<<<1, 32, 0, s>>>(mm, 4);
+    minmax4_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, n, mm);
+    mm4_finish<<<1, 32, 0, s>>>(mm, minmax, 4);
+    M3D_CHECK_LAUNCH();
+    dev_free(mm, s);
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_saliency_blend(const float* dk, const float* dn, int64_t n, const float* minmax,
+                                     double curvature_weight, float* sal, float* sal_minmax, void* stream) {
+    M3D_REQUIRE(dk && dn && minmax && sal && n > 0, "NULL / empty argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* mm = nullptr;
+    if (sal_minmax) {
+        M3D_TRY(dev_alloc(&mm, 2, s));
+        mm4_init<<<1, 32, 0, s>>>(mm, 2);
+    }
+    const double nw = 1.0 - curvature_weight;   // DM_saliency.py:572
+    blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, n, minmax, curvature_weight, nw, sal, mm);
+    if (sal_minmax) mm4_finish<<<1, 32, 0, s>>>(mm, sal_minmax, 2);
+    M3D_CHECK_LAUNCH();
+    dev_free(mm, s);
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_histogram256(const float* v, int64_t n, const double* edges, int64_t* hist, void* stream) {
+    M3D_REQUIRE(v && edges && hist && n > 0, "NULL / empty argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    M3D_CUDA(cudaMemsetAsync(hist, 0, 256 * sizeof(int64_t), s));
+    hist256_kernel<<<148 * 4, 256, 0, s>>>(v, n, edges, (unsigned long long*)hist);
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}

@@ -1,0 +1,262 @@
+// Hand-written stable LSD radix sort (8-bit digits) and exclusive scans for the grid build,
+// voxel keys and CSR offsets.  sm_100a; no CUB on the product path.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace m3d {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan: tile sums -> single-block scan of the sums -> tile scan + offset
+// ------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* smem /* 32 entries */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : T(0);
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    T res = smem[warp] + inc - v;
+    if (total) *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SC_THREADS) scan_tile_sums(const Tin* __restrict__ in, int64_t n,
+                                                             Tout* __restrict__ sums) {
+    __shared__ Tout sm[33];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    Tout s = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i)
+        if (base + i < n) s += (Tout)in[base + i];
+    Tout total;
+    block_exclusive_scan<Tout>(s, &total, sm);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+template <typename Tout>
+__global__ void __launch_bounds__(1024) scan_sums_single(Tout* __restrict__ sums, int64_t m,
+                                                         Tout* __restrict__ grand_total) {
+    __shared__ Tout sm[33];
+    Tout carry = 0;
+    for (int64_t base = 0; base < m; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        Tout v = (i < m) ? sums[i] : Tout(0);
+        Tout total;
+        Tout ex = block_exclusive_scan<Tout>(v, &total, sm);
+        if (i < m) sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SC_THREADS) scan_tile_apply(const Tin* in, int64_t n,
+                                                              const Tout* __restrict__ sums, Tout* out) {
+    __shared__ Tout sm[33];
+    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    Tout v[SC_ITEMS];
+    Tout s = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        v[i] = (base + i < n) ? (Tout)in[base + i] : Tout(0);
+        s += v[i];
+    }
+    Tout ex = block_exclusive_scan<Tout>(s, nullptr, sm) + sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+}
+
+template <typename Tin, typename Tout>
+static int exclusive_scan_impl(const Tin* in, Tout* out, int64_t n, cudaStream_t s) {
+    if (n <= 0) {
+        M3D_CUDA(cudaMemsetAsync(out, 0, sizeof(Tout), s));
+        return MORE3D_OK;
+    }
+    int64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    Tout* sums = nullptr;
+    M3D_TRY(dev_alloc(&sums, (size_t)tiles, s));
+    scan_tile_sums<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, n, sums);
+    scan_sums_single<Tout><<<1, 1024, 0, s>>>(sums, tiles, out + n);
+    scan_tile_apply<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, n, sums, out);
+    M3D_CHECK_LAUNCH();
+    dev_free(sums, s);
+    return MORE3D_OK;
+}
+
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t s) {
+    return exclusive_scan_impl<uint32_t, uint32_t>(in, out, n, s);
+}
+int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s) {
+    return exclusive_scan_impl<int32_t, int64_t>(in, out, n, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// radix sort
+// ------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                    // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+constexpr int RS_WTILE = RS_TILE / RS_WARPS;    // 512 consecutive keys per warp
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys, int64_t n, int shift,
+                                                      uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        int64_t p = base + i;
+        if (p < n) atomicAdd(&h[(unsigned)(keys[p] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+// Stable scatter: warp w owns keys [w*512, (w+1)*512) of the tile, walks them in 16 rounds of 32;
+// __match_any_sync gives each key its rank among equal digits of the round, per-warp running
+// counters (seeded with the scanned global histogram + the counts of lower warps) give the rest.
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys,
+                                                         const uint32_t* __restrict__ vals,
+                                                         K* __restrict__ keys_out,
+                                                         uint32_t* __restrict__ vals_out, int64_t n,
+                                                         int shift, const uint32_t* __restrict__ hist_ex,
+                                                         int nblocks) {
+    __shared__ uint32_t wcnt[RS_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_WTILE;
+    K k[RS_ITEMS];
+    uint32_t v[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        int64_t p = wbase + j * 32 + lane;
+        bool ok = p < n;
+        k[j] = ok ? keys[p] : K(0);
+        v[j] = ok ? vals[p] : 0u;
+    }
+    // phase A: per-warp digit counts
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        bool ok = (wbase + j * 32 + lane) < n;
+        unsigned d = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (ok && (peers & lt) == 0u) wcnt[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;  // RS_THREADS == 256 digits
+        uint32_t run = hist_ex[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase B: ranks and scatter
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        bool ok = (wbase + j * 32 + lane) < n;
+        unsigned d = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pos = 0;
+        if (ok) pos = wcnt[warp][d] + __popc(peers & lt);
+        __syncwarp();
+        if (ok && (peers & lt) == 0u) wcnt[warp][d] += __popc(peers);
+        __syncwarp();
+        if (ok) {
+            keys_out[pos] = k[j];
+            vals_out[pos] = v[j];
+        }
+    }
+}
+
+template <typename K>
+static int radix_sort_impl(K* keys, uint32_t* vals, K* keys_alt, uint32_t* vals_alt, int64_t n,
+                           int key_bits, K** keys_sorted, uint32_t** vals_sorted, cudaStream_t s) {
+    *keys_sorted = keys;
+    *vals_sorted = vals;
+    if (n <= 1 || key_bits <= 0) return MORE3D_OK;
+    if (n >= (int64_t)1 << 32) {
+        set_error("radix sort: n >= 2^32 not supported");
+        return MORE3D_E_RANGE;
+    }
+    const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+    uint32_t* hist = nullptr;
+    M3D_TRY(dev_alloc(&hist, (size_t)256 * nblocks + 1, s));
+    K* kin = keys;
+    K* kout = keys_alt;
+    uint32_t* vin = vals;
+    uint32_t* vout = vals_alt;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        rs_hist<K><<<nblocks, RS_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
+        M3D_TRY(exclusive_scan_u32(hist, hist, (int64_t)256 * nblocks, s));
+        rs_scatter<K><<<nblocks, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
+        M3D_CHECK_LAUNCH();
+        K* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    dev_free(hist, s);
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    return MORE3D_OK;
+}
+
+int radix_sort_pairs_u32(uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
+                         int64_t n, int key_bits, uint32_t** keys_sorted, uint32_t** vals_sorted,
+                         cudaStream_t s) {
+    return radix_sort_impl<uint32_t>(keys, vals, keys_alt, vals_alt, n, key_bits, keys_sorted, vals_sorted, s);
+}
+int radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uint32_t* vals_alt,
+                         int64_t n, int key_bits, uint64_t** keys_sorted, uint32_t** vals_sorted,
+                         cudaStream_t s) {
+    return radix_sort_impl<uint64_t>(keys, vals, keys_alt, vals_alt, n, key_bits, keys_sorted, vals_sorted, s);
+}
+
+}  // namespace m3d
+
+extern "C" const char* more3d_last_error(void) { return m3d::get_error(); }
+extern "C" int more3d_version(void) { return 100; }

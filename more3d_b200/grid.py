@@ -1,0 +1,139 @@
+"""Device-resident uniform grid: thin host wrapper over the C-ABI (include/more3d_b200.h).
+
+torch is used for device memory and streams only; all compute is in libmore3d_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+CELL_MARGIN = 1.0 + 1.0 / 65536.0
+
+
+def as_device_points(points, device=None):
+    """(N,3) float64 C-order CUDA tensor from numpy / torch input (host inputs are copied H2D)."""
+    _lib.require_cuda()
+    if isinstance(points, torch.Tensor):
+        t = points
+    else:
+        a = np.ascontiguousarray(points, dtype=np.float64)
+        t = torch.from_numpy(a)
+    if t.ndim != 2 or t.shape[1] != 3:
+        raise ValueError("points must have shape (N, 3)")
+    dev = torch.device(device if device is not None else "cuda")
+    return t.to(device=dev, dtype=torch.float64).contiguous()
+
+
+class UniformGrid:
+    """Spatial index replacing the reference's ball tree (BallTreePointSet.py:35)."""
+
+    def __init__(self, xyz, cell):
+        self.lib = _lib.load()
+        self.xyz = as_device_points(xyz)
+        self.n = int(self.xyz.shape[0])
+        if self.n == 0:
+            raise ValueError("empty cloud")
+        self.device = self.xyz.device
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.more3d_grid_create(ptr(self.xyz), self.n, float(cell), stream_ptr(), C.byref(h)))
+        self._h = h
+        info = (C.c_int64 * 3)()
+        geom = (C.c_double * 3)()
+        check(self.lib.more3d_grid_info(self._h, info, geom))
+        self.nx, self.ny = int(info[1]), int(info[2])
+        self.cell, self.ox, self.oy = float(geom[0]), float(geom[1]), float(geom[2])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.more3d_grid_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------------------
+    def _new(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def order(self):
+        o = self._new((self.n,), torch.int32)
+        check(self.lib.more3d_grid_order(self._h, ptr(o), stream_ptr()))
+        return o
+
+    def radius_csr(self, q, r, idx_dtype=torch.int32):
+        """CSR neighbour lists: (offsets int64 [nq+1], idx [total]).  q=None -> the cloud itself."""
+        with torch.cuda.device(self.device):
+            qd = None if q is None else as_device_points(q, self.device)
+            nq = self.n if qd is None else int(qd.shape[0])
+            counts = self._new((max(nq, 1),), torch.int32)
+            offsets = self._new((nq + 1,), torch.int64)
+            check(self.lib.more3d_radius_count(self._h, ptr(qd), nq, float(r), ptr(counts), stream_ptr()))
+            total = C.c_int64(0)
+            check(self.lib.more3d_offsets_from_counts(ptr(counts), nq, ptr(offsets), C.byref(total), stream_ptr()))
+            idx = self._new((max(int(total.value), 1),), idx_dtype)
+            nbytes = 4 if idx_dtype == torch.int32 else 8
+            check(self.lib.more3d_radius_fill(self._h, ptr(qd), nq, float(r), ptr(offsets), ptr(idx), nbytes,
+                                              stream_ptr()))
+            return offsets, idx[:int(total.value)]
+
+    def radius_count(self, q, r):
+        with torch.cuda.device(self.device):
+            qd = None if q is None else as_device_points(q, self.device)
+            nq = self.n if qd is None else int(qd.shape[0])
+            counts = self._new((max(nq, 1),), torch.int32)
+            check(self.lib.more3d_radius_count(self._h, ptr(qd), nq, float(r), ptr(counts), stream_ptr()))
+            return counts[:nq]
+
+    def knn(self, q, k, return_distance=True):
+        with torch.cuda.device(self.device):
+            qd = None if q is None else as_device_points(q, self.device)
+            nq = self.n if qd is None else int(qd.shape[0])
+            idx = self._new((nq, k), torch.int64)
+            dist = self._new((nq, k), torch.float64) if return_distance else None
+            check(self.lib.more3d_knn(self._h, ptr(qd), nq, int(k), ptr(idx), ptr(dist), stream_ptr()))
+            return idx, dist
+
+    def normals_pca(self, r):
+        with torch.cuda.device(self.device):
+            normals = self._new((self.n, 3), torch.float64)
+            ratio = self._new((self.n,), torch.float64)
+            counts = self._new((self.n,), torch.int32)
+            check(self.lib.more3d_normals_pca(self._h, float(r), ptr(normals), ptr(ratio), ptr(counts), stream_ptr()))
+            return normals, ratio, counts
+
+    def nonparam_curvature(self, r, normals, eps, min_points):
+        """normals (N,3) f64 device tensor, flipped in place where the reference flips."""
+        with torch.cuda.device(self.device):
+            K = self._new((self.n,), torch.float32)
+            pcount = self._new((self.n,), torch.int32)
+            check(self.lib.more3d_nonparam_curvature(self._h, float(r), ptr(normals), float(eps), int(min_points),
+                                                     ptr(K), ptr(pcount), stream_ptr()))
+            return K, pcount
+
+    def normals_curvature(self, r, eps, min_points):
+        with torch.cuda.device(self.device):
+            normals = self._new((self.n, 3), torch.float64)
+            ratio = self._new((self.n,), torch.float64)
+            K = self._new((self.n,), torch.float32)
+            pcount = self._new((self.n,), torch.int32)
+            check(self.lib.more3d_normals_curvature(self._h, float(r), float(eps), int(min_points), ptr(normals),
+                                                    ptr(ratio), ptr(K), ptr(pcount), stream_ptr()))
+            return normals, ratio, K, pcount
+
+    def dk_dn(self, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, min_points):
+        """chi2_table: device f64 tensor, chi2.ppf(alpha, df) for df = 0..len-1."""
+        with torch.cuda.device(self.device):
+            dk = self._new((self.n,), torch.float32)
+            dn = self._new((self.n,), torch.float32)
+            minmax = self._new((4,), torch.float32)
+            check(self.lib.more3d_dk_dn(self._h, float(r), ptr(normals), ptr(K), float(rho), float(sigma_normal),
+                                        float(sigma_curvature), ptr(chi2_table), int(chi2_table.numel()),
+                                        int(min_points), ptr(dk), ptr(dn), ptr(minmax), stream_ptr()))
+            return dk, dn, minmax

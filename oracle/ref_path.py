@@ -63,6 +63,20 @@ def query_knn(tree, pnts, k, return_distnaces=False):
 # --------------------------------------------------------------------------------------------
 # H4b  centroid-PCA normals + surface variation  (named by north_star; downsample_compare.py:53-64)
 # --------------------------------------------------------------------------------------------
+def pca_point(p, q):
+    """PCA of one neighbourhood q (m,3) of the point p.  Returns (normal, ratio); m < 3 -> NaN."""
+    m = q.shape[0]
+    if m < 3:
+        return np.full(3, np.nan), 0.0
+    d = q - p
+    c = d.mean(axis=0)
+    e = d - c
+    cov = e.T @ e / m
+    w, v = np.linalg.eigh(cov)
+    s = w.sum()
+    return v[:, 0], (w[0] / s if s > 0 else 0.0)
+
+
 def pca_normals(points, nbrs):
     """Unit eigenvector of the smallest eigenvalue of the centroid-centred covariance of each
     neighbourhood, and lambda_min / sum(lambda).  Sign is arbitrary.  m < 3 -> NaN normal."""
@@ -70,18 +84,7 @@ def pca_normals(points, nbrs):
     normals = np.full((n, 3), np.nan)
     ratio = np.zeros(n)
     for i in range(n):
-        q = points[nbrs[i]]
-        m = q.shape[0]
-        if m < 3:
-            continue
-        d = q - points[i]
-        c = d.mean(axis=0)
-        e = d - c
-        cov = e.T @ e / m
-        w, v = np.linalg.eigh(cov)
-        normals[i] = v[:, 0]
-        s = w.sum()
-        ratio[i] = w[0] / s if s > 0 else 0.0
+        normals[i], ratio[i] = pca_point(points[i], points[nbrs[i]])
     return normals, ratio
 
 
