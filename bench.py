@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: full DM_saliency pipeline (grid build + normals/curvature + dk/dn +
+normalise/blend) on a synthetic 10 M-point terrain at 3 neighbourhood radii (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (one JSON line on stdout)
+    python bench.py --impl reference --gpus 1 ...            # reference CPU path on the host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # weak scaling
+
+A "step" = one pass of the whole pipeline over the cloud (all 3 radii).  `value` = points/s with the
+cloud resident in HBM; `e2e` = the same through the public API with HOST buffers (H2D of the cloud
+and D2H of the three saliency columns inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RADII = (0.5, 0.75, 1.0)
+PARAMS = dict(roughness=0.02, alpha=0.05, sigma_normal=0.01, sigma_curvature=0.01, min_points=4)
+CW = 0.5
+METRIC = "saliency points/sec (10M pts, 3 radii)"
+UNIT = "points/s"
+
+
+def workload_name(n):
+    return "configs[1]: full DM_saliency (curvature + dk/dn + normalise/blend) on %d synthetic terrain points, radii %s" % (
+        n, "/".join(str(r) for r in RADII))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU path (oracle port: sklearn BallTree + per-point processors) on all host cores."""
+    if rank != 0:
+        return
+    from more3d_b200 import synthetic
+    from oracle.cpu_bench import CpuSaliencyBaseline, host_cores
+    n = args.n
+    pts = synthetic.terrain(n, seed=2)
+    cores = host_cores()
+    base = CpuSaliencyBaseline(pts, RADII, PARAMS, workers=cores, seed=1)
+    q = args.cpu_q * cores
+    for _ in range(args.warmup):
+        base.step(max(q // 4, cores))
+    times = []
+    for _ in range(args.steps):
+        total, raw = base.step(q)
+        times.append(total)
+    base.close()
+    t = float(np.mean(times))
+    value = n / t
+    sample = ("oracle port (sklearn BallTree.query_radius + per-point PCA/Curvature_Kernel/Saliency_Kernel restatement); "
+              "tree over all %d points built once (%.1f s, included in every step), %d random query points per radius per step "
+              "on %d worker processes, extrapolated x N/Q" % (n, base.t_tree, q, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "points": n, "radii": list(RADII)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from more3d_b200 import synthetic, _lib
+    from more3d_b200.pipeline import multiscale_saliency
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    _lib.load()
+
+    if distributed:
+        from more3d_b200.distributed import StripSaliency
+        job = StripSaliency(n, rank, world, dev, RADII, PARAMS, CW, seed=2)
+        step_resident = job.step_resident
+        step_e2e = job.step_e2e
+        h2d, d2h = job.h2d_bytes, job.d2h_bytes
+        sum_m = job.sum_m
+    else:
+        pts = synthetic.terrain(n, seed=2)
+        host = torch.from_numpy(pts).pin_memory()
+        resident = host.to(dev)
+        out_host = {r: torch.empty(n, dtype=torch.float32).pin_memory() for r in RADII}
+        h2d = host.numel() * 8
+        d2h = sum(t.numel() * 4 for t in out_host.values())
+
+        def step_resident():
+            return multiscale_saliency(resident, RADII, curvature_weight=CW, **PARAMS)
+
+        def step_e2e():
+            res = multiscale_saliency(host.to(dev, non_blocking=True), RADII, curvature_weight=CW,
+                                      out_host=out_host, **PARAMS)
+            torch.cuda.current_stream().synchronize()
+            return res
+
+        # neighbour counts for the algorithmic-bytes figure (outside the timed region)
+        res = multiscale_saliency(resident, RADII, curvature_weight=CW, keep=True, **PARAMS)
+        sum_m = {r: float(res[r]["_pcount"].double().sum()) for r in RADII}
+        nonzero = {r: (float((res[r]["_dk"] != 0).double().mean()), float((res[r]["_dn"] != 0).double().mean()))
+                   for r in RADII}
+        gpu_normals = res[RADII[0]]["normals"].cpu().numpy() if args.cpu_baseline else None
+        gpu_K = res[RADII[0]]["_nonparam_K"].cpu().numpy() if args.cpu_baseline else None
+        del res
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if distributed:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_all()
+    _lib.profile_enable(False)
+    ms_e2e_warm = timed(step_e2e, 1)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    del ms_e2e_warm
+
+    total_pts = float(n) * world
+    value = total_pts * args.steps / (ms * 1e-3)
+    e2e_value = total_pts * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel (algorithmic bytes: SURVEY.md §8d)
+    peak, peak_src = measured_peak()
+    alg = {"dkdn": sum(n * 40.0 + 32.0 * sum_m[r] for r in RADII),
+           "moments": sum(n * 48.0 + 16.0 * sum_m[r] for r in RADII)}
+    kern = {}
+    for name, (tot_ms, cnt) in prof.items():
+        kern[name] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps}
+        if name in alg and tot_ms > 0:
+            kern[name]["algorithmic_GBs"] = alg[name] * args.steps / (tot_ms * 1e-3) / 1e9
+    dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms_per_step"])
+    achieved = kern[dom]["algorithmic_GBs"]
+    tr = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (tr or {}).get(dom), "algorithmic_bytes_per_step": alg[dom],
+                "kernel_share_of_step": kern[dom]["ms_per_step"] / (ms / args.steps)}
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "points_per_gpu": n, "radii": list(RADII),
+                       "l2": "inputs (240 MB cloud + 320..640 MB records per radius) exceed the 126 MB L2",
+                       "parallelism": "x-strips with 2*r_max ghost halos over NCCL" if distributed else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern}
+    if not distributed:
+        line["nonzero_fraction_dk_dn"] = {str(r): nonzero[r] for r in RADII}
+
+    if args.cpu_baseline and not distributed:
+        from oracle.cpu_bench import CpuSaliencyBaseline
+        base = CpuSaliencyBaseline(pts, RADII, PARAMS, workers=1, normals=gpu_normals, K=gpu_K, seed=1)
+        total, raw = base.step(args.cpu_q)
+        line["cpu_baseline"] = {
+            "value": n / total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": ("oracle port (sklearn BallTree.query_radius + per-point PCA/Curvature_Kernel/Saliency_Kernel "
+                       "restatement, scipy constants hoisted); tree over all %d points (%.1f s) + %d random query points "
+                       "per radius (%.1f s), extrapolated x N/Q; 1 core" % (n, base.t_tree, args.cpu_q, raw))}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="points per GPU")
+    ap.add_argument("--cpu-q", type=int, default=2000, help="CPU-baseline sample: query points per radius (per core)")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world == 1 and args.gpus > 1:
+            # launched without torchrun: re-exec under it so `python bench.py --gpus N` works too
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

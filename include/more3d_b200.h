@@ -32,6 +32,16 @@ typedef struct more3d_grid more3d_grid;
 int more3d_version(void);
 const char* more3d_last_error(void);
 
+/* ---- optional per-kernel timing (CUDA events on the launching stream; used by bench.py) ----------
+ * enable(1) makes every library kernel group record an event pair; get() synchronises the recorded
+ * events and returns the accumulated milliseconds / launch count of one named group, e.g.
+ * "moments", "dkdn", "grid_build", "build_feat".  names() writes a comma-separated list. */
+int64_t more3d_launch_count(void); /* kernels launched by this library since it was loaded */
+int more3d_profile_enable(int on);
+int more3d_profile_reset(void);
+int more3d_profile_get(const char* name, double* ms_h, int64_t* count_h);
+int more3d_profile_names(char* buf_h, int len);
+
 /* ---- spatial index --------------------------------------------------------------------------
  * Replaces BallTreePointSet.__init__ -> sklearn BallTree build (Downsampling/BallTreePointSet.py:19-53).
  * Uniform xy-column grid: fp64 cell keys -> LSD radix sort -> column-start table -> sorted
@@ -105,6 +115,16 @@ int more3d_saliency_blend(const float* dk, const float* dn, int64_t n, const flo
 /* 256-bin histogram of sal over [lo, hi] with numpy.histogram's binning; edges: 257 float64 from
  * numpy.linspace (host computed, device resident).  hist: 256 int64 (zeroed by the call). */
 int more3d_histogram256(const float* v, int64_t n, const double* edges, int64_t* hist, void* stream);
+
+/* ---- multi-GPU strip partition helpers (no reference equivalent; OPALS tile streaming,
+ * DM_saliency.py:76-86, is the analogue) ----------------------------------------------------------
+ * band_select: indices i (ascending, stable) with lo <= xyz[i][axis] < hi; idx has room for n int64;
+ * *count_h receives how many were written.  gather_rows: dst[r][:] = src[idx[r]][:] for m rows of
+ * ncols elements of elem_bytes (4 or 8). */
+int more3d_band_select(const double* xyz, int64_t n, int axis, double lo, double hi, int64_t* idx,
+                       int64_t* count_h, void* stream);
+int more3d_gather_rows(const void* src, const int64_t* idx, int64_t m, int ncols, int elem_bytes,
+                       void* dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,10 @@ _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
 
 # name -> argtypes; every function returns int except the two noted below
 SIGNATURES = {
+    "more3d_profile_enable": [_i32],
+    "more3d_profile_reset": [],
+    "more3d_profile_get": [C.c_char_p, C.POINTER(_f64), C.POINTER(_i64)],
+    "more3d_profile_names": [C.c_char_p, _i32],
     "more3d_grid_create": [_vp, _i64, _f64, _vp, C.POINTER(_vp)],
     "more3d_grid_destroy": [_vp],
     "more3d_grid_info": [_vp, C.POINTER(_i64), C.POINTER(_f64)],
@@ -30,6 +34,8 @@ SIGNATURES = {
     "more3d_minmax4": [_vp, _vp, _i64, _vp, _vp],
     "more3d_saliency_blend": [_vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp],
     "more3d_histogram256": [_vp, _i64, _vp, _vp, _vp],
+    "more3d_band_select": [_vp, _i64, _i32, _f64, _f64, _vp, C.POINTER(_i64), _vp],
+    "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
 }
 
 
@@ -57,6 +63,8 @@ def load(build_if_needed=True):
     lib.more3d_last_error.argtypes = []
     lib.more3d_version.restype = C.c_int
     lib.more3d_version.argtypes = []
+    lib.more3d_launch_count.restype = C.c_int64
+    lib.more3d_launch_count.argtypes = []
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name, None)
         if fn is None:
@@ -87,3 +95,29 @@ def require_cuda():
     import torch
     if not torch.cuda.is_available():
         raise More3DError("more3d_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def profile_enable(on=True):
+    check(load().more3d_profile_enable(1 if on else 0))
+
+
+def profile_reset():
+    check(load().more3d_profile_reset())
+
+
+def profile_get(name):
+    """(total ms, launches) of one kernel group since the last reset (synchronises its events)."""
+    ms, cnt = C.c_double(0.0), C.c_int64(0)
+    check(load().more3d_profile_get(name.encode(), C.byref(ms), C.byref(cnt)))
+    return float(ms.value), int(cnt.value)
+
+
+def profile_all():
+    buf = C.create_string_buffer(4096)
+    check(load().more3d_profile_names(buf, 4096))
+    names = [n for n in buf.value.decode().split(",") if n]
+    return {n: profile_get(n) for n in names}
+
+
+def launch_count():
+    return int(load().more3d_launch_count())

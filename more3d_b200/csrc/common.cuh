@@ -24,6 +24,8 @@ void set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void count_launches(int n);
 #define M3D_CHECK_LAUNCH() M3D_CUDA(cudaGetLastError())
 
 #define M3D_TRY(expr)                  \
@@ -39,6 +41,19 @@ void set_error(const char* fmt, ...);
             return MORE3D_E_INVALID;                   \
         }                                              \
     } while (0)
+
+// one-time per-device setup: keep stream-ordered pool memory cached instead of returning it to the
+// driver at every synchronisation (otherwise each call pays cudaMalloc-class latencies)
+void init_device_pool();
+
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+// Disabled by default: a scope is then a no-op.
+struct ProfScope {
+    int slot;
+    cudaStream_t s;
+    ProfScope(const char* name, cudaStream_t stream);
+    ~ProfScope();
+};
 
 // stream-ordered scratch allocation
 template <typename T>
@@ -77,6 +92,7 @@ struct more3d_grid {
     int nx, ny;
     double cell, inv_cell, ox, oy;
     int device;
+    cudaStream_t stream;    // creation stream: grid arrays are stream-ordered allocations on it
     uint32_t* order;        // n: sorted pos -> original index
     m3d::PointRec* rec;     // n sorted records
     uint32_t* col_start;    // nx*ny + 1

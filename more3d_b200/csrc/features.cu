@@ -341,12 +341,14 @@ static int launch_moments(const more3d_grid* g, int mode, double r, double eps, 
     prm.r2 = r * r; prm.eps = eps; prm.min_points = min_points; prm.s = stencil_halfwidth(g, r);
     const unsigned nb = (unsigned)((g->n + 255) / 256);
     GridView v = make_view(g);
+    ProfScope prof("moments", s);
     if (mode == MODE_NORMALS)
         moments_kernel<MODE_NORMALS><<<nb, 256, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount);
     else if (mode == MODE_CURV)
         moments_kernel<MODE_CURV><<<nb, 256, 0, s>>>(v, prm, normals, nullptr, K, pcount);
     else
         moments_kernel<MODE_FUSED><<<nb, 256, 0, s>>>(v, prm, normals, lam_ratio, K, pcount);
+    count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }
@@ -386,14 +388,21 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
     M3D_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
     const unsigned nb = (unsigned)((g->n + 255) / 256);
     GridView v = make_view(g);
-    build_feat_kernel<<<nb, 256, 0, s>>>(v, normals, K, feat);
+    {
+        ProfScope prof("build_feat", s);
+        build_feat_kernel<<<nb, 256, 0, s>>>(v, normals, K, feat);
+    }
     minmax_init<<<1, 32, 0, s>>>(mm);
     DkDnParams prm;
     prm.r2 = r * r; prm.rho2 = rho * rho; prm.inv_rho2 = 1.0 / (rho * rho);
     prm.sigma_n = sigma_normal; prm.sigma_k = sigma_curvature;
     prm.min_points = min_points; prm.s = stencil_halfwidth(g, r); prm.table_len = table_len;
-    dkdn_kernel<<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+    {
+        ProfScope prof("dkdn", s);
+        dkdn_kernel<<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+    }
     if (minmax) minmax_finish<<<1, 32, 0, s>>>(mm, minmax);
+    count_launches(minmax ? 4 : 3);
     M3D_CHECK_LAUNCH();
     int err_h = 0;
     M3D_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, s));

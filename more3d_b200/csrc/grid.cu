@@ -126,6 +126,8 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         return MORE3D_E_RANGE;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    init_device_pool();
+    ProfScope prof("grid_build", s);
 
     // bounding box (host needs it to size the table: one small sync per build)
     const int nparts = 592;  // 4 CTAs per SM on 148 SMs
@@ -133,6 +135,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
     M3D_TRY(dev_alloc(&part, (size_t)4 * nparts + 4, s));
     bbox_partial<<<nparts, BB_THREADS, 0, s>>>(xyz, n, part);
     bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 4 * nparts);
+    count_launches(2);
     M3D_CHECK_LAUNCH();
     double bb[4];
     M3D_CUDA(cudaMemcpyAsync(bb, part + 4 * nparts, sizeof(bb), cudaMemcpyDeviceToHost, s));
@@ -161,6 +164,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
     g->nx = (int)floor(ex / c) + 3;
     g->ny = (int)floor(ey / c) + 3;
     cudaGetDevice(&g->device);
+    g->stream = s;
     g->order = nullptr; g->rec = nullptr; g->col_start = nullptr; g->dup = nullptr;
     const size_t ncols = (size_t)g->nx * g->ny;
 
@@ -169,10 +173,10 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
 #define G_TRY(e) do { rc = (e); if (rc != MORE3D_OK) goto fail; } while (0)
 #define G_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); rc = (_e == cudaErrorMemoryAllocation) ? MORE3D_E_NOMEM : MORE3D_E_CUDA; goto fail; } } while (0)
     {
-        G_CUDA(cudaMalloc((void**)&g->col_start, (ncols + 1) * sizeof(uint32_t)));
-        G_CUDA(cudaMalloc((void**)&g->order, (size_t)n * sizeof(uint32_t)));
-        G_CUDA(cudaMalloc((void**)&g->rec, (size_t)n * sizeof(PointRec)));
-        G_CUDA(cudaMalloc((void**)&g->dup, (size_t)n));
+        G_CUDA(cudaMallocAsync((void**)&g->col_start, (ncols + 1) * sizeof(uint32_t), s));
+        G_CUDA(cudaMallocAsync((void**)&g->order, (size_t)n * sizeof(uint32_t), s));
+        G_CUDA(cudaMallocAsync((void**)&g->rec, (size_t)n * sizeof(PointRec), s));
+        G_CUDA(cudaMallocAsync((void**)&g->dup, (size_t)n, s));
         G_TRY(dev_alloc(&keys, (size_t)n, s));
         G_TRY(dev_alloc(&vals, (size_t)n, s));
         G_TRY(dev_alloc(&keys2, (size_t)n, s));
@@ -191,6 +195,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec);
         dup_flags<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny,
                                      g->dup);
+        count_launches(3);  // cell_keys, gather_records, dup_flags
         G_CUDA(cudaGetLastError());
     }
     dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s);
@@ -206,10 +211,10 @@ fail:
 
 extern "C" int more3d_grid_destroy(more3d_grid* g) {
     if (!g) return MORE3D_OK;
-    cudaFree(g->order);
-    cudaFree(g->rec);
-    cudaFree(g->col_start);
-    cudaFree(g->dup);
+    if (g->order) cudaFreeAsync(g->order, g->stream);
+    if (g->rec) cudaFreeAsync(g->rec, g->stream);
+    if (g->col_start) cudaFreeAsync(g->col_start, g->stream);
+    if (g->dup) cudaFreeAsync(g->dup, g->stream);
     delete g;
     return MORE3D_OK;
 }

@@ -113,6 +113,7 @@ extern "C" int more3d_knn(const more3d_grid* g, const double* q, int64_t nq, int
     if (k <= 4) launch_knn<4>(g, q, nq, k, idx, dist, s);
     else if (k <= 16) launch_knn<16>(g, q, nq, k, idx, dist, s);
     else launch_knn<64>(g, q, nq, k, idx, dist, s);
+    count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }

@@ -72,10 +72,12 @@ extern "C" int more3d_radius_count(const more3d_grid* g, const double* q, int64_
     cudaStream_t s = (cudaStream_t)stream;
     const int sw = stencil_halfwidth(g, r);
     const unsigned nb = (unsigned)((nq + 255) / 256);
+    ProfScope prof("radius_count", s);
     if (q)
         radius_count_kernel<false><<<nb, 256, 0, s>>>(make_view(g), q, nq, r * r, sw, counts);
     else
         radius_count_kernel<true><<<nb, 256, 0, s>>>(make_view(g), nullptr, nq, r * r, sw, counts);
+    count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }
@@ -103,6 +105,7 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
     const unsigned nb = (unsigned)((nq + 255) / 256);
     GridView v = make_view(g);
     const double r2 = r * r;
+    ProfScope prof("radius_fill", s);
     if (q) {
         if (idx_bytes == 4) radius_fill_kernel<false, int32_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, offsets, (int32_t*)idx);
         else radius_fill_kernel<false, int64_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, offsets, (int64_t*)idx);
@@ -110,6 +113,7 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
         if (idx_bytes == 4) radius_fill_kernel<true, int32_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, offsets, (int32_t*)idx);
         else radius_fill_kernel<true, int64_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, offsets, (int64_t*)idx);
     }
+    count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }

@@ -103,6 +103,7 @@ extern "C" int more3d_minmax4(const float* dk, const float* dn, int64_t n, float
     mm4_init<<<1, 32, 0, s>>>(mm, 4);
     minmax4_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, n, mm);
     mm4_finish<<<1, 32, 0, s>>>(mm, minmax, 4);
+    count_launches(3);
     M3D_CHECK_LAUNCH();
     dev_free(mm, s);
     return MORE3D_OK;
@@ -118,8 +119,10 @@ extern "C" int more3d_saliency_blend(const float* dk, const float* dn, int64_t n
         mm4_init<<<1, 32, 0, s>>>(mm, 2);
     }
     const double nw = 1.0 - curvature_weight;   // DM_saliency.py:572
+    ProfScope prof("blend", s);
     blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, n, minmax, curvature_weight, nw, sal, mm);
     if (sal_minmax) mm4_finish<<<1, 32, 0, s>>>(mm, sal_minmax, 2);
+    count_launches(sal_minmax ? 3 : 1);
     M3D_CHECK_LAUNCH();
     dev_free(mm, s);
     return MORE3D_OK;
@@ -130,6 +133,7 @@ extern "C" int more3d_histogram256(const float* v, int64_t n, const double* edge
     cudaStream_t s = (cudaStream_t)stream;
     M3D_CUDA(cudaMemsetAsync(hist, 0, 256 * sizeof(int64_t), s));
     hist256_kernel<<<148 * 4, 256, 0, s>>>(v, n, edges, (unsigned long long*)hist);
+    count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }

@@ -1,6 +1,11 @@
 // Hand-written stable LSD radix sort (8-bit digits) and exclusive scans for the grid build,
 // voxel keys and CSR offsets.  sm_100a; no CUB on the product path.
 #include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 #include "common.cuh"
 
 namespace m3d {
@@ -13,6 +18,73 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long get_launches() { return g_launches.load(); }
+
+void init_device_pool() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = true;
+}
+
+// ---- profiler ---------------------------------------------------------------------------------
+struct ProfRec { int name; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::string> g_prof_names;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<double> g_prof_ms;
+static std::vector<int64_t> g_prof_cnt;
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : slot(-1), s(stream) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int id = -1;
+    for (size_t i = 0; i < g_prof_names.size(); ++i)
+        if (g_prof_names[i] == name) { id = (int)i; break; }
+    if (id < 0) {
+        id = (int)g_prof_names.size();
+        g_prof_names.push_back(name);
+        g_prof_ms.push_back(0.0);
+        g_prof_cnt.push_back(0);
+    }
+    ProfRec r;
+    r.name = id;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    slot = (int)g_prof_recs.size();
+    g_prof_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof_recs[slot].b, s);
+}
+static void prof_collect() {
+    for (auto& r : g_prof_recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_prof_ms[r.name] += ms;
+            g_prof_cnt[r.name] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof_recs.clear();
+}
 
 // ------------------------------------------------------------------------------------------
 // exclusive scan: tile sums -> single-block scan of the sums -> tile scan + offset
@@ -112,6 +184,7 @@ static int exclusive_scan_impl(const Tin* in, Tout* out, int64_t n, cudaStream_t
     scan_tile_sums<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, n, sums);
     scan_sums_single<Tout><<<1, 1024, 0, s>>>(sums, tiles, out + n);
     scan_tile_apply<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, n, sums, out);
+    count_launches(3);
     M3D_CHECK_LAUNCH();
     dev_free(sums, s);
     return MORE3D_OK;
@@ -235,6 +308,7 @@ static int radix_sort_impl(K* keys, uint32_t* vals, K* keys_alt, uint32_t* vals_
         rs_hist<K><<<nblocks, RS_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
         M3D_TRY(exclusive_scan_u32(hist, hist, (int64_t)256 * nblocks, s));
         rs_scatter<K><<<nblocks, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
+        count_launches(2);
         M3D_CHECK_LAUNCH();
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
@@ -258,5 +332,40 @@ int radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uin
 
 }  // namespace m3d
 
+extern "C" int64_t more3d_launch_count(void) { return (int64_t)m3d::get_launches(); }
+extern "C" int more3d_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(m3d::g_prof_mu);
+    m3d::g_prof_on = on != 0;
+    return MORE3D_OK;
+}
+extern "C" int more3d_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(m3d::g_prof_mu);
+    m3d::prof_collect();
+    for (auto& v : m3d::g_prof_ms) v = 0.0;
+    for (auto& v : m3d::g_prof_cnt) v = 0;
+    return MORE3D_OK;
+}
+extern "C" int more3d_profile_get(const char* name, double* ms_h, int64_t* count_h) {
+    std::lock_guard<std::mutex> lk(m3d::g_prof_mu);
+    m3d::prof_collect();
+    for (size_t i = 0; i < m3d::g_prof_names.size(); ++i)
+        if (m3d::g_prof_names[i] == name) {
+            if (ms_h) *ms_h = m3d::g_prof_ms[i];
+            if (count_h) *count_h = m3d::g_prof_cnt[i];
+            return MORE3D_OK;
+        }
+    if (ms_h) *ms_h = 0.0;
+    if (count_h) *count_h = 0;
+    return MORE3D_OK;
+}
+extern "C" int more3d_profile_names(char* buf_h, int len) {
+    std::lock_guard<std::mutex> lk(m3d::g_prof_mu);
+    std::string all;
+    for (auto& n : m3d::g_prof_names) { if (!all.empty()) all += ","; all += n; }
+    if (!buf_h || len <= 0) return MORE3D_E_INVALID;
+    strncpy(buf_h, all.c_str(), (size_t)len - 1);
+    buf_h[len - 1] = 0;
+    return MORE3D_OK;
+}
 extern "C" const char* more3d_last_error(void) { return m3d::get_error(); }
 extern "C" int more3d_version(void) { return 100; }

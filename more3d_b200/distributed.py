@@ -1,0 +1,179 @@
+"""Multi-GPU saliency: the cloud is cut into x-strips, one per rank (one process per GPU), each
+holding ghost halos of width 2*r_max from both neighbours.
+
+Data-path collectives (NCCL over NVLink / NVSwitch through torch.distributed):
+  * halo exchange of coordinates -- once per cloud, point-to-point with the two strip neighbours;
+  * all-reduce(min/max) of the four dk/dn extrema -- once per radius (the Histo pass of
+    DM_saliency.py:562-568 must see the whole cloud).
+With a 2*r halo every owned point AND every ghost within r of the strip has a complete
+neighbourhood, so ghost normals / curvatures are recomputed locally instead of being exchanged.
+The communication logic is backend-agnostic (gloo on CPU tensors in the tests).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .grid import UniformGrid, CELL_MARGIN
+
+
+def strip_bounds(x_min, x_max, world):
+    """Equal-width strip edges; the last edge is +inf-safe (points exactly on x_max belong to the last strip)."""
+    edges = np.linspace(x_min, x_max, world + 1)
+    return edges
+
+
+def band_select(xyz, axis, lo, hi):
+    """Stable indices of the device points with lo <= coord < hi (hand-written flag/scan/scatter kernels)."""
+    lib = _lib.load()
+    n = int(xyz.shape[0])
+    idx = torch.empty(n, dtype=torch.int64, device=xyz.device)
+    cnt = C.c_int64(0)
+    with torch.cuda.device(xyz.device):
+        check(lib.more3d_band_select(ptr(xyz), n, int(axis), float(lo), float(hi), ptr(idx), C.byref(cnt), stream_ptr()))
+    return idx[:int(cnt.value)]
+
+
+def gather_rows(src, idx):
+    lib = _lib.load()
+    m = int(idx.shape[0])
+    ncols = int(src.shape[1]) if src.ndim == 2 else 1
+    out = torch.empty((m, ncols) if src.ndim == 2 else (m,), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.more3d_gather_rows(ptr(src), ptr(idx), m, ncols, src.element_size(), ptr(out), stream_ptr()))
+    return out
+
+
+def exchange_halos(send_left, send_right, rank, world, group=None):
+    """Send boundary strips to the two x-neighbours and receive theirs.  Tensors are (m, 3) float64 on
+    the backend's device.  Returns (from_left, from_right); missing neighbours give empty tensors."""
+    dev, dt = send_left.device, send_left.dtype
+    left, right = rank - 1, rank + 1
+    # 1) sizes
+    n_to = torch.tensor([send_left.shape[0], send_right.shape[0]], dtype=torch.int64, device=dev)
+    n_from = torch.zeros(2, dtype=torch.int64, device=dev)
+    ops = []
+    if left >= 0:
+        ops += [dist.P2POp(dist.isend, n_to[0:1], left, group), dist.P2POp(dist.irecv, n_from[0:1], left, group)]
+    if right < world:
+        ops += [dist.P2POp(dist.isend, n_to[1:2], right, group), dist.P2POp(dist.irecv, n_from[1:2], right, group)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    n_from = n_from.cpu()
+    from_left = torch.empty((int(n_from[0]), 3), dtype=dt, device=dev)
+    from_right = torch.empty((int(n_from[1]), 3), dtype=dt, device=dev)
+    # 2) payload
+    ops = []
+    if left >= 0:
+        if send_left.shape[0]:
+            ops.append(dist.P2POp(dist.isend, send_left.contiguous(), left, group))
+        if from_left.shape[0]:
+            ops.append(dist.P2POp(dist.irecv, from_left, left, group))
+    if right < world:
+        if send_right.shape[0]:
+            ops.append(dist.P2POp(dist.isend, send_right.contiguous(), right, group))
+        if from_right.shape[0]:
+            ops.append(dist.P2POp(dist.irecv, from_right, right, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return from_left, from_right
+
+
+def allreduce_minmax(minmax, group=None):
+    """Global {min_dk, max_dk, min_dn, max_dn} (in place): MIN over slots 0, 2 and MAX over 1, 3."""
+    v = minmax.clone()
+    v[1] = -v[1]
+    v[3] = -v[3]
+    dist.all_reduce(v, op=dist.ReduceOp.MIN, group=group)   # one collective: max(x) = -min(-x)
+    v[1] = -v[1]
+    v[3] = -v[3]
+    minmax.copy_(v)
+    return minmax
+
+
+def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=None, out_host=None):
+    """Saliency of the OWNED points of one strip.  own: (n,3) device f64; ghosts: (g,3) device f64
+    (points of the neighbouring strips within 2*r_max).  reduce_minmax(minmax) makes the extrema
+    global (None for a single strip).  Returns {r: saliency (n,) f32} (+ '_pcount' sums in .sum_m)."""
+    from .DM_saliency import Curvature_Kernel, _chi2_table
+    lib = _lib.load()
+    n = int(own.shape[0])
+    local = torch.cat([own, ghosts], dim=0) if ghosts.shape[0] else own
+    dev = local.device
+    ck = Curvature_Kernel()
+    ck.setArgs(alpha=params["alpha"], roughness=params["roughness"], min_points=params["min_points"])
+    eps = ck.epsilon()
+    out = {}
+    sum_m = {}
+    for r in radii:
+        rho = r / np.sqrt(2.0)
+        g = UniformGrid(local, r * CELL_MARGIN)
+        normals, _, K, pcount = g.normals_curvature(r, eps, params["min_points"])
+        length = 1024
+        while True:
+            try:
+                dk, dn, _ = g.dk_dn(r, normals, K, rho, params["sigma_normal"], params["sigma_curvature"],
+                                    _chi2_table(params["alpha"], length, dev), params["min_points"])
+                break
+            except _lib.More3DError as e:
+                if "error -4" not in str(e) or length >= (1 << 22):
+                    raise
+                length *= 8
+        with torch.cuda.device(dev):
+            minmax = torch.empty(4, dtype=torch.float32, device=dev)
+            check(lib.more3d_minmax4(ptr(dk), ptr(dn), n, ptr(minmax), stream_ptr()))   # owned points only
+            if reduce_minmax is not None:
+                reduce_minmax(minmax)
+            sal = torch.empty(n, dtype=torch.float32, device=dev)
+            check(lib.more3d_saliency_blend(ptr(dk), ptr(dn), n, ptr(minmax), float(curvature_weight), ptr(sal),
+                                            None, stream_ptr()))
+        if out_host is not None:
+            out_host[r].copy_(sal, non_blocking=True)
+        out[r] = sal
+        sum_m[r] = pcount[:n]
+        g.close()
+    return out, sum_m
+
+
+class StripSaliency:
+    """bench.py's weak-scaling job: rank k owns an n-point strip of a (world * W) x W tile."""
+
+    def __init__(self, n, rank, world, device, radii, params, curvature_weight, seed=2):
+        from . import synthetic
+        self.n, self.rank, self.world, self.dev = n, rank, world, device
+        self.radii, self.params, self.cw = tuple(radii), dict(params), curvature_weight
+        W = float(np.sqrt(n / synthetic.DENSITY))
+        self.W = W
+        pts = synthetic.terrain(n, seed=seed + rank, extent=(W, W), origin=(rank * W, 0.0),
+                                centre=(0.5 * world * W, 0.5 * W))
+        self.x_lo = rank * W - 0.5 * world * W
+        self.x_hi = self.x_lo + W
+        self.halo = 2.0 * max(radii) * CELL_MARGIN
+        self.host = torch.from_numpy(pts).pin_memory()
+        self.resident = self.host.to(device)
+        self.out_host = {r: torch.empty(n, dtype=torch.float32).pin_memory() for r in radii}
+        self.h2d_bytes = self.host.numel() * 8
+        self.d2h_bytes = n * 4 * len(radii)
+        _, pc = self._run(self.resident, None)
+        self.sum_m = {r: float(pc[r].double().sum()) for r in radii}
+
+    def _run(self, own, out_host):
+        left = gather_rows(own, band_select(own, 0, -np.inf, self.x_lo + self.halo))
+        right = gather_rows(own, band_select(own, 0, self.x_hi - self.halo, np.inf))
+        from_left, from_right = exchange_halos(left, right, self.rank, self.world)
+        ghosts = torch.cat([from_left, from_right], dim=0)
+        return strip_saliency(own, ghosts, self.radii, self.params, self.cw,
+                              reduce_minmax=allreduce_minmax, out_host=out_host)
+
+    def step_resident(self):
+        return self._run(self.resident, None)[0]
+
+    def step_e2e(self):
+        res = self._run(self.host.to(self.dev, non_blocking=True), self.out_host)[0]
+        torch.cuda.current_stream().synchronize()
+        return res

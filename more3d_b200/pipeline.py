@@ -1,0 +1,44 @@
+"""The full DM_saliency pipeline at several neighbourhood radii (BASELINE.json configs[1]).
+
+For every radius: DM_nonparam_curvature (normals at the same radius, fused) -> DM_dk_dn ->
+DM_saliency, exactly the call sequence a user of the reference runs (README "Saliency"), on one
+in-memory cloud.
+"""
+import numpy as np
+import torch
+
+from .DM_saliency import PointCloudDM, DM_nonparam_curvature, DM_dk_dn, DM_saliency
+
+DEFAULT_RADII = (0.5, 0.75, 1.0)
+DEFAULTS = dict(roughness=0.02, alpha=0.05, sigma_normal=0.01, sigma_curvature=0.01,
+                curvature_weight=0.5, min_points=4)
+
+
+def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, sigma_normal=0.01,
+                        sigma_curvature=0.01, curvature_weight=0.5, min_points=4, keep=False,
+                        out_host=None):
+    """Run the saliency pipeline at each radius (rho = r / sqrt(2)).
+
+    xyz: (N,3) float64, numpy (host; copied to the device here) or a CUDA tensor.
+    Returns {radius: saliency float32 CUDA tensor}; with ``keep`` also the intermediate columns.
+    ``out_host``: optional {radius: pinned float32 host tensor} to receive the result (D2H copy).
+    """
+    dm = PointCloudDM(xyz)
+    out = {}
+    for r in radii:
+        rho = r / np.sqrt(2.0)
+        dm.normals = None          # normals are re-estimated at every scale
+        DM_nonparam_curvature(dm, "sphere", roughness=roughness, alpha=alpha, min_points=min_points, radius=r)
+        DM_dk_dn(dm, "sphere", rho, rho, sigma_normal=sigma_normal, sigma_curvature=sigma_curvature,
+                 alpha=alpha, min_points=min_points, radius=r)
+        DM_saliency(dm, curvature_weight=curvature_weight)
+        sal = dm.attrs["_saliency"]
+        if out_host is not None:
+            out_host[r].copy_(sal, non_blocking=True)
+        if keep:
+            out[r] = {k: v for k, v in dm.attrs.items()}
+            out[r]["normals"] = dm.normals
+        else:
+            out[r] = sal
+        dm.drop_grids()
+    return out

@@ -11,12 +11,14 @@ import numpy as np
 DENSITY = 40.0  # points / m^2
 
 
-def terrain(n, seed, density=DENSITY, noise=0.02, boulders=0, extent=None):
+def terrain(n, seed, density=DENSITY, noise=0.02, boulders=0, extent=None, origin=(0.0, 0.0), centre=None):
     """Return an (n, 3) float64 C-order terrain cloud.
 
     ``boulders`` > 0 adds that many steep 0.5 m hemispherical bumps per 50 m block (the "stress
     tile" of SURVEY.md §8d that exercises the dn branch of the saliency processor).
-    ``extent`` = (Lx, Ly) overrides the square footprint (used for multi-GPU strips).
+    ``extent`` = (Lx, Ly) overrides the square footprint; ``origin`` = (x0, y0) places the footprint
+    in a larger tile (the relief is a function of the global position, so neighbouring strips join
+    continuously) and ``centre`` = the global point moved to x = y = 0 (default: footprint centre).
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     if extent is None:
@@ -29,7 +31,7 @@ def terrain(n, seed, density=DENSITY, noise=0.02, boulders=0, extent=None):
     z = np.zeros(n)
     for o in range(7):
         f = float(2 ** o)
-        z += 2.0 * 2.0 ** (-0.8 * o) * np.sin(f * x / 40.0 + o) * np.cos(f * y / 37.0 + 2 * o)
+        z += 2.0 * 2.0 ** (-0.8 * o) * np.sin(f * (x + origin[0]) / 40.0 + o) * np.cos(f * (y + origin[1]) / 37.0 + 2 * o)
     z += rng.normal(0.0, noise, n)
 
     # embedded entities: one Gaussian bump / pit per 50 m block, centre kept >= 10 m from the
@@ -56,8 +58,10 @@ def terrain(n, seed, density=DENSITY, noise=0.02, boulders=0, extent=None):
             z += np.sqrt(np.maximum(R * R - d2, 0.0))
 
     pts = np.empty((n, 3), dtype=np.float64)
-    pts[:, 0] = x - 0.5 * Lx
-    pts[:, 1] = y - 0.5 * Ly
+    if centre is None:
+        centre = (origin[0] + 0.5 * Lx, origin[1] + 0.5 * Ly)
+    pts[:, 0] = (x + origin[0]) - centre[0]
+    pts[:, 1] = (y + origin[1]) - centre[1]
     pts[:, 2] = z - 1000.0
     return pts
 

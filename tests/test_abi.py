@@ -1,0 +1,81 @@
+"""CPU: the C-ABI library loads and exports every symbol include/more3d_b200.h declares; host-side
+argument handling that needs no device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "more3d_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(more3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    for must in ("more3d_grid_create", "more3d_radius_count", "more3d_radius_fill", "more3d_knn",
+                 "more3d_normals_pca", "more3d_nonparam_curvature", "more3d_dk_dn", "more3d_saliency_blend"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from more3d_b200 import build, _lib
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.more3d_version() >= 100
+    # every declared int-returning entry point has a ctypes signature in the binding
+    unbound = [n for n in declared_symbols()
+               if n not in _lib.SIGNATURES and n not in ("more3d_version", "more3d_last_error", "more3d_launch_count")]
+    assert not unbound, unbound
+
+
+def test_argument_errors_need_no_device():
+    from more3d_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.more3d_grid_create(None, 0, 1.0, None, ctypes.byref(h))
+    assert rc == -1 and b"empty" in lib.more3d_last_error()
+    with pytest.raises(_lib.More3DError):
+        _lib.check(rc)
+    assert lib.more3d_grid_destroy(None) == 0
+
+
+def test_host_mirror_error_behaviour(capsys):
+    from more3d_b200 import DM_saliency as dm
+    # unreadable ODM path: print the IOError and return None (reference DM_saliency.py:361-365)
+    assert dm.DM_nonparam_curvature("/nonexistent/file.npz", "sphere", radius=0.5) is None
+    assert dm.DM_dk_dn("/nonexistent/file.npz", "sphere", 0.3, 0.3, radius=0.5) is None
+    assert "nonexistent" in capsys.readouterr().out
+    q = dm.QueryDescriptor("sphere(r=0.75)")
+    assert q.radius == 0.75
+    with pytest.raises(NotImplementedError):
+        dm.QueryDescriptor("circle(r=1)")
+    with pytest.raises(SystemExit):
+        dm._check_shape("sphere", {})                  # "must have radius for search", :368-370
+    with pytest.raises(SystemExit):
+        dm._check_shape("cylinder", {"radius": 1.0})   # :371-374
+    k = dm.Curvature_Kernel()
+    k.setArgs(alpha=0.05, roughness=0.02)
+    assert k._minPoints_neighbourhood == 4 and abs(k.epsilon() - 0.0391992796908) < 1e-12
+    s = dm.Saliency_Kernel()
+    s.setArgs(0.3, 0.3)
+    assert (s._sigma_normal, s._sigma_curvature, s._alpha, s._minPoints_neighbourhood) == (0.01, 0.1, 0.05, 4)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    from more3d_b200 import _lib
+    from more3d_b200.BallTreePointSet import BallTreePointSet
+    with pytest.raises(_lib.More3DError):
+        BallTreePointSet(np.zeros((10, 3)))
+    with pytest.raises(ValueError):
+        BallTreePointSet([[0, 0, 0]])                  # "Wrong input object.", BallTreePointSet.py:40-42
