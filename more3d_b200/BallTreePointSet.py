@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .grid import UniformGrid, CELL_MARGIN
+from .grid import UniformGrid, cell_for_radius
 
 
 class BallTreePointSet(object):
@@ -138,7 +138,7 @@ class BallTreePointSet(object):
             single = True
         pnts = np.ascontiguousarray(pnts, dtype=np.float64)
         radius = float(radius)
-        g = self._grid(max(radius, 1e-300) * CELL_MARGIN)
+        g = self._grid(cell_for_radius(radius))
         self_query = (pnts.shape == self.__points.shape and
                       (pnts is self.__points or np.shares_memory(pnts, self.__points) or
                        np.array_equal(pnts, self.__points)))
@@ -155,7 +155,7 @@ class BallTreePointSet(object):
     def queryRadiusCSR(self, pnts, radius):
         """Extension: the same query as device-resident CSR (offsets int64, indices int32), no host copy."""
         radius = float(radius)
-        g = self._grid(max(radius, 1e-300) * CELL_MARGIN)
+        g = self._grid(cell_for_radius(radius))
         return g.radius_csr(pnts, radius)
 
     def ToNumpy(self):

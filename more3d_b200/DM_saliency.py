@@ -22,7 +22,7 @@ from scipy import stats
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import UniformGrid, as_device_points, CELL_MARGIN
+from .grid import UniformGrid, as_device_points, cell_for_radius
 
 
 class PointCloudDM:
@@ -80,7 +80,7 @@ class PointCloudDM:
         key = float(radius)
         g = self._grids.get(key)
         if g is None:
-            g = UniformGrid(self.xyz, key * CELL_MARGIN)
+            g = UniformGrid(self.xyz, cell_for_radius(key))
             self._grids[key] = g
         return g
 

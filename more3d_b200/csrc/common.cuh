@@ -93,6 +93,10 @@ struct more3d_grid {
     double cell, inv_cell, ox, oy;
     int device;
     cudaStream_t stream;    // creation stream: grid arrays are stream-ordered allocations on it
+    double oz;              // z origin of the fp32 records (bbox z-min)
+    double lim32;           // delta32 holds for |coordinate - origin| < lim32
+    double delta32;         // bound on |fp32 record coordinate - exact coordinate| (2^-24 * extent)
+    float4* rec32;          // n sorted fp32 records (x-ox, y-oy, z-oz, 0): the fast distance filter
     uint32_t* order;        // n: sorted pos -> original index
     m3d::PointRec* rec;     // n sorted records
     uint32_t* col_start;    // nx*ny + 1

@@ -112,22 +112,28 @@ struct CurvParams {
     double eps;
     int min_points;
     int s;
+    Filter32 flt;
 };
+
+constexpr int WALK_THREADS = 256;
 
 // One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
 // query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
 template <int MODE>
-__global__ void __launch_bounds__(256) moments_kernel(GridView g, CurvParams prm,
-                                                      double* __restrict__ normals,
-                                                      double* __restrict__ lam_ratio,
-                                                      float* __restrict__ Kout,
-                                                      int32_t* __restrict__ pcount) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(WALK_THREADS) moments_kernel(GridView g, CurvParams prm,
+                                                               double* __restrict__ normals,
+                                                               double* __restrict__ lam_ratio,
+                                                               float* __restrict__ Kout,
+                                                               int32_t* __restrict__ pcount) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const PointRec p = load_rec(g.rec, i);
     const int64_t o = p.idx;
     int m = 0;
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    // The fp64 differences serve both the exact accept rule and the moments, so an fp32 pre-filter
+    // (used by the count/fill kernels) does not pay here: measured 2x slower (conditional fp64 loads
+    // lose the unrolled loop's memory-level parallelism).
     for_each_candidate(g, p.x, p.y, prm.s, [&](int64_t j) {
         const PointRec c = load_rec(g.rec, j);
         const double dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
@@ -225,14 +231,15 @@ __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
 struct DkDnParams {
     double r2, rho2, inv_rho2, sigma_n, sigma_k;
     int min_points, s, table_len;
+    Filter32 flt;
 };
 
-__global__ void __launch_bounds__(256) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
+__global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                    DkDnParams prm, const double* __restrict__ chi2_table,
                                                    float* __restrict__ dk_out, float* __restrict__ dn_out,
                                                    unsigned* __restrict__ mm /* ordered min/max x4 */,
                                                    int* __restrict__ err) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float dkf = 0.0f, dnf = 0.0f;
     const bool live = i < g.n;
     if (live) {
@@ -339,15 +346,16 @@ static int launch_moments(const more3d_grid* g, int mode, double r, double eps, 
     M3D_REQUIRE(normals != nullptr, "normals is NULL");
     CurvParams prm;
     prm.r2 = r * r; prm.eps = eps; prm.min_points = min_points; prm.s = stencil_halfwidth(g, r);
-    const unsigned nb = (unsigned)((g->n + 255) / 256);
+    prm.flt = make_filter(g, r);
+    const unsigned nb = (unsigned)((g->n + WALK_THREADS - 1) / WALK_THREADS);
     GridView v = make_view(g);
     ProfScope prof("moments", s);
     if (mode == MODE_NORMALS)
-        moments_kernel<MODE_NORMALS><<<nb, 256, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount);
+        moments_kernel<MODE_NORMALS><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount);
     else if (mode == MODE_CURV)
-        moments_kernel<MODE_CURV><<<nb, 256, 0, s>>>(v, prm, normals, nullptr, K, pcount);
+        moments_kernel<MODE_CURV><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, nullptr, K, pcount);
     else
-        moments_kernel<MODE_FUSED><<<nb, 256, 0, s>>>(v, prm, normals, lam_ratio, K, pcount);
+        moments_kernel<MODE_FUSED><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, K, pcount);
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
@@ -397,6 +405,7 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
     prm.r2 = r * r; prm.rho2 = rho * rho; prm.inv_rho2 = 1.0 / (rho * rho);
     prm.sigma_n = sigma_normal; prm.sigma_k = sigma_curvature;
     prm.min_points = min_points; prm.s = stencil_halfwidth(g, r); prm.table_len = table_len;
+    prm.flt = make_filter(g, r);
     {
         ProfScope prof("dkdn", s);
         dkdn_kernel<<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);

@@ -15,48 +15,45 @@ constexpr int BB_THREADS = 256;
 
 __global__ void __launch_bounds__(BB_THREADS) bbox_partial(const double* __restrict__ xyz, int64_t n,
                                                            double* __restrict__ part) {
-    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    // v[0..2] = min x,y,z   v[3..5] = max x,y,z (stored negated so one fmin reduction serves both)
+    double v[6] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        double x = xyz[3 * i], y = xyz[3 * i + 1];
-        mnx = fmin(mnx, x); mxx = fmax(mxx, x);
-        mny = fmin(mny, y); mxy = fmax(mxy, y);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double c = xyz[3 * i + a];
+            v[a] = fmin(v[a], c);
+            v[3 + a] = fmin(v[3 + a], -c);
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
-    __shared__ double sm[4][BB_THREADS / 32];
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[a] = fmin(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+    __shared__ double sm[6][BB_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { sm[0][warp] = mnx; sm[1][warp] = mny; sm[2][warp] = mxx; sm[3][warp] = mxy; }
+    if (lane == 0)
+        for (int a = 0; a < 6; ++a) sm[a][warp] = v[a];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < BB_THREADS / 32; ++w) {
-            mnx = fmin(mnx, sm[0][w]); mny = fmin(mny, sm[1][w]);
-            mxx = fmax(mxx, sm[2][w]); mxy = fmax(mxy, sm[3][w]);
-        }
-        part[4 * blockIdx.x + 0] = mnx; part[4 * blockIdx.x + 1] = mny;
-        part[4 * blockIdx.x + 2] = mxx; part[4 * blockIdx.x + 3] = mxy;
+    if (threadIdx.x < 6) {
+        double r = sm[threadIdx.x][0];
+        for (int w = 1; w < BB_THREADS / 32; ++w) r = fmin(r, sm[threadIdx.x][w]);
+        part[6 * blockIdx.x + threadIdx.x] = r;
     }
 }
 
+// out = {min x, min y, min z, max x, max y, max z}
 __global__ void bbox_final(const double* __restrict__ part, int nparts, double* __restrict__ out) {
-    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (int i = threadIdx.x; i < nparts; i += 32) {
-        mnx = fmin(mnx, part[4 * i]); mny = fmin(mny, part[4 * i + 1]);
-        mxx = fmax(mxx, part[4 * i + 2]); mxy = fmax(mxy, part[4 * i + 3]);
-    }
+    double v[6] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+    for (int i = threadIdx.x; i < nparts; i += 32)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
-    if (threadIdx.x == 0) { out[0] = mnx; out[1] = mny; out[2] = mxx; out[3] = mxy; }
+        for (int a = 0; a < 6; ++a) v[a] = fmin(v[a], part[6 * i + a]);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[a] = fmin(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+    if (threadIdx.x == 0)
+        for (int a = 0; a < 6; ++a) out[a] = (a < 3) ? v[a] : -v[a];
 }
 
 // K1: column key per point + column population (spread-address REDG)
@@ -79,7 +76,8 @@ __global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz,
 // K2 tail: gather the sorted records
 __global__ void __launch_bounds__(256) gather_records(const double* __restrict__ xyz,
                                                       const uint32_t* __restrict__ order, int64_t n,
-                                                      PointRec* __restrict__ rec) {
+                                                      PointRec* __restrict__ rec, double ox, double oy,
+                                                      double oz, float4* __restrict__ rec32) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t o = order[i];
@@ -89,6 +87,8 @@ __global__ void __launch_bounds__(256) gather_records(const double* __restrict__
     r.z = xyz[3 * (int64_t)o + 2];
     r.idx = (long long)o;
     rec[i] = r;
+    // fp32 copy relative to the grid origin: |error| <= 2^-24 * extent per coordinate (delta32)
+    rec32[i] = make_float4((float)(r.x - ox), (float)(r.y - oy), (float)(r.z - oz), 0.0f);
 }
 
 // coincident-point flags: the np.unique(axis=1) of Saliency_Kernel.process (DM_saliency.py:247)
@@ -132,16 +132,18 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
     // bounding box (host needs it to size the table: one small sync per build)
     const int nparts = 592;  // 4 CTAs per SM on 148 SMs
     double* part = nullptr;
-    M3D_TRY(dev_alloc(&part, (size_t)4 * nparts + 4, s));
+    M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
     bbox_partial<<<nparts, BB_THREADS, 0, s>>>(xyz, n, part);
-    bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 4 * nparts);
+    bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
     count_launches(2);
     M3D_CHECK_LAUNCH();
-    double bb[4];
-    M3D_CUDA(cudaMemcpyAsync(bb, part + 4 * nparts, sizeof(bb), cudaMemcpyDeviceToHost, s));
+    double b6[6];
+    M3D_CUDA(cudaMemcpyAsync(b6, part + 6 * nparts, sizeof(b6), cudaMemcpyDeviceToHost, s));
     M3D_CUDA(cudaStreamSynchronize(s));
     dev_free(part, s);
-    if (!(isfinite(bb[0]) && isfinite(bb[1]) && isfinite(bb[2]) && isfinite(bb[3]))) {
+    const double bb[4] = {b6[0], b6[1], b6[3], b6[4]};   // min x, min y, max x, max y
+    if (!(isfinite(b6[0]) && isfinite(b6[1]) && isfinite(b6[2]) && isfinite(b6[3]) && isfinite(b6[4]) &&
+          isfinite(b6[5]))) {
         set_error("non-finite coordinates in cloud");
         return MORE3D_E_INVALID;
     }
@@ -165,6 +167,16 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
     g->ny = (int)floor(ey / c) + 3;
     cudaGetDevice(&g->device);
     g->stream = s;
+    g->oz = b6[2];
+    {
+        // largest |coordinate - origin| any record (or query clamped to the stencil) can have
+        double ext = fmax(fmax(ex + 3.0 * c, ey + 3.0 * c), b6[5] - b6[2]);
+        int e2 = 0;
+        frexp(ext, &e2);                           // ext < 2^e2
+        g->delta32 = ldexp(1.0, e2 - 24);
+        g->lim32 = ldexp(1.0, e2);
+    }
+    g->rec32 = nullptr;
     g->order = nullptr; g->rec = nullptr; g->col_start = nullptr; g->dup = nullptr;
     const size_t ncols = (size_t)g->nx * g->ny;
 
@@ -177,6 +189,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         G_CUDA(cudaMallocAsync((void**)&g->order, (size_t)n * sizeof(uint32_t), s));
         G_CUDA(cudaMallocAsync((void**)&g->rec, (size_t)n * sizeof(PointRec), s));
         G_CUDA(cudaMallocAsync((void**)&g->dup, (size_t)n, s));
+        G_CUDA(cudaMallocAsync((void**)&g->rec32, (size_t)n * sizeof(float4), s));
         G_TRY(dev_alloc(&keys, (size_t)n, s));
         G_TRY(dev_alloc(&vals, (size_t)n, s));
         G_TRY(dev_alloc(&keys2, (size_t)n, s));
@@ -192,7 +205,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         uint32_t *ks = nullptr, *vs = nullptr;
         G_TRY(radix_sort_pairs_u32(keys, vals, keys2, vals2, n, bits, &ks, &vs, s));
         G_CUDA(cudaMemcpyAsync(g->order, vs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-        gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec);
+        gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec, g->ox, g->oy, g->oz, g->rec32);
         dup_flags<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny,
                                      g->dup);
         count_launches(3);  // cell_keys, gather_records, dup_flags
@@ -215,6 +228,7 @@ extern "C" int more3d_grid_destroy(more3d_grid* g) {
     if (g->rec) cudaFreeAsync(g->rec, g->stream);
     if (g->col_start) cudaFreeAsync(g->col_start, g->stream);
     if (g->dup) cudaFreeAsync(g->dup, g->stream);
+    if (g->rec32) cudaFreeAsync(g->rec32, g->stream);
     delete g;
     return MORE3D_OK;
 }

@@ -1,4 +1,4 @@
-// Device-side view of the grid and the stencil walk shared by every neighbourhood kernel.
+// Device-side view of the grid and the stencil walks shared by every neighbourhood kernel.
 #pragma once
 #include "common.cuh"
 
@@ -6,17 +6,20 @@ namespace m3d {
 
 struct GridView {
     const PointRec* rec;
+    const float4* rec32;
     const uint32_t* col_start;
     const uint8_t* dup;
     int64_t n;
     int nx, ny;
-    double ox, oy, inv;
+    double ox, oy, oz, inv;
+    double lim32;
 };
 
 static inline GridView make_view(const more3d_grid* g) {
     GridView v;
-    v.rec = g->rec; v.col_start = g->col_start; v.dup = g->dup; v.n = g->n;
-    v.nx = g->nx; v.ny = g->ny; v.ox = g->ox; v.oy = g->oy; v.inv = g->inv_cell;
+    v.rec = g->rec; v.rec32 = g->rec32; v.col_start = g->col_start; v.dup = g->dup; v.n = g->n;
+    v.nx = g->nx; v.ny = g->ny; v.ox = g->ox; v.oy = g->oy; v.oz = g->oz; v.inv = g->inv_cell;
+    v.lim32 = g->lim32;
     return v;
 }
 
@@ -27,6 +30,35 @@ static inline int stencil_halfwidth(const more3d_grid* g, double r) {
     if (s > lim) s = lim;
     if (s < 1) s = 1;
     return (int)s;
+}
+
+// fp32 distance filter.  With every fp32 record coordinate within delta32 of the exact one, the fp32
+// squared distance of a pair near the sphere surface is within h of the exact fp64 rule's value:
+//   |d2_32 - d2| <= (2 delta + 2^-24 r)(2 sqrt(3) r + ...) + 3 * 2^-24 r^2  <  8 delta r + 1e-6 r^2
+// (derivation in DESIGN.md §3).  Twice that is used.  d2_32 < lo: certainly inside; d2_32 > hi:
+// certainly outside; otherwise the pair is re-evaluated with the exact fp64 rule (dist2_rule).
+struct Filter32 {
+    float lo, hi;
+};
+static inline Filter32 make_filter(const more3d_grid* g, double r) {
+    const double r2 = r * r, d = g->delta32;
+    const double h = 16.0 * d * r + 4e-6 * r2 + 64.0 * d * d;
+    Filter32 f;
+    if (!(h < 0.25 * r2)) {          // extent too large for this radius: everything goes the exact way
+        f.lo = -1.0f;
+        f.hi = INFINITY;
+    } else {
+        f.lo = (float)(r2 - h) * (1.0f - 1e-6f);
+        f.hi = (float)(r2 + h) * (1.0f + 1e-6f);
+    }
+    return f;
+}
+
+// a query far outside the cloud's box has a larger fp32 rounding error than delta32: exact path only
+__device__ __forceinline__ Filter32 filter_for_query(const GridView& g, Filter32 f, double px, double py, double pz) {
+    const bool ok = fabs(px - g.ox) < g.lim32 && fabs(py - g.oy) < g.lim32 && fabs(pz - g.oz) < g.lim32;
+    if (!ok) { f.lo = -1.0f; f.hi = INFINITY; }
+    return f;
 }
 
 __device__ __forceinline__ PointRec load_rec(const PointRec* __restrict__ rec, int64_t j) {
@@ -52,6 +84,28 @@ __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx,
         const uint32_t e = __ldg(g.col_start + row + x1 + 1);
         for (uint32_t j = b; j < e; ++j) f((int64_t)j);
     }
+}
+
+// Exact-set neighbour enumeration with the fp32 filter: accept(j) is called for every sorted position
+// j whose point satisfies the fp64 rule ((dx*dx)+(dy*dy))+(dz*dz) <= r2 -- bit-identical to the
+// all-fp64 walk, only cheaper: fp64 is touched for the thin shell around the sphere surface only.
+template <typename F>
+__device__ __forceinline__ void for_each_neighbour(const GridView& g, const Filter32 flt, double r2, int s,
+                                                   double px, double py, double pz, F&& accept) {
+    const float qx = (float)(px - g.ox), qy = (float)(py - g.oy), qz = (float)(pz - g.oz);
+    for_each_candidate(g, px, py, s, [&](int64_t j) {
+        const float4 c = __ldg(g.rec32 + j);
+        const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d2 <= flt.hi) {
+            bool in = d2 < flt.lo;
+            if (!in) {
+                const PointRec e = load_rec(g.rec, j);
+                in = dist2_rule(px - e.x, py - e.y, pz - e.z) <= r2;
+            }
+            if (in) accept(j);
+        }
+    });
 }
 
 }  // namespace m3d

@@ -8,7 +8,7 @@ namespace m3d {
 // stencil rows, so candidate loads are L1 broadcasts); results land at the ORIGINAL index.
 template <bool SELF>
 __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const double* __restrict__ q,
-                                                           int64_t nq, double r2, int s,
+                                                           int64_t nq, double r2, int s, Filter32 flt,
                                                            int32_t* __restrict__ counts) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -21,17 +21,14 @@ __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const dou
         px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
     }
     int c = 0;
-    for_each_candidate(g, px, py, s, [&](int64_t j) {
-        PointRec c_ = load_rec(g.rec, j);
-        double d2 = dist2_rule(px - c_.x, py - c_.y, pz - c_.z);
-        c += (d2 <= r2) ? 1 : 0;
-    });
+    if (!SELF) flt = filter_for_query(g, flt, px, py, pz);
+    for_each_neighbour(g, flt, r2, s, px, py, pz, [&](int64_t) { ++c; });
     counts[out] = c;
 }
 
 template <bool SELF, typename IdxT>
 __global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const double* __restrict__ q,
-                                                          int64_t nq, double r2, int s,
+                                                          int64_t nq, double r2, int s, Filter32 flt,
                                                           const int64_t* __restrict__ offsets,
                                                           IdxT* __restrict__ idx) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,10 +42,9 @@ __global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const doub
         px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
     }
     int64_t w = offsets[out];
-    for_each_candidate(g, px, py, s, [&](int64_t j) {
-        PointRec c_ = load_rec(g.rec, j);
-        double d2 = dist2_rule(px - c_.x, py - c_.y, pz - c_.z);
-        if (d2 <= r2) idx[w++] = (IdxT)c_.idx;
+    if (!SELF) flt = filter_for_query(g, flt, px, py, pz);
+    for_each_neighbour(g, flt, r2, s, px, py, pz, [&](int64_t j) {
+        idx[w++] = (IdxT)__double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + j) + 3));
     });
 }
 
@@ -74,9 +70,9 @@ extern "C" int more3d_radius_count(const more3d_grid* g, const double* q, int64_
     const unsigned nb = (unsigned)((nq + 255) / 256);
     ProfScope prof("radius_count", s);
     if (q)
-        radius_count_kernel<false><<<nb, 256, 0, s>>>(make_view(g), q, nq, r * r, sw, counts);
+        radius_count_kernel<false><<<nb, 256, 0, s>>>(make_view(g), q, nq, r * r, sw, make_filter(g, r), counts);
     else
-        radius_count_kernel<true><<<nb, 256, 0, s>>>(make_view(g), nullptr, nq, r * r, sw, counts);
+        radius_count_kernel<true><<<nb, 256, 0, s>>>(make_view(g), nullptr, nq, r * r, sw, make_filter(g, r), counts);
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
@@ -105,13 +101,14 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
     const unsigned nb = (unsigned)((nq + 255) / 256);
     GridView v = make_view(g);
     const double r2 = r * r;
+    const Filter32 flt = make_filter(g, r);
     ProfScope prof("radius_fill", s);
     if (q) {
-        if (idx_bytes == 4) radius_fill_kernel<false, int32_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, offsets, (int32_t*)idx);
-        else radius_fill_kernel<false, int64_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, offsets, (int64_t*)idx);
+        if (idx_bytes == 4) radius_fill_kernel<false, int32_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, flt, offsets, (int32_t*)idx);
+        else radius_fill_kernel<false, int64_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, flt, offsets, (int64_t*)idx);
     } else {
-        if (idx_bytes == 4) radius_fill_kernel<true, int32_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, offsets, (int32_t*)idx);
-        else radius_fill_kernel<true, int64_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, offsets, (int64_t*)idx);
+        if (idx_bytes == 4) radius_fill_kernel<true, int32_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, flt, offsets, (int32_t*)idx);
+        else radius_fill_kernel<true, int64_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, flt, offsets, (int64_t*)idx);
     }
     count_launches(1);
     M3D_CHECK_LAUNCH();

@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import UniformGrid, CELL_MARGIN
+from .grid import UniformGrid, CELL_MARGIN, cell_for_radius
 
 
 def strip_bounds(x_min, x_max, world):
@@ -112,7 +112,7 @@ def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=N
     sum_m = {}
     for r in radii:
         rho = r / np.sqrt(2.0)
-        g = UniformGrid(local, r * CELL_MARGIN)
+        g = UniformGrid(local, cell_for_radius(r))
         normals, _, K, pcount = g.normals_curvature(r, eps, params["min_points"])
         length = 1024
         while True:

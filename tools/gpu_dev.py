@@ -27,6 +27,9 @@ def timed(fn, reps=3):
     return best, out
 
 
+DIV = int(os.environ.get("MORE3D_CELLS_PER_RADIUS", "1"))
+
+
 def main():
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1000000
     radii = [float(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.5, 0.75, 1.0]
@@ -36,7 +39,7 @@ def main():
     d = torch.from_numpy(pts).cuda()
     table = _chi2_table(0.05, 4096, d.device)
     for r in radii:
-        tb, g = timed(lambda: UniformGrid(d, r * CELL_MARGIN))
+        tb, g = timed(lambda: UniformGrid(d, r * CELL_MARGIN / DIV))
         tc, cnt = timed(lambda: g.radius_count(None, r))
         tm, (nrm, ratio, K, pc) = timed(lambda: g.normals_curvature(r, 0.0392, 4))
         td, (dk, dn, mm) = timed(lambda: g.dk_dn(r, nrm, K, r / np.sqrt(2), 0.01, 0.01, table, 4))
