@@ -114,7 +114,39 @@ int more3d_saliency_blend(const float* dk, const float* dn, int64_t n, const flo
                           double curvature_weight, float* sal, float* sal_minmax, void* stream);
 /* 256-bin histogram of sal over [lo, hi] with numpy.histogram's binning; edges: 257 float64 from
  * numpy.linspace (host computed, device resident).  hist: 256 int64 (zeroed by the call). */
-int more3d_histogram256(const float* v, int64_t n, const double* edges, int64_t* hist, void* stream);
+int more3d_histogram256(const void* v, int elem_bytes, int64_t n, const double* edges, int64_t* hist,
+                        void* stream);
+
+/* ---- voxel-grid downsampling -----------------------------------------------------------------------
+ * Replaces open3d voxel_down_sample as used by Downsampling/Downsample.py:86-89: voxel index =
+ * floor((p - (min_bound - voxel/2)) / voxel) per axis; one output point per occupied voxel = mean of its
+ * members (accumulated in original point order).  Outputs are sorted by voxel index (x, then y, then z;
+ * open3d's own order is hash-map order).  out_xyz: capacity n*3 f64; out_keys: capacity n*3 int64 or
+ * NULL; voxel_of_point: n int32 (output row of every input point) or NULL; *nout_h = voxels. */
+int more3d_voxel_downsample(const double* xyz, int64_t n, double voxel, double* out_xyz,
+                            int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h, void* stream);
+
+/* ---- level-of-detail cells: ball-tree-equivalent hierarchy -------------------------------------------
+ * Replaces the sklearn BallTree build + the hierarchy bookkeeping of BallTreePointSet.__init__
+ * (Downsampling/BallTreePointSet.py:35-53): same node membership as sklearn's recursive median split
+ * (heap layout, children of i = 2i+1, 2i+2).  shape(): host helper giving n_levels / n_nodes for a
+ * cloud size (sklearn _binary_tree.pxi.tp:872-873).  build(): idx_array n int64; idx_start / idx_end
+ * n_nodes int64; is_leaf n_nodes int32; radius n_nodes f64 (node_data of BallTree.get_arrays()). */
+int more3d_balltree_shape(int64_t n, int leaf_size, int64_t* n_levels_h, int64_t* n_nodes_h);
+int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size, int64_t* idx_array,
+                          int64_t* idx_start, int64_t* idx_end, int32_t* is_leaf, double* radius,
+                          void* stream);
+/* Per-cell rule of the saliency downsampler (Downsampling/Downsample.py:56-75, with the declared repair
+ * of :58/:67 -- see DESIGN.md): cells are ranges [cell_start[c], cell_start[c+1]) of idx_array.
+ * mask = saliency > thresh (and |saliency| < zero_thresh when literal != 0); a cell with more than 60 %
+ * masked points is kept whole, otherwise its masked points are kept and the rest is replaced by their
+ * mean.  keep: n uint8 per idx_array POSITION; keep_all: ncells uint8; mean_xyz: ncells*3 f64 (NaN when
+ * unused). */
+int more3d_lod_cell_rule(const double* xyz, const double* saliency, const int64_t* idx_array,
+                         const int64_t* cell_start, int64_t ncells, double thresh, double zero_thresh,
+                         int literal, uint8_t* keep, uint8_t* keep_all, double* mean_xyz, void* stream);
+/* stable compaction: idx = positions i with flags[i] != 0 (ascending); idx has room for n int64 */
+int more3d_select_flagged(const uint8_t* flags, int64_t n, int64_t* idx, int64_t* count_h, void* stream);
 
 /* ---- multi-GPU strip partition helpers (no reference equivalent; OPALS tile streaming,
  * DM_saliency.py:76-86, is the analogue) ----------------------------------------------------------

@@ -1,0 +1,141 @@
+"""Saliency-driven and voxel-grid downsampling (the body of the reference's Downsampling/Downsample.py
+script, :44-91, as functions) on the B200 kernels.
+
+``saliency_downsample`` follows Downsample.py:44-83 with the DECLARED REPAIR of two lines that cannot run
+as shipped: ``:58`` applies Python ``and`` to arrays (ValueError) and its two conjuncts
+are mutually exclusive for any useful threshold -> ``idx_saliency = saliency > s_thresh``; ``:67`` indexes
+with ``1 - bool_array`` (rows 0/1, not a complement) -> the mean runs over ``~idx_saliency``.
+``literal=True`` keeps both conjuncts of :58 (``and`` -> ``&``) instead.
+``voxel_downsample`` replaces ``open3d ... voxel_down_sample(voxel_size=LOD)`` (:86-89).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .BallTreePointSet import BallTreePointSet
+from .grid import as_device_points
+
+
+def threshold_otsu(values, nbins=256):
+    """skimage.filters.threshold_otsu (0.19.x, README.md:90) of a device or host array: the 256-bin
+    histogram is built on the GPU with numpy.histogram's exact binning; the 256-entry scan runs on the host."""
+    lib = _lib.load()
+    _lib.require_cuda()
+    v = values if isinstance(values, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(values))
+    if v.dtype not in (torch.float32, torch.float64):
+        v = v.double()
+    v = v.to(device="cuda").contiguous().reshape(-1)
+    lo, hi = float(v.min()), float(v.max())
+    if lo == hi:
+        return lo
+    if nbins != 256:
+        raise NotImplementedError("only nbins=256 (the skimage default used by the reference)")
+    edges = np.linspace(lo, hi, nbins + 1)          # numpy.histogram's bin edges for range=(min, max)
+    with torch.cuda.device(v.device):
+        de = torch.from_numpy(edges).to(v.device)
+        hist = torch.empty(256, dtype=torch.int64, device=v.device)
+        check(lib.more3d_histogram256(ptr(v), v.element_size(), int(v.numel()), ptr(de), ptr(hist), stream_ptr()))
+    counts = hist.cpu().numpy().astype(np.float64)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    with np.errstate(all="ignore"):
+        w1 = np.cumsum(counts)
+        w2 = np.cumsum(counts[::-1])[::-1]
+        m1 = np.cumsum(counts * centers) / w1
+        m2 = (np.cumsum((counts * centers)[::-1]) / w2[::-1])[::-1]
+        var12 = w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2
+    return float(centers[int(np.argmax(var12))])
+
+
+def voxel_downsample(pts, voxel_size, return_keys=False, return_device=False):
+    """Mean point of every occupied voxel (Downsample.py:86-89).  Returns an (V,3) float64 array sorted by
+    voxel index (open3d's own order is hash-map order: compare as sets), optionally the (V,3) int64 voxel
+    indices."""
+    lib = _lib.load()
+    d = as_device_points(pts)
+    n = int(d.shape[0])
+    with torch.cuda.device(d.device):
+        out = torch.empty((n, 3), dtype=torch.float64, device=d.device)
+        keys = torch.empty((n, 3), dtype=torch.int64, device=d.device) if return_keys else None
+        nout = C.c_int64(0)
+        check(lib.more3d_voxel_downsample(ptr(d), n, float(voxel_size), ptr(out), ptr(keys), None, C.byref(nout),
+                                          stream_ptr()))
+    v = int(nout.value)
+    out = out[:v]
+    if not return_device:
+        out = out.cpu().numpy()
+    if return_keys:
+        k = keys[:v] if return_device else keys[:v].cpu().numpy()
+        return out, k
+    return out
+
+
+def saliency_downsample(pts, saliency, lod, leaf_size=40, zero_thresh=1e-4, literal=False, btP=None,
+                        s_thresh=None, return_details=False):
+    """One LOD of the loop at Downsample.py:44-83.  pts (N,3); saliency (N,).  Returns the (M,4) array the
+    script writes (xyz + flag: 1 = salient / kept cell, 0 = representative of the averaged rest), rows in
+    the reference's order (cell by cell, kept points in ball-tree order then the representative)."""
+    lib = _lib.load()
+    if btP is None:
+        btP = BallTreePointSet(np.asarray(pts), leaf_size=leaf_size)
+    tree = btP._hierarchy()
+    dev = btP.device_points
+    n = tree.n
+    sal = saliency if isinstance(saliency, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(saliency))
+    sal64 = sal.to(device=dev.device, dtype=torch.float64).contiguous().reshape(-1)
+    if s_thresh is None:
+        s_thresh = threshold_otsu(sal)                                      # :54
+    cells = np.atleast_1d(btP.getSmallestNodesOfSize(lod))                  # :47
+    starts = np.append(tree.idx_start[cells], n).astype(np.int64)
+    ncells = len(cells)
+    with torch.cuda.device(dev.device):
+        cs = torch.from_numpy(starts).to(dev.device)
+        keep = torch.empty(n, dtype=torch.uint8, device=dev.device)
+        keep_all = torch.empty(ncells, dtype=torch.uint8, device=dev.device)
+        mean = torch.empty((ncells, 3), dtype=torch.float64, device=dev.device)
+        check(lib.more3d_lod_cell_rule(ptr(dev), ptr(sal64), ptr(tree.idx_array_dev), ptr(cs), ncells, float(s_thresh),
+                                       float(zero_thresh), 1 if literal else 0, ptr(keep), ptr(keep_all), ptr(mean),
+                                       stream_ptr()))
+        kept_pos = torch.empty(n, dtype=torch.int64, device=dev.device)
+        cnt = C.c_int64(0)
+        check(lib.more3d_select_flagged(ptr(keep), n, ptr(kept_pos), C.byref(cnt), stream_ptr()))
+        kept_pos = kept_pos[:int(cnt.value)]
+    keep_all_h = keep_all.cpu().numpy().astype(bool)
+    avg_cells = np.nonzero(~keep_all_h)[0]
+    # closest original point to every averaged rest (btP.query(average_pt[None, :], 1), :70)
+    near = np.zeros(0, np.int64)
+    if len(avg_cells):
+        mean_h = mean.cpu().numpy()[avg_cells]
+        near = btP.query(mean_h, 1)[:, 0]
+    kept_pos_h = kept_pos.cpu().numpy()
+    kept_idx = tree.idx_array[kept_pos_h]
+    kept_cell = np.searchsorted(starts, kept_pos_h, side="right") - 1
+    # reference order: cell by cell, kept points first (flag 1), then the representative (flag 0)
+    all_idx = np.concatenate([kept_idx, near])
+    all_cell = np.concatenate([kept_cell, avg_cells])
+    all_flag = np.concatenate([np.ones(len(kept_idx)), np.zeros(len(near))])
+    order = np.lexsort((1 - all_flag, all_cell))
+    P = btP.ToNumpy()
+    out = np.hstack((P[all_idx[order]], all_flag[order][:, None]))
+    if return_details:
+        return out, dict(idx=all_idx[order], cell=all_cell[order], cells=cells, s_thresh=s_thresh,
+                         keep_all=keep_all_h)
+    return out
+
+
+if __name__ == '__main__':   # the reference script's driver (Downsample.py:30-91), paths as arguments
+    import sys
+    if len(sys.argv) < 3:
+        raise SystemExit("usage: python -m more3d_b200.Downsample <saliency.txt (x y z s)> <out_prefix> [LOD ...]")
+    saliency = np.loadtxt(sys.argv[1])
+    pts = saliency[:, :3]
+    lods = [float(a) for a in sys.argv[3:]] or [1, 2, 5, 7, 10]
+    btP = BallTreePointSet(pts, leaf_size=40)
+    for LOD in lods:
+        print('computing {}'.format(LOD))
+        np.savetxt(sys.argv[2] + '_' + str(LOD) + '_saliency.txt', saliency_downsample(pts, saliency[:, 3], LOD, btP=btP))
+        voxel_down = voxel_downsample(pts, LOD)
+        print('number of points', str(voxel_down.shape[0]))
+        np.savetxt(sys.argv[2] + '_' + str(LOD) + '_voxel.txt', voxel_down)

@@ -72,3 +72,35 @@ extern "C" int more3d_gather_rows(const void* src, const int64_t* idx, int64_t m
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }
+
+namespace m3d {
+__global__ void __launch_bounds__(256) flag_to_u32(const uint8_t* __restrict__ f, int64_t n, uint32_t* __restrict__ o) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = f[i] ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) flag_scatter(const uint8_t* __restrict__ f, int64_t n,
+                                                    const uint32_t* __restrict__ pos, int64_t* __restrict__ idx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && f[i]) idx[pos[i]] = i;
+}
+}  // namespace m3d
+
+extern "C" int more3d_select_flagged(const uint8_t* flags, int64_t n, int64_t* idx, int64_t* count_h, void* stream) {
+    M3D_REQUIRE(flags && idx && count_h && n > 0, "NULL / empty argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    init_device_pool();
+    uint32_t* pos = nullptr;
+    M3D_TRY(dev_alloc(&pos, (size_t)n + 1, s));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    flag_to_u32<<<nb, 256, 0, s>>>(flags, n, pos);
+    M3D_TRY(exclusive_scan_u32(pos, pos, n, s));
+    flag_scatter<<<nb, 256, 0, s>>>(flags, n, pos, idx);
+    count_launches(2);
+    M3D_CHECK_LAUNCH();
+    uint32_t total = 0;
+    M3D_CUDA(cudaMemcpyAsync(&total, pos + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    dev_free(pos, s);
+    *count_h = (int64_t)total;
+    return MORE3D_OK;
+}

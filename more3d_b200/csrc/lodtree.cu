@@ -1,0 +1,360 @@
+// K9: ball-tree-equivalent node hierarchy for the level-of-detail cells of the saliency downsampler.
+// Replaces BallTreePointSet.__init__'s sklearn BallTree build + hierarchy reconstruction
+// (Downsampling/BallTreePointSet.py:35-53), getPointsOfNode (:240-254) and getNodeRadius (:226).
+//
+// sklearn builds the tree by recursive median splits (neighbors/_binary_tree.pxi.tp:1033-1083):
+// split dimension = largest (max - min) spread, first maximum wins (:598-645); the left child
+// receives the floor(n/2) smallest points by (value on that dimension, point index)
+// (neighbors/_partition_nodes.pyx:24-57), heap layout (children of i are 2i+1, 2i+2), all leaves on the
+// last of n_levels = int(log2(max(1, (n-1)/leaf_size)) + 1) levels.  Node membership is therefore a
+// deterministic function of the cloud, and is what this file reproduces -- level by level for all
+// nodes at once, with three index lists kept sorted by x, y and z inside every node (stable segmented
+// partitions = one global scan per list per level) instead of a recursive nth_element.
+// Node radius = sqrt(max squared distance to the node centroid) (neighbors/_ball_tree.pyx.tp:86-145);
+// the centroid here is a pairwise (children-first) fp64 sum, sklearn's is a sequential one in an
+// implementation-defined order, so radii agree to a few ulp, not bit for bit.
+#include <vector>
+#include "common.cuh"
+
+namespace m3d {
+
+constexpr int LT_THREADS = 256;
+
+__device__ __forceinline__ uint64_t sortable_key(double v) {
+    v = v + 0.0;   // -0.0 -> +0.0 (the comparator treats them as equal)
+    const uint64_t u = (uint64_t)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(LT_THREADS) lt_keys(const double* __restrict__ xyz, int64_t n, int d,
+                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = sortable_key(xyz[3 * i + d]);
+    vals[i] = (uint32_t)i;
+}
+
+struct Lists {
+    uint32_t* p[3];
+};
+
+// one thread per node of the level: choose the split dimension from the sorted lists' end points
+__global__ void __launch_bounds__(LT_THREADS) lt_split_dim(const double* __restrict__ xyz, Lists L,
+                                                           const int64_t* __restrict__ nstart,
+                                                           const int64_t* __restrict__ nend,
+                                                           const int32_t* __restrict__ is_leaf, int64_t first,
+                                                           int64_t count, int8_t* __restrict__ split_dim) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int64_t node = first + k;
+    const int64_t b = nstart[node], e = nend[node];
+    int8_t best = -1;
+    if (!is_leaf[node] && e - b >= 2) {
+        double max_spread = 0.0;
+        best = 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double lo = xyz[3 * (int64_t)L.p[d][b] + d], hi = xyz[3 * (int64_t)L.p[d][e - 1] + d];
+            const double spread = hi - lo;
+            if (spread > max_spread) { max_spread = spread; best = (int8_t)d; }   // first maximum wins
+        }
+    }
+    split_dim[k] = best;
+}
+
+// per position: mark the side (0 = left child, 1 = right child) of the point sitting at rank t - start
+// of its node's split-dimension list
+__global__ void __launch_bounds__(LT_THREADS) lt_mark_sides(Lists L, int64_t n, const uint32_t* __restrict__ pos_node,
+                                                            const int64_t* __restrict__ nstart,
+                                                            const int64_t* __restrict__ nend, int64_t first,
+                                                            const int8_t* __restrict__ split_dim,
+                                                            uint8_t* __restrict__ side) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t node = pos_node[t];
+    const int d = split_dim[node - first];
+    if (d < 0) return;    // leaf: stays where it is
+    const int64_t b = nstart[node], e = nend[node];
+    const int64_t n_mid = (e - b) / 2;
+    side[L.p[d][t]] = (uint8_t)((t - b) >= n_mid);
+}
+
+__global__ void __launch_bounds__(LT_THREADS) lt_left_flags(const uint32_t* __restrict__ list, int64_t n,
+                                                            const uint32_t* __restrict__ pos_node, int64_t first,
+                                                            const int8_t* __restrict__ split_dim,
+                                                            const uint8_t* __restrict__ side,
+                                                            uint32_t* __restrict__ flag) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t node = pos_node[t];
+    flag[t] = (split_dim[node - first] < 0 || side[list[t]] == 0) ? 1u : 0u;
+}
+
+// stable segmented partition of one list: lefts keep their order at the front of the node's range
+__global__ void __launch_bounds__(LT_THREADS) lt_partition(const uint32_t* __restrict__ list, int64_t n,
+                                                           const uint32_t* __restrict__ pos_node,
+                                                           const int64_t* __restrict__ nstart,
+                                                           const int64_t* __restrict__ nend, int64_t first,
+                                                           const int8_t* __restrict__ split_dim,
+                                                           const uint8_t* __restrict__ side,
+                                                           const uint32_t* __restrict__ scan,
+                                                           uint32_t* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t node = pos_node[t];
+    const uint32_t pt = list[t];
+    if (split_dim[node - first] < 0) { out[t] = pt; return; }
+    const int64_t b = nstart[node], e = nend[node];
+    const int64_t n_mid = (e - b) / 2;
+    const int64_t lrank = (int64_t)scan[t] - (int64_t)scan[b];
+    const int64_t dst = (side[pt] == 0) ? b + lrank : b + n_mid + ((t - b) - lrank);
+    out[dst] = pt;
+}
+
+__global__ void __launch_bounds__(LT_THREADS) lt_descend(int64_t n, uint32_t* __restrict__ pos_node,
+                                                         const int64_t* __restrict__ nstart,
+                                                         const int64_t* __restrict__ nend, int64_t first,
+                                                         const int8_t* __restrict__ split_dim) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t node = pos_node[t];
+    if (split_dim[node - first] < 0) return;
+    const int64_t b = nstart[node], e = nend[node];
+    pos_node[t] = (uint32_t)((t - b) < (e - b) / 2 ? 2 * node + 1 : 2 * node + 2);
+}
+
+// sums of the deepest visited nodes (thread per node, sequential over its points), then parents
+__global__ void __launch_bounds__(LT_THREADS) lt_leaf_sums(const double* __restrict__ xyz,
+                                                           const uint32_t* __restrict__ list,
+                                                           const int64_t* __restrict__ nstart,
+                                                           const int64_t* __restrict__ nend,
+                                                           const int32_t* __restrict__ is_leaf, int64_t n_nodes,
+                                                           double* __restrict__ sums) {
+    int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n_nodes || !is_leaf[node]) return;
+    double sx = 0, sy = 0, sz = 0;
+    for (int64_t t = nstart[node]; t < nend[node]; ++t) {
+        const int64_t o = list[t];
+        sx += xyz[3 * o]; sy += xyz[3 * o + 1]; sz += xyz[3 * o + 2];
+    }
+    sums[3 * node] = sx; sums[3 * node + 1] = sy; sums[3 * node + 2] = sz;
+}
+__global__ void __launch_bounds__(LT_THREADS) lt_parent_sums(const int32_t* __restrict__ is_leaf,
+                                                             const int64_t* __restrict__ nstart,
+                                                             const int64_t* __restrict__ nend, int64_t first,
+                                                             int64_t count, double* __restrict__ sums) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int64_t node = first + k;
+    if (is_leaf[node] || nend[node] - nstart[node] < 1) return;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sums[3 * node + a] = sums[3 * (2 * node + 1) + a] + sums[3 * (2 * node + 2) + a];
+}
+
+// every position walks from the root to its leaf, raising the max squared distance of every node on
+// the way (non-negative doubles order like their bit patterns, so a 64-bit integer atomicMax serves)
+__global__ void __launch_bounds__(LT_THREADS) lt_radii(const double* __restrict__ xyz,
+                                                       const uint32_t* __restrict__ list, int64_t n,
+                                                       const int64_t* __restrict__ nstart,
+                                                       const int64_t* __restrict__ nend,
+                                                       const int32_t* __restrict__ is_leaf,
+                                                       const double* __restrict__ sums,
+                                                       unsigned long long* __restrict__ r2) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t o = list[t];
+    const double x = xyz[3 * o], y = xyz[3 * o + 1], z = xyz[3 * o + 2];
+    int64_t node = 0;
+    while (true) {
+        const int64_t b = nstart[node], e = nend[node];
+        const double cnt = (double)(e - b);
+        const double cx = sums[3 * node] / cnt, cy = sums[3 * node + 1] / cnt, cz = sums[3 * node + 2] / cnt;
+        const double d2 = dist2_rule(cx - x, cy - y, cz - z);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(d2);
+        if (bits > r2[node]) atomicMax(r2 + node, bits);   // racy pre-read only skips redundant atomics
+        if (is_leaf[node]) break;
+        node = (t - b) < (e - b) / 2 ? 2 * node + 1 : 2 * node + 2;
+    }
+}
+
+__global__ void __launch_bounds__(LT_THREADS) lt_finish(const unsigned long long* __restrict__ r2,
+                                                        const uint32_t* __restrict__ list, int64_t n,
+                                                        int64_t n_nodes, double* __restrict__ radius,
+                                                        int64_t* __restrict__ idx_array) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_nodes) radius[t] = sqrt(__longlong_as_double((long long)r2[t]));
+    if (t < n) idx_array[t] = (int64_t)list[t];
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+extern "C" int more3d_balltree_shape(int64_t n, int leaf_size, int64_t* n_levels_h, int64_t* n_nodes_h) {
+    M3D_REQUIRE(n > 0 && leaf_size >= 1 && n_levels_h && n_nodes_h, "bad argument");
+    // sklearn/neighbors/_binary_tree.pxi.tp:872-873
+    double ratio = (double)(n - 1) / (double)leaf_size;
+    if (ratio < 1.0) ratio = 1.0;
+    const int64_t levels = (int64_t)(log2(ratio) + 1.0);
+    *n_levels_h = levels;
+    *n_nodes_h = ((int64_t)1 << levels) - 1;
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size, int64_t* idx_array,
+                                     int64_t* idx_start, int64_t* idx_end, int32_t* is_leaf, double* radius,
+                                     void* stream) {
+    M3D_REQUIRE(xyz && idx_array && idx_start && idx_end && is_leaf && radius, "NULL argument");
+    int64_t n_levels = 0, n_nodes = 0;
+    M3D_TRY(more3d_balltree_shape(n, leaf_size, &n_levels, &n_nodes));
+    if (n >= ((int64_t)1 << 32) || n_levels > 31) { set_error("cloud too large for the LOD tree"); return MORE3D_E_RANGE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    init_device_pool();
+    ProfScope prof("balltree_build", s);
+
+    // node ranges are analytic: recursive halving (host, n_nodes <= a few million)
+    std::vector<int64_t> hs((size_t)n_nodes, 0), he((size_t)n_nodes, 0);
+    std::vector<int32_t> hl((size_t)n_nodes, 0);
+    hs[0] = 0; he[0] = n;
+    for (int64_t i = 0; i < n_nodes; ++i) {
+        const int64_t cnt = he[i] - hs[i];
+        if (i > 0) {
+            const int64_t par = (i - 1) / 2;
+            if (hl[par] || he[par] - hs[par] < 2) { hs[i] = he[i] = 0; continue; }   // never visited by sklearn
+        }
+        if (2 * i + 1 >= n_nodes || cnt < 2) { hl[i] = 1; continue; }               // :1060-1070
+        const int64_t n_mid = cnt / 2;
+        hs[2 * i + 1] = hs[i]; he[2 * i + 1] = hs[i] + n_mid;
+        hs[2 * i + 2] = hs[i] + n_mid; he[2 * i + 2] = he[i];
+    }
+    M3D_CUDA(cudaMemcpyAsync(idx_start, hs.data(), (size_t)n_nodes * 8, cudaMemcpyHostToDevice, s));
+    M3D_CUDA(cudaMemcpyAsync(idx_end, he.data(), (size_t)n_nodes * 8, cudaMemcpyHostToDevice, s));
+    M3D_CUDA(cudaMemcpyAsync(is_leaf, hl.data(), (size_t)n_nodes * 4, cudaMemcpyHostToDevice, s));
+    M3D_CUDA(cudaStreamSynchronize(s));   // the host vectors go out of scope below
+
+    const unsigned nb = (unsigned)((n + LT_THREADS - 1) / LT_THREADS);
+    uint64_t *k1 = nullptr, *k2 = nullptr, *ks = nullptr;
+    uint32_t *v1 = nullptr, *v2 = nullptr, *vs = nullptr;
+    uint32_t *lists[3] = {nullptr, nullptr, nullptr}, *alt = nullptr, *pos_node = nullptr, *scan = nullptr;
+    uint8_t* side = nullptr;
+    int8_t* split_dim = nullptr;
+    double* sums = nullptr;
+    unsigned long long* r2 = nullptr;
+    M3D_TRY(dev_alloc(&k1, (size_t)n, s)); M3D_TRY(dev_alloc(&k2, (size_t)n, s));
+    M3D_TRY(dev_alloc(&v1, (size_t)n, s)); M3D_TRY(dev_alloc(&v2, (size_t)n, s));
+    for (int d = 0; d < 3; ++d) M3D_TRY(dev_alloc(&lists[d], (size_t)n, s));
+    M3D_TRY(dev_alloc(&alt, (size_t)n, s));
+    M3D_TRY(dev_alloc(&pos_node, (size_t)n, s));
+    M3D_TRY(dev_alloc(&scan, (size_t)n + 1, s));
+    M3D_TRY(dev_alloc(&side, (size_t)n, s));
+    M3D_TRY(dev_alloc(&split_dim, (size_t)((n_nodes + 1) / 2 + 1), s));
+    M3D_TRY(dev_alloc(&sums, (size_t)3 * n_nodes, s));
+    M3D_TRY(dev_alloc(&r2, (size_t)n_nodes, s));
+
+    // three lists sorted by (coordinate, index): stable LSD sort of order-preserving 64-bit keys
+    for (int d = 0; d < 3; ++d) {
+        lt_keys<<<nb, LT_THREADS, 0, s>>>(xyz, n, d, k1, v1);
+        count_launches(1);
+        M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, 64, &ks, &vs, s));
+        M3D_CUDA(cudaMemcpyAsync(lists[d], vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    M3D_CUDA(cudaMemsetAsync(pos_node, 0, (size_t)n * 4, s));
+    M3D_CUDA(cudaMemsetAsync(side, 0, (size_t)n, s));
+
+    for (int64_t lev = 0; lev + 1 < n_levels; ++lev) {
+        const int64_t first = ((int64_t)1 << lev) - 1, count = (int64_t)1 << lev;
+        Lists L; L.p[0] = lists[0]; L.p[1] = lists[1]; L.p[2] = lists[2];
+        lt_split_dim<<<(unsigned)((count + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(
+            xyz, L, idx_start, idx_end, is_leaf, first, count, split_dim);
+        lt_mark_sides<<<nb, LT_THREADS, 0, s>>>(L, n, pos_node, idx_start, idx_end, first, split_dim, side);
+        count_launches(2);
+        for (int d = 0; d < 3; ++d) {
+            lt_left_flags<<<nb, LT_THREADS, 0, s>>>(lists[d], n, pos_node, first, split_dim, side, scan);
+            M3D_TRY(exclusive_scan_u32(scan, scan, n, s));
+            lt_partition<<<nb, LT_THREADS, 0, s>>>(lists[d], n, pos_node, idx_start, idx_end, first, split_dim,
+                                                   side, scan, alt);
+            count_launches(2);
+            uint32_t* tmp = lists[d]; lists[d] = alt; alt = tmp;
+        }
+        lt_descend<<<nb, LT_THREADS, 0, s>>>(n, pos_node, idx_start, idx_end, first, split_dim);
+        count_launches(1);
+        M3D_CHECK_LAUNCH();
+    }
+
+    // centroids bottom-up, radii top-down
+    M3D_CUDA(cudaMemsetAsync(sums, 0, (size_t)3 * n_nodes * 8, s));
+    M3D_CUDA(cudaMemsetAsync(r2, 0, (size_t)n_nodes * 8, s));
+    lt_leaf_sums<<<(unsigned)((n_nodes + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(
+        xyz, lists[0], idx_start, idx_end, is_leaf, n_nodes, sums);
+    count_launches(1);
+    for (int64_t lev = n_levels - 2; lev >= 0; --lev) {
+        const int64_t first = ((int64_t)1 << lev) - 1, count = (int64_t)1 << lev;
+        lt_parent_sums<<<(unsigned)((count + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(
+            is_leaf, idx_start, idx_end, first, count, sums);
+        count_launches(1);
+    }
+    lt_radii<<<nb, LT_THREADS, 0, s>>>(xyz, lists[0], n, idx_start, idx_end, is_leaf, sums, r2);
+    const int64_t m = n > n_nodes ? n : n_nodes;
+    lt_finish<<<(unsigned)((m + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(r2, lists[0], n, n_nodes, radius,
+                                                                                   idx_array);
+    count_launches(2);
+    M3D_CHECK_LAUNCH();
+    dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s);
+    for (int d = 0; d < 3; ++d) dev_free(lists[d], s);
+    dev_free(alt, s); dev_free(pos_node, s); dev_free(scan, s); dev_free(side, s); dev_free(split_dim, s);
+    dev_free(sums, s); dev_free(r2, s);
+    return MORE3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-cell rule of the saliency downsampler (Downsampling/Downsample.py:56-75)
+// ------------------------------------------------------------------------------------------
+namespace m3d {
+__global__ void __launch_bounds__(LT_THREADS) lt_cell_rule(const double* __restrict__ xyz,
+                                                           const double* __restrict__ sal,
+                                                           const int64_t* __restrict__ idx_array,
+                                                           const int64_t* __restrict__ cell_start, int64_t ncells,
+                                                           double thresh, double zero_thresh, int literal,
+                                                           uint8_t* __restrict__ keep, uint8_t* __restrict__ keep_all,
+                                                           double* __restrict__ mean_xyz) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int64_t b = cell_start[c], e = cell_start[c + 1];
+    int64_t nsal = 0;
+    double sx = 0, sy = 0, sz = 0;
+    for (int64_t t = b; t < e; ++t) {
+        const int64_t o = idx_array[t];
+        const double v = sal[o];
+        bool m = v > thresh;                                    // :58 (repaired: first conjunct)
+        if (literal) m = m && (fabs(v) < zero_thresh);          // :58 literal: both conjuncts, and -> &
+        keep[t] = m ? 1 : 0;
+        if (m) ++nsal;
+        else { sx += xyz[3 * o]; sy += xyz[3 * o + 1]; sz += xyz[3 * o + 2]; }   // :67 mean of the complement
+    }
+    const int64_t cnt = e - b;
+    const bool all = (double)(nsal * 100) / (double)cnt > 60.0;  // :60
+    keep_all[c] = all ? 1 : 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (all) {
+        for (int64_t t = b; t < e; ++t) keep[t] = 1;            // :61-63 keep the cell as is
+        mean_xyz[3 * c] = mean_xyz[3 * c + 1] = mean_xyz[3 * c + 2] = nan;
+    } else {
+        const double k = (double)(cnt - nsal);
+        mean_xyz[3 * c] = sx / k; mean_xyz[3 * c + 1] = sy / k; mean_xyz[3 * c + 2] = sz / k;
+    }
+}
+}  // namespace m3d
+
+extern "C" int more3d_lod_cell_rule(const double* xyz, const double* saliency, const int64_t* idx_array,
+                                    const int64_t* cell_start, int64_t ncells, double thresh, double zero_thresh,
+                                    int literal, uint8_t* keep, uint8_t* keep_all, double* mean_xyz, void* stream) {
+    M3D_REQUIRE(xyz && saliency && idx_array && cell_start && keep && keep_all && mean_xyz, "NULL argument");
+    if (ncells <= 0) return MORE3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof("lod_cell_rule", s);
+    lt_cell_rule<<<(unsigned)((ncells + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(
+        xyz, saliency, idx_array, cell_start, ncells, thresh, zero_thresh, literal, keep, keep_all, mean_xyz);
+    count_launches(1);
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}

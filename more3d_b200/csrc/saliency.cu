@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk
 // numpy.histogram's uniform-bin path (numpy/lib/_histograms_impl.py): index from the scaled
 // offset, then the two edge fix-ups against the linspace edges.  CTA-private smem histogram,
 // match_any warp aggregation in front of the shared-memory atomics, one global atomic per bin per CTA.
-__global__ void __launch_bounds__(256) hist256_kernel(const float* __restrict__ v, int64_t n,
+template <typename T>
+__global__ void __launch_bounds__(256) hist256_kernel(const T* __restrict__ v, int64_t n,
                                                       const double* __restrict__ edges,
                                                       unsigned long long* __restrict__ hist) {
     __shared__ unsigned h[256];
@@ -128,11 +129,14 @@ extern "C" int more3d_saliency_blend(const float* dk, const float* dn, int64_t n
     return MORE3D_OK;
 }
 
-extern "C" int more3d_histogram256(const float* v, int64_t n, const double* edges, int64_t* hist, void* stream) {
+extern "C" int more3d_histogram256(const void* v, int elem_bytes, int64_t n, const double* edges, int64_t* hist,
+                                   void* stream) {
+    M3D_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 (float32) or 8 (float64)");
     M3D_REQUIRE(v && edges && hist && n > 0, "NULL / empty argument");
     cudaStream_t s = (cudaStream_t)stream;
     M3D_CUDA(cudaMemsetAsync(hist, 0, 256 * sizeof(int64_t), s));
-    hist256_kernel<<<148 * 4, 256, 0, s>>>(v, n, edges, (unsigned long long*)hist);
+    if (elem_bytes == 4) hist256_kernel<float><<<148 * 4, 256, 0, s>>>((const float*)v, n, edges, (unsigned long long*)hist);
+    else hist256_kernel<double><<<148 * 4, 256, 0, s>>>((const double*)v, n, edges, (unsigned long long*)hist);
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;

@@ -1,0 +1,189 @@
+// K8: voxel-grid downsampling = fp64 voxel key -> stable radix sort -> segmented mean.
+// Replaces open3d voxel_down_sample as called by the reference (Downsampling/Downsample.py:86-89):
+// voxel index = floor((p - (min_bound - voxel/2)) / voxel) per axis, output = mean of the member points,
+// members accumulated in original point order (the stable sort keeps it, so the fp64 sums are the ones a
+// sequential host loop produces).
+#include "common.cuh"
+
+namespace m3d {
+
+constexpr int VX_THREADS = 256;
+
+// min/max of x, y, z: reuse the pattern of grid.cu with one fmin tree over (v, -v)
+__global__ void __launch_bounds__(VX_THREADS) vx_bbox_partial(const double* __restrict__ xyz, int64_t n,
+                                                              double* __restrict__ part) {
+    double v[6] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double c = xyz[3 * i + a];
+            v[a] = fmin(v[a], c);
+            v[3 + a] = fmin(v[3 + a], -c);
+        }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[a] = fmin(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+    __shared__ double sm[6][VX_THREADS / 32];
+    if ((threadIdx.x & 31) == 0)
+        for (int a = 0; a < 6; ++a) sm[a][threadIdx.x >> 5] = v[a];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double r = sm[threadIdx.x][0];
+        for (int w = 1; w < VX_THREADS / 32; ++w) r = fmin(r, sm[threadIdx.x][w]);
+        part[6 * blockIdx.x + threadIdx.x] = r;
+    }
+}
+__global__ void vx_bbox_final(const double* __restrict__ part, int nparts, double* __restrict__ out) {
+    double v[6] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+    for (int i = threadIdx.x; i < nparts; i += 32)
+#pragma unroll
+        for (int a = 0; a < 6; ++a) v[a] = fmin(v[a], part[6 * i + a]);
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[a] = fmin(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+    if (threadIdx.x == 0)
+        for (int a = 0; a < 6; ++a) out[a] = (a < 3) ? v[a] : -v[a];
+}
+
+struct VoxelGeom {
+    double vmin[3];
+    double voxel;
+    long long ny, nz;   // key = (kx * ny + ky) * nz + kz
+};
+
+__device__ __forceinline__ void voxel_index(const double* __restrict__ xyz, int64_t i, const VoxelGeom& vg,
+                                            long long k[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        k[a] = (long long)floor(__ddiv_rn(__dsub_rn(xyz[3 * i + a], vg.vmin[a]), vg.voxel));
+}
+
+__global__ void __launch_bounds__(VX_THREADS) vx_keys(const double* __restrict__ xyz, int64_t n, VoxelGeom vg,
+                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long k[3];
+    voxel_index(xyz, i, vg, k);
+    keys[i] = (uint64_t)((k[0] * vg.ny + k[1]) * vg.nz + k[2]);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(VX_THREADS) vx_heads(const uint64_t* __restrict__ keys, int64_t n,
+                                                       uint32_t* __restrict__ head) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// seg[i] = exclusive scan of head + head[i] - 1 = voxel row of sorted position i; starts[row] = i at heads
+__global__ void __launch_bounds__(VX_THREADS) vx_starts(const uint64_t* __restrict__ keys,
+                                                        const uint32_t* __restrict__ scan, int64_t n,
+                                                        uint32_t* __restrict__ starts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0 || keys[i] != keys[i - 1]) starts[scan[i]] = (uint32_t)i;
+    if (i == n - 1) starts[scan[n]] = (uint32_t)n;
+}
+
+__global__ void __launch_bounds__(VX_THREADS) vx_means(const double* __restrict__ xyz,
+                                                       const uint64_t* __restrict__ keys,
+                                                       const uint32_t* __restrict__ order,
+                                                       const uint32_t* __restrict__ starts, int64_t nvox,
+                                                       VoxelGeom vg, double* __restrict__ out_xyz,
+                                                       int64_t* __restrict__ out_keys,
+                                                       int32_t* __restrict__ voxel_of_point) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    const uint32_t b = starts[v], e = starts[v + 1];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (uint32_t t = b; t < e; ++t) {                 // original point order inside the voxel
+        const int64_t o = order[t];
+        sx += xyz[3 * o]; sy += xyz[3 * o + 1]; sz += xyz[3 * o + 2];
+        if (voxel_of_point) voxel_of_point[o] = (int32_t)v;
+    }
+    const double cnt = (double)(e - b);
+    out_xyz[3 * v] = sx / cnt; out_xyz[3 * v + 1] = sy / cnt; out_xyz[3 * v + 2] = sz / cnt;
+    if (out_keys) {
+        const long long key = (long long)keys[b];
+        const long long kz = key % vg.nz, kxy = key / vg.nz;
+        out_keys[3 * v] = kxy / vg.ny; out_keys[3 * v + 1] = kxy % vg.ny; out_keys[3 * v + 2] = kz;
+    }
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+extern "C" int more3d_voxel_downsample(const double* xyz, int64_t n, double voxel, double* out_xyz,
+                                       int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h,
+                                       void* stream) {
+    M3D_REQUIRE(xyz && out_xyz && nout_h && n > 0, "NULL / empty argument");
+    M3D_REQUIRE(voxel > 0 && isfinite(voxel), "voxel_size must be > 0");   // open3d raises on <= 0
+    if (n >= ((int64_t)1 << 32)) { set_error("n >= 2^32 not supported"); return MORE3D_E_RANGE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    init_device_pool();
+    ProfScope prof("voxel_downsample", s);
+
+    const int nparts = 592;
+    double* part = nullptr;
+    M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
+    vx_bbox_partial<<<nparts, VX_THREADS, 0, s>>>(xyz, n, part);
+    vx_bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
+    count_launches(2);
+    M3D_CHECK_LAUNCH();
+    double bb[6];
+    M3D_CUDA(cudaMemcpyAsync(bb, part + 6 * nparts, sizeof(bb), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    dev_free(part, s);
+    for (int a = 0; a < 6; ++a)
+        if (!isfinite(bb[a])) { set_error("non-finite coordinates in cloud"); return MORE3D_E_INVALID; }
+
+    VoxelGeom vg;
+    vg.voxel = voxel;
+    double dims[3];
+    for (int a = 0; a < 3; ++a) {
+        vg.vmin[a] = bb[a] - voxel * 0.5;              // min_bound - voxel_size * 0.5
+        dims[a] = floor((bb[3 + a] - vg.vmin[a]) / voxel) + 2.0;
+    }
+    if (dims[0] * dims[1] * dims[2] >= 9.0e18) {
+        set_error("voxel_size is too small for this cloud's extent (voxel index overflow)");   // open3d: "voxel_size is too small."
+        return MORE3D_E_RANGE;
+    }
+    vg.ny = (long long)dims[1];
+    vg.nz = (long long)dims[2];
+    int bits = 1;
+    {
+        const double total = dims[0] * dims[1] * dims[2];
+        while (bits < 63 && ldexp(1.0, bits) < total) ++bits;
+    }
+
+    uint64_t *k1 = nullptr, *k2 = nullptr, *ks = nullptr;
+    uint32_t *v1 = nullptr, *v2 = nullptr, *vs = nullptr, *head = nullptr, *starts = nullptr;
+    M3D_TRY(dev_alloc(&k1, (size_t)n, s));
+    M3D_TRY(dev_alloc(&k2, (size_t)n, s));
+    M3D_TRY(dev_alloc(&v1, (size_t)n, s));
+    M3D_TRY(dev_alloc(&v2, (size_t)n, s));
+    M3D_TRY(dev_alloc(&head, (size_t)n + 1, s));
+    M3D_TRY(dev_alloc(&starts, (size_t)n + 1, s));
+    const unsigned nb = (unsigned)((n + VX_THREADS - 1) / VX_THREADS);
+    vx_keys<<<nb, VX_THREADS, 0, s>>>(xyz, n, vg, k1, v1);
+    count_launches(1);
+    M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, bits, &ks, &vs, s));
+    vx_heads<<<nb, VX_THREADS, 0, s>>>(ks, n, head);
+    M3D_TRY(exclusive_scan_u32(head, head, n, s));
+    vx_starts<<<nb, VX_THREADS, 0, s>>>(ks, head, n, starts);
+    count_launches(2);
+    M3D_CHECK_LAUNCH();
+    uint32_t nvox = 0;
+    M3D_CUDA(cudaMemcpyAsync(&nvox, head + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    vx_means<<<(unsigned)((nvox + VX_THREADS - 1) / VX_THREADS), VX_THREADS, 0, s>>>(
+        xyz, ks, vs, starts, (int64_t)nvox, vg, out_xyz, out_keys, voxel_of_point);
+    count_launches(1);
+    M3D_CHECK_LAUNCH();
+    dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s); dev_free(head, s); dev_free(starts, s);
+    *nout_h = (int64_t)nvox;
+    return MORE3D_OK;
+}

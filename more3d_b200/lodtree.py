@@ -1,0 +1,106 @@
+"""Level-of-detail node hierarchy behind ``BallTreePointSet`` (ball-tree-equivalent, built on the GPU).
+
+Mirrors what the reference keeps after ``BallTree.get_arrays()`` (Downsampling/BallTreePointSet.py:45-53):
+``idx_array``, ``node_data`` (idx_start, idx_end, is_leaf, radius) and the parent / child / sibling /
+level relations, which for sklearn's heap layout are index arithmetic (children of i = 2i+1, 2i+2)
+instead of the reference's O(nodes^2) reconstruction (:57-126).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+class LodTree:
+    def __init__(self, xyz_dev, leaf_size=40):
+        lib = _lib.load()
+        self.n = int(xyz_dev.shape[0])
+        self.leaf_size = int(leaf_size)
+        nl, nn = C.c_int64(0), C.c_int64(0)
+        check(lib.more3d_balltree_shape(self.n, self.leaf_size, C.byref(nl), C.byref(nn)))
+        self.n_levels, self.n_nodes = int(nl.value), int(nn.value)
+        dev = xyz_dev.device
+        with torch.cuda.device(dev):
+            self.idx_array_dev = torch.empty(self.n, dtype=torch.int64, device=dev)
+            start = torch.empty(self.n_nodes, dtype=torch.int64, device=dev)
+            end = torch.empty(self.n_nodes, dtype=torch.int64, device=dev)
+            leaf = torch.empty(self.n_nodes, dtype=torch.int32, device=dev)
+            rad = torch.empty(self.n_nodes, dtype=torch.float64, device=dev)
+            check(lib.more3d_balltree_build(ptr(xyz_dev), self.n, self.leaf_size, ptr(self.idx_array_dev), ptr(start),
+                                            ptr(end), ptr(leaf), ptr(rad), stream_ptr()))
+        # node tables are small (<= a few million rows): host copies drive the hierarchy queries
+        self.idx_start = start.cpu().numpy()
+        self.idx_end = end.cpu().numpy()
+        self.is_leaf = leaf.cpu().numpy()
+        self.node_radius = rad.cpu().numpy()
+        self._idx_array = None
+        # a node exists (was visited by the recursive build) iff it is the root or its parent is internal
+        ids = np.arange(self.n_nodes)
+        par = (ids - 1) // 2
+        self.exists = np.ones(self.n_nodes, bool)
+        for lev in range(1, self.n_levels):
+            a, b = (1 << lev) - 1, min((1 << (lev + 1)) - 1, self.n_nodes)
+            p = par[a:b]
+            self.exists[a:b] = self.exists[p] & (self.is_leaf[p] == 0)
+        self.levels = np.floor(np.log2(ids + 1)).astype(np.int64)
+
+    @property
+    def idx_array(self):
+        if self._idx_array is None:
+            self._idx_array = self.idx_array_dev.cpu().numpy()
+        return self._idx_array
+
+    # -- reference getters (None where the reference's relation dictionaries have no entry) --------
+    def _child(self, i, k):
+        c = 2 * int(i) + k
+        return c if (self.is_leaf[i] == 0 and c < self.n_nodes and self.exists[c]) else None
+
+    def left(self, i):
+        return self._child(i, 1)
+
+    def right(self, i):
+        return self._child(i, 2)
+
+    def parent(self, i):
+        return None if int(i) == 0 else (int(i) - 1) // 2
+
+    def sibling(self, i):
+        i = int(i)
+        if i == 0:
+            return None
+        s = i + 1 if i % 2 == 1 else i - 1
+        return s if (s < self.n_nodes and self.exists[s]) else None
+
+    def level(self, i):
+        return int(self.levels[i]) if self.exists[i] else 0
+
+    def max_level(self):
+        return int(self.levels[self.exists].max())
+
+    def leaves(self):
+        return np.nonzero(self.is_leaf == 1)[0]
+
+    def radius(self, i):
+        return self.node_radius[i]
+
+    def points_of_node(self, i):
+        return self.idx_array[self.idx_start[i]:self.idx_end[i]]
+
+    def smallest_nodes_of_size(self, radius):
+        """First node on every branch with radius < `radius` or leaf, in the reference's depth-first,
+        left-before-right order (BallTreePointSet.py:128-147) -- level-synchronous and vectorised."""
+        stop = (self.node_radius < radius) | (self.is_leaf == 1)
+        reach = np.zeros(self.n_nodes, bool)     # reached by the descent (all ancestors kept descending)
+        reach[0] = True
+        for lev in range(1, self.n_levels):
+            a, b = (1 << lev) - 1, min((1 << (lev + 1)) - 1, self.n_nodes)
+            p = (np.arange(a, b) - 1) // 2
+            reach[a:b] = reach[p] & ~stop[p]
+        sel = np.nonzero(reach & stop & self.exists)[0]
+        sel = sel[np.argsort(self.idx_start[sel], kind="stable")]   # DFS order == order of the ranges
+        if sel.size == 1:
+            return int(sel[0])       # the reference returns a bare index when the root itself qualifies
+        return sel

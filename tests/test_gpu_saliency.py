@@ -184,7 +184,7 @@ def test_histogram_matches_numpy():
     dv = torch.from_numpy(v).cuda()
     de = torch.from_numpy(edges).cuda()
     hist = torch.empty(256, dtype=torch.int64, device="cuda")
-    check(lib.more3d_histogram256(ptr(dv), len(v), ptr(de), ptr(hist), stream_ptr()))
+    check(lib.more3d_histogram256(ptr(dv), 4, len(v), ptr(de), ptr(hist), stream_ptr()))
     assert np.array_equal(hist.cpu().numpy(), counts)
 
 
