@@ -148,6 +148,52 @@ int more3d_lod_cell_rule(const double* xyz, const double* saliency, const int64_
 /* stable compaction: idx = positions i with flags[i] != 0 (ascending); idx has room for n int64 */
 int more3d_select_flagged(const uint8_t* flags, int64_t n, int64_t* idx, int64_t* count_h, void* stream);
 
+/* ---- point-based level set (levelsets_func.py) ------------------------------------------------------
+ * more3d_ls_frames: the part of build_neighborhoods (levelsets_func.py:154-172) after the kNN query.
+ * knn2k: n x 2k int64 sorted neighbours, self first (more3d_knn with q == NULL).  normals (n x 3 f64): when
+ * has_normals == 0 they are computed as in compute_normals (:112-117: PCA of the offsets about the
+ * query point), otherwise read; in both cases they are normalised in place (:140).  t1, t2: n x 3 f64
+ * tangent frame (:141-146); neighbors: n x k int32 = knn2k[:, 1:k+1] (:172). */
+int more3d_ls_frames(const double* xyz, int64_t n, int k, const int64_t* knn2k, int has_normals,
+                     double* normals, double* t1, double* t2, int32_t* neighbors, void* stream);
+
+/* Derivative.__init__ (levelsets_func.py:246-275): per-point weighted-least-squares operator.  weights:
+ * n x k f64 out (self.weights); D: n x 5 x (k+3) f64 out or NULL (self.D); *singular_h = 1 if some
+ * singular value is < 1e-12 (where the reference drops into pdb, :269-271).  The returned graph keeps the
+ * device-resident structure-of-arrays form used by the calls below. */
+typedef struct more3d_ls_graph more3d_ls_graph;
+int more3d_ls_graph_create(const double* xyz, int64_t n, int k, const int32_t* neighbors, const double* t1,
+                           const double* t2, double max_d, double* weights, double* D, int* singular_h,
+                           void* stream, more3d_ls_graph** out);
+int more3d_ls_graph_destroy(more3d_ls_graph* g);
+/* Derivative.__call__ (:277-291): out4[i] = (dx, dy, ddx, ddy) of u at the points with mask[i] != 0
+ * (mask NULL = all); zeros elsewhere.  u: n f64; out4: n x 4 f64. */
+int more3d_ls_diff(const more3d_ls_graph* g, const double* u, const uint8_t* mask, double* out4, void* stream);
+/* smooth (:350-358): out[i] = sum_j u[nbr_ij] w_ij / sum_j w_ij where mask[i] != 0 (NULL = all), else u[i]. */
+int more3d_ls_smooth(const more3d_ls_graph* g, const double* u, const uint8_t* mask, double* out, void* stream);
+/* Solver.zero_crossings (:524-534): out[i] = any neighbour sign differs, for mask[i] != 0 (NULL = all). */
+int more3d_ls_zero_crossings(const more3d_ls_graph* g, const double* u, const uint8_t* mask, uint8_t* out,
+                             void* stream);
+/* Solver.initialize_from_voxels (:591-594): phi = -max_val where sum(points // h) is even else +max_val,
+ * with numpy's float floor division. */
+int more3d_ls_init_voxels(const double* xyz, int64_t n, double h, double max_val, double* phi, void* stream);
+/* Solver.run with the Chan-Vese model (:598-642 + _chan_vese_step :386-437).  phi: n f64 in/out; zeta: n x
+ * channels f64; active / last_active: n uint8 in/out; alias_last_active != 0 reproduces the reference's
+ * aliasing of the two masks after initialize_from_voxels / seeds / point (:581, :589, :596).  epsilon is
+ * already multiplied by h (:611).  rmsc_h: iterations f64 (host) or NULL; tolerance <= 0 never stops early. */
+int more3d_ls_run(const more3d_ls_graph* g, double* phi, const double* zeta, int channels, uint8_t* active,
+                  uint8_t* last_active, int alias_last_active, int iterations, double stepsize, double nu,
+                  double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
+                  double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream);
+
+/* Module-level helpers of levelsets_func.py on the caller's own arrays: smooth (:350-358) with u: n x cols
+ * f64, nbs: n x k int64, w: n x k f64, mask: n uint8 or NULL; and the elementwise heaviside (op 0, param =
+ * epsilon; :319-321), delta (op 1, param = epsilon; :332-333), dp (op 2; :336-342), wendland (op 3, param = h;
+ * :92-97). */
+int more3d_ls_smooth_raw(const double* u, int cols, const int64_t* nbs, const double* w, int64_t n, int k,
+                         const uint8_t* mask, double* out, void* stream);
+int more3d_ls_elementwise(int op, const double* x, double param, int64_t n, double* out, void* stream);
+
 /* ---- multi-GPU strip partition helpers (no reference equivalent; OPALS tile streaming,
  * DM_saliency.py:76-86, is the analogue) ----------------------------------------------------------
  * band_select: indices i (ascending, stable) with lo <= xyz[i][axis] < hi; idx has room for n int64;

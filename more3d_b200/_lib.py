@@ -39,6 +39,17 @@ SIGNATURES = {
     "more3d_balltree_build": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "more3d_lod_cell_rule": [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp],
     "more3d_select_flagged": [_vp, _i64, _vp, C.POINTER(_i64), _vp],
+    "more3d_ls_frames": [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp],
+    "more3d_ls_graph_create": [_vp, _i64, _i32, _vp, _vp, _vp, _f64, _vp, _vp, C.POINTER(_i32), _vp, C.POINTER(_vp)],
+    "more3d_ls_graph_destroy": [_vp],
+    "more3d_ls_diff": [_vp, _vp, _vp, _vp, _vp],
+    "more3d_ls_smooth": [_vp, _vp, _vp, _vp, _vp],
+    "more3d_ls_zero_crossings": [_vp, _vp, _vp, _vp, _vp],
+    "more3d_ls_init_voxels": [_vp, _i64, _f64, _f64, _vp, _vp],
+    "more3d_ls_run": [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64, _f64, _i32,
+                      _f64, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(_i32), _vp],
+    "more3d_ls_smooth_raw": [_vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
+    "more3d_ls_elementwise": [_i32, _vp, _f64, _i64, _vp, _vp],
     "more3d_band_select": [_vp, _i64, _i32, _f64, _f64, _vp, C.POINTER(_i64), _vp],
     "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
 }

@@ -1,0 +1,137 @@
+"""GPU parity tests of the point-based level set against golden vectors produced by executing the
+reference's levelsets_func.py verbatim (tests/golden/levelset_4k.npz, tools/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RUN = dict(stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "levelset_4k.npz"))
+
+
+def test_build_neighborhoods(g):
+    from more3d_b200 import levelsets_func as ls
+    pts, h, k = g["points"], float(g["h"]), int(g["k"])
+    nb, nrm, (t1, t2) = ls.build_neighborhoods(pts.copy(), h, k)
+    assert nb.dtype == np.int64 and np.array_equal(nb, g["neighbors"])          # kNN indices: bit-exact
+    sgn = np.sign(np.sum(nrm * g["normals"], axis=1))
+    assert np.all(np.abs(np.sum(nrm * g["normals"], axis=1)) > 1 - 1e-12)       # normals modulo sign
+    np.testing.assert_allclose(t1, g["t1"], atol=1e-10)
+    np.testing.assert_allclose(t2 * sgn[:, None], g["t2"], atol=1e-10)
+    # with the normals supplied, the frame is reproduced sign and all
+    nb2, nrm2, (a1, a2) = ls.build_neighborhoods(pts.copy(), h, k, normals=g["normals"].copy())
+    np.testing.assert_allclose(a2, g["t2"], atol=1e-12)
+    np.testing.assert_allclose(nrm2, g["normals"], atol=1e-15)
+    # stand-alone helpers on a full 2k table
+    from oracle import ref_path as rp
+    knn2k = rp.query_knn(rp.build_tree(pts, 64), pts, 2 * k)
+    n3 = ls.compute_normals(pts, knn2k)
+    assert np.all(np.abs(np.sum(n3 * g["normals"], axis=1)) > 1 - 1e-12)
+    nn = g["normals"] * 3.0
+    b1, b2 = ls.compute_tangent_planes(pts, knn2k, nn)
+    np.testing.assert_allclose(nn, g["normals"], atol=1e-15)                    # normalised in place, like :140
+    np.testing.assert_allclose(b1, g["t1"], atol=1e-12)
+    np.testing.assert_allclose(b2, g["t2"], atol=1e-12)
+
+
+def test_derivative_operator(g):
+    from more3d_b200 import levelsets_func as ls
+    pts, h = g["points"], float(g["h"])
+    d = ls.Derivative(pts, 3 * h, g["neighbors"], (g["t1"], g["t2"]))
+    assert not d.singular
+    np.testing.assert_allclose(d.weights, g["weights"], rtol=1e-14)
+    np.testing.assert_allclose(d.D[:300], g["D"], rtol=1e-9, atol=1e-11)        # pinv: Jacobi vs LAPACK gesdd
+    dx, dy, ddx, ddy = d(g["phi_s"])
+    for a, b in ((dx, g["dx"]), (dy, g["dy"]), (ddx, g["ddx"]), (ddy, g["ddy"])):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-10)
+    sub = np.arange(0, len(pts), 7)
+    fx, fy = d(g["phi_s"], sub, first_only=True)
+    np.testing.assert_allclose(fx, g["dx"][sub], rtol=1e-9, atol=1e-10)
+    gr = d.grad(g["phi_s"], None)
+    np.testing.assert_allclose(gr, g["dx"][:, None] * g["t1"] + g["dy"][:, None] * g["t2"], rtol=1e-9, atol=1e-10)
+
+
+def test_elementwise_and_smooth(g):
+    from more3d_b200 import levelsets_func as ls
+    x = np.linspace(-3, 3, 1001)
+    np.testing.assert_allclose(ls.heaviside(x, 0.5), 0.5 * (1 + 2 / np.pi * np.arctan(x / 0.5)), rtol=1e-15, atol=1e-16)
+    np.testing.assert_allclose(ls.delta(x, 0.5), 1 / np.pi * 0.5 / (0.25 + x ** 2), rtol=1e-15)
+    s = np.abs(x)
+    want = np.where(s < 1, np.sinc(2 * s), 1 - 1 / np.where(s < 1, 1, s))
+    np.testing.assert_allclose(ls.dp(s), want, rtol=1e-13, atol=1e-15)
+    w = np.where(s < 2.0, (1 - s / 2.0) ** 4 * (4 * s / 2.0 + 1), 0.0)
+    np.testing.assert_allclose(ls.wendland(s, 2.0), w, rtol=1e-14, atol=1e-16)
+    sm = ls.smooth(g["phi0"], slice(None), g["neighbors"], g["weights"])
+    np.testing.assert_allclose(sm, g["phi_s"], rtol=1e-14, atol=1e-15)
+    m = g["active0"]
+    sm2 = ls.smooth(g["phi0"], m, g["neighbors"], g["weights"])
+    np.testing.assert_allclose(sm2, g["phi_s"][m], rtol=1e-14, atol=1e-15)
+    z2 = np.column_stack([g["phi0"], 2 * g["phi0"]])
+    sm3 = ls.smooth(z2, slice(None), g["neighbors"], g["weights"])
+    np.testing.assert_allclose(sm3[:, 1], 2 * g["phi_s"], rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("own_frames", [False, True])
+def test_solver_run_matches_reference(g, own_frames):
+    from more3d_b200 import levelsets_func as ls
+    pts, h, k = g["points"], float(g["h"]), int(g["k"])
+    if own_frames:      # normals with whatever sign our eigen-solver picks: phi must not depend on it
+        nb, _, tang = ls.build_neighborhoods(pts.copy(), h, k)
+    else:
+        nb, tang = g["neighbors"], (g["t1"], g["t2"])
+    solver = ls.Solver(h, g["zeta"], pts, nb, tang, "chan_vese")
+    solver.initialize_from_voxels(2.0)
+    assert np.array_equal(solver.phi, g["phi0"])                                # numpy floor-division parity
+    assert np.array_equal(solver.active, g["active0"])
+    assert solver.last_active is solver.active                                   # the reference's aliasing
+    solver.phi[:] = ls.smooth(solver.phi, slice(None), nb, solver.diff.weights)
+    np.testing.assert_allclose(solver.phi, g["phi_s"], rtol=1e-14, atol=1e-15)
+    if own_frames:
+        # The reference's own trajectory depends on the SIGN LAPACK happens to give each normal (the xy
+        # regulariser row of the WLS system is not frame-covariant): flipping signs in the reference itself
+        # changes phi by 6e-8 after one step and by 0.2 after two (a discrete lonely/cap decision flips).
+        # So with our own sign convention only the first step is comparable; see DESIGN.md §5.
+        solver.run(1, **RUN)
+        ref = ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "chan_vese")
+        ref.initialize_from_voxels(2.0)
+        ref.phi[:] = g["phi_s"]
+        ref.run(1, **RUN)
+        np.testing.assert_allclose(solver.phi, ref.phi, rtol=0, atol=1e-6)
+        solver.run(9, **RUN)
+        assert np.all(np.isfinite(solver.phi)) and np.abs(solver.phi).max() <= 2 * h + 1e-12
+        return
+    conv = solver.run(10, **RUN)
+    assert conv is False and bool(g["conv"]) is False
+    assert np.array_equal(solver.active, g["act10"])                            # active set: exact
+    np.testing.assert_allclose(solver.phi, g["phi10"], rtol=1e-8, atol=1e-10)
+    solver.run(15, **RUN)
+    assert np.array_equal(solver.active, g["act25"])
+    np.testing.assert_allclose(solver.phi, g["phi25"], rtol=1e-8, atol=1e-10)
+    assert len(solver.rmsc_history) == 15 and all(np.isfinite(solver.rmsc_history))
+    sal = solver.extract(4)
+    assert sal.dtype == bool and 0 < sal.sum() < len(pts)
+
+
+def test_solver_mask_init_and_tolerance(g):
+    """initialize_from_mask keeps separate masks (the re-clamp path runs) and tolerance stops early:
+    compare against the reference semantics restated with numpy on the golden operator."""
+    from more3d_b200 import levelsets_func as ls
+    pts, h = g["points"], float(g["h"])
+    solver = ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "chan_vese")
+    mask = pts[:, 0] < 0.3
+    solver.initialize_from_mask(mask)
+    assert solver.last_active is not solver.active
+    assert np.array_equal(solver.active, solver.zero_crossings(solver.phi))
+    assert solver.run(200, **dict(RUN, tolerance=1e9)) is True                   # stops after the first step
+    assert len(solver.rmsc_history) == 1
+    solver.run(5, **RUN)
+    phi = solver.phi
+    assert np.all(np.isfinite(phi)) and np.abs(phi).max() <= 2 * h + 1e-12
+    with pytest.raises(NotImplementedError):
+        ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "lmv").run(1, **RUN)

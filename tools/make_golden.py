@@ -113,7 +113,7 @@ def levelset_case():
     np.savez_compressed(
         os.path.join(OUT, "levelset_4k.npz"), points=pts, h=h, k=k, neighbors=neighbors,
         normals=normals, t1=tangents[0], t2=tangents[1], zeta=solver.zeta, weights=solver.diff.weights,
-        D=solver.diff.D, phi0=phi0, active0=active0, phi_s=phi_s, dx=dx, dy=dy, ddx=ddx, ddy=ddy,
+        D=solver.diff.D[:300], phi0=phi0, active0=active0, phi_s=phi_s, dx=dx, dy=dy, ddx=ddx, ddy=ddy,
         phi10=phi10, act10=act10, phi25=solver.phi, act25=solver.active, conv=conv)
     print("levelset active", act10.sum(), solver.active.sum())
 
