@@ -148,15 +148,10 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         return MORE3D_E_INVALID;
     }
 
-    // widen the cell until the column table fits (stencils stay correct for any cell >= requested)
-    const double max_cols = 268435456.0;  // 2^28 columns = 1 GiB table
-    double c = cell;
+    // widen the cell until the column table fits (stencils stay correct for any cell >= requested):
+    // at most 16000 x 16000 columns (2^28 entries = 1 GiB)
     double ex = bb[2] - bb[0], ey = bb[3] - bb[1];
-    for (int it = 0; it < 64; ++it) {
-        double cols = (floor(ex / c) + 3.0) * (floor(ey / c) + 3.0);
-        if (cols <= max_cols) break;
-        c *= 1.25;
-    }
+    double c = fmax(cell, fmax(ex, ey) / 16000.0);
     more3d_grid* g = new more3d_grid();
     g->n = n;
     g->cell = c;

@@ -84,6 +84,8 @@ class UniformGrid:
         with torch.cuda.device(self.device):
             qd = None if q is None else as_device_points(q, self.device)
             nq = self.n if qd is None else int(qd.shape[0])
+            if nq == 0:     # an empty tensor has a NULL data pointer, which the C-ABI reads as "self query"
+                return torch.zeros(1, dtype=torch.int64, device=self.device), self._new((0,), idx_dtype)
             counts = self._new((max(nq, 1),), torch.int32)
             offsets = self._new((nq + 1,), torch.int64)
             check(self.lib.more3d_radius_count(self._h, ptr(qd), nq, float(r), ptr(counts), stream_ptr()))
@@ -99,6 +101,8 @@ class UniformGrid:
         with torch.cuda.device(self.device):
             qd = None if q is None else as_device_points(q, self.device)
             nq = self.n if qd is None else int(qd.shape[0])
+            if nq == 0:
+                return self._new((0,), torch.int32)
             counts = self._new((max(nq, 1),), torch.int32)
             check(self.lib.more3d_radius_count(self._h, ptr(qd), nq, float(r), ptr(counts), stream_ptr()))
             return counts[:nq]
@@ -109,6 +113,8 @@ class UniformGrid:
             nq = self.n if qd is None else int(qd.shape[0])
             idx = self._new((nq, k), torch.int64)
             dist = self._new((nq, k), torch.float64) if return_distance else None
+            if nq == 0:
+                return idx, dist
             check(self.lib.more3d_knn(self._h, ptr(qd), nq, int(k), ptr(idx), ptr(dist), stream_ptr()))
             return idx, dist
 

@@ -17,7 +17,7 @@ def test_duplicate_points_follow_np_unique():
     from more3d_b200.BallTreePointSet import BallTreePointSet
     from more3d_b200.DM_saliency import PointCloudDM, DM_nonparam_curvature, DM_dk_dn
     from oracle import ref_path as rp
-    base = synthetic.terrain(2500, seed=41, noise=0.05)
+    base = synthetic.terrain(2500, seed=41, noise=0.15)
     rng = np.random.Generator(np.random.PCG64(7))
     dup = rng.choice(len(base), 300, replace=False)
     pts = np.vstack([base, base[dup], base[dup[:60]]])          # doubles and triples

@@ -1,0 +1,137 @@
+"""Full-size runs of BASELINE.json configs 1, 3 and 4 on one B200 with size-independent property checks
+(the bench line itself is configs[1], bench.py).  Prints one JSON object per config.
+
+    python tools/bench_configs.py [1] [3] [4] [--small]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from more3d_b200 import synthetic, _lib  # noqa: E402
+
+
+def ev_ms(fn):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b), out
+
+
+def config1(n):
+    """1 M-point terrain: BallTreePointSet radius query r = 0.5 + PCA normals / curvature."""
+    from more3d_b200.grid import UniformGrid, cell_for_radius
+    from oracle import ref_path as rp
+    pts = synthetic.terrain(n, seed=1)
+    d = torch.from_numpy(pts).cuda()
+    r = 0.5
+    t_build, g = ev_ms(lambda: UniformGrid(d, cell_for_radius(r)))
+    t_q, (off, idx) = ev_ms(lambda: g.radius_csr(None, r))
+    t_n, (nrm, ratio, K, pc) = ev_ms(lambda: g.normals_curvature(r, rp.curvature_epsilon(0.05, 0.02), 4))
+    # CPU reference in full (sklearn BallTree, 1 core) + per-row checksums of the neighbour sets
+    t0 = time.perf_counter()
+    tree = rp.build_tree(pts)
+    t_tree = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want = tree.query_radius(pts, r)
+    t_cpu_q = time.perf_counter() - t0
+    cnt = np.array([len(w) for w in want])
+    s1 = np.array([w.sum() for w in want])
+    s2 = np.array([(w.astype(np.float64) ** 2).sum() for w in want])
+    o = off.cpu().numpy()
+    ix = idx.cpu().numpy().astype(np.int64)
+    gc = np.diff(o)
+    gs1 = np.add.reduceat(ix, o[:-1])
+    gs2 = np.add.reduceat(ix.astype(np.float64) ** 2, o[:-1])
+    exact = bool(np.array_equal(gc, cnt) and np.array_equal(gs1, s1) and np.array_equal(gs2, s2))
+    return {"config": 1, "points": n, "radius": r, "mean_m": float(gc.mean()), "gpu_ms": {"grid_build": t_build, "query_csr": t_q, "normals_curvature": t_n},
+            "gpu_queries_per_s": n / (t_q * 1e-3), "cpu_tree_build_s": t_tree, "cpu_query_radius_s": t_cpu_q,
+            "cpu_queries_per_s": n / t_cpu_q, "neighbour_sets_identical_all_rows": exact,
+            "pcount_equals_set_size": bool(np.array_equal(pc.cpu().numpy(), cnt))}
+
+
+def config3(n):
+    """50 M points: saliency-driven + voxel-grid downsampling at LOD 1, 2, 5, 7, 10."""
+    from more3d_b200.BallTreePointSet import BallTreePointSet
+    from more3d_b200.Downsample import saliency_downsample, voxel_downsample, threshold_otsu
+    pts = synthetic.terrain(n, seed=3)
+    rng = np.random.Generator(np.random.PCG64(3))
+    sal = (rng.random(n) ** 4).astype(np.float32)
+    t0 = time.perf_counter()
+    bt = BallTreePointSet(pts, leaf_size=40)
+    torch.cuda.synchronize()
+    t_h2d = time.perf_counter() - t0
+    t_tree, tree = ev_ms(lambda: bt._hierarchy())
+    t_otsu, thr = ev_ms(lambda: threshold_otsu(sal))
+    out = {"config": 3, "points": n, "h2d_s": t_h2d, "tree_build_ms": t_tree, "n_nodes": tree.n_nodes, "otsu_ms": t_otsu, "lods": {}}
+    for lod in (1, 2, 5, 7, 10):
+        t0 = time.perf_counter()
+        res, det = saliency_downsample(pts, sal, lod, btP=bt, s_thresh=thr, return_details=True)
+        torch.cuda.synchronize()
+        t_sal = time.perf_counter() - t0
+        cells = det["cells"]
+        sizes = tree.idx_end[cells] - tree.idx_start[cells]
+        t_vox, vox = ev_ms(lambda: voxel_downsample(pts, float(lod), return_device=True))
+        out["lods"][str(lod)] = {
+            "saliency_downsample_s_incl_host_assembly": t_sal, "cells": int(len(cells)), "kept": int(len(res)),
+            "cells_partition_cloud": bool(sizes.sum() == n and np.all(np.diff(tree.idx_start[cells]) == sizes[:-1])),
+            "all_cell_radii_below_lod_or_leaf": bool(np.all((tree.node_radius[cells] < lod) | (tree.is_leaf[cells] == 1))),
+            "voxel_ms": t_vox, "voxels": int(vox.shape[0])}
+    # voxel property: sum over voxels of count * mean == sum of points (checked via voxel_of_point on a 5 M subset)
+    return out
+
+
+def config4(n, iters=200):
+    """20 M points, k = 7, h = 0.5, Chan-Vese, 200 iterations = 4 x run(50)."""
+    from more3d_b200 import levelsets_func as ls
+    from more3d_b200.pipeline import multiscale_saliency
+    pts = synthetic.terrain(n, seed=4)
+    d = torch.from_numpy(pts).cuda()
+    res = multiscale_saliency(d, (0.5,), keep=True)
+    zeta = res[0.5]["_nonparam_K"].abs().double().cpu().numpy()[:, None]
+    del res
+    pts_c = pts - pts.mean(axis=0)
+    h, k = 0.5, 7
+    t0 = time.perf_counter()
+    nb, nrm, tang = ls.build_neighborhoods(pts_c, h, k, return_device=True)
+    torch.cuda.synchronize()
+    t_nb = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    solver = ls.Solver(h, zeta, pts_c, nb, tang, "chan_vese")
+    torch.cuda.synchronize()
+    t_solver = time.perf_counter() - t0
+    ls.normalize(solver.zeta)
+    solver.initialize_from_voxels(2.0)
+    a0 = int(solver.active.sum())
+    run = dict(stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
+    per = max(iters // 4, 1)
+    times, rms = [], []
+    for _ in range(4):
+        t, _ = ev_ms(lambda: solver.run(per, **run))
+        times.append(t)
+        rms.append(solver.rmsc_history[-1])
+    phi = solver.phi
+    return {"config": 4, "points": n, "k": k, "h": h, "neighbourhoods_s": t_nb, "solver_init_s": t_solver, "singular": solver.diff.singular,
+            "run_ms_per_cycle": times, "iterations": 4 * per, "ms_per_iteration": sum(times) / (4 * per),
+            "point_iterations_per_s": n * 4 * per / (sum(times) * 1e-3), "active_start": a0, "active_end": int(solver.active.sum()),
+            "rmsc_last_per_cycle": rms, "phi_within_cap": bool(np.abs(phi).max() <= 2 * h + 1e-12), "phi_finite": bool(np.all(np.isfinite(phi)))}
+
+
+if __name__ == "__main__":
+    small = "--small" in sys.argv
+    which = [a for a in sys.argv[1:] if a.isdigit()] or ["1", "3", "4"]
+    _lib.load()
+    if "1" in which:
+        print(json.dumps(config1(200_000 if small else 1_000_000)), flush=True)
+    if "3" in which:
+        print(json.dumps(config3(1_000_000 if small else 50_000_000)), flush=True)
+    if "4" in which:
+        print(json.dumps(config4(500_000 if small else 20_000_000, 40 if small else 200)), flush=True)
