@@ -27,7 +27,7 @@ def timed(fn, reps=3):
     return best, out
 
 
-DIV = int(os.environ.get("MORE3D_CELLS_PER_RADIUS", "1"))
+DIV = int(os.environ.get("MORE3D_CELLS_PER_RADIUS", "2"))
 
 
 def main():
@@ -39,7 +39,8 @@ def main():
     d = torch.from_numpy(pts).cuda()
     table = _chi2_table(0.05, 4096, d.device)
     for r in radii:
-        tb, g = timed(lambda: UniformGrid(d, r * CELL_MARGIN / DIV))
+        cell = float(os.environ["MORE3D_FIXED_CELL"]) if "MORE3D_FIXED_CELL" in os.environ else r * CELL_MARGIN / DIV
+        tb, g = timed(lambda: UniformGrid(d, cell))
         tc, cnt = timed(lambda: g.radius_count(None, r))
         tm, (nrm, ratio, K, pc) = timed(lambda: g.normals_curvature(r, 0.0392, 4))
         td, (dk, dn, mm) = timed(lambda: g.dk_dn(r, nrm, K, r / np.sqrt(2), 0.01, 0.01, table, 4))
