@@ -100,6 +100,8 @@ int more3d_normals_curvature(const more3d_grid* g, double r, double eps, int min
  * Saliency_Kernel.process for every point (DM_saliency.py:219-324).  chi2_table[df] =
  * chi2.ppf(alpha, df) for df = 0..table_len-1, computed by the caller with scipy (:282); a
  * neighbourhood with more active neighbours than table_len-1 returns MORE3D_E_RANGE.
+ * normals and K may BOTH be NULL: the call then uses the sorted feature records the grid cached during the
+ * last more3d_normals_curvature on it (valid only while those outputs are unmodified) and skips the gather.
  * dk, dn: n float32 (_dk, _dn; :491-492).  minmax (may be NULL): 4 float32 {min_dk, max_dk, min_dn,
  * max_dn} over this call's outputs, reduced on the device (the Histo pass of DM_saliency, :562-568). */
 int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,

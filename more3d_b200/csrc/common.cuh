@@ -80,9 +80,12 @@ struct __align__(32) PointRec {
 // sorted feature record for the dk/dn pass: 64 B
 struct __align__(32) FeatRec {
     double x, y, z;
-    double K;        // _nonparam_K (f32 value widened)
+    double K;        // _nonparam_K (f32 value widened: 29 zero mantissa bits) with two flags in bits 0-1:
+                     // bit 0 = coincident with an earlier point (np.unique drop), bit 1 = raw normal was NaN.
+                     // Keeping the flags in the FIRST 32-B half lets the accept/dedup decision be taken
+                     // before the second half (the normal) is requested: one dependent load, not two.
     double nx, ny, nz;  // unit normal (n / ||n||), NaN if the point has no normal
-    long long flags;    // bit 0: coincident with an earlier point (np.unique drop), bit 1: raw normal was NaN
+    double pad;
 };
 
 }  // namespace m3d
@@ -101,6 +104,7 @@ struct more3d_grid {
     m3d::PointRec* rec;     // n sorted records
     uint32_t* col_start;    // nx*ny + 1
     uint8_t* dup;           // n (sorted order): 1 if coincident with an earlier sorted point
+    m3d::FeatRec* feat;     // n sorted feature records cached by the last more3d_normals_curvature (or NULL)
 };
 
 namespace m3d {

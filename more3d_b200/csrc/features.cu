@@ -25,11 +25,12 @@ constexpr int WALK_THREADS = 256;
 // One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
 // query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
 template <int MODE>
-__global__ void __launch_bounds__(WALK_THREADS) moments_kernel(GridView g, CurvParams prm,
+__global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, CurvParams prm,
                                                                double* __restrict__ normals,
                                                                double* __restrict__ lam_ratio,
                                                                float* __restrict__ Kout,
-                                                               int32_t* __restrict__ pcount) {
+                                                               int32_t* __restrict__ pcount,
+                                                               FeatRec* __restrict__ feat_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const PointRec p = load_rec(g.rec, i);
@@ -101,6 +102,17 @@ __global__ void __launch_bounds__(WALK_THREADS) moments_kernel(GridView g, CurvP
     if (MODE == MODE_FUSED || flipped) {
         normals[3 * o] = nx; normals[3 * o + 1] = ny; normals[3 * o + 2] = nz;
     }
+    if (MODE == MODE_FUSED && feat_out) {
+        // the dk/dn pass's sorted feature record, written here (coalesced) instead of being gathered
+        // from the original-order columns by build_feat_kernel; same arithmetic as there
+        const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
+        FeatRec f;
+        f.x = p.x; f.y = p.y; f.z = p.z;
+        f.K = __longlong_as_double(__double_as_longlong((double)K) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL));
+        f.nx = nx / nn; f.ny = ny / nn; f.nz = nz / nn;
+        f.pad = 0.0;
+        feat_out[i] = f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -118,9 +130,9 @@ __global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const doubl
     const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
     FeatRec f;
     f.x = p.x; f.y = p.y; f.z = p.z;
-    f.K = (double)K[o];
+    f.K = __longlong_as_double(__double_as_longlong((double)K[o]) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL));
     f.nx = nx / nn; f.ny = ny / nn; f.nz = nz / nn;
-    f.flags = (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL);
+    f.pad = 0.0;
     feat[i] = f;
 }
 
@@ -149,25 +161,28 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
     const bool live = i < g.n;
     if (live) {
         const D4 pa = ld_d4(feat + i, 0), pb = ld_d4(feat + i, 1);   // (x y z K) (nx ny nz flags)
-        const double px = pa.x, py = pa.y, pz = pa.z, Kp = pa.w;
+        const double px = pa.x, py = pa.y, pz = pa.z;
+        const long long pflags = __double_as_longlong(pa.w) & 3LL;
+        const double Kp = __longlong_as_double(__double_as_longlong(pa.w) & ~3LL);
         const double pnx = pb.x, pny = pb.y, pnz = pb.z;
-        const long long pflags = __double_as_longlong(pb.w);
         int m = 0, mu = 0, nact = 0, zn = 0, zk = 0, zk100 = 0;
         double s1n = 0, s2n = 0, s1k = 0, s2k = 0, wn = 0, wk = 0, wsum = 0;
         for_each_candidate(g, px, py, prm.s, [&](int64_t j) {
             const D4 qa = ld_d4(feat + j, 0);
             const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);   // :256-257
             if (d2 <= prm.r2) {
-                const D4 qb = ld_d4(feat + j, 1);
                 ++m;
-                if (!(__double_as_longlong(qb.w) & 1LL)) {                    // np.unique, :247
+                const long long kb = __double_as_longlong(qa.w);
+                if (!(kb & 1LL)) {                                            // np.unique, :247
+                    const D4 qb = ld_d4(feat + j, 1);
                     ++mu;
                     const double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);   // :261
-                    const double dk = Kp - qa.w;                              // :262
-                    double w = 0.0;                                           // :272-275
-                    if (d2 < prm.rho2) w = __dmul_rn(prm.inv_rho2, d2);
-                    else if (d2 > prm.rho2) w = __dadd_rn(__dmul_rn(-prm.inv_rho2, d2), 2.0);
-                    if (w < 0.0) w = 0.0;
+                    const double dk = Kp - __longlong_as_double(kb & ~3LL);   // :262
+                    // ring weight on the squared distance (:272-275): d/rho2 below rho2, 2 - d/rho2 above,
+                    // 0 at equality, clamped at 0.  (-1/rho2)*d + 2 == 2 - (1/rho2)*d bit for bit.
+                    const double t = __dmul_rn(prm.inv_rho2, d2);
+                    double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
+                    if (d2 == prm.rho2 || w < 0.0) w = 0.0;
                     const bool act = w > 0.01;                                // :279
                     s1n += dn; s2n += dn * dn;
                     s1k += dk; s2k += dk * dk;
@@ -256,11 +271,17 @@ static int launch_moments(const more3d_grid* g, int mode, double r, double eps, 
     GridView v = make_view(g);
     ProfScope prof("moments", s);
     if (mode == MODE_NORMALS)
-        moments_kernel<MODE_NORMALS><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount);
+        moments_kernel<MODE_NORMALS><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount, nullptr);
     else if (mode == MODE_CURV)
-        moments_kernel<MODE_CURV><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, nullptr, K, pcount);
-    else
-        moments_kernel<MODE_FUSED><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, K, pcount);
+        moments_kernel<MODE_CURV><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, nullptr, K, pcount, nullptr);
+    else {
+        more3d_grid* gm = const_cast<more3d_grid*>(g);     // the feature-record cache is mutable state of the grid
+        if (!gm->feat && cudaMallocAsync((void**)&gm->feat, (size_t)g->n * sizeof(FeatRec), s) != cudaSuccess) {
+            cudaGetLastError();
+            gm->feat = nullptr;                            // no cache: dk/dn will gather instead
+        }
+        moments_kernel<MODE_FUSED><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, K, pcount, gm->feat);
+    }
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
@@ -289,19 +310,23 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
                             int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream) {
     M3D_REQUIRE(g != nullptr, "grid is NULL");
     M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
-    M3D_REQUIRE(normals && K && chi2_table && dk && dn, "NULL argument");
+    M3D_REQUIRE(chi2_table && dk && dn, "NULL argument");
+    M3D_REQUIRE((normals != nullptr) == (K != nullptr), "normals and K must both be given or both be NULL");
+    const bool cached = normals == nullptr;
+    M3D_REQUIRE(!cached || g->feat != nullptr, "no cached feature records: run more3d_normals_curvature on this grid first");
     M3D_REQUIRE(table_len > 0, "chi2 table is empty");
     cudaStream_t s = (cudaStream_t)stream;
     FeatRec* feat = nullptr;
     unsigned* mm = nullptr;
     int* err = nullptr;
-    M3D_TRY(dev_alloc(&feat, (size_t)g->n, s));
+    if (cached) feat = g->feat;
+    else M3D_TRY(dev_alloc(&feat, (size_t)g->n, s));
     M3D_TRY(dev_alloc(&mm, 4, s));
     M3D_TRY(dev_alloc(&err, 1, s));
     M3D_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
     const unsigned nb = (unsigned)((g->n + 255) / 256);
     GridView v = make_view(g);
-    {
+    if (!cached) {
         ProfScope prof("build_feat", s);
         build_feat_kernel<<<nb, 256, 0, s>>>(v, normals, K, feat);
     }
@@ -321,7 +346,8 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
     int err_h = 0;
     M3D_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, s));
     M3D_CUDA(cudaStreamSynchronize(s));
-    dev_free(feat, s); dev_free(mm, s); dev_free(err, s);
+    if (!cached) dev_free(feat, s);
+    dev_free(mm, s); dev_free(err, s);
     if (err_h) {
         set_error("dk/dn: a neighbourhood has more active neighbours than chi2_table covers (table_len=%d)", table_len);
         return MORE3D_E_RANGE;

@@ -172,6 +172,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         g->lim32 = ldexp(1.0, e2);
     }
     g->rec32 = nullptr;
+    g->feat = nullptr;
     g->order = nullptr; g->rec = nullptr; g->col_start = nullptr; g->dup = nullptr;
     const size_t ncols = (size_t)g->nx * g->ny;
 
@@ -224,6 +225,7 @@ extern "C" int more3d_grid_destroy(more3d_grid* g) {
     if (g->col_start) cudaFreeAsync(g->col_start, g->stream);
     if (g->dup) cudaFreeAsync(g->dup, g->stream);
     if (g->rec32) cudaFreeAsync(g->rec32, g->stream);
+    if (g->feat) cudaFreeAsync(g->feat, g->stream);
     delete g;
     return MORE3D_OK;
 }

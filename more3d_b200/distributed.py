@@ -110,9 +110,14 @@ def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=N
     eps = ck.epsilon()
     out = {}
     sum_m = {}
-    for r in radii:
+    g = None
+    for r in sorted(radii):
         rho = r / np.sqrt(2.0)
-        g = UniformGrid(local, cell_for_radius(r))
+        want = cell_for_radius(r)
+        if g is None or not (g.cell <= want * (1 + 1e-12) and want / g.cell <= 2.05):
+            if g is not None:
+                g.close()
+            g = UniformGrid(local, want)       # shared by the wider radii (see PointCloudDM.grid)
         normals, _, K, pcount = g.normals_curvature(r, eps, params["min_points"])
         length = 1024
         while True:
@@ -136,6 +141,7 @@ def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=N
             out_host[r].copy_(sal, non_blocking=True)
         out[r] = sal
         sum_m[r] = pcount[:n]
+    if g is not None:
         g.close()
     return out, sum_m
 

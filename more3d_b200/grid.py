@@ -133,6 +133,7 @@ class UniformGrid:
             pcount = self._new((self.n,), torch.int32)
             check(self.lib.more3d_nonparam_curvature(self._h, float(r), ptr(normals), float(eps), int(min_points),
                                                      ptr(K), ptr(pcount), stream_ptr()))
+            self._feat_key = None       # normals may have been flipped in place
             return K, pcount
 
     def normals_curvature(self, r, eps, min_points):
@@ -143,6 +144,8 @@ class UniformGrid:
             pcount = self._new((self.n,), torch.int32)
             check(self.lib.more3d_normals_curvature(self._h, float(r), float(eps), int(min_points), ptr(normals),
                                                     ptr(ratio), ptr(K), ptr(pcount), stream_ptr()))
+            # the grid now caches the sorted (xyz, K, unit normal) records of exactly these two tensors
+            self._feat_key = (normals, normals._version, K, K._version)
             return normals, ratio, K, pcount
 
     def dk_dn(self, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, min_points):
@@ -151,6 +154,10 @@ class UniformGrid:
             dk = self._new((self.n,), torch.float32)
             dn = self._new((self.n,), torch.float32)
             minmax = self._new((4,), torch.float32)
+            key = getattr(self, "_feat_key", None)
+            if key is not None and key[0] is normals and key[2] is K and key[1] == normals._version \
+                    and key[3] == K._version:
+                normals = K = None      # untouched since the fused pass: use the grid's cached feature records
             check(self.lib.more3d_dk_dn(self._h, float(r), ptr(normals), ptr(K), float(rho), float(sigma_normal),
                                         float(sigma_curvature), ptr(chi2_table), int(chi2_table.numel()),
                                         int(min_points), ptr(dk), ptr(dn), ptr(minmax), stream_ptr()))

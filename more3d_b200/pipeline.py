@@ -25,7 +25,8 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
     """
     dm = PointCloudDM(xyz)
     out = {}
-    for r in radii:
+    copy_stream = torch.cuda.Stream(device=dm.device) if out_host is not None else None
+    for r in sorted(radii):      # ascending: the finest grid is built first and shared by the wider radii
         rho = r / np.sqrt(2.0)
         dm.normals = None          # normals are re-estimated at every scale
         DM_nonparam_curvature(dm, "sphere", roughness=roughness, alpha=alpha, min_points=min_points, radius=r)
@@ -34,11 +35,19 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
         DM_saliency(dm, curvature_weight=curvature_weight)
         sal = dm.attrs["_saliency"]
         if out_host is not None:
-            out_host[r].copy_(sal, non_blocking=True)
+            # device -> host on a side stream so the copy overlaps the next radius' kernels
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dm.device))
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                out_host[r].copy_(sal, non_blocking=True)
+                sal.record_stream(copy_stream)
         if keep:
             out[r] = {k: v for k, v in dm.attrs.items()}
             out[r]["normals"] = dm.normals
         else:
             out[r] = sal
-        dm.drop_grids()
+    if copy_stream is not None:
+        torch.cuda.current_stream(dm.device).wait_stream(copy_stream)
+    dm.drop_grids()
     return out
