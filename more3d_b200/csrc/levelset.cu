@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_reclamp(int64_t n, const uint8_
 __global__ void __launch_bounds__(LS_THREADS) ls_step_a(LsGraph g, LsParams p, const double* __restrict__ phi,
                                                         const uint8_t* __restrict__ active, uint8_t* __restrict__ idx2,
                                                         double* __restrict__ laplace, double* __restrict__ dphi /* SoA 3n */,
-                                                        double* __restrict__ dpf, double* __restrict__ ctmp /* SoA 3n */) {
+                                                        double* __restrict__ aux /* AoS n x 4: dp_, ctmp xyz */) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     uint8_t on = 0;
@@ -345,8 +345,11 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_a(LsGraph g, LsParams p, c
         }
     }
     idx2[i] = on;
-    dpf[i] = dpv;                                           // dp_[~idx] = 0, :401
-    ctmp[i] = cx; ctmp[g.n + i] = cy; ctmp[2 * g.n + i] = cz;   // ctmp[:] = 0 elsewhere, :415
+    // dp_[~idx] = 0 (:401) and ctmp[:] = 0 elsewhere (:415); one 32-B record per point so that step b
+    // gathers a neighbour's four fields with a single sector instead of four
+    double2* a2 = reinterpret_cast<double2*>(aux + 4 * i);
+    a2[0] = make_double2(dpv, cx);
+    a2[1] = make_double2(cy, cz);
 }
 
 // the global region means need sum zeta (1-H), sum (1-H), sum zeta H, sum H over ALL points (:410-412)
@@ -375,7 +378,7 @@ __global__ void ls_reduce_final(const double* __restrict__ part, int nblocks, in
 __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, double* __restrict__ phi,
                                                         const uint8_t* __restrict__ idx2,
                                                         const double* __restrict__ laplace, const double* __restrict__ dphi,
-                                                        const double* __restrict__ dpf, const double* __restrict__ ctmp,
+                                                        const double* __restrict__ aux,
                                                         const double* __restrict__ zeta,
                                                         const double* __restrict__ region /* channels x 4 sums */,
                                                         double* __restrict__ phi_new, double* __restrict__ part /* RED_BLOCKS x 2 */) {
@@ -386,17 +389,33 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, d
             const double t1x = g.t1[i], t1y = g.t1[g.n + i], t1z = g.t1[2 * g.n + i];
             const double t2x = g.t2[i], t2y = g.t2[g.n + i], t2z = g.t2[2 * g.n + i];
             double R = 0.0, C = 0.0;
+            // first derivatives (rows 0, 1 of the WLS operator) of the four fields dp_, ctmp x/y/z in one
+            // pass over the neighbours: Derivative.grad / div, :293-305
+            const double2* own = reinterpret_cast<const double2*>(aux + 4 * i);
+            const double2 o0 = own[0], o1 = own[1];
+            double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
+            for (int j = 0; j < g.k; ++j) {
+                const int64_t q = g.nbr[(int64_t)j * g.n + i];
+                const double e0 = g.E[((int64_t)j) * g.n + i], e1 = g.E[((int64_t)(g.k + j)) * g.n + i];
+                const double2* nb2 = reinterpret_cast<const double2*>(aux + 4 * q);
+                const double2 v0 = nb2[0], v1 = nb2[1];
+                const double d0 = v0.x - o0.x, d1 = v0.y - o0.y, d2 = v1.x - o1.x, d3 = v1.y - o1.y;
+                ax[0] += e0 * d0; ay[0] += e1 * d0;
+                ax[1] += e0 * d1; ay[1] += e1 * d1;
+                ax[2] += e0 * d2; ay[2] += e1 * d2;
+                ax[3] += e0 * d3; ay[3] += e1 * d3;
+            }
+            const double c0 = g.cst[i], c1 = g.cst[g.n + i];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { ax[f] += c0; ay[f] += c1; }
             if (p.nu > 0) {
-                double a[2];
-                wls_apply<2>(g, i, dpf, a);
-                const double gx = a[0] * t1x + a[1] * t2x, gy = a[0] * t1y + a[1] * t2y, gz = a[0] * t1z + a[1] * t2z;
-                R = p.nu * (dpf[i] * laplace[i] + ((gx * dphi[i] + gy * dphi[g.n + i]) + gz * dphi[2 * g.n + i]));
+                const double gx = ax[0] * t1x + ay[0] * t2x, gy = ax[0] * t1y + ay[0] * t2y, gz = ax[0] * t1z + ay[0] * t2z;
+                R = p.nu * (o0.x * laplace[i] + ((gx * dphi[i] + gy * dphi[g.n + i]) + gz * dphi[2 * g.n + i]));
             }
             if (p.mu > 0) {
-                double a[2], dv = 0.0;
-                wls_apply<2>(g, i, ctmp, a);             dv = a[0] * t1x + a[1] * t2x;
-                wls_apply<2>(g, i, ctmp + g.n, a);       dv += a[0] * t1y + a[1] * t2y;
-                wls_apply<2>(g, i, ctmp + 2 * g.n, a);   dv += a[0] * t1z + a[1] * t2z;
+                double dv = ax[1] * t1x + ay[1] * t2x;
+                dv += ax[2] * t1y + ay[2] * t2y;
+                dv += ax[3] * t1z + ay[3] * t2z;
                 C = p.mu * dv;
             }
             double f1 = 0.0, f2 = 0.0;
@@ -595,11 +614,11 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     p.stepsize = stepsize; p.nu = nu; p.mu = mu; p.lambda1 = lambda1; p.lambda2 = lambda2; p.epsilon = epsilon;
     p.max_val = max_val; p.cap = cap; p.channels = channels;
     ProfScope prof("ls_run", s);
-    double *laplace = nullptr, *dphi = nullptr, *dpf = nullptr, *ctmp = nullptr, *bufA = nullptr, *bufB = nullptr;
+    double *laplace = nullptr, *dphi = nullptr, *aux = nullptr, *bufA = nullptr, *bufB = nullptr;
     double *part = nullptr, *region = nullptr, *incs = nullptr;
     uint8_t *idx2 = nullptr, *azc = nullptr, *outside = nullptr;
     M3D_TRY(dev_alloc(&laplace, (size_t)n, s)); M3D_TRY(dev_alloc(&dphi, (size_t)3 * n, s));
-    M3D_TRY(dev_alloc(&dpf, (size_t)n, s));     M3D_TRY(dev_alloc(&ctmp, (size_t)3 * n, s));
+    M3D_TRY(dev_alloc(&aux, (size_t)4 * n, s));
     M3D_TRY(dev_alloc(&bufA, (size_t)n, s));    M3D_TRY(dev_alloc(&bufB, (size_t)n, s));
     M3D_TRY(dev_alloc(&part, (size_t)RED_BLOCKS * 4, s));
     M3D_TRY(dev_alloc(&region, (size_t)4 * channels, s));
@@ -610,7 +629,7 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     for (int it = 0; it < iterations; ++it) {
         if (!alias_last_active) ls_reclamp<<<nb, LS_THREADS, 0, s>>>(n, active, last_active, max_val, phi);
         if (nu > 0 || mu > 0) {
-            ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, phi, active, idx2, laplace, dphi, dpf, ctmp);
+            ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, phi, active, idx2, laplace, dphi, aux);
         } else {
             M3D_CUDA(cudaMemcpyAsync(idx2, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // idx stays the active mask
         }
@@ -618,7 +637,7 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
             ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, epsilon, phi, zeta, c, part);
             ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c);
         }
-        ls_step_b<<<RED_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, dpf, ctmp, zeta, region, bufA, part);
+        ls_step_b<<<RED_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, bufA, part);
         ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 2, incs + 2 * it);
         if (!alias_last_active) M3D_CUDA(cudaMemcpyAsync(last_active, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // :617
         ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, bufA, active, azc, bufB, outside);
@@ -647,7 +666,7 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     }
     if (iterations_done_h) *iterations_done_h = done;
     if (converged_h) *converged_h = conv;
-    dev_free(laplace, s); dev_free(dphi, s); dev_free(dpf, s); dev_free(ctmp, s); dev_free(bufA, s); dev_free(bufB, s);
+    dev_free(laplace, s); dev_free(dphi, s); dev_free(aux, s); dev_free(bufA, s); dev_free(bufB, s);
     dev_free(part, s); dev_free(region, s); dev_free(incs, s); dev_free(idx2, s); dev_free(azc, s); dev_free(outside, s);
     return MORE3D_OK;
 }

@@ -183,12 +183,23 @@ class Derivative:
     def __init__(self, points, max_d, neighbors, tangents):
         """precalculate inverse for WLS approximation via SVD (:246-275)"""
         lib = _lib.load()
-        self._pts = _dev(points)
-        n = int(self._pts.shape[0])
+        pts = _dev(points)
+        n = int(pts.shape[0])
         nb = neighbors if isinstance(neighbors, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(neighbors))
-        self._nb = nb.to(device="cuda", dtype=torch.int32).contiguous()
+        nb = nb.to(device="cuda", dtype=torch.int64)
+        # Internal point order = the uniform grid's sorted order: a warp's 32 points then share their
+        # neighbours' cache lines, which turns the k random 32-B sector gathers per point of every iteration
+        # kernel into L1/L2 hits.  `_perm[i]` = original index of internal point i; everything that leaves
+        # this class is mapped back, so callers never see the permutation.
+        g = _knn_grid(pts, 8)
+        self._perm = g.order().long()
+        g.close()
+        self._inv = torch.empty_like(self._perm)
+        self._inv[self._perm] = torch.arange(n, device="cuda", dtype=torch.int64)
+        self._pts = pts[self._perm].contiguous()
+        self._nb = self._inv[nb[self._perm]].to(torch.int32).contiguous()
         self._k = int(self._nb.shape[1])
-        self._t1, self._t2 = _dev(tangents[0]), _dev(tangents[1])
+        self._t1, self._t2 = _dev(tangents[0])[self._perm].contiguous(), _dev(tangents[1])[self._perm].contiguous()
         self._w = torch.empty((n, self._k), dtype=torch.float64, device="cuda")
         self._D = None
         self._max_d = float(max_d)
@@ -217,23 +228,23 @@ class Derivative:
 
     @property
     def weights(self):
-        return self._h("weights", lambda: self._w.cpu().numpy())
+        return self._h("weights", lambda: self._w[self._inv].cpu().numpy())
 
     @property
     def neighbors(self):
-        return self._h("neighbors", lambda: self._nb.cpu().numpy().astype(np.int64))
+        return self._h("neighbors", lambda: self._perm[self._nb.long()][self._inv].cpu().numpy())
 
     @property
     def points(self):
-        return self._h("points", lambda: self._pts.cpu().numpy())
+        return self._h("points", lambda: self._pts[self._inv].cpu().numpy())
 
     @property
     def t1(self):
-        return self._h("t1", lambda: self._t1.cpu().numpy())
+        return self._h("t1", lambda: self._t1[self._inv].cpu().numpy())
 
     @property
     def t2(self):
-        return self._h("t2", lambda: self._t2.cpu().numpy())
+        return self._h("t2", lambda: self._t2[self._inv].cpu().numpy())
 
     @property
     def D(self):
@@ -246,15 +257,15 @@ class Derivative:
             check(lib.more3d_ls_graph_create(ptr(self._pts), n, self._k, ptr(self._nb), ptr(self._t1), ptr(self._t2),
                                              self._max_d, ptr(w), ptr(D), C.byref(sing), stream_ptr(), C.byref(h)))
             lib.more3d_ls_graph_destroy(h)
-            return D.cpu().numpy()
+            return D[self._inv].cpu().numpy()
         return self._h("D", make)
 
     def _diff(self, u):
         lib = _lib.load()
-        du = _dev(u)
+        du = _dev(u)[self._perm].contiguous()
         out = torch.empty((du.shape[0], 4), dtype=torch.float64, device="cuda")
         check(lib.more3d_ls_diff(self._g, ptr(du), None, ptr(out), stream_ptr()))
-        return out.cpu().numpy()
+        return out[self._inv].cpu().numpy()
 
     def __call__(self, u, idx=None, first_only=False):
         """first & optionally second derivatives of u at idx w.r.t. local tangent basis (:277-291)"""
@@ -285,22 +296,25 @@ class _Mirror:
     possibly modified (callers mutate ``solver.phi[:] = ...`` in place), so it is pushed back before the
     next device use."""
 
-    def __init__(self, host):
+    def __init__(self, host, perm=None, inv=None):
         self.host = host
-        self.dev = None
+        self.dev = None              # internal (grid-sorted) point order when perm is given
+        self.perm, self.inv = perm, inv
         self.host_touched = True     # host is authoritative
         self.host_stale = False
 
     def get_host(self):
         if self.host_stale:
-            self.host[...] = self.dev.cpu().numpy().astype(self.host.dtype, copy=False).reshape(self.host.shape)
+            d = self.dev if self.inv is None else self.dev[self.inv]
+            self.host[...] = d.cpu().numpy().astype(self.host.dtype, copy=False).reshape(self.host.shape)
             self.host_stale = False
         self.host_touched = True
         return self.host
 
     def get_dev(self, dtype):
         if self.dev is None or self.host_touched:
-            self.dev = torch.from_numpy(np.ascontiguousarray(self.host)).to(device="cuda", dtype=dtype).contiguous()
+            d = torch.from_numpy(np.ascontiguousarray(self.host)).to(device="cuda", dtype=dtype)
+            self.dev = (d if self.perm is None else d[self.perm]).contiguous()
             self.host_touched = False
         return self.dev
 
@@ -313,17 +327,20 @@ class Solver:
         """level set solver (:362-384)"""
         _print('initializing solver')
         zeta = np.asarray(zeta.cpu().numpy() if isinstance(zeta, torch.Tensor) else zeta, dtype=np.float64)
-        self._phi = _Mirror(np.zeros(zeta.shape[:-1]))
-        self._zeta = _Mirror(zeta.copy())
         self.h = h
         self.max_val = 2 * h
-        self._active = _Mirror(np.zeros(self._phi.host.shape, dtype='bool'))
-        self._last_active = _Mirror(self._active.host.copy())
+        _print('initializing WLS derivatives', 1)
+        self.diff = Derivative(points, 3 * h, neighbors, tangents)
+        self._phi = self._mirror(np.zeros(zeta.shape[:-1]))
+        self._zeta = self._mirror(zeta.copy())
+        self._active = self._mirror(np.zeros(self._phi.host.shape, dtype='bool'))
+        self._last_active = self._mirror(self._active.host.copy())
         self._alias = False
         self.seeds = None
         self.active_contour_model = active_contour_model
-        _print('initializing WLS derivatives', 1)
-        self.diff = Derivative(points, 3 * h, neighbors, tangents)
+
+    def _mirror(self, host):
+        return _Mirror(host, self.diff._perm, self.diff._inv)
 
     # -- reference attributes ---------------------------------------------------------------------
     @property
@@ -340,7 +357,7 @@ class Solver:
 
     @zeta.setter
     def zeta(self, v):
-        self._zeta = _Mirror(np.asarray(v, dtype=np.float64))
+        self._zeta = self._mirror(np.asarray(v, dtype=np.float64))
 
     @property
     def active(self):
@@ -348,7 +365,7 @@ class Solver:
 
     @active.setter
     def active(self, v):
-        self._active = _Mirror(np.asarray(v, dtype=bool).copy())
+        self._active = self._mirror(np.asarray(v, dtype=bool).copy())
 
     @property
     def last_active(self):
@@ -360,7 +377,7 @@ class Solver:
             self._alias = True
         else:
             self._alias = False
-            self._last_active = _Mirror(np.asarray(v, dtype=bool).copy())
+            self._last_active = self._mirror(np.asarray(v, dtype=bool).copy())
 
     @property
     def points(self):
@@ -382,11 +399,12 @@ class Solver:
         lib = _lib.load()
         n = int(self.diff._pts.shape[0])
         mask, sel = _mask_of(idx, n)
-        du = _dev(u)
-        dm = None if mask is None else _dev(mask, torch.uint8)
+        p, inv = self.diff._perm, self.diff._inv
+        du = _dev(u)[p].contiguous()
+        dm = None if mask is None else _dev(mask, torch.uint8)[p].contiguous()
         out = torch.empty(n, dtype=torch.uint8, device="cuda")
         check(lib.more3d_ls_zero_crossings(self.diff._g, ptr(du), ptr(dm), ptr(out), stream_ptr()))
-        return out.cpu().numpy().astype(bool)[sel]
+        return out[inv].cpu().numpy().astype(bool)[sel]
 
     def initialize_new(self, new, active):
         phi = self.phi
@@ -398,7 +416,11 @@ class Solver:
         n = int(self.diff._pts.shape[0])
         out = torch.empty(n, dtype=torch.uint8, device="cuda")
         check(lib.more3d_ls_zero_crossings(self.diff._g, ptr(self._phi.get_dev(torch.float64)), None, ptr(out), stream_ptr()))
-        self._active = _Mirror(out.cpu().numpy().astype(bool))
+        m = self._mirror(np.zeros(n, dtype=bool))
+        m.dev = out                      # already in internal order
+        m.host_touched = False
+        m.host_stale = True
+        self._active = m
 
     def initialize_from_mask(self, mask):
         _print('initializing from mask')
@@ -407,7 +429,7 @@ class Solver:
         phi[~mask] = self.max_val
         self._set_active_from_phi()
         self._alias = False
-        self._last_active = _Mirror(self._active.host.copy())          # last_active[:] = active, :553
+        self._last_active = self._mirror(self._active.get_host().copy())   # last_active[:] = active, :553
 
     def initialize_from_zeta(self, percentile):
         _print('initializing from zeta')
@@ -418,7 +440,7 @@ class Solver:
         phi[zeta > pc] = self.max_val
         self._set_active_from_phi()
         self._alias = False
-        self._last_active = _Mirror(self._active.host.copy())
+        self._last_active = self._mirror(self._active.get_host().copy())
 
     def initialize_from_seeds(self, num_seeds, seed_radius, reuse_seeds=True):
         pts = self.points
