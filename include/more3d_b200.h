@@ -196,6 +196,19 @@ int more3d_ls_smooth_raw(const double* u, int cols, const int64_t* nbs, const do
                          const uint8_t* mask, double* out, void* stream);
 int more3d_ls_elementwise(int op, const double* x, double param, int64_t n, double* out, void* stream);
 
+/* ---- evaluation terms of Downsampling/downsample_compare.py ("next" row) -----------------------------
+ * normals_from_knn: centroid-PCA normal over a kNN table (open3d estimate_normals(KDTreeSearchParamKNN),
+ * downsample_compare.py:57, :112-121); fewer than 3 valid neighbours -> (0, 0, 1).  orient_normals: NaN ->
+ * (0, 0, 1), then n[n.z < 0] = -n when upwards_z != 0 (:60-62).  compare_terms (:132-149): c2p_sq[i] for every
+ * original point (n_orig f64), angle_deg[i] for every downsampled point (n_down f64, folded to [0, 90]). */
+int more3d_normals_from_knn(const double* xyz, int64_t n, int k, const int64_t* knn, double* normals,
+                            double* lam_ratio, void* stream);
+int more3d_orient_normals(double* normals, int64_t n, int upwards_z, void* stream);
+int more3d_compare_terms(const double* orig, int64_t n_orig, const double* down, int64_t n_down,
+                         const int64_t* closest_of_down, const int64_t* closest_of_orig,
+                         const double* normals_orig, const double* normals_down, double* c2p_sq,
+                         double* angle_deg, void* stream);
+
 /* ---- multi-GPU strip partition helpers (no reference equivalent; OPALS tile streaming,
  * DM_saliency.py:76-86, is the analogue) ----------------------------------------------------------
  * band_select: indices i (ascending, stable) with lo <= xyz[i][axis] < hi; idx has room for n int64;

@@ -50,6 +50,9 @@ SIGNATURES = {
                       _f64, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(_i32), _vp],
     "more3d_ls_smooth_raw": [_vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "more3d_ls_elementwise": [_i32, _vp, _f64, _i64, _vp, _vp],
+    "more3d_normals_from_knn": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
+    "more3d_orient_normals": [_vp, _i64, _i32, _vp],
+    "more3d_compare_terms": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "more3d_band_select": [_vp, _i64, _i32, _f64, _f64, _vp, C.POINTER(_i64), _vp],
     "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
 }

@@ -350,3 +350,28 @@ def voxel_downsample(points, voxel_size):
             acc += points[j]
         means[v] = acc / float(b - a)
     return means, ks[starts]
+
+
+# --------------------------------------------------------------------------------------------
+# "next" row f-2: downsample_compare.py:132-150 (error terms for given normals)
+# --------------------------------------------------------------------------------------------
+def compare_downsampled(pts, downsampled, normals_pts, normals_down, leafsize=40):
+    """Literal restatement: c2c = avg(E2) + avg(E)/2 (:142-143), c2p with the original normals indexed by
+    closest2 (:145), dN = median folded angle (:146-150)."""
+    pts = np.asarray(pts, np.float64)[:, :3]
+    down = np.asarray(downsampled, np.float64)[:, :3]
+    btP = BallTree(pts, leafsize)
+    dbt = BallTree(down, leafsize)
+    E, closest = btP.query(down, 1)
+    closest = closest.flatten()
+    E2, closest2 = dbt.query(pts, 1)
+    closest2 = closest2.flatten()
+    vector_E2 = pts - down[closest2]
+    c2c = np.average(E2) + np.average(E) / 2
+    c2p = np.average(np.einsum('ij,ij->i', vector_E2, normals_pts[closest2, :]) ** 2)
+    dn = np.einsum('ij,ij->i', normals_pts[closest, :], normals_down)
+    dn[np.abs(dn) > 1] = 1
+    dn = np.degrees(np.arccos(dn))
+    dn[dn > 90] = 180 - dn[dn > 90]
+    return {"c2c": float(c2c), "c2p": float(c2p), "dN": float(np.median(dn)), "dn_all": dn,
+            "E": E.flatten(), "E2": E2.flatten()}
