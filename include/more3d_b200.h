@@ -147,6 +147,13 @@ int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size, int64_t* 
 int more3d_lod_cell_rule(const double* xyz, const double* saliency, const int64_t* idx_array,
                          const int64_t* cell_start, int64_t ncells, double thresh, double zero_thresh,
                          int literal, uint8_t* keep, uint8_t* keep_all, double* mean_xyz, void* stream);
+/* Output of the downsampler in the reference's row order (Downsample.py:60-83): per cell its kept points
+ * (flag 1) then, for averaged cells, the original point `near[a]` (a = rank of the cell among the averaged
+ * ones) with flag 0.  out_xyzf: (n + ncells) x 4 f64 capacity; out_idx: original index per row; out_cell
+ * (may be NULL): cell rank per row; *nrows_h = rows written. */
+int more3d_lod_assemble(const double* xyz, const int64_t* idx_array, int64_t n, const int64_t* cell_start,
+                        int64_t ncells, const uint8_t* keep, const uint8_t* keep_all, const int64_t* near,
+                        double* out_xyzf, int64_t* out_idx, int32_t* out_cell, int64_t* nrows_h, void* stream);
 /* stable compaction: idx = positions i with flags[i] != 0 (ascending); idx has room for n int64 */
 int more3d_select_flagged(const uint8_t* flags, int64_t n, int64_t* idx, int64_t* count_h, void* stream);
 

@@ -73,7 +73,7 @@ def voxel_downsample(pts, voxel_size, return_keys=False, return_device=False):
 
 
 def saliency_downsample(pts, saliency, lod, leaf_size=40, zero_thresh=1e-4, literal=False, btP=None,
-                        s_thresh=None, return_details=False):
+                        s_thresh=None, return_details=False, return_device=False):
     """One LOD of the loop at Downsample.py:44-83.  pts (N,3); saliency (N,).  Returns the (M,4) array the
     script writes (xyz + flag: 1 = salient / kept cell, 0 = representative of the averaged rest), rows in
     the reference's order (cell by cell, kept points in ball-tree order then the representative)."""
@@ -98,30 +98,28 @@ def saliency_downsample(pts, saliency, lod, leaf_size=40, zero_thresh=1e-4, lite
         check(lib.more3d_lod_cell_rule(ptr(dev), ptr(sal64), ptr(tree.idx_array_dev), ptr(cs), ncells, float(s_thresh),
                                        float(zero_thresh), 1 if literal else 0, ptr(keep), ptr(keep_all), ptr(mean),
                                        stream_ptr()))
-        kept_pos = torch.empty(n, dtype=torch.int64, device=dev.device)
-        cnt = C.c_int64(0)
-        check(lib.more3d_select_flagged(ptr(keep), n, ptr(kept_pos), C.byref(cnt), stream_ptr()))
-        kept_pos = kept_pos[:int(cnt.value)]
-    keep_all_h = keep_all.cpu().numpy().astype(bool)
-    avg_cells = np.nonzero(~keep_all_h)[0]
-    # closest original point to every averaged rest (btP.query(average_pt[None, :], 1), :70)
-    near = np.zeros(0, np.int64)
-    if len(avg_cells):
-        mean_h = mean.cpu().numpy()[avg_cells]
-        near = btP.query(mean_h, 1)[:, 0]
-    kept_pos_h = kept_pos.cpu().numpy()
-    kept_idx = tree.idx_array[kept_pos_h]
-    kept_cell = np.searchsorted(starts, kept_pos_h, side="right") - 1
-    # reference order: cell by cell, kept points first (flag 1), then the representative (flag 0)
-    all_idx = np.concatenate([kept_idx, near])
-    all_cell = np.concatenate([kept_cell, avg_cells])
-    all_flag = np.concatenate([np.ones(len(kept_idx)), np.zeros(len(near))])
-    order = np.lexsort((1 - all_flag, all_cell))
-    P = btP.ToNumpy()
-    out = np.hstack((P[all_idx[order]], all_flag[order][:, None]))
+        # closest original point to the mean of every averaged cell (btP.query(average_pt[None, :], 1), :70)
+        avg = keep_all == 0
+        near = None
+        if bool(avg.any()):
+            g = btP._grid(btP._knn_cell(1))
+            near = g.knn(mean[avg].contiguous(), 1, return_distance=False)[0][:, 0].contiguous()
+        cap = n + ncells
+        out = torch.empty((cap, 4), dtype=torch.float64, device=dev.device)
+        out_idx = torch.empty(cap, dtype=torch.int64, device=dev.device)
+        out_cell = torch.empty(cap, dtype=torch.int32, device=dev.device)
+        rows = C.c_int64(0)
+        check(lib.more3d_lod_assemble(ptr(dev), ptr(tree.idx_array_dev), n, ptr(cs), ncells, ptr(keep), ptr(keep_all),
+                                      ptr(near), ptr(out), ptr(out_idx), ptr(out_cell), C.byref(rows), stream_ptr()))
+    m = int(rows.value)
+    out, out_idx, out_cell = out[:m], out_idx[:m], out_cell[:m]
+    if not return_device:
+        out = out.cpu().numpy()
     if return_details:
-        return out, dict(idx=all_idx[order], cell=all_cell[order], cells=cells, s_thresh=s_thresh,
-                         keep_all=keep_all_h)
+        det = dict(idx=out_idx if return_device else out_idx.cpu().numpy(),
+                   cell=out_cell if return_device else out_cell.cpu().numpy(), cells=cells, s_thresh=s_thresh,
+                   keep_all=keep_all.cpu().numpy().astype(bool))
+        return out, det
     return out
 
 
