@@ -70,6 +70,8 @@ static inline void dev_free(void* p, cudaStream_t s) {
 // Margin between the grid's column width and the largest radius one stencil step covers: rounding
 // in floor((x - ox) * inv_cell) is ~1e-13 relative, 2^-16 leaves orders of magnitude of slack.
 #define M3D_CELL_MARGIN (1.0 + 1.0 / 65536.0)
+// a column with more points than this switches the grid to z-sorted columns (see grid.cu)
+#define M3D_TALL_COLUMN 128u
 
 // sorted point record: 32 B, two LDG.128
 struct __align__(32) PointRec {
@@ -95,6 +97,9 @@ struct more3d_grid {
     int nx, ny;
     double cell, inv_cell, ox, oy;
     int device;
+    int tall;               // 1: some xy column holds more than M3D_TALL_COLUMN points -> columns are z-sorted
+                            //    and the kernels bracket each column by z (vertical structures); 0: thin columns
+    uint32_t max_col_pop;   // largest column population
     cudaStream_t stream;    // creation stream: grid arrays are stream-ordered allocations on it
     double oz;              // z origin of the fp32 records (bbox z-min)
     double lim32;           // delta32 holds for |coordinate - origin| < lim32
@@ -135,6 +140,13 @@ __device__ __forceinline__ int cell_coord(double v, double o, double inv, int n)
     f = fmin(fmax(f, -1.0e9), 1.0e9);
     (void)n;
     return (int)f;
+}
+
+// order-preserving double -> uint64 mapping (radix-sortable); -0.0 and +0.0 map to the same key
+__device__ __forceinline__ uint64_t sortable_key(double v) {
+    v = v + 0.0;
+    const uint64_t u = (uint64_t)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
 // order-preserving float <-> uint mapping for atomic min/max

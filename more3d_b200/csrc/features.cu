@@ -13,7 +13,7 @@ namespace m3d {
 enum { MODE_NORMALS = 0, MODE_CURV = 1, MODE_FUSED = 2 };
 
 struct CurvParams {
-    double r2;
+    double r, r2;
     double eps;
     int min_points;
     int s;
@@ -24,7 +24,7 @@ constexpr int WALK_THREADS = 256;
 
 // One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
 // query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
-template <int MODE>
+template <int MODE, bool TALL>
 __global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, CurvParams prm,
                                                                double* __restrict__ normals,
                                                                double* __restrict__ lam_ratio,
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, Cu
     // The fp64 differences serve both the exact accept rule and the moments, so an fp32 pre-filter
     // (used by the count/fill kernels) does not pay here: measured 2x slower (conditional fp64 loads
     // lose the unrolled loop's memory-level parallelism).
-    for_each_candidate(g, p.x, p.y, prm.s, [&](int64_t j) {
+    walk_candidates<TALL>(g, p.x, p.y, p.z, prm.r, prm.s, [&](int64_t j) {
         const PointRec c = load_rec(g.rec, j);
         const double dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
         if (dist2_rule(dx, dy, dz) <= prm.r2) {
@@ -146,11 +146,12 @@ __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
 }
 
 struct DkDnParams {
-    double r2, rho2, inv_rho2, sigma_n, sigma_k;
+    double r, r2, rho2, inv_rho2, sigma_n, sigma_k;
     int min_points, s, table_len;
     Filter32 flt;
 };
 
+template <bool TALL>
 __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                    DkDnParams prm, const double* __restrict__ chi2_table,
                                                    float* __restrict__ dk_out, float* __restrict__ dn_out,
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
         const double pnx = pb.x, pny = pb.y, pnz = pb.z;
         int m = 0, mu = 0, nact = 0, zn = 0, zk = 0, zk100 = 0;
         double s1n = 0, s2n = 0, s1k = 0, s2k = 0, wn = 0, wk = 0, wsum = 0;
-        for_each_candidate(g, px, py, prm.s, [&](int64_t j) {
+        walk_candidates<TALL>(g, px, py, pz, prm.r, prm.s, [&](int64_t j) {
             const D4 qa = ld_d4(feat + j, 0);
             const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);   // :256-257
             if (d2 <= prm.r2) {
@@ -265,22 +266,25 @@ static int launch_moments(const more3d_grid* g, int mode, double r, double eps, 
     M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
     M3D_REQUIRE(normals != nullptr, "normals is NULL");
     CurvParams prm;
-    prm.r2 = r * r; prm.eps = eps; prm.min_points = min_points; prm.s = stencil_halfwidth(g, r);
+    prm.r = r; prm.r2 = r * r; prm.eps = eps; prm.min_points = min_points; prm.s = stencil_halfwidth(g, r);
     prm.flt = make_filter(g, r);
     const unsigned nb = (unsigned)((g->n + WALK_THREADS - 1) / WALK_THREADS);
     GridView v = make_view(g);
     ProfScope prof("moments", s);
-    if (mode == MODE_NORMALS)
-        moments_kernel<MODE_NORMALS><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount, nullptr);
-    else if (mode == MODE_CURV)
-        moments_kernel<MODE_CURV><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, nullptr, K, pcount, nullptr);
-    else {
+    if (mode == MODE_NORMALS) {
+        if (g->tall) moments_kernel<MODE_NORMALS, true><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount, nullptr);
+        else moments_kernel<MODE_NORMALS, false><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount, nullptr);
+    } else if (mode == MODE_CURV) {
+        if (g->tall) moments_kernel<MODE_CURV, true><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, nullptr, K, pcount, nullptr);
+        else moments_kernel<MODE_CURV, false><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, nullptr, K, pcount, nullptr);
+    } else {
         more3d_grid* gm = const_cast<more3d_grid*>(g);     // the feature-record cache is mutable state of the grid
         if (!gm->feat && cudaMallocAsync((void**)&gm->feat, (size_t)g->n * sizeof(FeatRec), s) != cudaSuccess) {
             cudaGetLastError();
             gm->feat = nullptr;                            // no cache: dk/dn will gather instead
         }
-        moments_kernel<MODE_FUSED><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, K, pcount, gm->feat);
+        if (g->tall) moments_kernel<MODE_FUSED, true><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, K, pcount, gm->feat);
+        else moments_kernel<MODE_FUSED, false><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, K, pcount, gm->feat);
     }
     count_launches(1);
     M3D_CHECK_LAUNCH();
@@ -332,13 +336,14 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
     }
     minmax_init<<<1, 32, 0, s>>>(mm);
     DkDnParams prm;
-    prm.r2 = r * r; prm.rho2 = rho * rho; prm.inv_rho2 = 1.0 / (rho * rho);
+    prm.r = r; prm.r2 = r * r; prm.rho2 = rho * rho; prm.inv_rho2 = 1.0 / (rho * rho);
     prm.sigma_n = sigma_normal; prm.sigma_k = sigma_curvature;
     prm.min_points = min_points; prm.s = stencil_halfwidth(g, r); prm.table_len = table_len;
     prm.flt = make_filter(g, r);
     {
         ProfScope prof("dkdn", s);
-        dkdn_kernel<<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+        if (g->tall) dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+        else dkdn_kernel<false><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
     }
     if (minmax) minmax_finish<<<1, 32, 0, s>>>(mm, minmax);
     count_launches(minmax ? 4 : 3);

@@ -73,6 +73,29 @@ __global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz,
     atomicAdd(&col_count[key], 1u);
 }
 
+__global__ void __launch_bounds__(256) col_max_pop(const uint32_t* __restrict__ col_start, size_t ncols,
+                                                   uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += (size_t)gridDim.x * blockDim.x)
+        m = max(m, col_start[c + 1] - col_start[c]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// tall clouds: z pre-sort keys, and the column keys re-read in z order for the second (stable) sort
+__global__ void __launch_bounds__(256) z_keys(const double* __restrict__ xyz, int64_t n, uint64_t* __restrict__ zk,
+                                              uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    zk[i] = sortable_key(xyz[3 * i + 2]);
+    vals[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256) gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx,
+                                                  int64_t n, uint32_t* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
 // K2 tail: gather the sorted records
 __global__ void __launch_bounds__(256) gather_records(const double* __restrict__ xyz,
                                                       const uint32_t* __restrict__ order, int64_t n,
@@ -107,6 +130,27 @@ __global__ void __launch_bounds__(256) dup_flags(const PointRec* __restrict__ re
     for (int64_t j = b; j < i; ++j) {
         PointRec q = rec[j];
         if (q.x == p.x && q.y == p.y && q.z == p.z) { f = 1; break; }
+    }
+    dup[i] = f;
+}
+
+// z-sorted columns: coincident points are adjacent (equal z, then original index), so only the run of
+// equal z before i has to be looked at
+__global__ void __launch_bounds__(256) dup_flags_tall(const PointRec* __restrict__ rec,
+                                                      const uint32_t* __restrict__ col_start, int64_t n, double ox,
+                                                      double oy, double inv, int nx, int ny,
+                                                      uint8_t* __restrict__ dup) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PointRec p = rec[i];
+    int ix = min(max(cell_coord(p.x, ox, inv, nx), 0), nx - 1);
+    int iy = min(max(cell_coord(p.y, oy, inv, ny), 0), ny - 1);
+    const int64_t b = col_start[(size_t)iy * nx + ix];
+    uint8_t f = 0;
+    for (int64_t j = i - 1; j >= b; --j) {
+        PointRec q = rec[j];
+        if (q.z != p.z) break;
+        if (q.x == p.x && q.y == p.y) { f = 1; break; }
     }
     dup[i] = f;
 }
@@ -198,13 +242,40 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         G_TRY(exclusive_scan_u32(g->col_start, g->col_start, (int64_t)ncols, s));
         int bits = 1;
         while (((size_t)1 << bits) < ncols) ++bits;
+        // thin or tall?  (one more 4-byte read-back per build)
+        uint32_t* d_max = nullptr;
+        G_TRY(dev_alloc(&d_max, 1, s));
+        G_CUDA(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), s));
+        col_max_pop<<<592, 256, 0, s>>>(g->col_start, ncols, d_max);
+        G_CUDA(cudaMemcpyAsync(&g->max_col_pop, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        G_CUDA(cudaStreamSynchronize(s));
+        dev_free(d_max, s);
+        g->tall = g->max_col_pop > M3D_TALL_COLUMN ? 1 : 0;
         uint32_t *ks = nullptr, *vs = nullptr;
-        G_TRY(radix_sort_pairs_u32(keys, vals, keys2, vals2, n, bits, &ks, &vs, s));
+        if (g->tall) {
+            // order = (column, z, original index): stable sort by z first, then by column key
+            uint64_t *zk = nullptr, *zk2 = nullptr, *zs = nullptr;
+            uint32_t* vz = nullptr;
+            G_TRY(dev_alloc(&zk, (size_t)n, s));
+            G_TRY(dev_alloc(&zk2, (size_t)n, s));
+            z_keys<<<nb, 256, 0, s>>>(xyz, n, zk, vals);
+            rc = radix_sort_pairs_u64(zk, vals, zk2, vals2, n, 64, &zs, &vz, s);
+            dev_free(zk, s); dev_free(zk2, s);
+            if (rc != MORE3D_OK) goto fail;
+            uint32_t* vother = (vz == vals) ? vals2 : vals;
+            gather_u32<<<nb, 256, 0, s>>>(keys, vz, n, keys2);          // column key of the z-ordered points
+            G_TRY(radix_sort_pairs_u32(keys2, vz, keys, vother, n, bits, &ks, &vs, s));
+            count_launches(2);
+        } else {
+            G_TRY(radix_sort_pairs_u32(keys, vals, keys2, vals2, n, bits, &ks, &vs, s));
+        }
         G_CUDA(cudaMemcpyAsync(g->order, vs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec, g->ox, g->oy, g->oz, g->rec32);
-        dup_flags<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny,
-                                     g->dup);
-        count_launches(3);  // cell_keys, gather_records, dup_flags
+        if (g->tall)
+            dup_flags_tall<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, g->dup);
+        else
+            dup_flags<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, g->dup);
+        count_launches(4);  // cell_keys, col_max_pop, gather_records, dup_flags
         G_CUDA(cudaGetLastError());
     }
     dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s);

@@ -13,6 +13,7 @@ struct GridView {
     int nx, ny;
     double ox, oy, oz, inv;
     double lim32;
+    int tall;
 };
 
 static inline GridView make_view(const more3d_grid* g) {
@@ -20,6 +21,7 @@ static inline GridView make_view(const more3d_grid* g) {
     v.rec = g->rec; v.rec32 = g->rec32; v.col_start = g->col_start; v.dup = g->dup; v.n = g->n;
     v.nx = g->nx; v.ny = g->ny; v.ox = g->ox; v.oy = g->oy; v.oz = g->oz; v.inv = g->inv_cell;
     v.lim32 = g->lim32;
+    v.tall = g->tall;
     return v;
 }
 
@@ -86,14 +88,57 @@ __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx,
     }
 }
 
+// Tall clouds (vertical structures: some column holds > M3D_TALL_COLUMN points; columns are z-sorted):
+// walk the stencil column by column and bracket long columns to z in [qz - r, qz + r] by binary search.
+// The bracket is widened by one ulp-scale slack and the exact rule still decides, so the candidate set is a
+// superset of the neighbourhood exactly as in the row walk.
+template <typename F>
+__device__ __forceinline__ void for_each_candidate_tall(const GridView& g, double qx, double qy, double qz, double r,
+                                                     int s, F&& f) {
+    const int ix = cell_coord(qx, g.ox, g.inv, g.nx);
+    const int iy = cell_coord(qy, g.oy, g.inv, g.ny);
+    const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
+    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
+    const double zlo = qz - r * (1.0 + 1e-12), zhi = qz + r * (1.0 + 1e-12);
+    for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) {
+            const size_t col = (size_t)y * g.nx + x;
+            uint32_t b = __ldg(g.col_start + col), e = __ldg(g.col_start + col + 1);
+            if (e - b > 32u) {
+                uint32_t lo = b, hi = e;                     // first record with z >= zlo
+                while (lo < hi) {
+                    const uint32_t mid = lo + ((hi - lo) >> 1);
+                    if (__ldg(reinterpret_cast<const double*>(g.rec + mid) + 2) < zlo) lo = mid + 1; else hi = mid;
+                }
+                b = lo;
+                hi = e;                                       // first record with z > zhi
+                while (lo < hi) {
+                    const uint32_t mid = lo + ((hi - lo) >> 1);
+                    if (__ldg(reinterpret_cast<const double*>(g.rec + mid) + 2) <= zhi) lo = mid + 1; else hi = mid;
+                }
+                e = lo;
+            }
+            for (uint32_t j = b; j < e; ++j) f((int64_t)j);
+        }
+}
+
+// compile-time choice between the row walk (thin columns) and the column walk (tall columns): the host
+// launches the <TALL> instantiation that matches the grid, so the thin path's code is unchanged
+template <bool TALL, typename F>
+__device__ __forceinline__ void walk_candidates(const GridView& g, double qx, double qy, double qz, double r, int s,
+                                                F&& f) {
+    if (TALL) for_each_candidate_tall(g, qx, qy, qz, r, s, f);
+    else for_each_candidate(g, qx, qy, s, f);
+}
+
 // Exact-set neighbour enumeration with the fp32 filter: accept(j) is called for every sorted position
 // j whose point satisfies the fp64 rule ((dx*dx)+(dy*dy))+(dz*dz) <= r2 -- bit-identical to the
 // all-fp64 walk, only cheaper: fp64 is touched for the thin shell around the sphere surface only.
-template <typename F>
-__device__ __forceinline__ void for_each_neighbour(const GridView& g, const Filter32 flt, double r2, int s,
+template <bool TALL, typename F>
+__device__ __forceinline__ void for_each_neighbour(const GridView& g, const Filter32 flt, double r, double r2, int s,
                                                    double px, double py, double pz, F&& accept) {
     const float qx = (float)(px - g.ox), qy = (float)(py - g.oy), qz = (float)(pz - g.oz);
-    for_each_candidate(g, px, py, s, [&](int64_t j) {
+    walk_candidates<TALL>(g, px, py, pz, r, s, [&](int64_t j) {
         const float4 c = __ldg(g.rec32 + j);
         const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
         const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));

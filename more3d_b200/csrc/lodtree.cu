@@ -20,12 +20,6 @@ namespace m3d {
 
 constexpr int LT_THREADS = 256;
 
-__device__ __forceinline__ uint64_t sortable_key(double v) {
-    v = v + 0.0;   // -0.0 -> +0.0 (the comparator treats them as equal)
-    const uint64_t u = (uint64_t)__double_as_longlong(v);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-
 __global__ void __launch_bounds__(LT_THREADS) lt_keys(const double* __restrict__ xyz, int64_t n, int d,
                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -6,9 +6,9 @@ namespace m3d {
 
 // SELF: queries are the grid's own points, walked in sorted order (neighbouring threads share
 // stencil rows, so candidate loads are L1 broadcasts); results land at the ORIGINAL index.
-template <bool SELF>
+template <bool SELF, bool TALL>
 __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const double* __restrict__ q,
-                                                           int64_t nq, double r2, int s, Filter32 flt,
+                                                           int64_t nq, double r, double r2, int s, Filter32 flt,
                                                            int32_t* __restrict__ counts) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -22,13 +22,13 @@ __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const dou
     }
     int c = 0;
     if (!SELF) flt = filter_for_query(g, flt, px, py, pz);
-    for_each_neighbour(g, flt, r2, s, px, py, pz, [&](int64_t) { ++c; });
+    for_each_neighbour<TALL>(g, flt, r, r2, s, px, py, pz, [&](int64_t) { ++c; });
     counts[out] = c;
 }
 
-template <bool SELF, typename IdxT>
+template <bool SELF, typename IdxT, bool TALL>
 __global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const double* __restrict__ q,
-                                                          int64_t nq, double r2, int s, Filter32 flt,
+                                                          int64_t nq, double r, double r2, int s, Filter32 flt,
                                                           const int64_t* __restrict__ offsets,
                                                           IdxT* __restrict__ idx) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const doub
     }
     int64_t w = offsets[out];
     if (!SELF) flt = filter_for_query(g, flt, px, py, pz);
-    for_each_neighbour(g, flt, r2, s, px, py, pz, [&](int64_t j) {
+    for_each_neighbour<TALL>(g, flt, r, r2, s, px, py, pz, [&](int64_t j) {
         idx[w++] = (IdxT)__double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + j) + 3));
     });
 }
@@ -69,10 +69,15 @@ extern "C" int more3d_radius_count(const more3d_grid* g, const double* q, int64_
     const int sw = stencil_halfwidth(g, r);
     const unsigned nb = (unsigned)((nq + 255) / 256);
     ProfScope prof("radius_count", s);
-    if (q)
-        radius_count_kernel<false><<<nb, 256, 0, s>>>(make_view(g), q, nq, r * r, sw, make_filter(g, r), counts);
-    else
-        radius_count_kernel<true><<<nb, 256, 0, s>>>(make_view(g), nullptr, nq, r * r, sw, make_filter(g, r), counts);
+    const Filter32 flt = make_filter(g, r);
+    GridView v = make_view(g);
+    if (q) {
+        if (g->tall) radius_count_kernel<false, true><<<nb, 256, 0, s>>>(v, q, nq, r, r * r, sw, flt, counts);
+        else radius_count_kernel<false, false><<<nb, 256, 0, s>>>(v, q, nq, r, r * r, sw, flt, counts);
+    } else {
+        if (g->tall) radius_count_kernel<true, true><<<nb, 256, 0, s>>>(v, nullptr, nq, r, r * r, sw, flt, counts);
+        else radius_count_kernel<true, false><<<nb, 256, 0, s>>>(v, nullptr, nq, r, r * r, sw, flt, counts);
+    }
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
@@ -103,13 +108,15 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
     const double r2 = r * r;
     const Filter32 flt = make_filter(g, r);
     ProfScope prof("radius_fill", s);
+#define M3D_FILL(SELF_, T_, TALL_, Q_) radius_fill_kernel<SELF_, T_, TALL_><<<nb, 256, 0, s>>>(v, Q_, nq, r, r2, sw, flt, offsets, (T_*)idx)
     if (q) {
-        if (idx_bytes == 4) radius_fill_kernel<false, int32_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, flt, offsets, (int32_t*)idx);
-        else radius_fill_kernel<false, int64_t><<<nb, 256, 0, s>>>(v, q, nq, r2, sw, flt, offsets, (int64_t*)idx);
+        if (idx_bytes == 4) { if (g->tall) M3D_FILL(false, int32_t, true, q); else M3D_FILL(false, int32_t, false, q); }
+        else { if (g->tall) M3D_FILL(false, int64_t, true, q); else M3D_FILL(false, int64_t, false, q); }
     } else {
-        if (idx_bytes == 4) radius_fill_kernel<true, int32_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, flt, offsets, (int32_t*)idx);
-        else radius_fill_kernel<true, int64_t><<<nb, 256, 0, s>>>(v, nullptr, nq, r2, sw, flt, offsets, (int64_t*)idx);
+        if (idx_bytes == 4) { if (g->tall) M3D_FILL(true, int32_t, true, nullptr); else M3D_FILL(true, int32_t, false, nullptr); }
+        else { if (g->tall) M3D_FILL(true, int64_t, true, nullptr); else M3D_FILL(true, int64_t, false, nullptr); }
     }
+#undef M3D_FILL
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;

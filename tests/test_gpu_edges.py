@@ -107,3 +107,50 @@ def test_large_coordinates_keep_exact_sets():
         got = bt.queryRadius(pts, r)
         for a, b in zip(got, want):
             assert np.array_equal(np.sort(a), np.sort(b))
+
+
+def test_tall_columns_vertical_structures():
+    """A cloud with vertical structures (columns of > 128 points) switches the grid to z-sorted columns with
+    a per-column z bracket; results must be the same sets / values as the thin path's rule."""
+    from more3d_b200 import synthetic
+    from more3d_b200.BallTreePointSet import BallTreePointSet
+    from more3d_b200.DM_saliency import PointCloudDM, DM_nonparam_curvature, DM_dk_dn
+    from more3d_b200.grid import UniformGrid, cell_for_radius
+    from oracle import ref_path as rp
+    import torch
+    rng = np.random.Generator(np.random.PCG64(11))
+    tower = rng.random((60000, 3)) * [3.0, 3.0, 60.0] + [0.0, 0.0, -1030.0]         # 3 x 3 m footprint, 60 m high
+    wall = np.column_stack([rng.random(20000) * 12.0 - 6.0, np.full(20000, 4.0) + rng.normal(0, 0.01, 20000),
+                            rng.random(20000) * 25.0 - 1010.0])
+    ground = synthetic.terrain(8000, seed=5, noise=0.05)
+    pts = np.vstack([tower, wall, ground, tower[:500]])                              # + coincident copies
+    pts = pts[rng.permutation(len(pts))]
+    r = 0.5
+    g = UniformGrid(torch.from_numpy(pts).cuda(), cell_for_radius(r))
+    cnt = g.radius_count(None, r).cpu().numpy()
+    tree = rp.build_tree(pts)
+    sub = rng.choice(len(pts), 4000, replace=False)
+    want = rp.query_radius(tree, pts[sub], r)
+    assert np.array_equal(cnt[sub], [len(w) for w in want])
+    bt = BallTreePointSet(pts)
+    got = bt.queryRadius(pts[sub], r)
+    for a, b in zip(got, want):
+        assert np.array_equal(np.sort(a), np.sort(b))
+    dm = PointCloudDM(pts)
+    DM_nonparam_curvature(dm, "sphere", roughness=0.02, alpha=0.05, min_points=4, radius=r)
+    rho = r / np.sqrt(2)
+    DM_dk_dn(dm, "sphere", rho, rho, sigma_normal=1e-3, sigma_curvature=0.01, radius=r)
+    nrm, K, pc = dm.normals.cpu().numpy(), dm.get("_nonparam_K"), dm.get("_pcount")
+    dk, dn = dm.get("_dk"), dm.get("_dn")
+    assert np.array_equal(pc, cnt)
+    eps = rp.curvature_epsilon(0.05, 0.02)
+    table = rp.chi2_table(0.05, 4096)
+    full = rp.query_radius(tree, pts[sub[:600]], r)
+    bad = 0
+    for i, b in zip(sub[:600], full):
+        k_or, _, _ = rp.curvature_point(pts[i], nrm[i].copy(), pts[b], eps, 4)
+        a_dk, a_dn = rp.saliency_point(pts[i], nrm[i], float(K[i]), pts[b], nrm[b], K[b].astype(np.float64), rho, 1e-3,
+                                       0.01, table, 4)
+        ok = rel_close(K[i], np.float32(k_or)) and rel_close(dk[i], np.float32(a_dk)) and rel_close(dn[i], np.float32(a_dn))
+        bad += 0 if ok else 1
+    assert bad <= 3, bad
