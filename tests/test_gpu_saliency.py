@@ -13,7 +13,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SAL_CASES = ["terrain_r05", "terrain_r10", "rough_r05", "boulders_r075"]
+SAL_CASES = ["terrain_r05", "terrain_r10", "rough_r05", "boulders_r075", "dups_sparse_r06"]
 RTOL = 1e-4
 
 

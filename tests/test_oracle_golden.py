@@ -7,7 +7,7 @@ import pytest
 
 from oracle import ref_path as rp
 
-SAL_CASES = ["terrain_r05", "terrain_r10", "rough_r05", "boulders_r075"]
+SAL_CASES = ["terrain_r05", "terrain_r10", "rough_r05", "boulders_r075", "dups_sparse_r06"]
 
 
 def load(golden_dir, name):

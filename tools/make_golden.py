@@ -126,6 +126,13 @@ if __name__ == "__main__":
         saliency_case("terrain_r10", synthetic.terrain(2500, seed=12), 1.0, 0.01, 0.01)
         saliency_case("rough_r05", synthetic.terrain(3000, seed=13, noise=0.15), 0.5, 1e-3, 0.01)
         saliency_case("boulders_r075", synthetic.terrain(2500, seed=14, noise=0.05, boulders=40), 0.75, 1e-3, 0.01)
+        # coincident points (np.unique path, DM_saliency.py:247) and sparse fringes (m < min_points, NaN normals)
+        base = synthetic.terrain(1800, seed=15, noise=0.12)
+        rng = np.random.Generator(np.random.PCG64(15))
+        dup = rng.choice(len(base), 250, replace=False)
+        far = base[:40] + rng.normal(0, 6.0, (40, 3)) + [0, 0, 30.0]
+        pts = np.vstack([base, base[dup], base[dup[:50]], far])
+        saliency_case("dups_sparse_r06", pts[rng.permutation(len(pts))], 0.6, 1e-3, 0.01)
     if "lattice" in which:
         lattice_case()
     if "balltree" in which:
