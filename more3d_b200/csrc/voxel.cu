@@ -170,7 +170,10 @@ extern "C" int more3d_voxel_downsample(const double* xyz, int64_t n, double voxe
     const unsigned nb = (unsigned)((n + VX_THREADS - 1) / VX_THREADS);
     vx_keys<<<nb, VX_THREADS, 0, s>>>(xyz, n, vg, k1, v1);
     count_launches(1);
-    M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, bits, &ks, &vs, s));
+    {
+        ProfScope p2("voxel_sort", s);
+        M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, bits, &ks, &vs, s));
+    }
     vx_heads<<<nb, VX_THREADS, 0, s>>>(ks, n, head);
     M3D_TRY(exclusive_scan_u32(head, head, n, s));
     vx_starts<<<nb, VX_THREADS, 0, s>>>(ks, head, n, starts);
@@ -179,8 +182,11 @@ extern "C" int more3d_voxel_downsample(const double* xyz, int64_t n, double voxe
     uint32_t nvox = 0;
     M3D_CUDA(cudaMemcpyAsync(&nvox, head + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     M3D_CUDA(cudaStreamSynchronize(s));
-    vx_means<<<(unsigned)((nvox + VX_THREADS - 1) / VX_THREADS), VX_THREADS, 0, s>>>(
-        xyz, ks, vs, starts, (int64_t)nvox, vg, out_xyz, out_keys, voxel_of_point);
+    {
+        ProfScope p3("voxel_means", s);
+        vx_means<<<(unsigned)((nvox + VX_THREADS - 1) / VX_THREADS), VX_THREADS, 0, s>>>(
+            xyz, ks, vs, starts, (int64_t)nvox, vg, out_xyz, out_keys, voxel_of_point);
+    }
     count_launches(1);
     M3D_CHECK_LAUNCH();
     dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s); dev_free(head, s); dev_free(starts, s);
