@@ -295,7 +295,12 @@ def main():
     ap.add_argument("--n", type=int, default=10_000_000, help="points per GPU")
     ap.add_argument("--cpu-q", type=int, default=2000, help="CPU-baseline sample: query points per radius (per core)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--radii", default=None, help="comma-separated radii (default 0.5,0.75,1.0 = configs[1]); "
+                                                  "'--n 62500000 --radii 0.5' on 8 GPUs is configs[4] (500 M-point tile)")
     args = ap.parse_args()
+    if args.radii:
+        global RADII
+        RADII = tuple(float(x) for x in args.radii.split(","))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

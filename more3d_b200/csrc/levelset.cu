@@ -281,6 +281,7 @@ struct LsParams {
 };
 
 constexpr int RED_BLOCKS = 592;   // 4 CTAs per SM; fixed so the reduction tree (and the result) is reproducible
+constexpr int STEPB_BLOCKS = 148 * 64;   // step b is a latency-bound gather: more, shorter grid-stride threads
 
 __device__ __forceinline__ double heaviside(double x, double eps) { return 0.5 * (1.0 + 2.0 / M_PI * atan(x / eps)); }   // :319-321
 __device__ __forceinline__ double delta_fn(double x, double eps) { return 1.0 / M_PI * eps / (eps * eps + x * x); }     // :332-333
@@ -620,7 +621,7 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     M3D_TRY(dev_alloc(&laplace, (size_t)n, s)); M3D_TRY(dev_alloc(&dphi, (size_t)3 * n, s));
     M3D_TRY(dev_alloc(&aux, (size_t)4 * n, s));
     M3D_TRY(dev_alloc(&bufA, (size_t)n, s));    M3D_TRY(dev_alloc(&bufB, (size_t)n, s));
-    M3D_TRY(dev_alloc(&part, (size_t)RED_BLOCKS * 4, s));
+    M3D_TRY(dev_alloc(&part, (size_t)STEPB_BLOCKS * 4, s));
     M3D_TRY(dev_alloc(&region, (size_t)4 * channels, s));
     M3D_TRY(dev_alloc(&incs, (size_t)2 * (iterations + 1), s));
     M3D_TRY(dev_alloc(&idx2, (size_t)n, s)); M3D_TRY(dev_alloc(&azc, (size_t)n, s)); M3D_TRY(dev_alloc(&outside, (size_t)n, s));
@@ -637,8 +638,8 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
             ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, epsilon, phi, zeta, c, part);
             ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c);
         }
-        ls_step_b<<<RED_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, bufA, part);
-        ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 2, incs + 2 * it);
+        ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, bufA, part);
+        ls_reduce_final<<<1, 32, 0, s>>>(part, STEPB_BLOCKS, 2, incs + 2 * it);
         if (!alias_last_active) M3D_CUDA(cudaMemcpyAsync(last_active, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // :617
         ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, bufA, active, azc, bufB, outside);
         ls_step_d<<<nb, LS_THREADS, 0, s>>>(g, bufB, outside, bufA);
