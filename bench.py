@@ -292,11 +292,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="points per GPU")
+    ap.add_argument("--points", dest="n", type=int, default=10_000_000, help="points per GPU")
     ap.add_argument("--cpu-q", type=int, default=2000, help="CPU-baseline sample: query points per radius (per core)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--radii", default=None, help="comma-separated radii (default 0.5,0.75,1.0 = configs[1]); "
-                                                  "'--n 62500000 --radii 0.5' on 8 GPUs is configs[4] (500 M-point tile)")
+                                                  "'--points 62500000 --radii 0.5' on 8 GPUs is configs[4] (500 M-point tile)")
     args = ap.parse_args()
     if args.radii:
         global RADII

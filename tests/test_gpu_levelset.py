@@ -135,3 +135,20 @@ def test_solver_mask_init_and_tolerance(g):
     assert np.all(np.isfinite(phi)) and np.abs(phi).max() <= 2 * h + 1e-12
     with pytest.raises(NotImplementedError):
         ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "lmv").run(1, **RUN)
+
+
+@pytest.mark.parametrize("tag,kw", [("a", dict(nu=1e-4, mu=2.5e-3, cap=True)), ("b", dict(nu=0.0, mu=0.0, cap=True)),
+                                    ("c", dict(nu=2e-4, mu=0.0, cap=False))])
+def test_solver_mask_init_two_channels_matches_reference(golden_dir, tag, kw):
+    """initialize_from_mask keeps active / last_active apart, so the re-clamp of (de)activated points
+    (levelsets_func.py:603-608) runs; two cue channels, k = 5; variants without the curvature / regulariser
+    terms and without the cap.  Golden: the verbatim reference (tools/make_golden.py levelset_mask)."""
+    from more3d_b200 import levelsets_func as ls
+    g = np.load(os.path.join(golden_dir, "levelset_mask_3k.npz"))
+    solver = ls.Solver(float(g["h"]), g["zeta"], g["points"], g["neighbors"], (g["t1"], g["t2"]), "chan_vese")
+    solver.initialize_from_mask(g["mask"])
+    assert solver.last_active is not solver.active
+    solver.run(12, stepsize=.01, lambda1=1.5, lambda2=0.5, epsilon=0.8, tolerance=0, **kw)
+    assert np.array_equal(solver.active, g["act_" + tag])
+    assert np.array_equal(solver.last_active, g["last_" + tag])
+    np.testing.assert_allclose(solver.phi, g["phi_" + tag], rtol=1e-8, atol=1e-10)

@@ -1,6 +1,6 @@
 """BASELINE.json configs[4]: a 500 M-point tile, saliency pipeline at r = 0.5, strong scaling.
 
-    torchrun --nproc-per-node 8 bench.py --gpus 8 --n 62500000 --radii 0.5      # 8 GPUs, 62.5 M points each
+    torchrun --nproc-per-node 8 bench.py --gpus 8 --points 62500000 --radii 0.5      # 8 GPUs, 62.5 M points each
     python tools/bench_config5.py 8 62500000                                    # the SAME tile on one GPU
 
 The single-GPU run concatenates the eight strips exactly as the ranks generate them, so both runs process

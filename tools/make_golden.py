@@ -118,9 +118,34 @@ def levelset_case():
     print("levelset active", act10.sum(), solver.active.sum())
 
 
+def levelset_mask_case():
+    """initialize_from_mask (separate active / last_active -> the re-clamp of (de)activated points runs),
+    two cue channels, k = 5, no curvature term in one run and no cap in another."""
+    _, _, ls = ref_harness.load_reference()
+    pts = synthetic.terrain(3000, seed=33, noise=0.05)
+    pts = pts - pts.mean(axis=0)
+    h, k = 0.6, 5
+    neighbors, normals, tangents = ls.build_neighborhoods(pts.copy(), h, k)
+    rng = np.random.Generator(np.random.PCG64(9))
+    zeta = np.column_stack([np.abs(np.sin(pts[:, 0] / 2.0)), rng.random(len(pts)) ** 3])
+    out = dict(points=pts, h=h, k=k, neighbors=neighbors, normals=normals, t1=tangents[0], t2=tangents[1], zeta=zeta)
+    mask = (pts[:, 0] ** 2 + pts[:, 1] ** 2) < 9.0
+    for tag, kw in (("a", dict(nu=1e-4, mu=2.5e-3, cap=True)), ("b", dict(nu=0.0, mu=0.0, cap=True)),
+                    ("c", dict(nu=2e-4, mu=0.0, cap=False))):
+        solver = ls.Solver(h, zeta, pts, neighbors, tangents, "chan_vese")
+        solver.initialize_from_mask(mask)
+        solver.run(12, stepsize=.01, lambda1=1.5, lambda2=0.5, epsilon=0.8, tolerance=0, **kw)
+        out["phi_" + tag] = solver.phi.copy()
+        out["act_" + tag] = solver.active.copy()
+        out["last_" + tag] = solver.last_active.copy()
+    out["mask"] = mask
+    np.savez_compressed(os.path.join(OUT, "levelset_mask_3k.npz"), **out)
+    print("levelset mask case", [int(out["act_" + t].sum()) for t in "abc"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["sal", "lattice", "balltree", "levelset"]
+    which = sys.argv[1:] or ["sal", "lattice", "balltree", "levelset", "levelset_mask"]
     if "sal" in which:
         saliency_case("terrain_r05", synthetic.terrain(3000, seed=11), 0.5, 0.01, 0.01)
         saliency_case("terrain_r10", synthetic.terrain(2500, seed=12), 1.0, 0.01, 0.01)
@@ -139,3 +164,5 @@ if __name__ == "__main__":
         balltree_case()
     if "levelset" in which:
         levelset_case()
+    if "levelset_mask" in which:
+        levelset_mask_case()
