@@ -152,3 +152,32 @@ def test_solver_mask_init_two_channels_matches_reference(golden_dir, tag, kw):
     assert np.array_equal(solver.active, g["act_" + tag])
     assert np.array_equal(solver.last_active, g["last_" + tag])
     np.testing.assert_allclose(solver.phi, g["phi_" + tag], rtol=1e-8, atol=1e-10)
+
+
+def test_solver_against_oracle_other_size_and_params():
+    """A cloud / k / cue / parameter set that no golden covers: CUDA Solver vs oracle/ref_levelset.py (which is
+    itself pinned to the verbatim reference by tests/test_oracle_golden.py), frames supplied by the oracle."""
+    from more3d_b200 import synthetic
+    from more3d_b200 import levelsets_func as ls
+    from oracle import ref_levelset as rl
+    pts = synthetic.terrain(30000, seed=77, noise=0.04)
+    pts -= pts.mean(axis=0)
+    h, k = 0.4, 6
+    nb, n, t1, t2 = rl.knn_frames(pts, k)
+    rng = np.random.Generator(np.random.PCG64(3))
+    zeta = np.column_stack([rng.random(len(pts)) ** 2, np.abs(np.cos(pts[:, 1])), (pts[:, 2] - pts[:, 2].min())])
+    w, D = rl.wls_operator(pts, nb, t1, t2, 3 * h)
+    kw = dict(stepsize=.008, nu=3e-4, mu=1e-3, lambda1=0.7, lambda2=1.3, epsilon=1.2, cap=True, tolerance=0)
+    phi0 = rl.init_voxels(pts, 1.5, 2 * h)
+    act0 = rl.zero_crossings(phi0, nb, np.arange(len(pts)))
+    st = dict(points=pts, nbrs=nb, t1=t1, t2=t2, w=w, D=D, h=h, zeta=zeta, phi=phi0.copy(), active=act0, last_active=act0,
+              alias=True)
+    rl.run(st, 8, **kw)
+    nb2, n2, tang = ls.build_neighborhoods(pts.copy(), h, k, normals=n)
+    assert np.array_equal(nb2, nb)
+    solver = ls.Solver(h, zeta, pts, nb2, tang, "chan_vese")
+    solver.initialize_from_voxels(1.5)
+    assert np.array_equal(solver.phi, phi0) and np.array_equal(solver.active, act0)
+    solver.run(8, **kw)
+    assert np.array_equal(solver.active, st["active"])
+    np.testing.assert_allclose(solver.phi, st["phi"], rtol=1e-8, atol=1e-10)

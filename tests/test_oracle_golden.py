@@ -119,3 +119,49 @@ def test_otsu_and_voxel_restatements():
     assert len(means) == len(np.unique(k, axis=0))
     j = np.nonzero(np.all(k == keys[3], axis=1))[0]
     assert np.allclose(means[3], pts[j].mean(0))
+
+
+def test_levelset_oracle_matches_reference(golden_dir):
+    """oracle/ref_levelset.py against the verbatim-reference goldens (frames, WLS operator, 25 iterations)."""
+    from oracle import ref_levelset as rl
+    g = load(golden_dir, "levelset_4k")
+    pts, h, k = g["points"], float(g["h"]), int(g["k"])
+    nb, n, t1, t2 = rl.knn_frames(pts, k)
+    assert np.array_equal(nb, g["neighbors"])
+    np.testing.assert_allclose(n, g["normals"], atol=1e-14)
+    np.testing.assert_allclose(t1, g["t1"], atol=1e-13)
+    np.testing.assert_allclose(t2, g["t2"], atol=1e-13)
+    w, D = rl.wls_operator(pts, nb, g["t1"], g["t2"], 3 * h)
+    np.testing.assert_allclose(w, g["weights"], rtol=1e-14)
+    np.testing.assert_allclose(D[:300], g["D"], rtol=1e-9, atol=1e-12)
+    phi0 = rl.init_voxels(pts, 2.0, 2 * h)
+    assert np.array_equal(phi0, g["phi0"])
+    act0 = rl.zero_crossings(phi0, nb, np.arange(len(pts)))
+    assert np.array_equal(act0, g["active0"])
+    phi = rl.smooth(phi0, np.arange(len(pts)), nb, w)
+    np.testing.assert_allclose(phi, g["phi_s"], rtol=1e-14, atol=1e-15)
+    st = dict(points=pts, nbrs=nb, t1=g["t1"], t2=g["t2"], w=w, D=D, h=h, zeta=g["zeta"], phi=phi, active=act0,
+              last_active=act0, alias=True)
+    kw = dict(stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
+    assert rl.run(st, 10, **kw) is False
+    assert np.array_equal(st["active"], g["act10"])
+    np.testing.assert_allclose(st["phi"], g["phi10"], rtol=1e-9, atol=1e-11)
+    rl.run(st, 15, **kw)
+    assert np.array_equal(st["active"], g["act25"])
+    np.testing.assert_allclose(st["phi"], g["phi25"], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("tag,kw", [("a", dict(nu=1e-4, mu=2.5e-3, cap=True)), ("b", dict(nu=0.0, mu=0.0, cap=True)),
+                                    ("c", dict(nu=2e-4, mu=0.0, cap=False))])
+def test_levelset_oracle_mask_init(golden_dir, tag, kw):
+    from oracle import ref_levelset as rl
+    g = load(golden_dir, "levelset_mask_3k")
+    pts, h = g["points"], float(g["h"])
+    w, D = rl.wls_operator(pts, g["neighbors"], g["t1"], g["t2"], 3 * h)
+    phi = np.where(g["mask"], -2 * h, 2 * h)
+    act = rl.zero_crossings(phi, g["neighbors"], np.arange(len(pts)))
+    st = dict(points=pts, nbrs=g["neighbors"], t1=g["t1"], t2=g["t2"], w=w, D=D, h=h, zeta=g["zeta"], phi=phi,
+              active=act, last_active=act.copy(), alias=False)
+    rl.run(st, 12, stepsize=.01, lambda1=1.5, lambda2=0.5, epsilon=0.8, tolerance=0, **kw)
+    assert np.array_equal(st["active"], g["act_" + tag]) and np.array_equal(st["last_active"], g["last_" + tag])
+    np.testing.assert_allclose(st["phi"], g["phi_" + tag], rtol=1e-9, atol=1e-11)

@@ -122,7 +122,27 @@ def config4(n, iters=200):
         times.append(t)
         rms.append(solver.rmsc_history[-1])
     phi = solver.phi
-    return {"config": 4, "points": n, "k": k, "h": h, "neighbourhoods_s": t_nb, "solver_init_s": t_solver, "singular": solver.diff.singular,
+    # CPU reference leg: the level-set oracle (numpy restatement of the reference) on a 1 M-point tile, 3 iterations
+    from oracle import ref_levelset as rl
+    m = min(n, 1_000_000)
+    sub = synthetic.terrain(m, seed=4)
+    sub -= sub.mean(axis=0)
+    t0 = time.perf_counter()
+    cnb, cn, ct1, ct2 = rl.knn_frames(sub, k)
+    t_cpu_nb = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cw, cD = rl.wls_operator(sub, cnb, ct1, ct2, 3 * h)
+    t_cpu_op = time.perf_counter() - t0
+    cphi = rl.init_voxels(sub, 2.0, 2 * h)
+    cact = rl.zero_crossings(cphi, cnb, np.arange(m))
+    st = dict(points=sub, nbrs=cnb, t1=ct1, t2=ct2, w=cw, D=cD, h=h, zeta=np.abs(np.sin(sub[:, :1])), phi=cphi, active=cact,
+              last_active=cact, alias=True)
+    t0 = time.perf_counter()
+    rl.run(st, 3, **run)
+    t_cpu_it = (time.perf_counter() - t0) / 3
+    cpu = {"points": m, "neighbourhoods_s": t_cpu_nb, "operator_s": t_cpu_op, "s_per_iteration": t_cpu_it,
+           "point_iterations_per_s": m / t_cpu_it, "cores": "numpy/LAPACK threads", "kind": "oracle port"}
+    return {"config": 4, "cpu_reference": cpu, "points": n, "k": k, "h": h, "neighbourhoods_s": t_nb, "solver_init_s": t_solver, "singular": solver.diff.singular,
             "run_ms_per_cycle": times, "iterations": 4 * per, "ms_per_iteration": sum(times) / (4 * per),
             "point_iterations_per_s": n * 4 * per / (sum(times) * 1e-3), "active_start": a0, "active_end": int(solver.active.sum()),
             "rmsc_last_per_cycle": rms, "phi_within_cap": bool(np.abs(phi).max() <= 2 * h + 1e-12), "phi_finite": bool(np.all(np.isfinite(phi)))}
