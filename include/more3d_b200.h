@@ -167,13 +167,15 @@ int more3d_ls_frames(const double* xyz, int64_t n, int k, const int64_t* knn2k, 
                      double* normals, double* t1, double* t2, int32_t* neighbors, void* stream);
 
 /* Derivative.__init__ (levelsets_func.py:246-275): per-point weighted-least-squares operator.  weights:
- * n x k f64 out (self.weights); D: n x 5 x (k+3) f64 out or NULL (self.D); *singular_h = 1 if some
+ * n x k f64 (self.weights) -- written when weights_given == 0, read when != 0 (numpy's array pow in wendland
+ * is host-CPU dependent in the last bit; a caller reproducing a reference run bit for bit supplies the
+ * reference's weights); D: n x 5 x (k+3) f64 out or NULL (self.D); *singular_h = 1 if some
  * singular value is < 1e-12 (where the reference drops into pdb, :269-271).  The returned graph keeps the
  * device-resident structure-of-arrays form used by the calls below. */
 typedef struct more3d_ls_graph more3d_ls_graph;
 int more3d_ls_graph_create(const double* xyz, int64_t n, int k, const int32_t* neighbors, const double* t1,
-                           const double* t2, double max_d, double* weights, double* D, int* singular_h,
-                           void* stream, more3d_ls_graph** out);
+                           const double* t2, double max_d, int weights_given, double* weights, double* D,
+                           int* singular_h, void* stream, more3d_ls_graph** out);
 int more3d_ls_graph_destroy(more3d_ls_graph* g);
 /* Derivative.__call__ (:277-291): out4[i] = (dx, dy, ddx, ddy) of u at the points with mask[i] != 0
  * (mask NULL = all); zeros elsewhere.  u: n f64; out4: n x 4 f64. */

@@ -41,7 +41,7 @@ SIGNATURES = {
     "more3d_lod_assemble": [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp],
     "more3d_select_flagged": [_vp, _i64, _vp, C.POINTER(_i64), _vp],
     "more3d_ls_frames": [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp],
-    "more3d_ls_graph_create": [_vp, _i64, _i32, _vp, _vp, _vp, _f64, _vp, _vp, C.POINTER(_i32), _vp, C.POINTER(_vp)],
+    "more3d_ls_graph_create": [_vp, _i64, _i32, _vp, _vp, _vp, _f64, _i32, _vp, _vp, C.POINTER(_i32), _vp, C.POINTER(_vp)],
     "more3d_ls_graph_destroy": [_vp],
     "more3d_ls_diff": [_vp, _vp, _vp, _vp, _vp],
     "more3d_ls_smooth": [_vp, _vp, _vp, _vp, _vp],

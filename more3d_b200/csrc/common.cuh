@@ -149,6 +149,30 @@ __device__ __forceinline__ uint64_t sortable_key(double v) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
+// numpy's float64 add.reduce over a contiguous axis of n <= 128 elements (pairwise_sum in
+// numpy/_core/src/umath/loops_utils.h.src): plain left-to-right for n < 8, otherwise eight running sums over
+// blocks of 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail left to right.  Reproduced
+// bit for bit because `smooth` feeds the |phi| > max_val test of the next iteration: a weighted mean of equal
+// clamped values lands within 1 ulp of +-max_val, and which side decides whether the point is re-smoothed.
+__device__ __forceinline__ double np_pairwise_sum(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
 // order-preserving float <-> uint mapping for atomic min/max
 __device__ __forceinline__ unsigned f32_ordered(float f) {
     unsigned u = __float_as_uint(f);

@@ -60,17 +60,29 @@ __global__ void __launch_bounds__(LS_THREADS) ls_frames(const double* __restrict
 // ------------------------------------------------------------------------------------------
 // K11b: WLS operator = pseudo-inverse of the (k+3) x 5 design matrix, one-sided Jacobi SVD per point
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double wendland(double x, double h) {   // levelsets_func.py:92-97
+// (1 - x/h)**4 * (4*x/h + 1) (levelsets_func.py:92-97) with every operation rounded as written and a^4
+// correctly rounded (double-double: two FMA error terms, one final rounding) -- what libm pow() returns.
+// numpy's ARRAY power is a SIMD pow whose last bits depend on the host CPU's dispatch (measured: 3 % of the
+// weights differ by 1-2 ulp from libm on an AVX-512 host), so the reference's own weights are machine
+// dependent; callers that need a bit-identical trajectory pass the weights in (weights_given).
+__device__ __forceinline__ double wendland(double x, double h) {
     if (!(x < h)) return 0.0;
-    const double a = 1.0 - x / h;
-    const double a2 = a * a;
-    return a2 * a2 * (4.0 * x / h + 1.0);
+    const double a = __dsub_rn(1.0, __ddiv_rn(x, h));
+    const double p = __dmul_rn(a, a);
+    const double e = __fma_rn(a, a, -p);               // a^2 = p + e exactly
+    const double q = __dmul_rn(p, p);
+    const double e2 = __fma_rn(p, p, -q);              // p^2 = q + e2 exactly
+    const double c = __fma_rn(2.0 * p, e, e2);         // a^4 = q + (e2 + 2 p e) + O(e^2)
+    const double a4 = __dadd_rn(q, c);
+    const double b = __dadd_rn(__ddiv_rn(__dmul_rn(4.0, x), h), 1.0);
+    return __dmul_rn(a4, b);
 }
 
 __global__ void __launch_bounds__(128) ls_derivative_init(const double* __restrict__ xyz, int64_t n, int k,
                                                           const int32_t* __restrict__ nbr /* n x k */,
                                                           const double* __restrict__ t1, const double* __restrict__ t2,
-                                                          double max_d, double* __restrict__ w_aos /* n x k */,
+                                                          double max_d, int weights_given,
+                                                          double* __restrict__ w_aos /* n x k, in when given */,
                                                           double* __restrict__ D /* n x 5 x (k+3) or NULL */,
                                                           double* __restrict__ w_soa, double* __restrict__ E,
                                                           double* __restrict__ cst, int32_t* __restrict__ nbr_soa,
@@ -90,8 +102,10 @@ __global__ void __launch_bounds__(128) ls_derivative_init(const double* __restri
         const double dx = xyz[3 * q] - px, dy = xyz[3 * q + 1] - py, dz = xyz[3 * q + 2] - pz;
         const double x_ = dx * ax + dy * ay + dz * az;     // :251-254
         const double y_ = dx * bx + dy * by + dz * bz;
-        const double dist = sqrt(dx * dx + dy * dy + dz * dz);
-        const double wj = (sqrt(wendland(dist, max_d)) + 1e-8) / (1.0 + 1e-8);   // :264-266
+        // np.linalg.norm(..., axis=-1) = sqrt((dx^2 + dy^2) + dz^2), every product rounded
+        const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        const double wj = weights_given ? w_aos[i * k + j]
+                                        : __ddiv_rn(__dadd_rn(sqrt(wendland(dist, max_d)), 1e-8), 1.0 + 1e-8);   // :264-266
         w[j] = wj;
         A[0 * rows + j] = x_ * wj;                         // :256-260, :267
         A[1 * rows + j] = y_ * wj;
@@ -200,13 +214,14 @@ __device__ __forceinline__ void wls_apply(const LsGraph& g, int64_t i, const dou
 }
 
 __device__ __forceinline__ double smooth_at(const LsGraph& g, int64_t i, const double* __restrict__ u) {   // :350-358
-    double s = 0, ws = 0;
+    // (u[nbs] * w).sum(axis=-2) / w.sum(axis=-1) with numpy's exact rounding and summation order
+    double pr[LS_MAX_K], wt[LS_MAX_K];
     for (int j = 0; j < g.k; ++j) {
         const double wj = g.w[(int64_t)j * g.n + i];
-        s += u[g.nbr[(int64_t)j * g.n + i]] * wj;
-        ws += wj;
+        wt[j] = wj;
+        pr[j] = __dmul_rn(u[g.nbr[(int64_t)j * g.n + i]], wj);
     }
-    return s / ws;
+    return __ddiv_rn(np_pairwise_sum(pr, g.k), np_pairwise_sum(wt, g.k));
 }
 
 __global__ void __launch_bounds__(LS_THREADS) ls_diff_kernel(LsGraph g, const double* __restrict__ u,
@@ -518,8 +533,8 @@ extern "C" int more3d_ls_frames(const double* xyz, int64_t n, int k, const int64
 }
 
 extern "C" int more3d_ls_graph_create(const double* xyz, int64_t n, int k, const int32_t* neighbors, const double* t1,
-                                      const double* t2, double max_d, double* weights, double* D, int* singular_h,
-                                      void* stream, more3d_ls_graph** out) {
+                                      const double* t2, double max_d, int weights_given, double* weights, double* D,
+                                      int* singular_h, void* stream, more3d_ls_graph** out) {
     M3D_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     M3D_REQUIRE(xyz && neighbors && t1 && t2 && weights && n > 0, "NULL / empty argument");
@@ -540,7 +555,7 @@ extern "C" int more3d_ls_graph_create(const double* xyz, int64_t n, int k, const
         return rc;
     }
     cudaMemsetAsync(status, 0, sizeof(int), s);
-    ls_derivative_init<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(xyz, n, k, neighbors, t1, t2, max_d, weights, D, G->w,
+    ls_derivative_init<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(xyz, n, k, neighbors, t1, t2, max_d, weights_given, weights, D, G->w,
                                                                    G->E, G->cst, G->nbr, G->t1, G->t2, status);
     count_launches(1);
     int st = 0;

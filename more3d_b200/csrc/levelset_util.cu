@@ -15,13 +15,21 @@ __global__ void __launch_bounds__(256) smooth_raw_kernel(const double* __restric
     const int64_t i = t / cols;
     const int c = (int)(t - i * cols);
     if (mask && !mask[i]) { out[t] = u[t]; return; }
-    double s = 0, ws = 0;
+    // numpy's rounding and order: the weights are summed pairwise (contiguous axis); the products pairwise for
+    // a 1-D u (shape (m, k, 1): the k axis is contiguous) and left to right for an (N, C >= 2) u
+    double pr[64], wt[64];
     for (int j = 0; j < k; ++j) {
         const double wj = w[i * k + j];
-        s += u[nbs[i * k + j] * cols + c] * wj;
-        ws += wj;
+        wt[j] = wj;
+        pr[j] = __dmul_rn(u[nbs[i * k + j] * cols + c], wj);
     }
-    out[t] = s / ws;
+    double s;
+    if (cols == 1) s = np_pairwise_sum(pr, k);
+    else {
+        s = 0.0;
+        for (int j = 0; j < k; ++j) s = __dadd_rn(s, pr[j]);
+    }
+    out[t] = __ddiv_rn(s, np_pairwise_sum(wt, k));
 }
 
 enum { OP_HEAVISIDE = 0, OP_DELTA = 1, OP_DP = 2, OP_WENDLAND = 3 };
@@ -61,7 +69,7 @@ using namespace m3d;
 extern "C" int more3d_ls_smooth_raw(const double* u, int cols, const int64_t* nbs, const double* w, int64_t n, int k,
                                     const uint8_t* mask, double* out, void* stream) {
     M3D_REQUIRE(u && nbs && w && out && u != out, "NULL / aliased argument");
-    M3D_REQUIRE(n > 0 && k >= 1 && cols >= 1, "bad shape");
+    M3D_REQUIRE(n > 0 && k >= 1 && k <= 64 && cols >= 1, "bad shape (1 <= k <= 64)");
     cudaStream_t s = (cudaStream_t)stream;
     smooth_raw_kernel<<<(unsigned)((n * cols + 255) / 256), 256, 0, s>>>(u, cols, nbs, w, n, k, mask, out);
     count_launches(1);

@@ -180,8 +180,11 @@ def build_neighborhoods(points, h, k, normals=None, return_device=False):
 
 
 class Derivative:
-    def __init__(self, points, max_d, neighbors, tangents):
-        """precalculate inverse for WLS approximation via SVD (:246-275)"""
+    def __init__(self, points, max_d, neighbors, tangents, weights=None):
+        """precalculate inverse for WLS approximation via SVD (:246-275).
+        ``weights`` (extension): (N, k) array used instead of the computed Wendland weights -- numpy's array
+        power makes the reference's own weights host-CPU dependent in the last bit, and ``smooth`` decides ties
+        at the cap with them, so reproducing a given reference run bit for bit needs its weights."""
         lib = _lib.load()
         pts = _dev(points)
         n = int(pts.shape[0])
@@ -200,14 +203,16 @@ class Derivative:
         self._nb = self._inv[nb[self._perm]].to(torch.int32).contiguous()
         self._k = int(self._nb.shape[1])
         self._t1, self._t2 = _dev(tangents[0])[self._perm].contiguous(), _dev(tangents[1])[self._perm].contiguous()
-        self._w = torch.empty((n, self._k), dtype=torch.float64, device="cuda")
+        given = weights is not None
+        self._w = _dev(weights)[self._perm].contiguous() if given else torch.empty((n, self._k), dtype=torch.float64, device="cuda")
         self._D = None
         self._max_d = float(max_d)
         self._host = {}
         h = C.c_void_p()
         sing = C.c_int(0)
         check(lib.more3d_ls_graph_create(ptr(self._pts), n, self._k, ptr(self._nb), ptr(self._t1), ptr(self._t2),
-                                         self._max_d, ptr(self._w), None, C.byref(sing), stream_ptr(), C.byref(h)))
+                                         self._max_d, 1 if given else 0, ptr(self._w), None, C.byref(sing), stream_ptr(),
+                                         C.byref(h)))
         self._g = h
         self.singular = bool(sing.value)       # the reference opens pdb here (:269-271); we flag it instead
         self._neighbors_in, self._points_in, self._tangents_in = neighbors, points, tangents
@@ -252,10 +257,10 @@ class Derivative:
             lib = _lib.load()
             n = int(self._pts.shape[0])
             D = torch.empty((n, 5, self._k + 3), dtype=torch.float64, device="cuda")
-            w = torch.empty_like(self._w)
+            w = self._w.clone()
             h, sing = C.c_void_p(), C.c_int(0)
             check(lib.more3d_ls_graph_create(ptr(self._pts), n, self._k, ptr(self._nb), ptr(self._t1), ptr(self._t2),
-                                             self._max_d, ptr(w), ptr(D), C.byref(sing), stream_ptr(), C.byref(h)))
+                                             self._max_d, 1, ptr(w), ptr(D), C.byref(sing), stream_ptr(), C.byref(h)))
             lib.more3d_ls_graph_destroy(h)
             return D[self._inv].cpu().numpy()
         return self._h("D", make)
@@ -323,14 +328,14 @@ class _Mirror:
 
 
 class Solver:
-    def __init__(self, h, zeta, points, neighbors, tangents, active_contour_model='chan_vese'):
-        """level set solver (:362-384)"""
+    def __init__(self, h, zeta, points, neighbors, tangents, active_contour_model='chan_vese', weights=None):
+        """level set solver (:362-384); ``weights``: see :class:`Derivative`"""
         _print('initializing solver')
         zeta = np.asarray(zeta.cpu().numpy() if isinstance(zeta, torch.Tensor) else zeta, dtype=np.float64)
         self.h = h
         self.max_val = 2 * h
         _print('initializing WLS derivatives', 1)
-        self.diff = Derivative(points, 3 * h, neighbors, tangents)
+        self.diff = Derivative(points, 3 * h, neighbors, tangents, weights=weights)
         self._phi = self._mirror(np.zeros(zeta.shape[:-1]))
         self._zeta = self._mirror(zeta.copy())
         self._active = self._mirror(np.zeros(self._phi.host.shape, dtype='bool'))

@@ -132,8 +132,11 @@ def test_levelset_oracle_matches_reference(golden_dir):
     np.testing.assert_allclose(t1, g["t1"], atol=1e-13)
     np.testing.assert_allclose(t2, g["t2"], atol=1e-13)
     w, D = rl.wls_operator(pts, nb, g["t1"], g["t2"], 3 * h)
-    np.testing.assert_allclose(w, g["weights"], rtol=1e-14)
+    # numpy's array pow (wendland's **4) is SIMD code whose last bits depend on the host CPU: identical on the
+    # machine that generated the golden, within 2 ulp elsewhere.  The run below uses the golden's weights.
+    assert np.abs(w.view(np.int64) - g["weights"].view(np.int64)).max() <= 2
     np.testing.assert_allclose(D[:300], g["D"], rtol=1e-9, atol=1e-12)
+    w = g["weights"]
     phi0 = rl.init_voxels(pts, 2.0, 2 * h)
     assert np.array_equal(phi0, g["phi0"])
     act0 = rl.zero_crossings(phi0, nb, np.arange(len(pts)))
