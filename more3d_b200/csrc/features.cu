@@ -139,9 +139,8 @@ __global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const doubl
 struct D4 { double x, y, z, w; };
 // half h (0/1) of a 64-B feature record as two LDG.128 through the read-only path
 __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
-    const double2* p = reinterpret_cast<const double2*>(f) + 2 * h;
-    const double2 a = __ldg(p), b = __ldg(p + 1);
-    D4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    D4 r;
+    ldg256(reinterpret_cast<const char*>(f) + 32 * h, r.x, r.y, r.z, r.w);
     return r;
 }
 

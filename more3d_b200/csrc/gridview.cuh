@@ -63,11 +63,18 @@ __device__ __forceinline__ Filter32 filter_for_query(const GridView& g, Filter32
     return f;
 }
 
+// One 256-bit read-only load per 32-byte record (sm_100: LDG.E.256) instead of two LDG.128.  The hot kernels
+// are bound by the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 84-92 %); measured, the wider load
+// changes nothing (8.3 vs 8.5 ms, 15.9 vs 15.8 ms): the pipe moves 32 B per lane per candidate either way
+// (1 KiB per warp = 8 wavefronts), so only SMALLER records would help, not fewer instructions.
+__device__ __forceinline__ void ldg256(const void* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 __device__ __forceinline__ PointRec load_rec(const PointRec* __restrict__ rec, int64_t j) {
-    const double2* p = reinterpret_cast<const double2*>(rec + j);
-    double2 a = __ldg(p), b = __ldg(p + 1);
     PointRec r;
-    r.x = a.x; r.y = a.y; r.z = b.x; r.idx = __double_as_longlong(b.y);
+    double w;
+    ldg256(rec + j, r.x, r.y, r.z, w);
+    r.idx = __double_as_longlong(w);
     return r;
 }
 
