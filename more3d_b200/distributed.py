@@ -96,6 +96,45 @@ def allreduce_minmax(minmax, group=None):
     return minmax
 
 
+def otsu_from_counts(counts, edges):
+    """skimage.filters.threshold_otsu on a (globally reduced) 256-bin histogram -- host side, 256 entries."""
+    counts = np.asarray(counts, dtype=np.float64)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    with np.errstate(all="ignore"):
+        w1 = np.cumsum(counts)
+        w2 = np.cumsum(counts[::-1])[::-1]
+        m1 = np.cumsum(counts * centers) / w1
+        m2 = (np.cumsum((counts * centers)[::-1]) / w2[::-1])[::-1]
+        var12 = w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2
+    return float(centers[int(np.argmax(var12))])
+
+
+def global_otsu(values, local_histogram, group=None):
+    """Otsu threshold of a column that is sharded over the ranks (Downsample.py:54 on the whole cloud):
+    all-reduce(min, max) -> common bin edges -> local 256-bin histograms -> all-reduce(sum) -> host scan.
+    values: this rank's float32 / float64 tensor; local_histogram(values, edges) -> int64 tensor of 256 counts
+    (the CUDA kernel on GPUs, numpy in the gloo tests)."""
+    lo_hi = torch.stack([values.min().double(), -values.max().double()])
+    dist.all_reduce(lo_hi, op=dist.ReduceOp.MIN, group=group)
+    lo, hi = float(lo_hi[0]), -float(lo_hi[1])
+    if lo == hi:
+        return lo
+    edges = np.linspace(lo, hi, 257)
+    hist = local_histogram(values, edges)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return otsu_from_counts(hist.cpu().numpy(), edges)
+
+
+def cuda_histogram(values, edges):
+    lib = _lib.load()
+    v = values.contiguous()
+    with torch.cuda.device(v.device):
+        de = torch.from_numpy(edges).to(v.device)
+        hist = torch.empty(256, dtype=torch.int64, device=v.device)
+        check(lib.more3d_histogram256(ptr(v), v.element_size(), int(v.numel()), ptr(de), ptr(hist), stream_ptr()))
+    return hist
+
+
 def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=None, out_host=None):
     """Saliency of the OWNED points of one strip.  own: (n,3) device f64; ghosts: (g,3) device f64
     (points of the neighbouring strips within 2*r_max).  reduce_minmax(minmax) makes the extrema
@@ -173,8 +212,11 @@ class StripSaliency:
         right = gather_rows(own, band_select(own, 0, self.x_hi - self.halo, np.inf))
         from_left, from_right = exchange_halos(left, right, self.rank, self.world)
         ghosts = torch.cat([from_left, from_right], dim=0)
-        return strip_saliency(own, ghosts, self.radii, self.params, self.cw,
-                              reduce_minmax=allreduce_minmax, out_host=out_host)
+        out, pc = strip_saliency(own, ghosts, self.radii, self.params, self.cw,
+                                 reduce_minmax=allreduce_minmax, out_host=out_host)
+        # the global saliency histogram (256 bins, one all-reduce) and its Otsu threshold, per radius
+        self.otsu = {r: global_otsu(out[r], cuda_histogram) for r in self.radii}
+        return out, pc
 
     def step_resident(self):
         return self._run(self.resident, None)[0]

@@ -40,6 +40,15 @@ def _worker(rank, world, port, ret):
         mm = torch.tensor([1.0 + rank, 5.0 - rank, -2.0 * rank, 3.0 * rank], dtype=torch.float32)
         allreduce_minmax(mm)
         ok = ok and mm.tolist() == [1.0, 5.0, -2.0 * (world - 1), 3.0 * (world - 1)]
+        # sharded Otsu: all-reduced range + histogram == Otsu of the whole column (oracle restatement)
+        from more3d_b200.distributed import global_otsu
+        from oracle import ref_path as rp
+        col = (np.random.Generator(np.random.PCG64(7)).random(5000) ** 3).astype(np.float32)
+        mine = torch.from_numpy(col[rank::world].copy())
+
+        def np_hist(v, edges):
+            return torch.from_numpy(np.histogram(v.numpy().astype(np.float64), bins=edges)[0].astype(np.int64))
+        ok = ok and global_otsu(mine, np_hist) == rp.otsu_threshold(col)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
