@@ -197,6 +197,37 @@ int more3d_ls_run(const more3d_ls_graph* g, double* phi, const double* zeta, int
                   double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
                   double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream);
 
+/* The same iteration one phase at a time, for hosts that exchange ghost values between the phases
+ * (multi-GPU x-strips).  Points [0, n_own) of the graph are owned by the caller, the rest are ghosts
+ * (their neighbour rows list themselves; their phi / aux are supplied by the owner between phases).
+ * phase 0: re-clamp (de)activated points; 1: derivatives -> idx2, laplace, dphi, aux; 2: local region sums of
+ * the owned points -> region[4*channels] (all-reduce them); 3: update -> bufA, incs[2] = {sum inc^2, count};
+ * 4: zero crossings -> azc, cap -> bufB / outside; 5: smooth capped points bufB -> bufA; 6: smooth lonely
+ * points bufA -> phi; 7: active = azc dilated (ghost flags go back to their owners).  All arrays have n
+ * entries unless noted; part: more3d_ls_scratch_doubles() doubles. */
+typedef struct {
+    double* phi;
+    const double* zeta;
+    uint8_t* active;
+    uint8_t* last_active;
+    uint8_t* idx2;
+    double* laplace;
+    double* dphi;      /* 3n */
+    double* aux;       /* 4n */
+    double* bufA;
+    double* bufB;
+    uint8_t* azc;
+    uint8_t* outside;
+    double* part;
+    double* region;    /* 4 * channels */
+    double* incs;      /* 2 */
+    int64_t n_own;
+    double stepsize, nu, mu, lambda1, lambda2, epsilon, max_val;
+    int channels, cap;
+} more3d_ls_state;
+int more3d_ls_phase(const more3d_ls_graph* g, int phase, const more3d_ls_state* st, void* stream);
+int64_t more3d_ls_scratch_doubles(void);
+
 /* Module-level helpers of levelsets_func.py on the caller's own arrays: smooth (:350-358) with u: n x cols
  * f64, nbs: n x k int64, w: n x k f64, mask: n uint8 or NULL; and the elementwise heaviside (op 0, param =
  * epsilon; :319-321), delta (op 1, param = epsilon; :332-333), dp (op 2; :336-342), wendland (op 3, param = h;

@@ -49,6 +49,7 @@ SIGNATURES = {
     "more3d_ls_init_voxels": [_vp, _i64, _f64, _f64, _vp, _vp],
     "more3d_ls_run": [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64, _f64, _i32,
                       _f64, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(_i32), _vp],
+    "more3d_ls_phase": [_vp, _i32, _vp, _vp],
     "more3d_ls_smooth_raw": [_vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "more3d_ls_elementwise": [_i32, _vp, _f64, _i64, _vp, _vp],
     "more3d_normals_from_knn": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
@@ -85,6 +86,8 @@ def load(build_if_needed=True):
     lib.more3d_version.argtypes = []
     lib.more3d_launch_count.restype = C.c_int64
     lib.more3d_launch_count.argtypes = []
+    lib.more3d_ls_scratch_doubles.restype = C.c_int64
+    lib.more3d_ls_scratch_doubles.argtypes = []
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name, None)
         if fn is None:

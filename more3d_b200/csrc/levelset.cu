@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) ls_derivative_init(const double* __restri
         if (sqrt(s2) < 1e-12) bad = true;                  // the reference drops into pdb here, :269-271
         inv_s2[c] = 1.0 / s2;
     }
-    if (bad) atomicExch(status, 1);
+    if (bad && nbr[i * k] != (int32_t)i) atomicExch(status, 1);   // rows that list themselves are ghost placeholders
     // D = V S^-1 U^T = V S^-2 (U S)^T ; row r, column j                     :272
     const int rsel[4] = {0, 1, 3, 4};
     for (int r = 0; r < 5; ++r) {
@@ -686,3 +686,73 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     dev_free(part, s); dev_free(region, s); dev_free(incs, s); dev_free(idx2, s); dev_free(azc, s); dev_free(outside, s);
     return MORE3D_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// One phase of the iteration at a time, for hosts that interleave exchanges between the phases (multi-GPU:
+// ghost values of phi / aux travel between ranks, the region sums and the RMS change are all-reduced).
+// Points [0, n_own) are owned by this rank, the rest are ghosts whose values the owner supplies.
+// ------------------------------------------------------------------------------------------
+extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d_ls_state* st, void* stream) {
+    M3D_REQUIRE(G && st, "NULL argument");
+    M3D_REQUIRE(st->n_own >= 0 && st->n_own <= G->n, "n_own out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = G->n;
+    LsGraph g = view(G);
+    LsParams p;
+    p.stepsize = st->stepsize; p.nu = st->nu; p.mu = st->mu; p.lambda1 = st->lambda1; p.lambda2 = st->lambda2;
+    p.epsilon = st->epsilon; p.max_val = st->max_val; p.cap = st->cap; p.channels = st->channels;
+    const unsigned nb = (unsigned)((n + LS_THREADS - 1) / LS_THREADS);
+    switch (phase) {
+    case 0:   // re-clamp (de)activated points
+        ls_reclamp<<<nb, LS_THREADS, 0, s>>>(n, st->active, st->last_active, st->max_val, st->phi);
+        count_launches(1);
+        break;
+    case 1:   // derivatives of phi at the active points -> idx2, laplace, dphi, aux
+        if (st->nu > 0 || st->mu > 0) {
+            ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, st->phi, st->active, st->idx2, st->laplace, st->dphi, st->aux);
+            count_launches(1);
+        } else {
+            M3D_CUDA(cudaMemcpyAsync(st->idx2, st->active, (size_t)n, cudaMemcpyDeviceToDevice, s));
+        }
+        break;
+    case 2:   // local region sums over the OWNED points -> region[4 * channels] (caller all-reduces)
+        for (int c = 0; c < st->channels; ++c) {
+            ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(st->n_own, st->channels, st->epsilon, st->phi, st->zeta, c,
+                                                                st->part);
+            ls_reduce_final<<<1, 32, 0, s>>>(st->part, RED_BLOCKS, 4, st->region + 4 * c);
+        }
+        count_launches(2 * st->channels);
+        break;
+    case 3:   // update -> bufA (= phi + increment), incs[0..1] = local sum inc^2, count
+        ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, st->phi, st->idx2, st->laplace, st->dphi, st->aux, st->zeta,
+                                                      st->region, st->bufA, st->part);
+        ls_reduce_final<<<1, 32, 0, s>>>(st->part, STEPB_BLOCKS, 2, st->incs);
+        count_launches(2);
+        break;
+    case 4:   // zero crossings of the active points (-> azc), cap (-> bufB, outside)
+        ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, st->bufA, st->active, st->azc, st->bufB, st->outside);
+        count_launches(1);
+        break;
+    case 5:   // smooth the capped points: bufB -> bufA
+        ls_step_d<<<nb, LS_THREADS, 0, s>>>(g, st->bufB, st->outside, st->bufA);
+        count_launches(1);
+        break;
+    case 6:   // smooth the lonely points: bufA -> phi
+        ls_step_e<<<nb, LS_THREADS, 0, s>>>(g, st->bufA, st->phi);
+        count_launches(1);
+        break;
+    case 7:   // active = azc dilated by one neighbourhood (ghost flags are sent to their owners by the caller)
+        M3D_CUDA(cudaMemsetAsync(st->active, 0, (size_t)n, s));
+        ls_step_f<<<nb, LS_THREADS, 0, s>>>(g, st->azc, st->active);
+        count_launches(1);
+        break;
+    default:
+        set_error("unknown level-set phase %d", phase);
+        return MORE3D_E_INVALID;
+    }
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}
+
+extern "C" int64_t more3d_ls_scratch_doubles(void) { return (int64_t)STEPB_BLOCKS * 4; }

@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.more3d_version() >= 100
     # every declared int-returning entry point has a ctypes signature in the binding
     unbound = [n for n in declared_symbols()
-               if n not in _lib.SIGNATURES and n not in ("more3d_version", "more3d_last_error", "more3d_launch_count")]
+               if n not in _lib.SIGNATURES and n not in ("more3d_version", "more3d_last_error", "more3d_launch_count",
+                                                        "more3d_ls_scratch_doubles")]
     assert not unbound, unbound
 
 
