@@ -120,6 +120,19 @@ class StripLevelSet:
         own = torch.as_tensor(pts_own, dtype=torch.float64).to(dev).contiguous()
         n = self.n = int(own.shape[0])
         zeta = torch.as_tensor(zeta_own, dtype=torch.float64).to(dev).reshape(n, -1).contiguous()
+        # internal order of the owned points = grid-sorted (neighbour gathers become L1/L2 hits, see
+        # levelsets_func.Derivative); `perm[i]` = caller's index of internal point i, `own_order()` maps back
+        ext0 = (own.amax(0) - own.amin(0)).cpu().numpy()
+        c0 = float(np.sqrt(8.0 * max(float(ext0[0]) * float(ext0[1]), 1e-300) / (4.0 * n)))
+        g0 = UniformGrid(own, c0 if np.isfinite(c0) and c0 > 0 else 1.0)
+        self.perm = g0.order().long()
+        g0.close()
+        self.inv = torch.empty_like(self.perm)
+        self.inv[self.perm] = torch.arange(n, device=dev)
+        own = own[self.perm].contiguous()
+        zeta = zeta[self.perm].contiguous()
+        if normals is not None:
+            normals = torch.as_tensor(normals, dtype=torch.float64).to(dev)[self.perm]
         self.channels = int(zeta.shape[1])
         H = float(halo) if halo is not None else 6.0 * self.h
         left, right = comm.rank - 1, comm.rank + 1
@@ -255,8 +268,12 @@ class StripLevelSet:
         self.active = self._zero_crossings_all()
         self.alias = True
 
+    def own_values(self, t):
+        """a local per-point tensor -> the owned points' values in the caller's original order"""
+        return t[:self.n][self.inv]
+
     def initialize_from_mask(self, mask_own):
-        m = torch.as_tensor(mask_own, dtype=torch.bool).to(self.dev)
+        m = torch.as_tensor(mask_own, dtype=torch.bool).to(self.dev)[self.perm]
         self.phi[:self.n] = torch.where(m, -self.max_val, self.max_val)
         self._pull(self.phi)
         self.active = self._zero_crossings_all()
@@ -281,7 +298,9 @@ class StripLevelSet:
                     lambda2=lambda2, epsilon=epsilon * self.h, max_val=self.max_val, channels=self.channels,
                     cap=1 if cap else 0, **{k: v.data_ptr() for k, v in sc.items()})
         ph = lambda i: check(lib.more3d_ls_phase(self._g, i, C.byref(st), stream_ptr()))   # noqa: E731
-        for _ in range(iterations):
+        hist = torch.zeros((max(iterations, 1), 2), dtype=torch.float64, device=self.dev)
+        done = 0
+        for it in range(iterations):
             if not self.alias:
                 ph(0)
                 self._pull(self.phi)          # owners re-clamped some points: refresh their ghost copies
@@ -302,9 +321,14 @@ class StripLevelSet:
             self._pull(self.phi)
             ph(7)
             self._push_or(self.active)
-            inc = sc["incs"].cpu()
-            rmsc = float((inc[0] / inc[1]) ** 0.5) if float(inc[1]) > 0 else float("nan")
-            self.rmsc_history.append(rmsc)
-            if rmsc < tolerance:
-                return True
-        return False
+            hist[it] = sc["incs"]
+            done = it + 1
+            if tolerance > 0:                    # the reference checks every iteration (:635-638): one small read-back
+                inc = sc["incs"].cpu()
+                if float((inc[0] / inc[1]) ** 0.5) < tolerance:
+                    break
+        h = hist[:done].cpu().numpy()
+        with np.errstate(all="ignore"):
+            r = np.sqrt(h[:, 0] / h[:, 1])
+        self.rmsc_history.extend(float(v) for v in r)
+        return bool(done and tolerance > 0 and r[-1] < tolerance)

@@ -47,7 +47,8 @@ def test_logical_strips_match_single_gpu(G, init):
                 s.initialize_from_mask(mask[own[r]])
             s.run(12, **RUN)
             torch.cuda.synchronize()
-            out[r] = (s.phi[:s.n].cpu().numpy(), s.active[:s.n].cpu().numpy().astype(bool), s.nloc - s.n, list(s.rmsc_history))
+            out[r] = (s.own_values(s.phi).cpu().numpy(), s.own_values(s.active).cpu().numpy().astype(bool), s.nloc - s.n,
+                      list(s.rmsc_history))
         except Exception as e:      # pragma: no cover - surfaced below
             err.append((r, repr(e)))
             hub.barrier.abort()
