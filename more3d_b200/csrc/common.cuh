@@ -127,6 +127,11 @@ int radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uin
 int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t s);
 int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaStream_t s);
 
+// grid.cu: processing order for EXTERNAL query points -- their indices sorted by grid column, so that the 32
+// lanes of a warp walk the same stencil rows (the locality the self-query path gets from the sorted cloud).
+// *order is a stream-ordered allocation of nq uint32 (free with dev_free); NULL for small query sets.
+int sort_queries_by_column(const more3d_grid* g, const double* q, int64_t nq, cudaStream_t s, uint32_t** order);
+
 // device helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ double dist2_rule(double dx, double dy, double dz) {
     // ((dx*dx)+(dy*dy))+(dz*dz), round-to-nearest each step, never contracted to FMA:

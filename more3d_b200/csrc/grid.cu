@@ -289,6 +289,33 @@ fail:
 #undef G_CUDA
 }
 
+int m3d::sort_queries_by_column(const more3d_grid* g, const double* q, int64_t nq, cudaStream_t s, uint32_t** order) {
+    *order = nullptr;
+    if (nq < 4096 || nq >= ((int64_t)1 << 32)) return MORE3D_OK;
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *cnt = nullptr, *ks = nullptr, *vs = nullptr;
+    const size_t ncols = (size_t)g->nx * g->ny;
+    M3D_TRY(dev_alloc(&keys, (size_t)nq, s));
+    M3D_TRY(dev_alloc(&vals, (size_t)nq, s));
+    M3D_TRY(dev_alloc(&keys2, (size_t)nq, s));
+    M3D_TRY(dev_alloc(&vals2, (size_t)nq, s));
+    M3D_TRY(dev_alloc(&cnt, ncols + 1, s));      // cell_keys also counts; the counts are not used here
+    M3D_CUDA(cudaMemsetAsync(cnt, 0, (ncols + 1) * sizeof(uint32_t), s));
+    cell_keys<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(q, nq, g->ox, g->oy, g->inv_cell, g->nx, g->ny, keys, vals, cnt);
+    count_launches(1);
+    int bits = 1;
+    while (((size_t)1 << bits) < ncols) ++bits;
+    int rc = radix_sort_pairs_u32(keys, vals, keys2, vals2, nq, bits, &ks, &vs, s);
+    if (rc == MORE3D_OK) {
+        uint32_t* keep = vs;
+        if (vs == vals) { dev_free(vals2, s); } else { dev_free(vals, s); }
+        dev_free(keys, s); dev_free(keys2, s); dev_free(cnt, s);
+        *order = keep;
+        return MORE3D_OK;
+    }
+    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s); dev_free(cnt, s);
+    return rc;
+}
+
 extern "C" int more3d_grid_destroy(more3d_grid* g) {
     if (!g) return MORE3D_OK;
     if (g->order) cudaFreeAsync(g->order, g->stream);

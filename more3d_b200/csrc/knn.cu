@@ -30,7 +30,8 @@ struct KnnList {
 
 template <int KMAX, bool SELF>
 __global__ void __launch_bounds__(128) knn_kernel(GridView g, const double* __restrict__ q, int64_t nq, int k,
-                                                  double cell, int64_t* __restrict__ idx_out,
+                                                  double cell, const uint32_t* __restrict__ qorder,
+                                                  int64_t* __restrict__ idx_out,
                                                   double* __restrict__ dist_out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const double* __re
         PointRec p = load_rec(g.rec, i);
         px = p.x; py = p.y; pz = p.z; out = p.idx;
     } else {
-        px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
+        out = qorder ? (int64_t)qorder[i] : i;      // external queries are walked in grid-column order
+        px = q[3 * out]; py = q[3 * out + 1]; pz = q[3 * out + 2];
     }
     KnnList<KMAX> L;
     L.init(k);
@@ -93,11 +95,11 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const double* __re
 using namespace m3d;
 
 template <int KMAX>
-static void launch_knn(const more3d_grid* g, const double* q, int64_t nq, int k, int64_t* idx, double* dist,
-                       cudaStream_t s) {
+static void launch_knn(const more3d_grid* g, const double* q, int64_t nq, int k, const uint32_t* qo, int64_t* idx,
+                       double* dist, cudaStream_t s) {
     const unsigned nb = (unsigned)((nq + 127) / 128);
-    if (q) knn_kernel<KMAX, false><<<nb, 128, 0, s>>>(make_view(g), q, nq, k, g->cell, idx, dist);
-    else knn_kernel<KMAX, true><<<nb, 128, 0, s>>>(make_view(g), nullptr, nq, k, g->cell, idx, dist);
+    if (q) knn_kernel<KMAX, false><<<nb, 128, 0, s>>>(make_view(g), q, nq, k, g->cell, qo, idx, dist);
+    else knn_kernel<KMAX, true><<<nb, 128, 0, s>>>(make_view(g), nullptr, nq, k, g->cell, nullptr, idx, dist);
 }
 
 extern "C" int more3d_knn(const more3d_grid* g, const double* q, int64_t nq, int k, int64_t* idx, double* dist,
@@ -110,9 +112,12 @@ extern "C" int more3d_knn(const more3d_grid* g, const double* q, int64_t nq, int
     if (nq == 0) return MORE3D_OK;
     M3D_REQUIRE(idx != nullptr, "idx is NULL");
     cudaStream_t s = (cudaStream_t)stream;
-    if (k <= 4) launch_knn<4>(g, q, nq, k, idx, dist, s);
-    else if (k <= 16) launch_knn<16>(g, q, nq, k, idx, dist, s);
-    else launch_knn<64>(g, q, nq, k, idx, dist, s);
+    uint32_t* qo = nullptr;
+    if (q) M3D_TRY(sort_queries_by_column(g, q, nq, s, &qo));
+    if (k <= 4) launch_knn<4>(g, q, nq, k, qo, idx, dist, s);
+    else if (k <= 16) launch_knn<16>(g, q, nq, k, qo, idx, dist, s);
+    else launch_knn<64>(g, q, nq, k, qo, idx, dist, s);
+    dev_free(qo, s);
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;

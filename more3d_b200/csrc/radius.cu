@@ -9,6 +9,7 @@ namespace m3d {
 template <bool SELF, bool TALL>
 __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const double* __restrict__ q,
                                                            int64_t nq, double r, double r2, int s, Filter32 flt,
+                                                           const uint32_t* __restrict__ qorder,
                                                            int32_t* __restrict__ counts) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -18,7 +19,8 @@ __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const dou
         PointRec p = load_rec(g.rec, i);
         px = p.x; py = p.y; pz = p.z; out = p.idx;
     } else {
-        px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
+        out = qorder ? (int64_t)qorder[i] : i;      // external queries are walked in grid-column order
+        px = q[3 * out]; py = q[3 * out + 1]; pz = q[3 * out + 2];
     }
     int c = 0;
     if (!SELF) flt = filter_for_query(g, flt, px, py, pz);
@@ -29,6 +31,7 @@ __global__ void __launch_bounds__(256) radius_count_kernel(GridView g, const dou
 template <bool SELF, typename IdxT, bool TALL>
 __global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const double* __restrict__ q,
                                                           int64_t nq, double r, double r2, int s, Filter32 flt,
+                                                          const uint32_t* __restrict__ qorder,
                                                           const int64_t* __restrict__ offsets,
                                                           IdxT* __restrict__ idx) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,7 +42,8 @@ __global__ void __launch_bounds__(256) radius_fill_kernel(GridView g, const doub
         PointRec p = load_rec(g.rec, i);
         px = p.x; py = p.y; pz = p.z; out = p.idx;
     } else {
-        px = q[3 * i]; py = q[3 * i + 1]; pz = q[3 * i + 2]; out = i;
+        out = qorder ? (int64_t)qorder[i] : i;
+        px = q[3 * out]; py = q[3 * out + 1]; pz = q[3 * out + 2];
     }
     int64_t w = offsets[out];
     if (!SELF) flt = filter_for_query(g, flt, px, py, pz);
@@ -71,13 +75,16 @@ extern "C" int more3d_radius_count(const more3d_grid* g, const double* q, int64_
     ProfScope prof("radius_count", s);
     const Filter32 flt = make_filter(g, r);
     GridView v = make_view(g);
+    uint32_t* qo = nullptr;
+    if (q) M3D_TRY(sort_queries_by_column(g, q, nq, s, &qo));
     if (q) {
-        if (g->tall) radius_count_kernel<false, true><<<nb, 256, 0, s>>>(v, q, nq, r, r * r, sw, flt, counts);
-        else radius_count_kernel<false, false><<<nb, 256, 0, s>>>(v, q, nq, r, r * r, sw, flt, counts);
+        if (g->tall) radius_count_kernel<false, true><<<nb, 256, 0, s>>>(v, q, nq, r, r * r, sw, flt, qo, counts);
+        else radius_count_kernel<false, false><<<nb, 256, 0, s>>>(v, q, nq, r, r * r, sw, flt, qo, counts);
     } else {
-        if (g->tall) radius_count_kernel<true, true><<<nb, 256, 0, s>>>(v, nullptr, nq, r, r * r, sw, flt, counts);
-        else radius_count_kernel<true, false><<<nb, 256, 0, s>>>(v, nullptr, nq, r, r * r, sw, flt, counts);
+        if (g->tall) radius_count_kernel<true, true><<<nb, 256, 0, s>>>(v, nullptr, nq, r, r * r, sw, flt, nullptr, counts);
+        else radius_count_kernel<true, false><<<nb, 256, 0, s>>>(v, nullptr, nq, r, r * r, sw, flt, nullptr, counts);
     }
+    dev_free(qo, s);
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
@@ -108,7 +115,9 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
     const double r2 = r * r;
     const Filter32 flt = make_filter(g, r);
     ProfScope prof("radius_fill", s);
-#define M3D_FILL(SELF_, T_, TALL_, Q_) radius_fill_kernel<SELF_, T_, TALL_><<<nb, 256, 0, s>>>(v, Q_, nq, r, r2, sw, flt, offsets, (T_*)idx)
+    uint32_t* qo = nullptr;
+    if (q) M3D_TRY(sort_queries_by_column(g, q, nq, s, &qo));
+#define M3D_FILL(SELF_, T_, TALL_, Q_) radius_fill_kernel<SELF_, T_, TALL_><<<nb, 256, 0, s>>>(v, Q_, nq, r, r2, sw, flt, qo, offsets, (T_*)idx)
     if (q) {
         if (idx_bytes == 4) { if (g->tall) M3D_FILL(false, int32_t, true, q); else M3D_FILL(false, int32_t, false, q); }
         else { if (g->tall) M3D_FILL(false, int64_t, true, q); else M3D_FILL(false, int64_t, false, q); }
@@ -117,6 +126,7 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
         else { if (g->tall) M3D_FILL(true, int64_t, true, nullptr); else M3D_FILL(true, int64_t, false, nullptr); }
     }
 #undef M3D_FILL
+    dev_free(qo, s);
     count_launches(1);
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;

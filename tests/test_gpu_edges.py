@@ -154,3 +154,27 @@ def test_tall_columns_vertical_structures():
         ok = rel_close(K[i], np.float32(k_or)) and rel_close(dk[i], np.float32(a_dk)) and rel_close(dn[i], np.float32(a_dn))
         bad += 0 if ok else 1
     assert bad <= 3, bad
+
+
+def test_external_queries_in_any_order():
+    """External query sets are walked in grid-column order inside the library (>= 4096 queries); results must
+    land at the caller's query index whatever order the queries arrive in."""
+    from more3d_b200 import synthetic
+    from more3d_b200.BallTreePointSet import BallTreePointSet
+    from oracle import ref_path as rp
+    rng = np.random.Generator(np.random.PCG64(23))
+    pts = synthetic.terrain(30000, seed=29)
+    q = pts[rng.permutation(len(pts))[:9000]] + rng.normal(0, 0.2, (9000, 3))
+    q[::1000] += [500.0, -300.0, 0.0]                                          # some far outside the grid
+    tree = rp.build_tree(pts)
+    bt = BallTreePointSet(pts)
+    want = rp.query_radius(tree, q, 0.8)
+    got = bt.queryRadius(q, 0.8)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(np.sort(a), np.sort(b))
+    ki, kd = bt.query(q, 8, return_distnaces=True)
+    wi, wd = rp.query_knn(tree, q, 8, return_distnaces=True)
+    assert np.array_equal(kd, wd)
+    same = ki == wi
+    assert np.all(same | (kd == np.roll(kd, 1, axis=1)) | (kd == np.roll(kd, -1, axis=1)))   # ties may swap
