@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const doubl
 }
 
 struct D4 { double x, y, z, w; };
+struct D4x2 { D4 a, b; };
 // half h (0/1) of a 64-B feature record as two LDG.128 through the read-only path
 __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
     D4 r;
@@ -146,9 +147,18 @@ __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
 
 struct DkDnParams {
     double r, r2, rho2, inv_rho2, sigma_n, sigma_k;
+    double zk100_thr;   // largest x with fl(100 * x) <= 0.04 (rounding is monotone, so |100*dk| <= 0.04 <=> |dk| <= x)
     int min_points, s, table_len;
     Filter32 flt;
 };
+
+// largest double x >= 0 with fl(x * 100.0) <= 0.04: the rescue test of DM_saliency.py:290 without the multiply
+static double zk100_threshold() {
+    double x = 0.0004;
+    while (x * 100.0 <= 0.04) x = nextafter(x, 1.0);
+    while (x * 100.0 > 0.04) x = nextafter(x, 0.0);
+    return x;
+}
 
 template <bool TALL>
 __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
@@ -167,35 +177,62 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
         const double pnx = pb.x, pny = pb.y, pnz = pb.z;
         int m = 0, mu = 0, nact = 0, zn = 0, zk = 0, zk100 = 0;
         double s1n = 0, s2n = 0, s1k = 0, s2k = 0, wn = 0, wk = 0, wsum = 0;
-        walk_candidates<TALL>(g, px, py, pz, prm.r, prm.s, [&](int64_t j) {
-            const D4 qa = ld_d4(feat + j, 0);
+        // Branch-free candidate body: every lane evaluates the whole expression and the accept / np.unique
+        // decisions enter as selects.  With 32 lanes at independent positions of their rows some lane accepts at
+        // practically every step, so a branch saves no issue slots -- it only serialises two dependent loads per
+        // candidate (ncu: 45 % of the stall samples sat on the first use of each load).  Without control flow both
+        // 32-B halves of the unrolled candidates are requested up front.
+        walk_candidates_pipelined<TALL>(g, px, py, pz, prm.r, prm.s, [&](int64_t j) {
+            D4x2 c;
+            c.a = ld_d4(feat + j, 0);
+            c.b = ld_d4(feat + j, 1);
+            return c;
+        }, [&](const D4x2& c) {
+            const D4& qa = c.a;
+            const D4& qb = c.b;
             const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);   // :256-257
-            if (d2 <= prm.r2) {
-                ++m;
-                const long long kb = __double_as_longlong(qa.w);
-                if (!(kb & 1LL)) {                                            // np.unique, :247
-                    const D4 qb = ld_d4(feat + j, 1);
-                    ++mu;
-                    const double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);   // :261
-                    const double dk = Kp - __longlong_as_double(kb & ~3LL);   // :262
-                    // ring weight on the squared distance (:272-275): d/rho2 below rho2, 2 - d/rho2 above,
-                    // 0 at equality, clamped at 0.  (-1/rho2)*d + 2 == 2 - (1/rho2)*d bit for bit.
-                    const double t = __dmul_rn(prm.inv_rho2, d2);
-                    double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
-                    if (d2 == prm.rho2 || w < 0.0) w = 0.0;
-                    const bool act = w > 0.01;                                // :279
-                    s1n += dn; s2n += dn * dn;
-                    s1k += dk; s2k += dk * dk;
-                    const double adn = fabs(dn), adk = fabs(dk);
-                    if (act) {
-                        ++nact;
-                        zn += (adn < 0.016) ? 1 : 0;                          // :286
-                        zk += (adk <= 0.04) ? 1 : 0;                          // :287
-                        zk100 += (fabs(__dmul_rn(dk, 100.0)) <= 0.04) ? 1 : 0;  // :290
-                    }
-                    wn += adn * w; wk += dk * w; wsum += w;                   // :300, :316
-                }
-            }
+            const long long kb = __double_as_longlong(qa.w);
+            const bool in = d2 <= prm.r2;
+            const bool u = in & !((int)kb & 1);                               // np.unique, :247
+            double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);         // :261
+            double dk = Kp - __longlong_as_double(kb & ~3LL);                 // :262
+            dn = u ? dn : 0.0;
+            dk = u ? dk : 0.0;
+            // opaque to the optimiser: keeps |.| as an operand modifier of the consumers instead of a
+            // second, separately masked copy of each value
+            asm("" : "+d"(dn));
+            asm("" : "+d"(dk));
+            // ring weight on the squared distance (:272-275): d/rho2 below rho2, 2 - d/rho2 above,
+            // 0 at equality, clamped at 0.  (-1/rho2)*d + 2 == 2 - (1/rho2)*d bit for bit.
+            const double t = __dmul_rn(prm.inv_rho2, d2);
+            double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
+            const bool keep = u & (d2 != prm.rho2) & !(w < 0.0);
+            w = keep ? w : 0.0;
+            s1n += dn; s2n += dn * dn;
+            s1k += dk; s2k += dk * dk;
+            // counters as predicated adds (one instruction each): m, mu, then with act = w > 0.01 (:279)
+            // nact, zn (|dn| < 0.016, :286), zk (|dk| <= 0.04, :287), zk100 (|100 dk| <= 0.04, :290)
+            asm("{ .reg .pred pin, pu, pa, q;\n"
+                "  setp.ne.u32 pin, %6, 0;\n"
+                "  setp.ne.u32 pu, %7, 0;\n"
+                "  @pin add.s32 %0, %0, 1;\n"
+                "  @pu add.s32 %1, %1, 1;\n"
+                "  setp.gt.f64 pa, %8, %11;\n"
+                "  @pa add.s32 %2, %2, 1;\n"
+                "  .reg .f64 an, ak;\n"
+                "  abs.f64 an, %9;\n"
+                "  abs.f64 ak, %10;\n"
+                "  setp.lt.and.f64 q, an, %12, pa;\n"
+                "  @q add.s32 %3, %3, 1;\n"
+                "  setp.le.and.f64 q, ak, %13, pa;\n"
+                "  @q add.s32 %4, %4, 1;\n"
+                "  setp.le.and.f64 q, ak, %14, pa;\n"
+                "  @q add.s32 %5, %5, 1;\n"
+                "}"
+                : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zn), "+r"(zk), "+r"(zk100)
+                : "r"((unsigned)in), "r"((unsigned)u), "d"(w), "d"(dn), "d"(dk), "d"(0.01), "d"(0.016), "d"(0.04),
+                  "d"(prm.zk100_thr));
+            wn += fabs(dn) * w; wk += dk * w; wsum += w;                      // :300, :316
         });
         if (!(pflags & 2LL) && m >= prm.min_points) {                         // :225-229, :240-244
             if (nact >= prm.table_len) {
@@ -339,6 +376,7 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
     prm.sigma_n = sigma_normal; prm.sigma_k = sigma_curvature;
     prm.min_points = min_points; prm.s = stencil_halfwidth(g, r); prm.table_len = table_len;
     prm.flt = make_filter(g, r);
+    prm.zk100_thr = zk100_threshold();
     {
         ProfScope prof("dkdn", s);
         if (g->tall) dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);

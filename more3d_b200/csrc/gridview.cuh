@@ -68,7 +68,7 @@ __device__ __forceinline__ Filter32 filter_for_query(const GridView& g, Filter32
 // changes nothing (8.3 vs 8.5 ms, 15.9 vs 15.8 ms): the pipe moves 32 B per lane per candidate either way
 // (1 KiB per warp = 8 wavefronts), so only SMALLER records would help, not fewer instructions.
 __device__ __forceinline__ void ldg256(const void* p, double& a, double& b, double& c, double& d) {
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 __device__ __forceinline__ PointRec load_rec(const PointRec* __restrict__ rec, int64_t j) {
     PointRec r;
@@ -86,11 +86,17 @@ __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx,
     const int iy = cell_coord(qy, g.oy, g.inv, g.ny);
     const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
     const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
-    if (x0 > x1) return;
+    if (x0 > x1 || y0 > y1) return;
+    // the bounds of row y+1 are requested before row y is walked, so their latency hides behind the row
+    const uint32_t* cs = g.col_start + (size_t)y0 * g.nx;
+    uint32_t nb = __ldg(cs + x0), ne = __ldg(cs + x1 + 1);
     for (int y = y0; y <= y1; ++y) {
-        const size_t row = (size_t)y * g.nx;
-        const uint32_t b = __ldg(g.col_start + row + x0);
-        const uint32_t e = __ldg(g.col_start + row + x1 + 1);
+        const uint32_t b = nb, e = ne;
+        if (y < y1) {
+            cs += g.nx;
+            nb = __ldg(cs + x0);
+            ne = __ldg(cs + x1 + 1);
+        }
         for (uint32_t j = b; j < e; ++j) f((int64_t)j);
     }
 }
@@ -127,6 +133,48 @@ __device__ __forceinline__ void for_each_candidate_tall(const GridView& g, doubl
             }
             for (uint32_t j = b; j < e; ++j) f((int64_t)j);
         }
+}
+
+// Software-pipelined variant of the walks: load(j) returns the candidate's record (any POD), process(rec)
+// consumes it.  The record of candidate j+1 is requested before candidate j is processed, so a warp never
+// sits on the L1 latency of the record it is about to use (one exposed latency per row instead of one per
+// candidate).
+template <typename L, typename P>
+__device__ __forceinline__ void run_range_pipelined(uint32_t b, uint32_t e, L&& load, P&& process) {
+    if (b >= e) return;
+    auto cur = load((int64_t)b);
+#pragma unroll 2
+    for (uint32_t j = b + 1; j < e; ++j) {
+        auto nxt = load((int64_t)j);
+        process(cur);
+        cur = nxt;
+    }
+    process(cur);
+}
+
+template <bool TALL, typename L, typename P>
+__device__ __forceinline__ void walk_candidates_pipelined(const GridView& g, double qx, double qy, double qz, double r,
+                                                          int s, L&& load, P&& process) {
+    if (TALL) {
+        for_each_candidate_tall(g, qx, qy, qz, r, s, [&](int64_t j) { process(load(j)); });
+        return;
+    }
+    const int ix = cell_coord(qx, g.ox, g.inv, g.nx);
+    const int iy = cell_coord(qy, g.oy, g.inv, g.ny);
+    const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
+    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
+    if (x0 > x1 || y0 > y1) return;
+    const uint32_t* cs = g.col_start + (size_t)y0 * g.nx;
+    uint32_t nb = __ldg(cs + x0), ne = __ldg(cs + x1 + 1);
+    for (int y = y0; y <= y1; ++y) {
+        const uint32_t b = nb, e = ne;
+        if (y < y1) {
+            cs += g.nx;
+            nb = __ldg(cs + x0);
+            ne = __ldg(cs + x1 + 1);
+        }
+        run_range_pipelined(b, e, load, process);
+    }
 }
 
 // compile-time choice between the row walk (thin columns) and the column walk (tall columns): the host
