@@ -108,6 +108,26 @@ int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const fl
                  double sigma_normal, double sigma_curvature, const double* chi2_table, int table_len,
                  int min_points, float* dk, float* dn, float* minmax, void* stream);
 
+/* ---- grid-order variants of the two neighbourhood passes ------------------------------------------
+ * Same arithmetic, same values; every per-point output is written at the point's position in the grid's
+ * sorted order (row i belongs to original point order[i], more3d_grid_order) instead of at its original
+ * index.  Sorted writes are coalesced; the original-order calls scatter six partial 32-B sectors per point,
+ * which is half of their per-point cost on a cloud in random order.  A pipeline that only needs the final
+ * column back in the caller's order (DM_nonparam_curvature -> DM_dk_dn -> DM_saliency, DM_saliency.py:326-583)
+ * runs these, blends in grid order (more3d_saliency_blend is order-agnostic) and unpermutes one column (more3d_unpermute).
+ * more3d_dk_dn_gridorder always uses the feature records cached by the last
+ * more3d_normals_curvature[_gridorder] on the grid. */
+int more3d_normals_curvature_gridorder(const more3d_grid* g, double r, double eps, int min_points,
+                                       double* normals, double* lam_ratio, float* K, int32_t* pcount,
+                                       void* stream);
+int more3d_dk_dn_gridorder(const more3d_grid* g, double r, double rho, double sigma_normal,
+                           double sigma_curvature, const double* chi2_table, int table_len, int min_points,
+                           float* dk, float* dn, float* minmax, void* stream);
+/* dst[order[i]] = src[i], order as returned by more3d_grid_order (the grid itself is not needed any more);
+ * elem_bytes in {4, 8, 24} (f32 / i32 column, f64 column, n x 3 f64 normals). */
+int more3d_unpermute(const int32_t* order, int64_t n, const void* src_gridorder, void* dst, int elem_bytes,
+                     void* stream);
+
 /* ---- DM_saliency: min-max normalise (+min, as written) and blend (DM_saliency.py:565-580) ---------
  * minmax: 4 float32 on the device as produced by more3d_dk_dn / more3d_minmax4.
  * sal: n float32.  sal_minmax (may be NULL): 2 float32 {min, max} of sal. */

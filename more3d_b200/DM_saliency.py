@@ -22,7 +22,28 @@ from scipy import stats
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import UniformGrid, as_device_points, cell_for_radius
+from .grid import GridColumn, UniformGrid, as_device_points, cell_for_radius
+
+
+class _Columns(dict):
+    """Attribute table: name -> device tensor in the caller's point order.  A value may be stored as a
+    GridColumn (grid order); reading it through the mapping interface un-permutes it once, `raw` does not."""
+
+    def raw(self, name):
+        return dict.get(self, name)
+
+    def __getitem__(self, name):
+        v = dict.__getitem__(self, name)
+        return v.tensor() if isinstance(v, GridColumn) else v
+
+    def get(self, name, default=None):
+        return self[name] if name in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
 
 
 class PointCloudDM:
@@ -35,10 +56,20 @@ class PointCloudDM:
         self.xyz = as_device_points(xyz, device)
         self.device = self.xyz.device
         self.n = int(self.xyz.shape[0])
-        self.attrs = {}
-        self.normals = None if normals is None else as_device_points(normals, self.device).clone()
+        self.attrs = _Columns()
+        self._normals = None if normals is None else as_device_points(normals, self.device).clone()
         self._grids = {}
         self._minmax = None
+
+    @property
+    def normals(self):
+        """(N,3) f64 device tensor in point order (un-permuted on first access if held in grid order)."""
+        v = self._normals
+        return v.tensor() if isinstance(v, GridColumn) else v
+
+    @normals.setter
+    def normals(self, value):
+        self._normals = value
 
     # -- ODM-like surface ---------------------------------------------------------------
     @classmethod
@@ -59,7 +90,7 @@ class PointCloudDM:
 
     def save_as(self, path):
         out = {"xyz": self.xyz.cpu().numpy()}
-        if self.normals is not None:
+        if self._normals is not None:
             out["normals"] = self.normals.cpu().numpy()
         for k, v in self.attrs.items():
             out[k] = v.cpu().numpy()
@@ -151,8 +182,10 @@ class Curvature_Kernel(_KernelPointEx):
         Uses the normals stored in ``dm``; if there are none (the reference requires them,
         DM_saliency.py:329-330) centroid-PCA normals at the same radius are computed in the same pass."""
         g = dm.grid(radius)
-        if dm.normals is None:
-            normals, ratio, K, pcount = g.normals_curvature(radius, self.epsilon(), self._minPoints_neighbourhood)
+        if dm._normals is None:
+            # outputs stay in grid order (GridColumn): coalesced writes, un-permuted only if somebody reads them
+            normals, ratio, K, pcount = g.normals_curvature_gridorder(radius, self.epsilon(),
+                                                                      self._minPoints_neighbourhood)
             dm.normals = normals
             dm.attrs["_lam_ratio"] = ratio
         else:
@@ -195,16 +228,25 @@ class Saliency_Kernel(_KernelPointEx):
         self._minPoints_neighbourhood = min_points
 
     def process_all(self, dm, radius):
-        if dm.normals is None or "_nonparam_K" not in dm.attrs:
+        if dm._normals is None or "_nonparam_K" not in dm.attrs:
             raise ValueError("dk/dn needs normals and _nonparam_K (run DM_nonparam_curvature first)")
         g = dm.grid(radius)
+        rn, rk = dm._normals, dm.attrs.raw("_nonparam_K")
+        # the columns are still the untouched grid-order outputs of the fused pass on THIS grid: its cached
+        # feature records are current, and dk/dn can stay in grid order too
+        cached = isinstance(rn, GridColumn) and isinstance(rk, GridColumn) and rn.grid is g and rk.grid is g \
+            and getattr(g, "_feat_cols", None) == (rn, rk) and rn.clean() and rk.clean()
         length = 1024
         while True:
             table = _chi2_table(self._alpha, length, dm.device)
             try:
-                dk, dn, minmax = g.dk_dn(radius, dm.normals, dm.attrs["_nonparam_K"], self._rho_neighbourhood,
-                                         self._sigma_normal, self._sigma_curvature, table,
-                                         self._minPoints_neighbourhood)
+                if cached:
+                    dk, dn, minmax = g.dk_dn_gridorder(radius, self._rho_neighbourhood, self._sigma_normal,
+                                                       self._sigma_curvature, table, self._minPoints_neighbourhood)
+                else:
+                    dk, dn, minmax = g.dk_dn(radius, dm.normals, dm.attrs["_nonparam_K"], self._rho_neighbourhood,
+                                             self._sigma_normal, self._sigma_curvature, table,
+                                             self._minPoints_neighbourhood)
                 break
             except _lib.More3DError as e:
                 if "error -4" not in str(e) or length >= (1 << 22):
@@ -284,7 +326,12 @@ def DM_saliency(inFile, curvature_weight=.5, verbose=False, **kwargs):
     if dm is None:
         return
     lib = _lib.load()
-    dk, dn = dm.attrs["_dk"], dm.attrs["_dn"]
+    rdk, rdn = dm.attrs.raw("_dk"), dm.attrs.raw("_dn")
+    # normalise + blend are elementwise: when both inputs are untouched grid-order columns of one grid the blend
+    # runs in grid order and only _saliency is ever brought back to point order
+    grid = rdk if (isinstance(rdk, GridColumn) and isinstance(rdn, GridColumn) and rdk.order is rdn.order
+                   and rdk.clean() and rdn.clean()) else None
+    dk, dn = (rdk.data, rdn.data) if grid is not None else (dm.attrs["_dk"], dm.attrs["_dn"])
     with torch.cuda.device(dm.device):
         minmax = dm._minmax
         if minmax is None:
@@ -294,7 +341,7 @@ def DM_saliency(inFile, curvature_weight=.5, verbose=False, **kwargs):
         smm = torch.empty(2, dtype=torch.float32, device=dm.device)
         check(lib.more3d_saliency_blend(ptr(dk), ptr(dn), dm.n, ptr(minmax), float(curvature_weight),
                                         ptr(sal), ptr(smm), stream_ptr()))
-    dm.attrs["_saliency"] = sal
+    dm.attrs["_saliency"] = sal if grid is None else GridColumn(grid, sal)
     dm.attrs["_saliency_minmax"] = smm
     dm.attrs["_dkdn_minmax"] = minmax
     if verbose:

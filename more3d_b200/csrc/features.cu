@@ -17,6 +17,8 @@ struct CurvParams {
     double eps;
     int min_points;
     int s;
+    int grid_order;     // 1: per-point outputs are written at the point's GRID position (coalesced) instead of
+                        //    its original index (a scatter of six partial sectors per point)
     Filter32 flt;
 };
 
@@ -34,14 +36,15 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, Cu
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const PointRec p = load_rec(g.rec, i);
-    const int64_t o = p.idx;
+    const int64_t o = prm.grid_order ? i : p.idx;
     int m = 0;
     double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
     // The fp64 differences serve both the exact accept rule and the moments, so an fp32 pre-filter
     // (used by the count/fill kernels) does not pay here: measured 2x slower (conditional fp64 loads
     // lose the unrolled loop's memory-level parallelism).
-    walk_candidates<TALL>(g, p.x, p.y, p.z, prm.r, prm.s, [&](int64_t j) {
-        const PointRec c = load_rec(g.rec, j);
+    walk_candidates_pipelined<TALL>(g, p.x, p.y, p.z, prm.r, prm.s, [&](int64_t j) {
+        return load_rec(g.rec, j);
+    }, [&](const PointRec& c) {
         const double dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
         if (dist2_rule(dx, dy, dz) <= prm.r2) {
             ++m;
@@ -149,6 +152,7 @@ struct DkDnParams {
     double r, r2, rho2, inv_rho2, sigma_n, sigma_k;
     double zk100_thr;   // largest x with fl(100 * x) <= 0.04 (rounding is monotone, so |100*dk| <= 0.04 <=> |dk| <= x)
     int min_points, s, table_len;
+    int grid_order;     // 1: dk / dn are written at the grid position
     Filter32 flt;
 };
 
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
                 dkf = (float)dk; dnf = (float)dn;
             }
         }
-        const int64_t o = __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+        const int64_t o = prm.grid_order
+                              ? i : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
         dk_out[o] = dkf;
         dn_out[o] = dnf;
     }
@@ -297,13 +302,15 @@ __global__ void minmax_finish(const unsigned* mm, float* out) {
 using namespace m3d;
 
 static int launch_moments(const more3d_grid* g, int mode, double r, double eps, int min_points,
-                          double* normals, double* lam_ratio, float* K, int32_t* pcount, cudaStream_t s) {
+                          double* normals, double* lam_ratio, float* K, int32_t* pcount, cudaStream_t s,
+                          int grid_order = 0) {
     M3D_REQUIRE(g != nullptr, "grid is NULL");
     M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
     M3D_REQUIRE(normals != nullptr, "normals is NULL");
     CurvParams prm;
     prm.r = r; prm.r2 = r * r; prm.eps = eps; prm.min_points = min_points; prm.s = stencil_halfwidth(g, r);
     prm.flt = make_filter(g, r);
+    prm.grid_order = grid_order;
     const unsigned nb = (unsigned)((g->n + WALK_THREADS - 1) / WALK_THREADS);
     GridView v = make_view(g);
     ProfScope prof("moments", s);
@@ -345,9 +352,10 @@ extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double e
     return launch_moments(g, MODE_FUSED, r, eps, min_points, normals, lam_ratio, K, pcount, (cudaStream_t)stream);
 }
 
-extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
-                            double sigma_normal, double sigma_curvature, const double* chi2_table,
-                            int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream) {
+static int run_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
+                     double sigma_normal, double sigma_curvature, const double* chi2_table,
+                     int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream,
+                     int grid_order) {
     M3D_REQUIRE(g != nullptr, "grid is NULL");
     M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
     M3D_REQUIRE(chi2_table && dk && dn, "NULL argument");
@@ -377,6 +385,7 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
     prm.min_points = min_points; prm.s = stencil_halfwidth(g, r); prm.table_len = table_len;
     prm.flt = make_filter(g, r);
     prm.zk100_thr = zk100_threshold();
+    prm.grid_order = grid_order;
     {
         ProfScope prof("dkdn", s);
         if (g->tall) dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
@@ -395,4 +404,28 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
         return MORE3D_E_RANGE;
     }
     return MORE3D_OK;
+}
+
+extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
+                            double sigma_normal, double sigma_curvature, const double* chi2_table,
+                            int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream) {
+    return run_dk_dn(g, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, table_len, min_points,
+                     dk, dn, minmax, stream, 0);
+}
+
+// Grid-order variants: every per-point output is written at the point's position in the grid's sorted order
+// (more3d_grid_order), i.e. fully coalesced.  more3d_grid_unpermute brings a column back to the caller's order
+// when -- and only if -- it is asked for.
+extern "C" int more3d_normals_curvature_gridorder(const more3d_grid* g, double r, double eps, int min_points,
+                                                  double* normals, double* lam_ratio, float* K, int32_t* pcount,
+                                                  void* stream) {
+    M3D_REQUIRE(K != nullptr && pcount != nullptr, "K / pcount is NULL");
+    return launch_moments(g, MODE_FUSED, r, eps, min_points, normals, lam_ratio, K, pcount, (cudaStream_t)stream, 1);
+}
+
+extern "C" int more3d_dk_dn_gridorder(const more3d_grid* g, double r, double rho, double sigma_normal,
+                                      double sigma_curvature, const double* chi2_table, int table_len,
+                                      int min_points, float* dk, float* dn, float* minmax, void* stream) {
+    return run_dk_dn(g, r, nullptr, nullptr, rho, sigma_normal, sigma_curvature, chi2_table, table_len, min_points,
+                     dk, dn, minmax, stream, 1);
 }

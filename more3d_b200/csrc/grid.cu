@@ -341,3 +341,43 @@ extern "C" int more3d_grid_order(const more3d_grid* g, int32_t* order, void* str
                              (cudaStream_t)stream));
     return MORE3D_OK;
 }
+
+// dst[order[i]] = src[i] for elements of `words` 32-bit words (1: f32 / i32 columns, 2: f64, 6: f64 x 3 normals)
+namespace m3d {
+template <int W>
+__global__ void __launch_bounds__(256) unpermute_kernel(const uint32_t* __restrict__ order,
+                                                        const uint32_t* __restrict__ src,
+                                                        uint32_t* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t o = (size_t)__ldg(order + i) * W;
+    uint32_t v[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) v[k] = __ldg(src + (size_t)i * W + k);
+#pragma unroll
+    for (int k = 0; k < W; ++k) dst[o + k] = v[k];
+}
+}  // namespace m3d
+
+extern "C" int more3d_unpermute(const int32_t* order, int64_t n, const void* src_gridorder, void* dst,
+                                int elem_bytes, void* stream) {
+    M3D_REQUIRE(order != nullptr && src_gridorder != nullptr && dst != nullptr, "NULL argument");
+    M3D_REQUIRE(src_gridorder != dst, "in-place unpermute is not supported");
+    M3D_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return MORE3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    const uint32_t* ord = (const uint32_t*)order;
+    const uint32_t* src = (const uint32_t*)src_gridorder;
+    uint32_t* d = (uint32_t*)dst;
+    m3d::ProfScope prof("unpermute", s);
+    switch (elem_bytes) {
+        case 4: m3d::unpermute_kernel<1><<<nb, 256, 0, s>>>(ord, src, d, n); break;
+        case 8: m3d::unpermute_kernel<2><<<nb, 256, 0, s>>>(ord, src, d, n); break;
+        case 24: m3d::unpermute_kernel<6><<<nb, 256, 0, s>>>(ord, src, d, n); break;
+        default: M3D_REQUIRE(false, "elem_bytes must be 4, 8 or 24");
+    }
+    m3d::count_launches(1);
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}

@@ -3,6 +3,7 @@
 torch is used for device memory and streams only; all compute is in libmore3d_b200.so.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -37,6 +38,45 @@ def as_device_points(points, device=None):
         raise ValueError("points must have shape (N, 3)")
     dev = torch.device(device if device is not None else "cuda")
     return t.to(device=dev, dtype=torch.float64).contiguous()
+
+
+class GridColumn:
+    """A per-point column stored in the sorted order of a grid.  `tensor()` returns it in the caller's point
+    order (one un-permute pass, cached).  The neighbourhood passes write their outputs this way because sorted
+    writes are coalesced; consumers that are order-agnostic (the next pass on the same grid, the blend, min/max)
+    read `.data` directly and the un-permutation never happens for intermediate columns nobody looks at."""
+
+    def __init__(self, grid, data):
+        # weak: the grid remembers its latest columns (_feat_cols); a strong back-reference would make a cycle
+        # and keep hundreds of MB of HBM alive until the cyclic collector happens to run
+        if isinstance(grid, GridColumn):     # another column of the same grid
+            self._grid, self.order = grid._grid, grid.order
+        else:
+            self._grid = weakref.ref(grid)
+            self.order = grid.order_tensor()     # shared by all columns of the grid; outlives grid.close()
+        self.data = data
+        self._orig = None
+        self._v0 = data._version
+
+    @property
+    def grid(self):
+        return self._grid()
+
+    def tensor(self):
+        if self._orig is None:
+            t = self.data.contiguous()
+            with torch.cuda.device(t.device):
+                out = torch.empty_like(t)
+                nbytes = t.element_size() * (int(t.shape[1]) if t.ndim == 2 else 1)
+                check(_lib.load().more3d_unpermute(ptr(self.order), int(t.shape[0]), ptr(t), ptr(out), int(nbytes),
+                                                   stream_ptr()))
+            self._orig = out
+            self._v1 = out._version
+        return self._orig
+
+    def clean(self):
+        """True while neither representation has been modified in place since it was produced."""
+        return self.data._version == self._v0 and (self._orig is None or self._orig._version == self._v1)
 
 
 class UniformGrid:
@@ -147,6 +187,42 @@ class UniformGrid:
             # the grid now caches the sorted (xyz, K, unit normal) records of exactly these two tensors
             self._feat_key = (normals, normals._version, K, K._version)
             return normals, ratio, K, pcount
+
+    # -- grid-order variants: outputs stay in the grid's sorted order (coalesced writes) -------------------
+    def normals_curvature_gridorder(self, r, eps, min_points):
+        """Like normals_curvature, but row i of every output belongs to original point order()[i].
+        Returns GridColumn objects (lazy un-permutation)."""
+        with torch.cuda.device(self.device):
+            normals = self._new((self.n, 3), torch.float64)
+            ratio = self._new((self.n,), torch.float64)
+            K = self._new((self.n,), torch.float32)
+            pcount = self._new((self.n,), torch.int32)
+            check(self.lib.more3d_normals_curvature_gridorder(self._h, float(r), float(eps), int(min_points),
+                                                              ptr(normals), ptr(ratio), ptr(K), ptr(pcount),
+                                                              stream_ptr()))
+            cols = tuple(GridColumn(self, t) for t in (normals, ratio, K, pcount))
+            self._feat_key = None
+            self._feat_cols = (cols[0], cols[2])     # the cached feature records hold exactly these two
+            return cols
+
+    def dk_dn_gridorder(self, r, rho, sigma_normal, sigma_curvature, chi2_table, min_points):
+        """dk / dn from the feature records cached by the last normals_curvature[_gridorder]; GridColumns."""
+        with torch.cuda.device(self.device):
+            dk = self._new((self.n,), torch.float32)
+            dn = self._new((self.n,), torch.float32)
+            minmax = self._new((4,), torch.float32)
+            check(self.lib.more3d_dk_dn_gridorder(self._h, float(r), float(rho), float(sigma_normal),
+                                                  float(sigma_curvature), ptr(chi2_table), int(chi2_table.numel()),
+                                                  int(min_points), ptr(dk), ptr(dn), ptr(minmax), stream_ptr()))
+            return GridColumn(self, dk), GridColumn(self, dn), minmax
+
+    def order_tensor(self):
+        """order() cached on the grid (sorted position -> original index, int32)."""
+        o = getattr(self, "_order", None)
+        if o is None:
+            with torch.cuda.device(self.device):
+                o = self._order = self.order()
+        return o
 
     def dk_dn(self, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, min_points):
         """chi2_table: device f64 tensor, chi2.ppf(alpha, df) for df = 0..len-1."""

@@ -240,3 +240,52 @@ def test_mid_size_against_oracle_subsample():
         if not (rel_close(dk[i], np.float32(a_dk)) and rel_close(dn[i], np.float32(a_dn))):
             nbad += 1
     assert nbad <= 3, nbad
+
+
+def test_gridorder_columns_identical_to_point_order():
+    """The grid-order variants (coalesced writes + lazy un-permutation) return bit-identical columns, the
+    un-permute C entry point handles 4 / 8 / 24-byte elements, and a column survives the grid's destruction."""
+    import torch
+    from more3d_b200 import synthetic
+    from more3d_b200.grid import UniformGrid, cell_for_radius
+    from more3d_b200.DM_saliency import _chi2_table, PointCloudDM, DM_nonparam_curvature, DM_dk_dn, DM_saliency
+    from more3d_b200.grid import GridColumn
+    pts = synthetic.terrain(20000, seed=11)
+    pts = pts[np.random.default_rng(0).permutation(len(pts))]
+    r, rho = 0.6, 0.6 / np.sqrt(2)
+    d = torch.from_numpy(pts).cuda()
+    g = UniformGrid(d, cell_for_radius(r))
+    table = _chi2_table(0.05, 1024, d.device)
+    n0, ratio0, K0, pc0 = g.normals_curvature(r, 0.0392, 4)
+    dk0, dn0, mm0 = g.dk_dn(r, n0, K0, rho, 0.01, 0.01, table, 4)
+    n1, ratio1, K1, pc1 = g.normals_curvature_gridorder(r, 0.0392, 4)
+    dk1, dn1, mm1 = g.dk_dn_gridorder(r, rho, 0.01, 0.01, table, 4)
+    order = g.order().cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(len(pts)))
+    assert np.array_equal(n1.data.cpu().numpy(), n0.cpu().numpy()[order], equal_nan=True)   # row i <-> point order[i]
+    g.close()                                                                                  # columns outlive the grid
+    for a, b in ((n0, n1), (ratio0, ratio1), (K0, K1), (pc0, pc1), (dk0, dk1), (dn0, dn1)):
+        assert isinstance(b, GridColumn) and b.clean()
+        assert np.array_equal(a.cpu().numpy(), b.tensor().cpu().numpy(), equal_nan=True)
+    assert np.array_equal(mm0.cpu().numpy(), mm1.cpu().numpy())
+    # through the reference-named API: default (grid-order inside) == columns handed over in point order
+    dm = PointCloudDM(pts)
+    DM_nonparam_curvature(dm, "sphere", roughness=0.02, alpha=0.05, min_points=4, radius=r)
+    assert isinstance(dm.attrs.raw("_nonparam_K"), GridColumn)
+    DM_dk_dn(dm, "sphere", rho, rho, sigma_normal=0.01, sigma_curvature=0.01, radius=r)
+    DM_saliency(dm, curvature_weight=0.5)
+    assert isinstance(dm.attrs.raw("_saliency"), GridColumn)
+    dm2 = PointCloudDM(pts, normals=dm.normals)
+    dm2.attrs["_nonparam_K"] = dm.attrs["_nonparam_K"].clone()
+    DM_dk_dn(dm2, "sphere", rho, rho, sigma_normal=0.01, sigma_curvature=0.01, radius=r)
+    DM_saliency(dm2, curvature_weight=0.5)
+    assert not isinstance(dm2.attrs.raw("_saliency"), GridColumn)
+    for k in ("_dk", "_dn", "_saliency"):
+        assert np.array_equal(dm.get(k), dm2.get(k), equal_nan=True), k
+    # an in-place edit of a materialised column invalidates the cached feature records: dk/dn must see it
+    dm.attrs["_nonparam_K"].mul_(2.0)
+    DM_dk_dn(dm, "sphere", rho, rho, sigma_normal=0.01, sigma_curvature=0.01, radius=r)
+    dm2.attrs["_nonparam_K"].mul_(2.0)
+    DM_dk_dn(dm2, "sphere", rho, rho, sigma_normal=0.01, sigma_curvature=0.01, radius=r)
+    assert np.array_equal(dm.get("_dk"), dm2.get("_dk"), equal_nan=True)
+    assert not np.array_equal(dm.get("_dk"), dk0.cpu().numpy())
