@@ -116,13 +116,14 @@ int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const fl
  * column back in the caller's order (DM_nonparam_curvature -> DM_dk_dn -> DM_saliency, DM_saliency.py:326-583)
  * runs these, blends in grid order (more3d_saliency_blend is order-agnostic) and unpermutes one column (more3d_unpermute).
  * more3d_dk_dn_gridorder always uses the feature records cached by the last
- * more3d_normals_curvature[_gridorder] on the grid. */
+ * more3d_normals_curvature[_gridorder] on the grid.  n_owned: only points whose ORIGINAL index is < n_owned
+ * enter `minmax` (a strip's own points come first, its ghosts after them); <= 0 means all points. */
 int more3d_normals_curvature_gridorder(const more3d_grid* g, double r, double eps, int min_points,
                                        double* normals, double* lam_ratio, float* K, int32_t* pcount,
                                        void* stream);
 int more3d_dk_dn_gridorder(const more3d_grid* g, double r, double rho, double sigma_normal,
                            double sigma_curvature, const double* chi2_table, int table_len, int min_points,
-                           float* dk, float* dn, float* minmax, void* stream);
+                           int64_t n_owned, float* dk, float* dn, float* minmax, void* stream);
 /* dst[order[i]] = src[i], order as returned by more3d_grid_order (the grid itself is not needed any more);
  * elem_bytes in {4, 8, 24} (f32 / i32 column, f64 column, n x 3 f64 normals). */
 int more3d_unpermute(const int32_t* order, int64_t n, const void* src_gridorder, void* dst, int elem_bytes,

@@ -32,7 +32,7 @@ SIGNATURES = {
     "more3d_normals_curvature": [_vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
     "more3d_dk_dn": [_vp, _f64, _vp, _vp, _f64, _f64, _f64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "more3d_normals_curvature_gridorder": [_vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
-    "more3d_dk_dn_gridorder": [_vp, _f64, _f64, _f64, _f64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "more3d_dk_dn_gridorder": [_vp, _f64, _f64, _f64, _f64, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp],
     "more3d_unpermute": [_vp, _i64, _vp, _vp, _i32, _vp],
     "more3d_minmax4": [_vp, _vp, _i64, _vp, _vp],
     "more3d_saliency_blend": [_vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp],

@@ -153,6 +153,7 @@ struct DkDnParams {
     double zk100_thr;   // largest x with fl(100 * x) <= 0.04 (rounding is monotone, so |100*dk| <= 0.04 <=> |dk| <= x)
     int min_points, s, table_len;
     int grid_order;     // 1: dk / dn are written at the grid position
+    long long n_owned;  // only points with original index < n_owned enter the fused min/max (strip + ghosts)
     Filter32 flt;
 };
 
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float dkf = 0.0f, dnf = 0.0f;
     const bool live = i < g.n;
+    bool owned = false;
     if (live) {
         const D4 pa = ld_d4(feat + i, 0), pb = ld_d4(feat + i, 1);   // (x y z K) (nx ny nz flags)
         const double px = pa.x, py = pa.y, pz = pa.z;
@@ -267,15 +269,18 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
                 dkf = (float)dk; dnf = (float)dn;
             }
         }
-        const int64_t o = prm.grid_order
-                              ? i : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+        const int64_t orig = (prm.grid_order && prm.n_owned >= g.n)
+                                 ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+        const int64_t o = prm.grid_order ? i : orig;
         dk_out[o] = dkf;
         dn_out[o] = dnf;
+        owned = orig < prm.n_owned;
     }
     if (mm) {
         // fused Histo min/max (DM_saliency.py:562-568): warp shuffle, then one atomic per warp
-        unsigned lo_k = live ? f32_ordered(dkf) : 0xffffffffu, hi_k = live ? f32_ordered(dkf) : 0u;
-        unsigned lo_n = live ? f32_ordered(dnf) : 0xffffffffu, hi_n = live ? f32_ordered(dnf) : 0u;
+        const bool cnt = live && owned;
+        unsigned lo_k = cnt ? f32_ordered(dkf) : 0xffffffffu, hi_k = cnt ? f32_ordered(dkf) : 0u;
+        unsigned lo_n = cnt ? f32_ordered(dnf) : 0xffffffffu, hi_n = cnt ? f32_ordered(dnf) : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo_k = min(lo_k, __shfl_xor_sync(0xffffffffu, lo_k, o));
@@ -355,7 +360,7 @@ extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double e
 static int run_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
                      double sigma_normal, double sigma_curvature, const double* chi2_table,
                      int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream,
-                     int grid_order) {
+                     int grid_order, int64_t n_owned) {
     M3D_REQUIRE(g != nullptr, "grid is NULL");
     M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
     M3D_REQUIRE(chi2_table && dk && dn, "NULL argument");
@@ -386,6 +391,7 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     prm.flt = make_filter(g, r);
     prm.zk100_thr = zk100_threshold();
     prm.grid_order = grid_order;
+    prm.n_owned = (n_owned <= 0 || n_owned > g->n) ? g->n : n_owned;
     {
         ProfScope prof("dkdn", s);
         if (g->tall) dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
@@ -410,7 +416,7 @@ extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normal
                             double sigma_normal, double sigma_curvature, const double* chi2_table,
                             int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream) {
     return run_dk_dn(g, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, table_len, min_points,
-                     dk, dn, minmax, stream, 0);
+                     dk, dn, minmax, stream, 0, 0);
 }
 
 // Grid-order variants: every per-point output is written at the point's position in the grid's sorted order
@@ -425,7 +431,8 @@ extern "C" int more3d_normals_curvature_gridorder(const more3d_grid* g, double r
 
 extern "C" int more3d_dk_dn_gridorder(const more3d_grid* g, double r, double rho, double sigma_normal,
                                       double sigma_curvature, const double* chi2_table, int table_len,
-                                      int min_points, float* dk, float* dn, float* minmax, void* stream) {
+                                      int min_points, int64_t n_owned, float* dk, float* dn, float* minmax,
+                                      void* stream) {
     return run_dk_dn(g, r, nullptr, nullptr, rho, sigma_normal, sigma_curvature, chi2_table, table_len, min_points,
-                     dk, dn, minmax, stream, 1);
+                     dk, dn, minmax, stream, 1, n_owned);
 }

@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import UniformGrid, CELL_MARGIN, cell_for_radius
+from .grid import GridColumn, UniformGrid, CELL_MARGIN, cell_for_radius
 
 
 def strip_bounds(x_min, x_max, world):
@@ -135,6 +135,16 @@ def cuda_histogram(values, edges):
     return hist
 
 
+class _OwnedRows:
+    """The owned rows of a grid-order column, brought back to point order only when read."""
+
+    def __init__(self, col, n):
+        self.col, self.n = col, n
+
+    def tensor(self):
+        return self.col.tensor()[:self.n]
+
+
 def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=None, out_host=None):
     """Saliency of the OWNED points of one strip.  own: (n,3) device f64; ghosts: (g,3) device f64
     (points of the neighbouring strips within 2*r_max).  reduce_minmax(minmax) makes the extrema
@@ -157,29 +167,31 @@ def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=N
             if g is not None:
                 g.close()
             g = UniformGrid(local, want)       # shared by the wider radii (see PointCloudDM.grid)
-        normals, _, K, pcount = g.normals_curvature(r, eps, params["min_points"])
+        # grid-order columns (coalesced writes); dk/dn's fused min/max covers the owned points only
+        _, _, _, pcount = g.normals_curvature_gridorder(r, eps, params["min_points"])
         length = 1024
         while True:
             try:
-                dk, dn, _ = g.dk_dn(r, normals, K, rho, params["sigma_normal"], params["sigma_curvature"],
-                                    _chi2_table(params["alpha"], length, dev), params["min_points"])
+                dk, dn, minmax = g.dk_dn_gridorder(r, rho, params["sigma_normal"], params["sigma_curvature"],
+                                                   _chi2_table(params["alpha"], length, dev), params["min_points"],
+                                                   n_owned=n)
                 break
             except _lib.More3DError as e:
                 if "error -4" not in str(e) or length >= (1 << 22):
                     raise
                 length *= 8
         with torch.cuda.device(dev):
-            minmax = torch.empty(4, dtype=torch.float32, device=dev)
-            check(lib.more3d_minmax4(ptr(dk), ptr(dn), n, ptr(minmax), stream_ptr()))   # owned points only
             if reduce_minmax is not None:
                 reduce_minmax(minmax)
-            sal = torch.empty(n, dtype=torch.float32, device=dev)
-            check(lib.more3d_saliency_blend(ptr(dk), ptr(dn), n, ptr(minmax), float(curvature_weight), ptr(sal),
-                                            None, stream_ptr()))
+            nl = int(local.shape[0])
+            sal_g = torch.empty(nl, dtype=torch.float32, device=dev)      # blend is elementwise: grid order
+            check(lib.more3d_saliency_blend(ptr(dk.data), ptr(dn.data), nl, ptr(minmax), float(curvature_weight),
+                                            ptr(sal_g), None, stream_ptr()))
+            sal = GridColumn(dk, sal_g).tensor()[:n]                      # back to point order, owned rows
         if out_host is not None:
             out_host[r].copy_(sal, non_blocking=True)
         out[r] = sal
-        sum_m[r] = pcount[:n]
+        sum_m[r] = _OwnedRows(pcount, n)
     if g is not None:
         g.close()
     return out, sum_m
@@ -205,7 +217,7 @@ class StripSaliency:
         self.h2d_bytes = self.host.numel() * 8
         self.d2h_bytes = n * 4 * len(radii)
         _, pc = self._run(self.resident, None)
-        self.sum_m = {r: float(pc[r].double().sum()) for r in radii}
+        self.sum_m = {r: float(pc[r].tensor().double().sum()) for r in radii}
 
     def _run(self, own, out_host):
         left = gather_rows(own, band_select(own, 0, -np.inf, self.x_lo + self.halo))

@@ -205,15 +205,17 @@ class UniformGrid:
             self._feat_cols = (cols[0], cols[2])     # the cached feature records hold exactly these two
             return cols
 
-    def dk_dn_gridorder(self, r, rho, sigma_normal, sigma_curvature, chi2_table, min_points):
-        """dk / dn from the feature records cached by the last normals_curvature[_gridorder]; GridColumns."""
+    def dk_dn_gridorder(self, r, rho, sigma_normal, sigma_curvature, chi2_table, min_points, n_owned=0):
+        """dk / dn from the feature records cached by the last normals_curvature[_gridorder]; GridColumns.
+        n_owned > 0: minmax covers the points with original index < n_owned only (strip + ghosts)."""
         with torch.cuda.device(self.device):
             dk = self._new((self.n,), torch.float32)
             dn = self._new((self.n,), torch.float32)
             minmax = self._new((4,), torch.float32)
             check(self.lib.more3d_dk_dn_gridorder(self._h, float(r), float(rho), float(sigma_normal),
                                                   float(sigma_curvature), ptr(chi2_table), int(chi2_table.numel()),
-                                                  int(min_points), ptr(dk), ptr(dn), ptr(minmax), stream_ptr()))
+                                                  int(min_points), int(n_owned), ptr(dk), ptr(dn), ptr(minmax),
+                                                  stream_ptr()))
             return GridColumn(self, dk), GridColumn(self, dn), minmax
 
     def order_tensor(self):

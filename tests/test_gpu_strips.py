@@ -59,7 +59,7 @@ def test_logical_strips_match_untiled(G):
                                  reduce_minmax=lambda mm: mm.copy_(glob[next(it)]))
         oi = owned[k].cpu().numpy()
         for r in RADII:
-            assert np.array_equal(pc[r].cpu().numpy(), whole[r]["_pcount"].cpu().numpy()[oi])   # integer: exact
+            assert np.array_equal(pc[r].tensor().cpu().numpy(), whole[r]["_pcount"].cpu().numpy()[oi])   # integer: exact
             a = out[r].cpu().numpy().astype(np.float64)
             b = whole[r]["_saliency"].cpu().numpy()[oi].astype(np.float64)
             bad = np.abs(a - b) > 1e-5 * np.abs(b) + 1e-7
