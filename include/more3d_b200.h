@@ -218,6 +218,16 @@ int more3d_ls_run(const more3d_ls_graph* g, double* phi, const double* zeta, int
                   double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
                   double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream);
 
+/* Solver.run with active_contour_model='lmv' (_lmv_step, :439-513): same regularisation terms, the data term
+ * is the Gaussian log-likelihood difference of each point's (k+1)-neighbourhood under its local inside /
+ * outside means and deviations.  zeta: n f64, ONE channel (the reference's expressions only broadcast for a
+ * 1-D cue; with the (N, C) cue its Solver constructor requires, _lmv_step raises ValueError -- the caller
+ * squeezes an (N, 1) cue).  lambda1 / lambda2 do not enter (:520-521). */
+int more3d_ls_run_lmv(const more3d_ls_graph* g, double* phi, const double* zeta, uint8_t* active,
+                      uint8_t* last_active, int alias_last_active, int iterations, double stepsize, double nu,
+                      double mu, double epsilon, double max_val, int cap, double tolerance, double* rmsc_h,
+                      int* iterations_done_h, int* converged_h, void* stream);
+
 /* The same iteration one phase at a time, for hosts that exchange ghost values between the phases
  * (multi-GPU x-strips).  Points [0, n_own) of the graph are owned by the caller, the rest are ghosts
  * (their neighbour rows list themselves; their phi / aux are supplied by the owner between phases).

@@ -1,7 +1,7 @@
 // K10-K12: point-based level set (Chan-Vese active contour on a kNN graph with WLS derivatives).
 // Replaces levelsets_func.py: compute_normals (:112-129), compute_tangent_planes (:132-151),
 // Derivative.__init__/__call__/grad/div (:245-305), heaviside/delta/dp/smooth (:319-358) and
-// Solver.run/_chan_vese_step/zero_crossings/initialize_* (:386-437, :524-642).
+// Solver.run/_chan_vese_step/_lmv_step/zero_crossings/initialize_* (:386-513, :524-642).
 //
 // Per-point arrays are structure-of-arrays on the device so that thread i (= point i) reads
 // consecutive addresses: neighbours nbr[j*n + i] (int32), WLS weights w[j*n + i], the folded derivative
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_init_voxels_kernel(const double
 struct LsParams {
     double stepsize, nu, mu, lambda1, lambda2, epsilon, max_val;
     int cap, channels;
+    int model;   // 0 = Chan-Vese (_chan_vese_step), 1 = local mean and variance (_lmv_step, single-channel cue)
 };
 
 constexpr int RED_BLOCKS = 592;   // 4 CTAs per SM; fixed so the reduction tree (and the result) is reproducible
@@ -390,6 +391,81 @@ __global__ void ls_reduce_final(const double* __restrict__ part, int nblocks, in
     out[a] = r;
 }
 
+// ---- 'lmv' model (_lmv_step, levelsets_func.py:439-513): the data term compares each point's cue with the
+// LOCAL (k+1-neighbourhood, self first) Heaviside-weighted means and deviations instead of the global region
+// means.  The cue is a single channel: the reference's expressions only broadcast for a 1-D zeta.
+// idx_ = idx | neighbours of idx (:463-464); idxd is zeroed by the caller
+__global__ void __launch_bounds__(LS_THREADS) ls_lmv_dilate(LsGraph g, const uint8_t* __restrict__ idx2,
+                                                            uint8_t* __restrict__ idxd) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    if (idx2[i]) {
+        idxd[i] = 1;
+        for (int j = 0; j < g.k; ++j) idxd[g.nbr[(int64_t)j * g.n + i]] = 1;
+    }
+}
+// mu_in, mu_out, sigma_in, sigma_out of the points in idx_ (:473-495); one 32-B record per point.  Row sums follow
+// numpy's pairwise order (np_pairwise_sum), 1 - H and the products are rounded as written.
+__global__ void __launch_bounds__(LS_THREADS) ls_lmv_stats(LsGraph g, double eps, const double* __restrict__ phi,
+                                                           const double* __restrict__ zeta,
+                                                           const uint8_t* __restrict__ idxd,
+                                                           double* __restrict__ stats /* AoS n x 4 */) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    double2* out = reinterpret_cast<double2*>(stats + 4 * i);
+    if (!idxd[i]) {                                     // np.zeros_like(zeta) elsewhere (:466-469); never read
+        out[0] = make_double2(0.0, 0.0);
+        out[1] = make_double2(0.0, 0.0);
+        return;
+    }
+    const int m = g.k + 1;
+    double z[LS_MAX_K + 1], hin[LS_MAX_K + 1], hout[LS_MAX_K + 1], t[LS_MAX_K + 1];
+    for (int j = 0; j < m; ++j) {
+        const int64_t q = (j == 0) ? i : (int64_t)g.nbr[(int64_t)(j - 1) * g.n + i];
+        const double H = heaviside(phi[q], eps);
+        z[j] = zeta[q];
+        hout[j] = H;
+        hin[j] = __dsub_rn(1.0, H);
+    }
+    const double s_in = np_pairwise_sum(hin, m), s_out = np_pairwise_sum(hout, m);
+    for (int j = 0; j < m; ++j) t[j] = __dmul_rn(z[j], hin[j]);
+    const double mu_in = __ddiv_rn(np_pairwise_sum(t, m), s_in);                          // :473-475
+    for (int j = 0; j < m; ++j) t[j] = __dmul_rn(z[j], hout[j]);
+    const double mu_out = __ddiv_rn(np_pairwise_sum(t, m), s_out);                        // :476-478
+    for (int j = 0; j < m; ++j) { const double d = __dsub_rn(z[j], mu_in); t[j] = __dmul_rn(__dmul_rn(d, d), hin[j]); }
+    double sig_in = sqrt(__ddiv_rn(np_pairwise_sum(t, m), s_in));                         // :480-483
+    for (int j = 0; j < m; ++j) { const double d = __dsub_rn(z[j], mu_out); t[j] = __dmul_rn(__dmul_rn(d, d), hout[j]); }
+    double sig_out = sqrt(__ddiv_rn(np_pairwise_sum(t, m), s_out));                       // :484-487
+    sig_in = (sig_in >= 0.0001 || isnan(sig_in)) ? sig_in : 0.0001;                       // np.maximum, :492-493
+    sig_out = (sig_out >= 0.0001 || isnan(sig_out)) ? sig_out : 0.0001;
+    out[0] = make_double2(mu_in, mu_out);
+    out[1] = make_double2(sig_in, sig_out);
+}
+// F = e_in - e_out (:499-512) at point i
+__device__ __forceinline__ double lmv_force(const LsGraph& g, int64_t i, const double* __restrict__ zeta,
+                                            const double* __restrict__ stats) {
+    const int m = g.k + 1;
+    const double2 own = reinterpret_cast<const double2*>(stats + 4 * i)[1];
+    const double sig_in = own.x, sig_out = own.y;
+    const double l_out = log(__dmul_rn(2.5066282746310002, sig_out));    // np.log(np.sqrt(2*np.pi) * sigma_out)
+    const double l_in = log(__dmul_rn(2.5066282746310002, sig_in));
+    const double d_out = __dmul_rn(2.0, __dmul_rn(sig_out, sig_out));    // 2 * sigma_out**2
+    const double d_in = __dmul_rn(2.0, __dmul_rn(sig_in, sig_in));
+    double a[LS_MAX_K + 1], b[LS_MAX_K + 1];
+    for (int j = 0; j < m; ++j) {
+        const int64_t q = (j == 0) ? i : (int64_t)g.nbr[(int64_t)(j - 1) * g.n + i];
+        const double2 mq = reinterpret_cast<const double2*>(stats + 4 * q)[0];   // (mu_in, mu_out) of q
+        const double zq = zeta[q];
+        const double eo = __dsub_rn(zq, mq.y), ei = __dsub_rn(zq, mq.x);
+        a[j] = __dadd_rn(l_out, __ddiv_rn(__dmul_rn(eo, eo), d_out));
+        b[j] = __dadd_rn(l_in, __ddiv_rn(__dmul_rn(ei, ei), d_in));
+    }
+    const double im = 1.0 / (double)m;
+    const double e_in = __dmul_rn(im, np_pairwise_sum(a, m));
+    const double e_out = __dmul_rn(im, np_pairwise_sum(b, m));
+    return __dsub_rn(e_in, e_out);
+}
+
 // R + delta (C + F), phi update, increment statistics                      (:404-408, :414-418, :433-437, :614-616)
 __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, double* __restrict__ phi,
                                                         const uint8_t* __restrict__ idx2,
@@ -397,6 +473,7 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, d
                                                         const double* __restrict__ aux,
                                                         const double* __restrict__ zeta,
                                                         const double* __restrict__ region /* channels x 4 sums */,
+                                                        const double* __restrict__ stats /* lmv: n x 4, else NULL */,
                                                         double* __restrict__ phi_new, double* __restrict__ part /* RED_BLOCKS x 2 */) {
     double v[2] = {0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -424,23 +501,28 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, d
             const double c0 = g.cst[i], c1 = g.cst[g.n + i];
 #pragma unroll
             for (int f = 0; f < 4; ++f) { ax[f] += c0; ay[f] += c1; }
-            if (p.nu > 0) {
+            if (p.nu > 0 || p.model == 1) {
                 const double gx = ax[0] * t1x + ay[0] * t2x, gy = ax[0] * t1y + ay[0] * t2y, gz = ax[0] * t1z + ay[0] * t2z;
                 R = p.nu * (o0.x * laplace[i] + ((gx * dphi[i] + gy * dphi[g.n + i]) + gz * dphi[2 * g.n + i]));
             }
-            if (p.mu > 0) {
+            if (p.mu > 0 || p.model == 1) {
                 double dv = ax[1] * t1x + ay[1] * t2x;
                 dv += ax[2] * t1y + ay[2] * t2y;
                 dv += ax[3] * t1z + ay[3] * t2z;
                 C = p.mu * dv;
             }
-            double f1 = 0.0, f2 = 0.0;
-            for (int c = 0; c < p.channels; ++c) {
-                const double zin = region[4 * c] / region[4 * c + 1], zout = region[4 * c + 2] / region[4 * c + 3];
-                const double z = zeta[i * p.channels + c];
-                f1 += (z - zin) * (z - zin); f2 += (z - zout) * (z - zout);
+            double F;
+            if (p.model == 1) {
+                F = lmv_force(g, i, zeta, stats);
+            } else {
+                double f1 = 0.0, f2 = 0.0;
+                for (int c = 0; c < p.channels; ++c) {
+                    const double zin = region[4 * c] / region[4 * c + 1], zout = region[4 * c + 2] / region[4 * c + 3];
+                    const double z = zeta[i * p.channels + c];
+                    f1 += (z - zin) * (z - zin); f2 += (z - zout) * (z - zout);
+                }
+                F = p.lambda1 * f1 - p.lambda2 * f2;
             }
-            const double F = p.lambda1 * f1 - p.lambda2 * f2;
             const double inc = p.stepsize * (R + delta_fn(phi[i], p.epsilon) * (C + F));
             out = phi[i] + inc;
             v[0] += inc * inc; v[1] += 1.0;
@@ -617,19 +699,24 @@ extern "C" int more3d_ls_init_voxels(const double* xyz, int64_t n, double h, dou
     return MORE3D_OK;
 }
 
-extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double* zeta, int channels, uint8_t* active,
-                             uint8_t* last_active, int alias_last_active, int iterations, double stepsize, double nu,
-                             double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
-                             double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream) {
+static int ls_run_impl(const more3d_ls_graph* G, int model, double* phi, const double* zeta, int channels, uint8_t* active,
+                       uint8_t* last_active, int alias_last_active, int iterations, double stepsize, double nu,
+                       double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
+                       double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream) {
     M3D_REQUIRE(G && phi && zeta && active && last_active, "NULL argument");
     M3D_REQUIRE(channels >= 1 && iterations >= 0, "bad channels / iterations");
+    M3D_REQUIRE(model == 0 || model == 1, "model must be 0 (chan_vese) or 1 (lmv)");
+    M3D_REQUIRE(model == 0 || channels == 1, "the lmv model takes a single-channel cue");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n = G->n;
     LsGraph g = view(G);
     LsParams p;
     p.stepsize = stepsize; p.nu = nu; p.mu = mu; p.lambda1 = lambda1; p.lambda2 = lambda2; p.epsilon = epsilon;
-    p.max_val = max_val; p.cap = cap; p.channels = channels;
+    p.max_val = max_val; p.cap = cap; p.channels = channels; p.model = model;
     ProfScope prof("ls_run", s);
+    double* stats = nullptr;
+    uint8_t* idxd = nullptr;
+    if (model == 1) { M3D_TRY(dev_alloc(&stats, (size_t)4 * n, s)); M3D_TRY(dev_alloc(&idxd, (size_t)n, s)); }
     double *laplace = nullptr, *dphi = nullptr, *aux = nullptr, *bufA = nullptr, *bufB = nullptr;
     double *part = nullptr, *region = nullptr, *incs = nullptr;
     uint8_t *idx2 = nullptr, *azc = nullptr, *outside = nullptr;
@@ -644,16 +731,23 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     int done = 0, conv = 0;
     for (int it = 0; it < iterations; ++it) {
         if (!alias_last_active) ls_reclamp<<<nb, LS_THREADS, 0, s>>>(n, active, last_active, max_val, phi);
-        if (nu > 0 || mu > 0) {
+        if (nu > 0 || mu > 0 || model == 1) {             // _lmv_step differentiates unconditionally, :440-446
             ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, phi, active, idx2, laplace, dphi, aux);
         } else {
             M3D_CUDA(cudaMemcpyAsync(idx2, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // idx stays the active mask
         }
-        for (int c = 0; c < channels; ++c) {
-            ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, epsilon, phi, zeta, c, part);
-            ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c);
+        if (model == 1) {
+            M3D_CUDA(cudaMemsetAsync(idxd, 0, (size_t)n, s));
+            ls_lmv_dilate<<<nb, LS_THREADS, 0, s>>>(g, idx2, idxd);
+            ls_lmv_stats<<<nb, LS_THREADS, 0, s>>>(g, epsilon, phi, zeta, idxd, stats);
+            count_launches(2);
+        } else {
+            for (int c = 0; c < channels; ++c) {
+                ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, epsilon, phi, zeta, c, part);
+                ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c);
+            }
         }
-        ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, bufA, part);
+        ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, bufA, part);
         ls_reduce_final<<<1, 32, 0, s>>>(part, STEPB_BLOCKS, 2, incs + 2 * it);
         if (!alias_last_active) M3D_CUDA(cudaMemcpyAsync(last_active, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // :617
         ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, bufA, active, azc, bufB, outside);
@@ -661,7 +755,7 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
         ls_step_e<<<nb, LS_THREADS, 0, s>>>(g, bufA, phi);
         M3D_CUDA(cudaMemsetAsync(active, 0, (size_t)n, s));
         ls_step_f<<<nb, LS_THREADS, 0, s>>>(g, azc, active);
-        count_launches(7 + 2 * channels + (alias_last_active ? 0 : 1));
+        count_launches(7 + (model == 1 ? 0 : 2 * channels) + (alias_last_active ? 0 : 1));
         M3D_CHECK_LAUNCH();
         done = it + 1;
         if (tolerance > 0) {                               // the reference checks every iteration, :635-638
@@ -684,7 +778,24 @@ extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double
     if (converged_h) *converged_h = conv;
     dev_free(laplace, s); dev_free(dphi, s); dev_free(aux, s); dev_free(bufA, s); dev_free(bufB, s);
     dev_free(part, s); dev_free(region, s); dev_free(incs, s); dev_free(idx2, s); dev_free(azc, s); dev_free(outside, s);
+    dev_free(stats, s); dev_free(idxd, s);
     return MORE3D_OK;
+}
+
+extern "C" int more3d_ls_run(const more3d_ls_graph* G, double* phi, const double* zeta, int channels, uint8_t* active,
+                             uint8_t* last_active, int alias_last_active, int iterations, double stepsize, double nu,
+                             double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
+                             double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream) {
+    return ls_run_impl(G, 0, phi, zeta, channels, active, last_active, alias_last_active, iterations, stepsize, nu, mu,
+                       lambda1, lambda2, epsilon, max_val, cap, tolerance, rmsc_h, iterations_done_h, converged_h, stream);
+}
+
+extern "C" int more3d_ls_run_lmv(const more3d_ls_graph* G, double* phi, const double* zeta, uint8_t* active,
+                                 uint8_t* last_active, int alias_last_active, int iterations, double stepsize, double nu,
+                                 double mu, double epsilon, double max_val, int cap, double tolerance, double* rmsc_h,
+                                 int* iterations_done_h, int* converged_h, void* stream) {
+    return ls_run_impl(G, 1, phi, zeta, 1, active, last_active, alias_last_active, iterations, stepsize, nu, mu, 0.0, 0.0,
+                       epsilon, max_val, cap, tolerance, rmsc_h, iterations_done_h, converged_h, stream);
 }
 
 
@@ -701,7 +812,7 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
     LsGraph g = view(G);
     LsParams p;
     p.stepsize = st->stepsize; p.nu = st->nu; p.mu = st->mu; p.lambda1 = st->lambda1; p.lambda2 = st->lambda2;
-    p.epsilon = st->epsilon; p.max_val = st->max_val; p.cap = st->cap; p.channels = st->channels;
+    p.epsilon = st->epsilon; p.max_val = st->max_val; p.cap = st->cap; p.channels = st->channels; p.model = 0;
     const unsigned nb = (unsigned)((n + LS_THREADS - 1) / LS_THREADS);
     switch (phase) {
     case 0:   // re-clamp (de)activated points
@@ -726,7 +837,7 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
         break;
     case 3:   // update -> bufA (= phi + increment), incs[0..1] = local sum inc^2, count
         ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, st->phi, st->idx2, st->laplace, st->dphi, st->aux, st->zeta,
-                                                      st->region, st->bufA, st->part);
+                                                      st->region, nullptr, st->bufA, st->part);
         ls_reduce_final<<<1, 32, 0, s>>>(st->part, STEPB_BLOCKS, 2, st->incs);
         count_launches(2);
         break;

@@ -5,8 +5,9 @@ Same names, signatures and defaults: ``wendland, normalize, clip, compute_normal
 compute_tangent_planes, build_neighborhoods, Derivative, heaviside, delta, dp, smooth, Solver``
 (levelsets_func.py:92-667).  Arrays go in and come out as numpy arrays exactly like the reference;
 ``Solver`` keeps its state in HBM between calls and mirrors it to the host lazily (only when an attribute
-such as ``solver.phi`` is touched).  Out of scope here: the LAS / PLY readers (:43-84) and the
-``'lmv'`` active-contour model (:439-513, a "next" row of SURVEY.md §8f).
+such as ``solver.phi`` is touched).  Both active-contour models run on the device: ``'chan_vese'``
+(:386-437) and ``'lmv'`` (:439-513, single-channel cue -- see ``Solver.run``).  The LAS / PLY readers
+(:43-84) live in ``more3d_b200/io_formats.py``.
 
 Reference quirks kept on purpose: normals are PCA of offsets about the QUERY point
 (:116); ``compute_tangent_planes`` normalises the caller's normals in place (:140); after
@@ -485,12 +486,10 @@ class Solver:
 
     # -- the iteration ----------------------------------------------------------------------------------
     def run(self, iterations, stepsize, nu, mu, lambda1, lambda2, epsilon, cap=True, tolerance=1e-4):
-        """explicit Euler iterations of the Chan-Vese flow (:598-642).  Returns True when the RMS change
-        drops below ``tolerance``."""
+        """explicit Euler iterations of the Chan-Vese or local-mean-and-variance flow (:598-642).  Returns True
+        when the RMS change drops below ``tolerance``."""
         _print(f"running {iterations} steps")
         assert self.active_contour_model in ['chan_vese', 'lmv']
-        if self.active_contour_model != 'chan_vese':
-            raise NotImplementedError("the 'lmv' model is a next-row item (SURVEY.md §8f-1)")
         lib = _lib.load()
         phi = self._phi.get_dev(torch.float64)
         zeta = self._zeta.get_dev(torch.float64)
@@ -499,10 +498,23 @@ class Solver:
         last = active if self._alias else self._last_active.get_dev(torch.uint8)
         rmsc = (C.c_double * max(int(iterations), 1))()
         done, conv = C.c_int(0), C.c_int(0)
-        check(lib.more3d_ls_run(self.diff._g, ptr(phi), ptr(zeta), channels, ptr(active), ptr(last), 1 if self._alias else 0,
-                                int(iterations), float(stepsize), float(nu), float(mu), float(lambda1), float(lambda2),
-                                float(epsilon * self.h), float(self.max_val), 1 if cap else 0, float(tolerance), rmsc,
-                                C.byref(done), C.byref(conv), stream_ptr()))
+        if self.active_contour_model == 'lmv':
+            # _lmv_step (:439-513) is written for a 1-D cue: with the (N, C) cue the constructor asks for, its
+            # zeta[nb] * (1 - Hphi[nb]) raises ValueError (shapes (a, k+1, C) x (a, k+1)), and it runs verbatim
+            # once the caller sets solver.zeta = solver.zeta[:, 0].  Here a single-channel cue runs either way
+            # ((N, 1) is squeezed); more channels raise like the reference.
+            if channels != 1:
+                raise ValueError("operands could not be broadcast together: the 'lmv' model takes a "
+                                 "single-channel cue, got %d channels" % channels)
+            check(lib.more3d_ls_run_lmv(self.diff._g, ptr(phi), ptr(zeta), ptr(active), ptr(last),
+                                        1 if self._alias else 0, int(iterations), float(stepsize), float(nu), float(mu),
+                                        float(epsilon * self.h), float(self.max_val), 1 if cap else 0, float(tolerance),
+                                        rmsc, C.byref(done), C.byref(conv), stream_ptr()))
+        else:
+            check(lib.more3d_ls_run(self.diff._g, ptr(phi), ptr(zeta), channels, ptr(active), ptr(last), 1 if self._alias else 0,
+                                    int(iterations), float(stepsize), float(nu), float(mu), float(lambda1), float(lambda2),
+                                    float(epsilon * self.h), float(self.max_val), 1 if cap else 0, float(tolerance), rmsc,
+                                    C.byref(done), C.byref(conv), stream_ptr()))
         self._phi.dev_written()
         self._active.dev_written()
         if not self._alias:

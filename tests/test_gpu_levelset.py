@@ -139,8 +139,9 @@ def test_solver_mask_init_and_tolerance(g):
     solver.run(5, **RUN)
     phi = solver.phi
     assert np.all(np.isfinite(phi)) and np.abs(phi).max() <= 2 * h + 1e-12
-    with pytest.raises(NotImplementedError):
-        ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "lmv").run(1, **RUN)
+    two = np.column_stack([g["zeta"][:, 0], g["zeta"][:, 0]])
+    with pytest.raises(ValueError):                                              # lmv: single-channel cue only
+        ls.Solver(h, two, pts, g["neighbors"], (g["t1"], g["t2"]), "lmv").run(1, **RUN)
 
 
 @pytest.mark.parametrize("tag,kw", [("a", dict(nu=1e-4, mu=2.5e-3, cap=True)), ("b", dict(nu=0.0, mu=0.0, cap=True)),
@@ -190,3 +191,61 @@ def test_solver_against_oracle_other_size_and_params():
     solver.run(8, **kw)
     assert np.array_equal(solver.active, st["active"])
     np.testing.assert_allclose(solver.phi, st["phi"], rtol=1e-8, atol=1e-10)
+
+
+LMV_RUNS = {"v": dict(stepsize=.005, nu=1e-4, mu=2.5e-3, epsilon=1, cap=True),
+            "m": dict(stepsize=.01, nu=2e-4, mu=1e-3, epsilon=0.8, cap=True)}
+
+
+@pytest.mark.parametrize("tag", ["v", "m"])
+@pytest.mark.parametrize("squeeze", [False, True])
+def test_solver_lmv_matches_reference(golden_dir, tag, squeeze):
+    """active_contour_model='lmv' (_lmv_step, levelsets_func.py:439-513) against the verbatim reference run with
+    the 1-D cue it is written for (tests/golden/levelset_lmv_3k.npz).  Both the (N, 1) cue and the caller-side
+    squeeze the reference needs are accepted; voxel init (aliased masks) and mask init (re-clamp path)."""
+    from more3d_b200 import levelsets_func as ls
+    g = np.load(os.path.join(golden_dir, "levelset_lmv_3k.npz"))
+    pts, h = g["points"], float(g["h"])
+    solver = ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "lmv", weights=g["weights"])
+    if squeeze:
+        solver.zeta = solver.zeta[:, 0]
+    if tag == "v":
+        solver.initialize_from_voxels(2.0)
+    else:
+        solver.initialize_from_mask((pts[:, 0] ** 2 + pts[:, 1] ** 2) < 9.0)
+    kw = dict(LMV_RUNS[tag], lambda1=1, lambda2=1, tolerance=0)
+    solver.run(1, **kw)
+    assert np.array_equal(solver.active, g["act1_" + tag])
+    np.testing.assert_allclose(solver.phi, g["phi1_" + tag], rtol=1e-8, atol=1e-10)
+    solver.run(11, **kw)
+    assert np.array_equal(solver.active, g["act12_" + tag])                      # active set: exact
+    assert np.array_equal(solver.last_active, g["last12_" + tag])
+    np.testing.assert_allclose(solver.phi, g["phi12_" + tag], rtol=1e-8, atol=1e-10)
+
+
+def test_solver_lmv_against_oracle_other_size():
+    """lmv on a cloud / k / parameter set no golden covers: CUDA vs oracle/ref_levelset.py (pinned to the verbatim
+    reference by tests/test_oracle_golden.py::test_levelset_oracle_lmv)."""
+    from more3d_b200 import synthetic
+    from more3d_b200 import levelsets_func as ls
+    from oracle import ref_levelset as rl
+    pts = synthetic.terrain(20000, seed=78, noise=0.04)
+    pts -= pts.mean(axis=0)
+    h, k = 0.45, 6
+    nb, n, t1, t2 = rl.knn_frames(pts, k)
+    rng = np.random.Generator(np.random.PCG64(4))
+    zeta = (np.abs(np.cos(pts[:, 1] / 2.0)) * (pts[:, 0] > 0) + 0.2 * rng.random(len(pts)))[:, None]
+    w, D = rl.wls_operator(pts, nb, t1, t2, 3 * h)
+    kw = dict(stepsize=.008, nu=3e-4, mu=1e-3, lambda1=0.7, lambda2=1.3, epsilon=1.2, cap=True, tolerance=0)
+    phi0 = rl.init_voxels(pts, 1.5, 2 * h)
+    act0 = rl.zero_crossings(phi0, nb, np.arange(len(pts)))
+    st = dict(points=pts, nbrs=nb, t1=t1, t2=t2, w=w, D=D, h=h, zeta=zeta, phi=phi0.copy(), active=act0, last_active=act0,
+              alias=True)
+    rl.run(st, 8, model="lmv", **kw)
+    nb2, n2, tang = ls.build_neighborhoods(pts.copy(), h, k, normals=n)
+    solver = ls.Solver(h, zeta, pts, nb2, tang, "lmv", weights=w)
+    solver.initialize_from_voxels(1.5)
+    solver.run(8, **kw)
+    assert np.array_equal(solver.active, st["active"])
+    np.testing.assert_allclose(solver.phi, st["phi"], rtol=1e-8, atol=1e-10)
+    assert np.abs(solver.phi - phi0).max() > 1e-3                                # the flow moved

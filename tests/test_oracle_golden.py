@@ -168,3 +168,37 @@ def test_levelset_oracle_mask_init(golden_dir, tag, kw):
     rl.run(st, 12, stepsize=.01, lambda1=1.5, lambda2=0.5, epsilon=0.8, tolerance=0, **kw)
     assert np.array_equal(st["active"], g["act_" + tag]) and np.array_equal(st["last_active"], g["last_" + tag])
     np.testing.assert_allclose(st["phi"], g["phi_" + tag], rtol=1e-9, atol=1e-11)
+
+
+LMV_RUNS = {"v": dict(stepsize=.005, nu=1e-4, mu=2.5e-3, epsilon=1, cap=True),
+            "m": dict(stepsize=.01, nu=2e-4, mu=1e-3, epsilon=0.8, cap=True)}
+
+
+@pytest.mark.parametrize("tag", ["v", "m"])
+def test_levelset_oracle_lmv(golden_dir, tag):
+    """model='lmv' (_lmv_step): oracle vs the verbatim reference run with the caller-squeezed 1-D cue
+    (tools/make_golden.py levelset_lmv); the golden also records that the (N, 1) cue raises in the reference."""
+    from oracle import ref_levelset as rl
+    g = load(golden_dir, "levelset_lmv_3k")
+    assert "could not be broadcast" in str(g["raised_on_2d_cue"])
+    pts, h = g["points"], float(g["h"])
+    _, D = rl.wls_operator(pts, g["neighbors"], g["t1"], g["t2"], 3 * h)
+    w = g["weights"]
+    if tag == "v":
+        phi = rl.init_voxels(pts, 2.0, 2 * h)
+        alias = True
+    else:
+        phi = np.where((pts[:, 0] ** 2 + pts[:, 1] ** 2) < 9.0, -2 * h, 2 * h)
+        alias = False
+    act = rl.zero_crossings(phi, g["neighbors"], np.arange(len(pts)))
+    st = dict(points=pts, nbrs=g["neighbors"], t1=g["t1"], t2=g["t2"], w=w, D=D, h=h, zeta=g["zeta"], phi=phi,
+              active=act, last_active=act if alias else act.copy(), alias=alias)
+    kw = dict(LMV_RUNS[tag], lambda1=1, lambda2=1, tolerance=0, model="lmv")
+    rl.run(st, 1, **kw)
+    assert np.array_equal(st["active"], g["act1_" + tag])
+    np.testing.assert_allclose(st["phi"], g["phi1_" + tag], rtol=1e-9, atol=1e-11)
+    rl.run(st, 11, **kw)
+    assert np.array_equal(st["active"], g["act12_" + tag])
+    np.testing.assert_allclose(st["phi"], g["phi12_" + tag], rtol=1e-9, atol=1e-11)
+    if not alias:
+        assert np.array_equal(st["last_active"], g["last12_" + tag])

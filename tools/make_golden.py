@@ -143,9 +143,51 @@ def levelset_mask_case():
     print("levelset mask case", [int(out["act_" + t].sum()) for t in "abc"])
 
 
+def levelset_lmv_case():
+    """Solver.run with active_contour_model='lmv' (_lmv_step, levelsets_func.py:439-513), executed verbatim.
+    With the (N, C) cue the constructor requires, the step raises ValueError (zeta[nb] * (1 - Hphi[nb]) cannot
+    broadcast); it is written for a 1-D cue and runs unmodified once the CALLER squeezes the attribute --
+    that one assignment is the only thing this harness adds."""
+    _, _, ls = ref_harness.load_reference()
+    pts = synthetic.terrain(3000, seed=41, noise=0.03)
+    pts = pts - pts.mean(axis=0)
+    h, k = 0.5, 7
+    neighbors, normals, tangents = ls.build_neighborhoods(pts.copy(), h, k)
+    rng = np.random.Generator(np.random.PCG64(13))
+    zeta = np.abs(np.sin(pts[:, :1] / 3.0) * np.cos(pts[:, 1:2] / 2.0)) + 0.1 * rng.random((len(pts), 1))
+    out = dict(points=pts, h=h, k=k, neighbors=neighbors, normals=normals, t1=tangents[0], t2=tangents[1], zeta=zeta)
+    s0 = ls.Solver(h, zeta, pts, neighbors, tangents, "lmv")
+    s0.initialize_from_voxels(2.0)
+    try:
+        s0.run(1, stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
+        raised = ""
+    except ValueError as e:
+        raised = str(e)
+    assert raised, "the reference's lmv step was expected to raise on an (N, 1) cue"
+    out["raised_on_2d_cue"] = raised
+    for tag, init, kw in (("v", "voxels", dict(stepsize=.005, nu=1e-4, mu=2.5e-3, epsilon=1, cap=True)),
+                          ("m", "mask", dict(stepsize=.01, nu=2e-4, mu=1e-3, epsilon=0.8, cap=True))):
+        solver = ls.Solver(h, zeta, pts, neighbors, tangents, "lmv")
+        solver.zeta = solver.zeta[:, 0]                 # the caller-side squeeze
+        if init == "voxels":
+            solver.initialize_from_voxels(2.0)
+        else:
+            solver.initialize_from_mask((pts[:, 0] ** 2 + pts[:, 1] ** 2) < 9.0)
+        out["weights"] = solver.diff.weights
+        solver.run(1, lambda1=1, lambda2=1, tolerance=0, **kw)
+        out["phi1_" + tag] = solver.phi.copy()
+        out["act1_" + tag] = solver.active.copy()
+        solver.run(11, lambda1=1, lambda2=1, tolerance=0, **kw)
+        out["phi12_" + tag] = solver.phi.copy()
+        out["act12_" + tag] = solver.active.copy()
+        out["last12_" + tag] = solver.last_active.copy()
+    np.savez_compressed(os.path.join(OUT, "levelset_lmv_3k.npz"), **out)
+    print("levelset lmv case", int(out["act12_v"].sum()), int(out["act12_m"].sum()), "|", raised)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["sal", "lattice", "balltree", "levelset", "levelset_mask"]
+    which = sys.argv[1:] or ["sal", "lattice", "balltree", "levelset", "levelset_mask", "levelset_lmv"]
     if "sal" in which:
         saliency_case("terrain_r05", synthetic.terrain(3000, seed=11), 0.5, 0.01, 0.01)
         saliency_case("terrain_r10", synthetic.terrain(2500, seed=12), 1.0, 0.01, 0.01)
@@ -166,3 +208,5 @@ if __name__ == "__main__":
         levelset_case()
     if "levelset_mask" in which:
         levelset_mask_case()
+    if "levelset_lmv" in which:
+        levelset_lmv_case()
