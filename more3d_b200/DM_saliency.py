@@ -5,7 +5,7 @@ Same names, argument meaning and error behaviour as the reference:
 ``DM_nonparam_curvature`` (:326), ``DM_dk_dn`` (:419), ``DM_saliency`` (:539),
 ``DM_saliency_stats`` (:585).  Where the reference takes the path of an OPALS ODM file, these take
 a :class:`PointCloudDM` (an in-memory, device-resident attribute table -- ODM is a proprietary
-format) or the path of an ``.npz`` written by ``PointCloudDM.save_as``.
+format), the path of an ``.npz`` written by ``PointCloudDM.save_as``, or an uncompressed ``.las`` file.
 
 The OPALS per-point callback dispatch (``pyDM.ProcessorEx(dm, query, ...).run(kernel)``,
 DM_saliency.py:403-407) is kept as :class:`ProcessorEx`; ``run`` launches ONE bulk CUDA pass that
@@ -74,6 +74,22 @@ class PointCloudDM:
     # -- ODM-like surface ---------------------------------------------------------------
     @classmethod
     def load(cls, path, *_):
+        if str(path).lower().endswith(".las"):
+            # an uncompressed LAS file: coordinates as stored (not centred), NormalX/Y/Z and every other
+            # extra-bytes dimension as an attribute column
+            from .io_formats import parse_las
+            try:
+                las = parse_las(path)
+            except (OSError, ValueError) as e:
+                raise IOError(str(e))
+            nrm = None
+            if all(k in las.extra for k in ("NormalX", "NormalY", "NormalZ")):
+                nrm = np.column_stack([las.extra[k] for k in ("NormalX", "NormalY", "NormalZ")]).astype(np.float64)
+            dm = cls(np.column_stack((las.x, las.y, las.z)), nrm)
+            for k, v in las.extra.items():
+                if k not in ("NormalX", "NormalY", "NormalZ"):
+                    dm.attrs[k] = torch.from_numpy(np.ascontiguousarray(v)).to(dm.device)
+            return dm
         try:
             z = np.load(path)
         except (OSError, ValueError) as e:

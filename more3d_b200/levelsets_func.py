@@ -22,6 +22,7 @@ import torch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 from .grid import UniformGrid
+from .io_formats import read_las, read_ply  # noqa: F401  (levelsets_func.py:43-84)
 
 verbose = False
 

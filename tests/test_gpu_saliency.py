@@ -289,3 +289,18 @@ def test_gridorder_columns_identical_to_point_order():
     DM_dk_dn(dm2, "sphere", rho, rho, sigma_normal=0.01, sigma_curvature=0.01, radius=r)
     assert np.array_equal(dm.get("_dk"), dm2.get("_dk"), equal_nan=True)
     assert not np.array_equal(dm.get("_dk"), dk0.cpu().numpy())
+
+
+def test_dm_functions_take_a_las_path(tmp_path):
+    """DM_* accept the path of a LAS file where the reference takes an ODM path (DM_saliency.py:326)."""
+    from more3d_b200 import synthetic, io_formats
+    from more3d_b200.DM_saliency import PointCloudDM, DM_nonparam_curvature
+    pts = synthetic.terrain(3000, seed=5)
+    path = str(tmp_path / "tile.las")
+    io_formats.write_las(path, pts, scale=(1e-4, 1e-4, 1e-4))
+    dm = DM_nonparam_curvature(path, "sphere", roughness=0.02, alpha=0.05, min_points=4, radius=0.5)
+    q = io_formats.parse_las(path)
+    ref = PointCloudDM(np.column_stack((q.x, q.y, q.z)))
+    DM_nonparam_curvature(ref, "sphere", roughness=0.02, alpha=0.05, min_points=4, radius=0.5)
+    assert np.array_equal(dm.get("_pcount"), ref.get("_pcount"))
+    assert np.array_equal(dm.get("_nonparam_K"), ref.get("_nonparam_K"))
