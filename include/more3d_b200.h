@@ -218,6 +218,12 @@ int more3d_ls_run(const more3d_ls_graph* g, double* phi, const double* zeta, int
                   double mu, double lambda1, double lambda2, double epsilon, double max_val, int cap,
                   double tolerance, double* rmsc_h, int* iterations_done_h, int* converged_h, void* stream);
 
+/* The region-growing part of Solver.save(extract=True) (:651-661): the region (phi > 0 or phi <= 0) with the
+ * larger mean cue, grown by the points with >= extraction_threshold salient neighbours, pruned of the points
+ * without any salient neighbour.  phi: n f64; zeta: n x channels f64; salient: n uint8 out. */
+int more3d_ls_extract(const more3d_ls_graph* g, const double* phi, const double* zeta, int channels,
+                      int extraction_threshold, uint8_t* salient, void* stream);
+
 /* Solver.run with active_contour_model='lmv' (_lmv_step, :439-513): same regularisation terms, the data term
  * is the Gaussian log-likelihood difference of each point's (k+1)-neighbourhood under its local inside /
  * outside means and deviations.  zeta: n f64, ONE channel (the reference's expressions only broadcast for a

@@ -52,6 +52,7 @@ SIGNATURES = {
     "more3d_ls_init_voxels": [_vp, _i64, _f64, _f64, _vp, _vp],
     "more3d_ls_run": [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _f64, _f64, _i32,
                       _f64, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(_i32), _vp],
+    "more3d_ls_extract": [_vp, _vp, _vp, _i32, _i32, _vp, _vp],
     "more3d_ls_run_lmv": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _i32, _f64,
                           C.POINTER(_f64), C.POINTER(_i32), C.POINTER(_i32), _vp],
     "more3d_ls_phase": [_vp, _i32, _vp, _vp],

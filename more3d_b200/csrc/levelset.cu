@@ -583,6 +583,41 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_f(LsGraph g, const uint8_t
     }
 }
 
+// ---- Solver.save(extract=True), the region-growing part (levelsets_func.py:651-661) ----------------------
+// sums of the cue over phi > 0 and phi <= 0 (all channels) and the element counts
+__global__ void __launch_bounds__(LS_THREADS) ls_extract_partial(int64_t n, int channels, const double* __restrict__ phi,
+                                                                 const double* __restrict__ zeta,
+                                                                 double* __restrict__ part /* RED_BLOCKS x 4 */) {
+    double v[4] = {0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double z = 0.0;
+        for (int c = 0; c < channels; ++c) z += zeta[i * channels + c];
+        if (phi[i] > 0.0) { v[0] += z; v[1] += (double)channels; } else { v[2] += z; v[3] += (double)channels; }
+    }
+    block_sum_store<4>(v, part);
+}
+// salient = region | (sum(region[neighbors]) >= threshold)                                  :658-659
+__global__ void __launch_bounds__(LS_THREADS) ls_extract_grow(LsGraph g, const double* __restrict__ phi,
+                                                              const double* __restrict__ sums, int threshold,
+                                                              uint8_t* __restrict__ s1) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    // region1 (phi > 0) is the salient one iff its mean cue is larger; an empty region gives NaN -> region2 (:653-656)
+    const bool pos = (sums[0] / sums[1]) > (sums[2] / sums[3]);
+    int cnt = 0;
+    for (int j = 0; j < g.k; ++j) cnt += ((phi[g.nbr[(int64_t)j * g.n + i]] > 0.0) == pos) ? 1 : 0;
+    s1[i] = (((phi[i] > 0.0) == pos) || cnt >= threshold) ? 1 : 0;
+}
+// salient &= any(salient[neighbors])                                                        :660
+__global__ void __launch_bounds__(LS_THREADS) ls_extract_prune(LsGraph g, const uint8_t* __restrict__ s1,
+                                                               uint8_t* __restrict__ s2) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    uint8_t any = 0;
+    for (int j = 0; j < g.k; ++j) any |= s1[g.nbr[(int64_t)j * g.n + i]];
+    s2[i] = s1[i] & any;
+}
+
 }  // namespace m3d
 
 using namespace m3d;
@@ -687,6 +722,27 @@ extern "C" int more3d_ls_zero_crossings(const more3d_ls_graph* G, const double* 
     ls_zero_cross_kernel<<<(unsigned)((G->n + LS_THREADS - 1) / LS_THREADS), LS_THREADS, 0, s>>>(view(G), u, mask, out);
     count_launches(1);
     M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_ls_extract(const more3d_ls_graph* G, const double* phi, const double* zeta, int channels,
+                                 int extraction_threshold, uint8_t* salient, void* stream) {
+    M3D_REQUIRE(G && phi && zeta && salient && channels >= 1, "NULL / bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = G->n;
+    double *part = nullptr, *sums = nullptr;
+    uint8_t* s1 = nullptr;
+    M3D_TRY(dev_alloc(&part, (size_t)RED_BLOCKS * 4, s));
+    M3D_TRY(dev_alloc(&sums, 4, s));
+    M3D_TRY(dev_alloc(&s1, (size_t)n, s));
+    const unsigned nb = (unsigned)((n + LS_THREADS - 1) / LS_THREADS);
+    ls_extract_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, phi, zeta, part);
+    ls_reduce_final<<<1, 32, 0, s>>>(part, RED_BLOCKS, 4, sums);
+    ls_extract_grow<<<nb, LS_THREADS, 0, s>>>(view(G), phi, sums, extraction_threshold, s1);
+    ls_extract_prune<<<nb, LS_THREADS, 0, s>>>(view(G), s1, salient);
+    count_launches(4);
+    M3D_CHECK_LAUNCH();
+    dev_free(part, s); dev_free(sums, s); dev_free(s1, s);
     return MORE3D_OK;
 }
 

@@ -529,14 +529,16 @@ class Solver:
         return False
 
     def extract(self, extraction_threshold=4):
-        """the region-growing part of Solver.save(extract=True) (:651-661), without the file output"""
-        phi, zeta, nb = self.phi, self.zeta, self.neighbors
-        region1 = (phi > 0)
-        region2 = (phi <= 0)
-        salient = region1 if (zeta[region1].mean() > zeta[region2].mean()) else region2
-        salient |= (np.sum(salient[nb], axis=-1) >= extraction_threshold)
-        salient &= np.any(salient[nb], axis=-1)
-        return salient
+        """the region-growing part of Solver.save(extract=True) (:651-661), without the file output; on the device"""
+        lib = _lib.load()
+        phi = self._phi.get_dev(torch.float64)
+        zeta = self._zeta.get_dev(torch.float64)
+        channels = int(zeta.shape[-1]) if zeta.ndim > 1 else 1
+        n = int(self.diff._pts.shape[0])
+        out = torch.empty(n, dtype=torch.uint8, device="cuda")
+        check(lib.more3d_ls_extract(self.diff._g, ptr(phi), ptr(zeta), channels, int(extraction_threshold), ptr(out),
+                                    stream_ptr()))
+        return out[self.diff._inv].cpu().numpy().astype(bool)
 
     def save(self, basepath, origin=np.r_[0, 0, 0], extract=False, extraction_threshold=4):
         """text output of the active points (and the extracted region), :644-667 -- host-side I/O"""

@@ -120,8 +120,18 @@ def test_solver_run_matches_reference(g, own_frames):
     assert np.array_equal(solver.active, g["act25"])
     np.testing.assert_allclose(solver.phi, g["phi25"], rtol=1e-8, atol=1e-10)
     assert len(solver.rmsc_history) == 15 and all(np.isfinite(solver.rmsc_history))
-    sal = solver.extract(4)
-    assert sal.dtype == bool and 0 < sal.sum() < len(pts)
+    for thr in (4, 2, 7):                                                        # Solver.save(extract=True), :651-661
+        phi, zeta, nbs = solver.phi, solver.zeta, solver.neighbors
+        r1, r2 = phi > 0, phi <= 0
+        want = r1 if zeta[r1].mean() > zeta[r2].mean() else r2
+        want = want | (np.sum(want[nbs], axis=-1) >= thr)
+        want = want & np.any(want[nbs], axis=-1)
+        sal = solver.extract(thr)
+        assert sal.dtype == bool and 0 < sal.sum() < len(pts) and np.array_equal(sal, want)
+    flipped = ls.Solver(h, 1.0 - g["zeta"], pts, nb, tang, "chan_vese", weights=g["weights"])   # the other region wins
+    flipped.phi[:] = solver.phi
+    assert np.array_equal(flipped.extract(4), (lambda w: (w | (np.sum(w[nbs], axis=-1) >= 4)) & np.any(
+        (w | (np.sum(w[nbs], axis=-1) >= 4))[nbs], axis=-1))(r2 if zeta[r1].mean() > zeta[r2].mean() else r1))
 
 
 def test_solver_mask_init_and_tolerance(g):
