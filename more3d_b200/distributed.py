@@ -145,7 +145,8 @@ class _OwnedRows:
         return self.col.tensor()[:self.n]
 
 
-def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=None, out_host=None):
+def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=None, out_host=None,
+                   copy_stream=None):
     """Saliency of the OWNED points of one strip.  own: (n,3) device f64; ghosts: (g,3) device f64
     (points of the neighbouring strips within 2*r_max).  reduce_minmax(minmax) makes the extrema
     global (None for a single strip).  Returns {r: saliency (n,) f32} (+ '_pcount' sums in .sum_m)."""
@@ -189,7 +190,15 @@ def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=N
                                             ptr(sal_g), None, stream_ptr()))
             sal = GridColumn(dk, sal_g).tensor()[:n]                      # back to point order, owned rows
         if out_host is not None:
-            out_host[r].copy_(sal, non_blocking=True)
+            if copy_stream is None:
+                out_host[r].copy_(sal, non_blocking=True)
+            else:                                   # D2H on a side stream: overlaps the next radius' kernels
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev)
+                    out_host[r].copy_(sal, non_blocking=True)
+                    sal.record_stream(copy_stream)
         out[r] = sal
         sum_m[r] = _OwnedRows(pcount, n)
     if g is not None:
@@ -219,13 +228,13 @@ class StripSaliency:
         _, pc = self._run(self.resident, None)
         self.sum_m = {r: float(pc[r].tensor().double().sum()) for r in radii}
 
-    def _run(self, own, out_host):
+    def _run(self, own, out_host, copy_stream=None):
         left = gather_rows(own, band_select(own, 0, -np.inf, self.x_lo + self.halo))
         right = gather_rows(own, band_select(own, 0, self.x_hi - self.halo, np.inf))
         from_left, from_right = exchange_halos(left, right, self.rank, self.world)
         ghosts = torch.cat([from_left, from_right], dim=0)
         out, pc = strip_saliency(own, ghosts, self.radii, self.params, self.cw,
-                                 reduce_minmax=allreduce_minmax, out_host=out_host)
+                                 reduce_minmax=allreduce_minmax, out_host=out_host, copy_stream=copy_stream)
         # the global saliency histogram (256 bins, one all-reduce) and its Otsu threshold, per radius
         self.otsu = {r: global_otsu(out[r], cuda_histogram) for r in self.radii}
         return out, pc
@@ -236,4 +245,32 @@ class StripSaliency:
     def step_e2e(self):
         res = self._run(self.host.to(self.dev, non_blocking=True), self.out_host)[0]
         torch.cuda.current_stream().synchronize()
+        return res
+
+    def steps_e2e(self, k):
+        """k strips one after the other from pinned host memory; the upload of strip i+1 runs on a copy stream
+        while strip i is computed (the D2H of the saliency columns is issued per radius by strip_saliency)."""
+        cur = torch.cuda.current_stream(self.dev)
+        up = torch.cuda.Stream(device=self.dev)
+        down = torch.cuda.Stream(device=self.dev)
+
+        def upload():
+            with torch.cuda.stream(up):
+                d = self.host.to(self.dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+            return d, ev
+
+        res = None
+        nxt = upload()
+        for i in range(k):
+            d, ev = nxt
+            if i + 1 < k:
+                nxt = upload()
+            cur.wait_event(ev)
+            d.record_stream(cur)
+            res = self._run(d, self.out_host, copy_stream=down)[0]
+            del d
+        cur.wait_stream(down)
+        cur.synchronize()
         return res

@@ -16,16 +16,20 @@ DEFAULTS = dict(roughness=0.02, alpha=0.05, sigma_normal=0.01, sigma_curvature=0
 
 def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, sigma_normal=0.01,
                         sigma_curvature=0.01, curvature_weight=0.5, min_points=4, keep=False,
-                        out_host=None):
+                        out_host=None, copy_stream=None):
     """Run the saliency pipeline at each radius (rho = r / sqrt(2)).
 
     xyz: (N,3) float64, numpy (host; copied to the device here) or a CUDA tensor.
     Returns {radius: saliency float32 CUDA tensor}; with ``keep`` also the intermediate columns.
     ``out_host``: optional {radius: pinned float32 host tensor} to receive the result (D2H copy).
+    ``copy_stream``: the stream those D2H copies run on; when given, the caller waits for it (the compute stream
+    does not, so the next tile's kernels start while the last column of this one is still travelling).
     """
     dm = PointCloudDM(xyz)
     out = {}
-    copy_stream = torch.cuda.Stream(device=dm.device) if out_host is not None else None
+    own_copy_stream = copy_stream is None
+    if out_host is not None and copy_stream is None:
+        copy_stream = torch.cuda.Stream(device=dm.device)
     for r in sorted(radii):      # ascending: the finest grid is built first and shared by the wider radii
         rho = r / np.sqrt(2.0)
         dm.normals = None          # normals are re-estimated at every scale
@@ -47,7 +51,44 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
             out[r]["normals"] = dm.normals
         else:
             out[r] = sal
-    if copy_stream is not None:
+    if out_host is not None and own_copy_stream:
         torch.cuda.current_stream(dm.device).wait_stream(copy_stream)
     dm.drop_grids()
     return out
+
+
+def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, device=None, **params):
+    """The pipeline over a sequence of host-resident tiles (pinned (N,3) float64 tensors), tile after tile on one
+    GPU, with the transfers taken off the critical path: tile k+1 is uploaded on a copy stream while tile k is
+    computed, and the saliency columns of tile k travel back (into ``out_hosts[k]``, {radius: pinned float32 tensor})
+    while tile k+1 is computed.  Returns the per-tile results of :func:`multiscale_saliency`; all copies have
+    completed on return."""
+    tiles = list(host_tiles)
+    if not tiles:
+        return []
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    cur = torch.cuda.current_stream(dev)
+    up = torch.cuda.Stream(device=dev)
+    down = torch.cuda.Stream(device=dev)
+
+    def upload(t):
+        with torch.cuda.stream(up):
+            d = t.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(up)
+        return d, ev
+
+    results = []
+    nxt = upload(tiles[0])
+    for k in range(len(tiles)):
+        d, ev = nxt
+        if k + 1 < len(tiles):
+            nxt = upload(tiles[k + 1])        # enqueued before tile k's kernels: overlaps them
+        cur.wait_event(ev)
+        d.record_stream(cur)                   # allocated on the upload stream, consumed on the compute stream
+        results.append(multiscale_saliency(d, radii, out_host=None if out_hosts is None else out_hosts[k],
+                                           copy_stream=down, **params))
+        del d
+    cur.wait_stream(down)
+    cur.synchronize()
+    return results
