@@ -125,11 +125,43 @@ def global_otsu(values, local_histogram, group=None):
     return otsu_from_counts(hist.cpu().numpy(), edges)
 
 
+class DeviceOtsu:
+    """global_otsu without host round trips between its steps: extrema (one min/max kernel), all-reduce, bin edges
+    with numpy.linspace's arithmetic evaluated on the device (arange * step + start, last edge = stop: separate
+    multiply and add, so no FMA), local histogram, all-reduce.  Nothing synchronises until result(): a strip can
+    queue the Otsu of all its radii behind the saliency kernels and read the three thresholds with one wait."""
+
+    def __init__(self, values, group=None):
+        lib = _lib.load()
+        v = values.contiguous()
+        dev = v.device
+        with torch.cuda.device(dev):
+            mm = torch.empty(4, dtype=torch.float32, device=dev)
+            check(lib.more3d_minmax4(ptr(v), ptr(v), int(v.numel()), ptr(mm), stream_ptr()))
+            lo_hi = torch.stack([mm[0].double(), -mm[1].double()])
+            dist.all_reduce(lo_hi, op=dist.ReduceOp.MIN, group=group)
+            lo, hi = lo_hi[0], -lo_hi[1]
+            step = (hi - lo) / 256.0
+            edges = torch.arange(257, dtype=torch.float64, device=dev) * step
+            edges = edges + lo
+            edges[256] = hi
+            self.hist = cuda_histogram(v, edges)
+            dist.all_reduce(self.hist, op=dist.ReduceOp.SUM, group=group)
+            self.packed = torch.cat([torch.stack([lo, hi]), edges])
+
+    def result(self):
+        p = self.packed.cpu().numpy()
+        lo, hi, edges = float(p[0]), float(p[1]), p[2:]
+        if lo == hi:
+            return lo
+        return otsu_from_counts(self.hist.cpu().numpy(), edges)
+
+
 def cuda_histogram(values, edges):
     lib = _lib.load()
     v = values.contiguous()
     with torch.cuda.device(v.device):
-        de = torch.from_numpy(edges).to(v.device)
+        de = edges if isinstance(edges, torch.Tensor) else torch.from_numpy(edges).to(v.device)
         hist = torch.empty(256, dtype=torch.int64, device=v.device)
         check(lib.more3d_histogram256(ptr(v), v.element_size(), int(v.numel()), ptr(de), ptr(hist), stream_ptr()))
     return hist
@@ -236,7 +268,8 @@ class StripSaliency:
         out, pc = strip_saliency(own, ghosts, self.radii, self.params, self.cw,
                                  reduce_minmax=allreduce_minmax, out_host=out_host, copy_stream=copy_stream)
         # the global saliency histogram (256 bins, one all-reduce) and its Otsu threshold, per radius
-        self.otsu = {r: global_otsu(out[r], cuda_histogram) for r in self.radii}
+        jobs = {r: DeviceOtsu(out[r]) for r in self.radii}     # all queued behind the saliency kernels ...
+        self.otsu = {r: j.result() for r, j in jobs.items()}   # ... and read with one wait at the end of the step
         return out, pc
 
     def step_resident(self):

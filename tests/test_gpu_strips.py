@@ -64,3 +64,26 @@ def test_logical_strips_match_untiled(G):
             b = whole[r]["_saliency"].cpu().numpy()[oi].astype(np.float64)
             bad = np.abs(a - b) > 1e-5 * np.abs(b) + 1e-7
             assert bad.sum() <= 2, (k, r, bad.sum())       # threshold straddlers under a different sum order
+
+
+def test_device_otsu_matches_oracle():
+    """DeviceOtsu (extrema, linspace edges and histogram on the device, all-reduces, one final wait) == the oracle's
+    skimage.threshold_otsu restatement on the same column; a one-rank NCCL group stands in for the strips."""
+    import torch
+    import torch.distributed as dist
+    from more3d_b200.distributed import DeviceOtsu
+    from oracle import ref_path as rp
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29631", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        rng = np.random.default_rng(5)
+        for col in (rng.random(200000).astype(np.float32) ** 4, (rng.normal(size=50001) * 3 - 1).astype(np.float32),
+                    np.full(1000, 0.25, dtype=np.float32)):
+            got = DeviceOtsu(torch.from_numpy(col).cuda()).result()
+            assert got == rp.otsu_threshold(col)
+    finally:
+        if created:
+            dist.destroy_process_group()
