@@ -202,9 +202,9 @@ int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaSt
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                    // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
-constexpr int RS_WTILE = RS_TILE / RS_WARPS;    // 512 consecutive keys per warp
+constexpr int RS_ITEMS = 8;                     // keys per thread (8: 4 CTAs per SM; the kernel is latency-bound, 16 was slower)
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per CTA
+constexpr int RS_WTILE = RS_TILE / RS_WARPS;    // 256 consecutive keys per warp
 
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys, int64_t n, int shift,
@@ -222,23 +222,32 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
 }
 
-// Stable scatter: warp w owns keys [w*512, (w+1)*512) of the tile, walks them in 16 rounds of 32;
-// __match_any_sync gives each key its rank among equal digits of the round, per-warp running
-// counters (seeded with the scanned global histogram + the counts of lower warps) give the rest.
+// Stable scatter: warp w owns RS_WTILE consecutive keys of the tile, walks them in RS_ITEMS rounds of 32;
+// __match_any_sync gives each key its rank among equal digits of the round, per-warp running counters give the
+// rank among the earlier keys of the tile.  The tile is first sorted by digit INTO SHARED MEMORY and then
+// written out linearly: consecutive threads hold consecutive keys of one digit run, so the global stores are
+// contiguous runs (avg 16 keys = 64 B per digit and tile) instead of 4-byte scatters to 256 places.
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys,
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict__ keys,
                                                          const uint32_t* __restrict__ vals,
                                                          K* __restrict__ keys_out,
                                                          uint32_t* __restrict__ vals_out, int64_t n,
                                                          int shift, const uint32_t* __restrict__ hist_ex,
                                                          int nblocks) {
-    __shared__ uint32_t wcnt[RS_WARPS][256];
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    K* keys_s = reinterpret_cast<K*>(rs_smem);                                   // RS_TILE keys
+    uint32_t* vals_s = reinterpret_cast<uint32_t*>(keys_s + RS_TILE);             // RS_TILE values
+    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(vals_s + RS_TILE);   // RS_WARPS x 256
+    uint32_t* tile_start = &wcnt[0][0] + RS_WARPS * 256;                          // 256: first tile slot of a digit
+    uint32_t* gbase = tile_start + 256;                                           // 256: first global slot
+    uint32_t* scan_sm = gbase + 256;                                              // 33
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
     __syncthreads();
 
-    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_WTILE;
+    const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+    const int64_t wbase = tbase + (int64_t)warp * RS_WTILE;
     K k[RS_ITEMS];
     uint32_t v[RS_ITEMS];
 #pragma unroll
@@ -260,16 +269,21 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ k
     __syncthreads();
     {
         const int d = threadIdx.x;  // RS_THREADS == 256 digits
-        uint32_t run = hist_ex[(size_t)d * nblocks + blockIdx.x];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             uint32_t c = wcnt[w][d];
-            wcnt[w][d] = run;
+            wcnt[w][d] = run;           // keys of digit d in lower warps
             run += c;
         }
+        const uint32_t ts = block_exclusive_scan<uint32_t>(run, nullptr, scan_sm);   // digits below d in the tile
+        tile_start[d] = ts;
+        gbase[d] = hist_ex[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) wcnt[w][d] += ts;
     }
     __syncthreads();
-    // phase B: ranks and scatter
+    // phase B: tile-local ranks, keys and values go to their sorted slot of the tile
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         bool ok = (wbase + j * 32 + lane) < n;
@@ -281,10 +295,25 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ k
         if (ok && (peers & lt) == 0u) wcnt[warp][d] += __popc(peers);
         __syncwarp();
         if (ok) {
-            keys_out[pos] = k[j];
-            vals_out[pos] = v[j];
+            keys_s[pos] = k[j];
+            vals_s[pos] = v[j];
         }
     }
+    __syncthreads();
+    // phase C: linear write-out
+    const int tile_n = (int)min((int64_t)RS_TILE, n - tbase);
+    for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+        const K kk = keys_s[i];
+        const unsigned d = (unsigned)(kk >> shift) & 255u;
+        const uint32_t g = gbase[d] + ((uint32_t)i - tile_start[d]);
+        keys_out[g] = kk;
+        vals_out[g] = vals_s[i];
+    }
+}
+
+template <typename K>
+static size_t rs_scatter_smem() {
+    return (size_t)RS_TILE * (sizeof(K) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + 256 + 33) * sizeof(uint32_t);
 }
 
 template <typename K>
@@ -298,6 +327,8 @@ static int radix_sort_impl(K* keys, uint32_t* vals, K* keys_alt, uint32_t* vals_
         return MORE3D_E_RANGE;
     }
     const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+    const size_t smem = rs_scatter_smem<K>();
+    M3D_CUDA(cudaFuncSetAttribute(rs_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t* hist = nullptr;
     M3D_TRY(dev_alloc(&hist, (size_t)256 * nblocks + 1, s));
     K* kin = keys;
@@ -307,7 +338,7 @@ static int radix_sort_impl(K* keys, uint32_t* vals, K* keys_alt, uint32_t* vals_
     for (int shift = 0; shift < key_bits; shift += 8) {
         rs_hist<K><<<nblocks, RS_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
         M3D_TRY(exclusive_scan_u32(hist, hist, (int64_t)256 * nblocks, s));
-        rs_scatter<K><<<nblocks, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
+        rs_scatter<K><<<nblocks, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
         count_launches(2);
         M3D_CHECK_LAUNCH();
         K* tk = kin; kin = kout; kout = tk;

@@ -31,4 +31,13 @@ s.initialize_from_voxels(2.0)
 s.run(6, stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
 s.initialize_from_mask(c[:, 0] < 0)
 s.run(4, stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
-print("sanitize target ok", float(np.abs(s.phi).max()))
+s.extract(4)
+m = ls.Solver(0.5, np.abs(np.sin(c[:, :1])), c, nb, tang, "lmv")
+m.initialize_from_voxels(2.0)
+m.run(4, stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
+import torch  # noqa: E402
+from more3d_b200.pipeline import multiscale_saliency_tiles  # noqa: E402
+tiles = [torch.from_numpy(pts[:15000]).pin_memory(), torch.from_numpy(pts[5000:]).pin_memory()]
+outs = [{r: torch.empty(len(t), dtype=torch.float32).pin_memory() for r in (0.5, 0.75)} for t in tiles]
+multiscale_saliency_tiles(tiles, (0.5, 0.75), out_hosts=outs)
+print("sanitize target ok", float(np.abs(s.phi).max()), float(np.abs(m.phi).max()))
