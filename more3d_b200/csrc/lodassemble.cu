@@ -22,32 +22,36 @@ __global__ void __launch_bounds__(256) la_near_table(const uint8_t* __restrict__
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ncells) near_of_cell[c] = keep_all[c] ? (int64_t)-1 : near[apos[c]];
 }
-// one thread per cell: rows of its kept points, then its representative
+// one warp per cell: rows of its kept points (row = kept points before it in the whole cloud + representatives of
+// the cells before it), then its representative
 __global__ void __launch_bounds__(256) la_rows(const double* __restrict__ xyz, const int64_t* __restrict__ idx_array,
                                                const int64_t* __restrict__ cell_start, int64_t ncells,
                                                const uint8_t* __restrict__ keep, const uint32_t* __restrict__ kpos,
                                                const uint32_t* __restrict__ apos, const int64_t* __restrict__ near_of_cell,
                                                double* __restrict__ out /* M x 4 */, int64_t* __restrict__ out_idx,
                                                int32_t* __restrict__ out_cell) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    const int64_t b = cell_start[c], e = cell_start[c + 1];
-    int64_t row = (int64_t)kpos[b] + (int64_t)apos[c];
-    for (int64_t t = b; t < e; ++t) {
-        if (!keep[t]) continue;
-        const int64_t o = idx_array[t];
-        out[4 * row] = xyz[3 * o]; out[4 * row + 1] = xyz[3 * o + 1]; out[4 * row + 2] = xyz[3 * o + 2];
-        out[4 * row + 3] = 1.0;                                   // salient_tmp = 1, :63 / :75
-        out_idx[row] = o;
-        if (out_cell) out_cell[row] = (int32_t)c;
-        ++row;
-    }
-    const int64_t o = near_of_cell[c];
-    if (o >= 0) {                                                  // pts_tmp = vstack((salient, GetPoint(nearest))), :71
-        out[4 * row] = xyz[3 * o]; out[4 * row + 1] = xyz[3 * o + 1]; out[4 * row + 2] = xyz[3 * o + 2];
-        out[4 * row + 3] = 0.0;                                   // :74
-        out_idx[row] = o;
-        if (out_cell) out_cell[row] = (int32_t)c;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = (((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; c < ncells; c += warps) {
+        const int64_t b = cell_start[c], e = cell_start[c + 1];
+        const int64_t shift = (int64_t)apos[c];
+        for (int64_t t = b + lane; t < e; t += 32) {
+            if (!keep[t]) continue;
+            const int64_t row = (int64_t)kpos[t] + shift;
+            const int64_t o = idx_array[t];
+            out[4 * row] = xyz[3 * o]; out[4 * row + 1] = xyz[3 * o + 1]; out[4 * row + 2] = xyz[3 * o + 2];
+            out[4 * row + 3] = 1.0;                                   // salient_tmp = 1, :63 / :75
+            out_idx[row] = o;
+            if (out_cell) out_cell[row] = (int32_t)c;
+        }
+        const int64_t o = near_of_cell[c];
+        if (lane == 0 && o >= 0) {                                    // pts_tmp = vstack((salient, GetPoint(nearest))), :71
+            const int64_t row = (int64_t)kpos[e] + shift;
+            out[4 * row] = xyz[3 * o]; out[4 * row + 1] = xyz[3 * o + 1]; out[4 * row + 2] = xyz[3 * o + 2];
+            out[4 * row + 3] = 0.0;                                   // :74
+            out_idx[row] = o;
+            if (out_cell) out_cell[row] = (int32_t)c;
+        }
     }
 }
 
@@ -80,7 +84,8 @@ extern "C" int more3d_lod_assemble(const double* xyz, const int64_t* idx_array, 
     M3D_CUDA(cudaStreamSynchronize(s));
     M3D_REQUIRE(tot[1] == 0 || near != nullptr, "near is NULL but some cells are averaged");
     la_near_table<<<cb, 256, 0, s>>>(keep_all, ncells, apos, near, near_of_cell);
-    la_rows<<<cb, 256, 0, s>>>(xyz, idx_array, cell_start, ncells, keep, kpos, apos, near_of_cell, out_xyzf, out_idx,
+    const int64_t wb = (ncells * 32 + 255) / 256;
+    la_rows<<<(unsigned)(wb < 148 * 64 ? wb : 148 * 64), 256, 0, s>>>(xyz, idx_array, cell_start, ncells, keep, kpos, apos, near_of_cell, out_xyzf, out_idx,
                                out_cell);
     count_launches(4);
     M3D_CHECK_LAUNCH();

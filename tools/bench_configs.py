@@ -164,6 +164,6 @@ if __name__ == "__main__":
     if "1" in which:
         print(json.dumps(config1(200_000 if small else 1_000_000)), flush=True)
     if "3" in which:
-        print(json.dumps(config3(1_000_000 if small else 50_000_000)), flush=True)
+        print(json.dumps(config3(int(float(os.environ.get("MORE3D_BENCH_N3", 1e6 if small else 5e7))))), flush=True)
     if "4" in which:
         print(json.dumps(config4(500_000 if small else 20_000_000, 40 if small else 200)), flush=True)
