@@ -238,7 +238,8 @@ int more3d_ls_run_lmv(const more3d_ls_graph* g, double* phi, const double* zeta,
  * (multi-GPU x-strips).  Points [0, n_own) of the graph are owned by the caller, the rest are ghosts
  * (their neighbour rows list themselves; their phi / aux are supplied by the owner between phases).
  * phase 0: re-clamp (de)activated points; 1: derivatives -> idx2, laplace, dphi, aux; 2: local region sums of
- * the owned points -> region[4*channels] (all-reduce them); 3: update -> bufA, incs[2] = {sum inc^2, count};
+ * the owned points -> region[4*channels] (all-reduce them; 'lmv': local statistics -> stats, pull the ghosts');
+ * 3: update -> bufA, incs[2] = {sum inc^2, count};
  * 4: zero crossings -> azc, cap -> bufB / outside; 5: smooth capped points bufB -> bufA; 6: smooth lonely
  * points bufA -> phi; 7: active = azc dilated (ghost flags go back to their owners).  All arrays have n
  * entries unless noted; part: more3d_ls_scratch_doubles() doubles. */
@@ -261,6 +262,14 @@ typedef struct {
     int64_t n_own;
     double stepsize, nu, mu, lambda1, lambda2, epsilon, max_val;
     int channels, cap;
+    /* 'lmv' model (model = 1, channels = 1; model = 0 is Chan-Vese and ignores the rest): phase 2 then computes the
+     * local statistics records stats[4n] = {mu_in, mu_out, sigma_in, sigma_out} of every point of idx_ (:463-495)
+     * and of every point flagged in `force` (n uint8 or NULL: the points other ranks hold as ghosts) instead of the
+     * region sums; the caller then supplies the ghosts' records (and, once, their zeta) before phase 3. */
+    int model, reserved;
+    double* stats;          /* 4n */
+    uint8_t* idxd;          /* n, scratch */
+    const uint8_t* force;   /* n or NULL */
 } more3d_ls_state;
 int more3d_ls_phase(const more3d_ls_graph* g, int phase, const more3d_ls_state* st, void* stream);
 int64_t more3d_ls_scratch_doubles(void);

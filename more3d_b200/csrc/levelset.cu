@@ -423,11 +423,12 @@ __global__ void __launch_bounds__(LS_THREADS) ls_lmv_dilate(LsGraph g, const uin
 __global__ void __launch_bounds__(LS_THREADS) ls_lmv_stats(LsGraph g, double eps, const double* __restrict__ phi,
                                                            const double* __restrict__ zeta,
                                                            const uint8_t* __restrict__ idxd,
+                                                           const uint8_t* __restrict__ force /* or NULL */,
                                                            double* __restrict__ stats /* AoS n x 4 */) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     double2* out = reinterpret_cast<double2*>(stats + 4 * i);
-    if (!idxd[i]) {                                     // np.zeros_like(zeta) elsewhere (:466-469); never read
+    if (!idxd[i] && !(force && force[i])) {                                     // np.zeros_like(zeta) elsewhere (:466-469); never read
         out[0] = make_double2(0.0, 0.0);
         out[1] = make_double2(0.0, 0.0);
         return;
@@ -809,7 +810,7 @@ static int ls_run_impl(const more3d_ls_graph* G, int model, double* phi, const d
         if (model == 1) {
             M3D_CUDA(cudaMemsetAsync(idxd, 0, (size_t)n, s));
             ls_lmv_dilate<<<nb, LS_THREADS, 0, s>>>(g, idx2, idxd);
-            ls_lmv_stats<<<nb, LS_THREADS, 0, s>>>(g, epsilon, phi, zeta, idxd, stats);
+            ls_lmv_stats<<<nb, LS_THREADS, 0, s>>>(g, epsilon, phi, zeta, idxd, nullptr, stats);
             count_launches(2);
         } else {
             for (int c = 0; c < channels; ++c) {
@@ -882,7 +883,9 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
     LsGraph g = view(G);
     LsParams p;
     p.stepsize = st->stepsize; p.nu = st->nu; p.mu = st->mu; p.lambda1 = st->lambda1; p.lambda2 = st->lambda2;
-    p.epsilon = st->epsilon; p.max_val = st->max_val; p.cap = st->cap; p.channels = st->channels; p.model = 0;
+    p.epsilon = st->epsilon; p.max_val = st->max_val; p.cap = st->cap; p.channels = st->channels; p.model = st->model;
+    M3D_REQUIRE(st->model == 0 || st->model == 1, "model must be 0 (chan_vese) or 1 (lmv)");
+    M3D_REQUIRE(st->model == 0 || (st->channels == 1 && st->stats && st->idxd), "lmv: one channel, stats and idxd needed");
     const unsigned nb = (unsigned)((n + LS_THREADS - 1) / LS_THREADS);
     switch (phase) {
     case 0:   // re-clamp (de)activated points
@@ -890,7 +893,7 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
         count_launches(1);
         break;
     case 1:   // derivatives of phi at the active points -> idx2, laplace, dphi, aux
-        if (st->nu > 0 || st->mu > 0) {
+        if (st->nu > 0 || st->mu > 0 || st->model == 1) {
             ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, st->phi, st->active, st->idx2, st->laplace, st->dphi, st->aux);
             count_launches(1);
         } else {
@@ -898,6 +901,13 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
         }
         break;
     case 2:   // local region sums over the OWNED points -> region[4 * channels] (caller all-reduces)
+        if (st->model == 1) {   // lmv: local statistics of idx_ and of the exported points (caller pulls the ghosts')
+            M3D_CUDA(cudaMemsetAsync(st->idxd, 0, (size_t)n, s));
+            ls_lmv_dilate<<<nb, LS_THREADS, 0, s>>>(g, st->idx2, st->idxd);
+            ls_lmv_stats<<<nb, LS_THREADS, 0, s>>>(g, st->epsilon, st->phi, st->zeta, st->idxd, st->force, st->stats);
+            count_launches(2);
+            break;
+        }
         for (int c = 0; c < st->channels; ++c) {
             ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(st->n_own, st->channels, st->epsilon, st->phi, st->zeta, c,
                                                                 st->part);
@@ -907,7 +917,7 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
         break;
     case 3:   // update -> bufA (= phi + increment), incs[0..1] = local sum inc^2, count
         ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, st->phi, st->idx2, st->laplace, st->dphi, st->aux, st->zeta,
-                                                      st->region, nullptr, st->bufA, st->part);
+                                                      st->region, st->model == 1 ? st->stats : nullptr, st->bufA, st->part);
         ls_reduce_final<<<1, RF_THREADS, 0, s>>>(st->part, STEPB_BLOCKS, 2, st->incs);
         count_launches(2);
         break;

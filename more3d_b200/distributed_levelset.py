@@ -105,15 +105,19 @@ class _State(C.Structure):
                                           "bufA", "bufB", "azc", "outside", "part", "region", "incs")] + \
                [("n_own", C.c_int64)] + \
                [(n, C.c_double) for n in ("stepsize", "nu", "mu", "lambda1", "lambda2", "epsilon", "max_val")] + \
-               [("channels", C.c_int), ("cap", C.c_int)]
+               [("channels", C.c_int), ("cap", C.c_int), ("model", C.c_int), ("reserved", C.c_int),
+                ("stats", C.c_void_p), ("idxd", C.c_void_p), ("force", C.c_void_p)]
 
 
 class StripLevelSet:
     """The Solver of one x-strip.  pts_own / zeta_own: this rank's points (n, 3) and cue (n, C) in any order;
     [x_lo, x_hi): the strip; all ranks call the constructor and ``run`` collectively."""
 
-    def __init__(self, comm, pts_own, zeta_own, h, k, x_lo, x_hi, halo=None, normals=None):
+    def __init__(self, comm, pts_own, zeta_own, h, k, x_lo, x_hi, halo=None, normals=None,
+                 active_contour_model='chan_vese'):
         lib = _lib.load()
+        assert active_contour_model in ['chan_vese', 'lmv']
+        self.active_contour_model = active_contour_model
         self.comm, self.h, self.k = comm, float(h), int(k)
         self.max_val = 2 * self.h
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -226,6 +230,19 @@ class StripLevelSet:
             part=torch.zeros(int(lib.more3d_ls_scratch_doubles()), **f64), region=torch.zeros(4 * self.channels, **f64),
             incs=torch.zeros(2, **f64))
         self.rmsc_history = []
+        if active_contour_model == 'lmv':
+            # _lmv_step (levelsets_func.py:439-513): the data term reads the cue and the local statistics of every
+            # neighbour, ghosts included -> the ghosts' zeta once, their statistics records every iteration.  Owners
+            # always compute the record of a point some other rank holds as a ghost (`force`).
+            if self.channels != 1:
+                raise ValueError("operands could not be broadcast together: the 'lmv' model takes a "
+                                 "single-channel cue, got %d channels" % self.channels)
+            self._pull(self.zeta.view(-1))      # (nloc, 1) contiguous: the ghosts' cue, once
+            self._stats = torch.zeros(4 * nloc, **f64)
+            self._idxd = torch.zeros(nloc, dtype=torch.uint8, device=dev)
+            self._force = torch.zeros(nloc, dtype=torch.uint8, device=dev)
+            for p in peers:
+                self._force[self.send_idx[p]] = 1
 
     def __del__(self):
         try:
@@ -297,6 +314,9 @@ class StripLevelSet:
                     last_active=last.data_ptr(), n_own=self.n, stepsize=stepsize, nu=nu, mu=mu, lambda1=lambda1,
                     lambda2=lambda2, epsilon=epsilon * self.h, max_val=self.max_val, channels=self.channels,
                     cap=1 if cap else 0, **{k: v.data_ptr() for k, v in sc.items()})
+        lmv = self.active_contour_model == 'lmv'
+        if lmv:
+            st.model, st.stats, st.idxd, st.force = 1, self._stats.data_ptr(), self._idxd.data_ptr(), self._force.data_ptr()
         ph = lambda i: check(lib.more3d_ls_phase(self._g, i, C.byref(st), stream_ptr()))   # noqa: E731
         hist = torch.zeros((max(iterations, 1), 2), dtype=torch.float64, device=self.dev)
         done = 0
@@ -305,10 +325,13 @@ class StripLevelSet:
                 ph(0)
                 self._pull(self.phi)          # owners re-clamped some points: refresh their ghost copies
             ph(1)
-            if nu > 0 or mu > 0:
+            if nu > 0 or mu > 0 or lmv:
                 self._pull(sc["aux"], 4)
             ph(2)
-            self.comm.allreduce_sum(sc["region"])
+            if lmv:
+                self._pull(self._stats, 4)     # the ghosts' local statistics from their owners
+            else:
+                self.comm.allreduce_sum(sc["region"])
             ph(3)
             self.comm.allreduce_sum(sc["incs"])
             self._pull(sc["bufA"])

@@ -9,8 +9,9 @@ pytestmark = pytest.mark.gpu
 RUN = dict(stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
 
 
-@pytest.mark.parametrize("G,init", [(2, "voxels"), (3, "mask")])
-def test_logical_strips_match_single_gpu(G, init):
+@pytest.mark.parametrize("G,init,model", [(2, "voxels", "chan_vese"), (3, "mask", "chan_vese"), (3, "voxels", "lmv"),
+                                          (2, "mask", "lmv")])
+def test_logical_strips_match_single_gpu(G, init, model):
     import torch
     from more3d_b200 import synthetic, levelsets_func as ls
     from more3d_b200.distributed_levelset import StripLevelSet, ThreadComm
@@ -19,8 +20,10 @@ def test_logical_strips_match_single_gpu(G, init):
     h, k = 0.5, 7
     rng = np.random.Generator(np.random.PCG64(2))
     zeta = np.column_stack([np.abs(np.sin(pts[:, 0] / 3.0)), rng.random(len(pts)) ** 2])
+    if model == "lmv":
+        zeta = zeta[:, :1] + 0.1 * zeta[:, 1:]          # the local-mean-and-variance model takes one channel
     nb, nrm, tang = ls.build_neighborhoods(pts.copy(), h, k)
-    ref = ls.Solver(h, zeta, pts, nb, tang, "chan_vese")
+    ref = ls.Solver(h, zeta, pts, nb, tang, model)
     mask = (pts[:, 0] ** 2 + pts[:, 1] ** 2) < 60.0
     if init == "voxels":
         ref.initialize_from_voxels(2.0)
@@ -39,7 +42,7 @@ def test_logical_strips_match_single_gpu(G, init):
         try:
             torch.cuda.set_device(0)
             s = StripLevelSet(ThreadComm(hub, r), pts[own[r]], zeta[own[r]], h, k, edges[r], edges[r + 1],
-                              normals=nrm[own[r]])
+                              normals=nrm[own[r]], active_contour_model=model)
             if init == "voxels":
                 s.initialize_from_voxels(2.0)
                 s.smooth_phi()
