@@ -126,35 +126,49 @@ def global_otsu(values, local_histogram, group=None):
 
 
 class DeviceOtsu:
-    """global_otsu without host round trips between its steps: extrema (one min/max kernel), all-reduce, bin edges
-    with numpy.linspace's arithmetic evaluated on the device (arange * step + start, last edge = stop: separate
-    multiply and add, so no FMA), local histogram, all-reduce.  Nothing synchronises until result(): a strip can
-    queue the Otsu of all its radii behind the saliency kernels and read the three thresholds with one wait."""
+    """global_otsu for one or several sharded columns without host round trips between its steps: extrema (one
+    min/max kernel per column), ONE all-reduce for all columns, bin edges with numpy.linspace's arithmetic evaluated
+    on the device (arange * step + start, last edge = stop: separate multiply and add, so no FMA), local histograms,
+    ONE all-reduce.  Nothing synchronises until result(): a strip queues the Otsu of all its radii behind the
+    saliency kernels and reads the thresholds with one wait."""
 
     def __init__(self, values, group=None):
         lib = _lib.load()
-        v = values.contiguous()
-        dev = v.device
+        self.single = isinstance(values, torch.Tensor)
+        cols = [values.contiguous()] if self.single else [v.contiguous() for v in values]
+        dev = cols[0].device
+        m = len(cols)
         with torch.cuda.device(dev):
-            mm = torch.empty(4, dtype=torch.float32, device=dev)
-            check(lib.more3d_minmax4(ptr(v), ptr(v), int(v.numel()), ptr(mm), stream_ptr()))
-            lo_hi = torch.stack([mm[0].double(), -mm[1].double()])
+            mm = torch.empty((m, 4), dtype=torch.float32, device=dev)
+            for i, v in enumerate(cols):
+                check(lib.more3d_minmax4(ptr(v), ptr(v), int(v.numel()), ptr(mm[i]), stream_ptr()))
+            lo_hi = torch.stack([mm[:, 0].double(), -mm[:, 1].double()], dim=1)          # (m, 2)
             dist.all_reduce(lo_hi, op=dist.ReduceOp.MIN, group=group)
-            lo, hi = lo_hi[0], -lo_hi[1]
+            lo, hi = lo_hi[:, 0:1], -lo_hi[:, 1:2]
             step = (hi - lo) / 256.0
-            edges = torch.arange(257, dtype=torch.float64, device=dev) * step
+            edges = torch.arange(257, dtype=torch.float64, device=dev)[None, :] * step
             edges = edges + lo
-            edges[256] = hi
-            self.hist = cuda_histogram(v, edges)
+            edges[:, 256] = hi[:, 0]
+            edges = edges.contiguous()
+            self.hist = torch.empty((m, 256), dtype=torch.int64, device=dev)
+            for i, v in enumerate(cols):
+                check(lib.more3d_histogram256(ptr(v), v.element_size(), int(v.numel()), ptr(edges[i]), ptr(self.hist[i]),
+                                              stream_ptr()))
             dist.all_reduce(self.hist, op=dist.ReduceOp.SUM, group=group)
-            self.packed = torch.cat([torch.stack([lo, hi]), edges])
+            self.packed = torch.cat([lo, hi, edges], dim=1)                              # (m, 259)
+
+    def results(self):
+        p = self.packed.cpu().numpy()
+        h = self.hist.cpu().numpy()
+        out = []
+        for i in range(p.shape[0]):
+            lo, hi, edges = float(p[i, 0]), float(p[i, 1]), p[i, 2:]
+            out.append(lo if lo == hi else otsu_from_counts(h[i], edges))
+        return out
 
     def result(self):
-        p = self.packed.cpu().numpy()
-        lo, hi, edges = float(p[0]), float(p[1]), p[2:]
-        if lo == hi:
-            return lo
-        return otsu_from_counts(self.hist.cpu().numpy(), edges)
+        r = self.results()
+        return r[0] if self.single else r
 
 
 def cuda_histogram(values, edges):
@@ -268,8 +282,8 @@ class StripSaliency:
         out, pc = strip_saliency(own, ghosts, self.radii, self.params, self.cw,
                                  reduce_minmax=allreduce_minmax, out_host=out_host, copy_stream=copy_stream)
         # the global saliency histogram (256 bins, one all-reduce) and its Otsu threshold, per radius
-        jobs = {r: DeviceOtsu(out[r]) for r in self.radii}     # all queued behind the saliency kernels ...
-        self.otsu = {r: j.result() for r, j in jobs.items()}   # ... and read with one wait at the end of the step
+        job = DeviceOtsu([out[r] for r in self.radii])         # all radii queued behind the saliency kernels ...
+        self.otsu = dict(zip(self.radii, job.results()))       # ... and read with one wait at the end of the step
         return out, pc
 
     def step_resident(self):

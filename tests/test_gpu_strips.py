@@ -84,6 +84,9 @@ def test_device_otsu_matches_oracle():
                     np.full(1000, 0.25, dtype=np.float32)):
             got = DeviceOtsu(torch.from_numpy(col).cuda()).result()
             assert got == rp.otsu_threshold(col)
+        cols = [rng.random(30000).astype(np.float32) ** k for k in (1, 3, 6)]      # several columns in one job
+        got = DeviceOtsu([torch.from_numpy(c).cuda() for c in cols]).results()
+        assert got == [rp.otsu_threshold(c) for c in cols]
     finally:
         if created:
             dist.destroy_process_group()

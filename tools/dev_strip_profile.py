@@ -31,8 +31,8 @@ ghosts = torch.cat([fl, fr], dim=0)
 e2 = ev()
 out, pc = D.strip_saliency(own, ghosts, RADII, PARAMS, 0.5, reduce_minmax=D.allreduce_minmax)
 e3 = ev()
-jobs = {r: D.DeviceOtsu(out[r]) for r in RADII}
-res = {r: j.result() for r, j in jobs.items()}
+jobs = D.DeviceOtsu([out[r] for r in RADII])
+res = jobs.results()
 e4 = ev()
 torch.cuda.synchronize(); t1 = time.time()
 print("select %.3f | exchange %.3f | strip_saliency %.3f | otsu %.3f | total gpu %.3f | wall %.3f ms"
