@@ -72,8 +72,10 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
     down = torch.cuda.Stream(device=dev)
 
     def upload(t):
+        if not isinstance(t, torch.Tensor):      # numpy input: pageable memory, the copy is then synchronous
+            t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64))
         with torch.cuda.stream(up):
-            d = t.to(dev, non_blocking=True)
+            d = t.to(dev, dtype=torch.float64, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(up)
         return d, ev

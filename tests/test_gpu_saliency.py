@@ -329,3 +329,5 @@ def test_tile_stream_matches_single_calls():
             assert np.array_equal(o[r].numpy(), w, equal_nan=True)
     assert finite > 0        # (an all-zero dn or dk column normalises to NaN, DM_saliency.py:577-578)
     assert multiscale_saliency_tiles([], radii) == []
+    plain = multiscale_saliency_tiles([tiles[0].numpy()], radii, **kw)           # pageable numpy input works too
+    assert np.array_equal(plain[0][0.5].cpu().numpy(), res[0][0.5].cpu().numpy(), equal_nan=True)
