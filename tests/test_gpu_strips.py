@@ -75,8 +75,15 @@ def test_device_otsu_matches_oracle():
     from oracle import ref_path as rp
     created = False
     if not dist.is_initialized():
-        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29631", rank=0, world_size=1,
-                                device_id=torch.device("cuda", 0))
+        import socket
+        with socket.socket() as sock:                       # a free port, not a fixed one
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        try:
+            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1,
+                                    device_id=torch.device("cuda", 0))
+        except Exception as e:                              # no NCCL rendezvous on this box: not a parity failure
+            pytest.skip("cannot create a one-rank NCCL group: %r" % (e,))
         created = True
     try:
         rng = np.random.default_rng(5)
