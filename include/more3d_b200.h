@@ -148,6 +148,13 @@ int more3d_histogram256(const void* v, int elem_bytes, int64_t n, const double* 
  * NULL; voxel_of_point: n int32 (output row of every input point) or NULL; *nout_h = voxels. */
 int more3d_voxel_downsample(const double* xyz, int64_t n, double voxel, double* out_xyz,
                             int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h, void* stream);
+/* The same on one SHARD of a cloud: bounds_h = {min x, y, z, max x, y, z} of the whole cloud (6 host doubles), so
+ * that every shard bins on the lattice the unsharded call would use.  With voxel-aligned shards (all members of a
+ * voxel on one rank, in the whole cloud's point order) the union of the shards' outputs is the unsharded output,
+ * bit for bit; all points must lie inside the bounds. */
+int more3d_voxel_downsample_bounds(const double* xyz, int64_t n, double voxel, const double* bounds_h,
+                                   double* out_xyz, int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h,
+                                   void* stream);
 
 /* ---- level-of-detail cells: ball-tree-equivalent hierarchy -------------------------------------------
  * Replaces the sklearn BallTree build + the hierarchy bookkeeping of BallTreePointSet.__init__

@@ -116,9 +116,24 @@ __global__ void __launch_bounds__(VX_THREADS) vx_means(const double* __restrict_
 
 using namespace m3d;
 
+static int voxel_downsample_impl(const double* xyz, int64_t n, double voxel, const double* bounds_h, double* out_xyz,
+                                 int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h, void* stream);
+
 extern "C" int more3d_voxel_downsample(const double* xyz, int64_t n, double voxel, double* out_xyz,
                                        int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h,
                                        void* stream) {
+    return voxel_downsample_impl(xyz, n, voxel, nullptr, out_xyz, out_keys, voxel_of_point, nout_h, stream);
+}
+
+extern "C" int more3d_voxel_downsample_bounds(const double* xyz, int64_t n, double voxel, const double* bounds_h,
+                                              double* out_xyz, int64_t* out_keys, int32_t* voxel_of_point,
+                                              int64_t* nout_h, void* stream) {
+    M3D_REQUIRE(bounds_h != nullptr, "bounds_h is NULL");
+    return voxel_downsample_impl(xyz, n, voxel, bounds_h, out_xyz, out_keys, voxel_of_point, nout_h, stream);
+}
+
+static int voxel_downsample_impl(const double* xyz, int64_t n, double voxel, const double* bounds_h, double* out_xyz,
+                                 int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h, void* stream) {
     M3D_REQUIRE(xyz && out_xyz && nout_h && n > 0, "NULL / empty argument");
     M3D_REQUIRE(voxel > 0 && isfinite(voxel), "voxel_size must be > 0");   // open3d raises on <= 0
     if (n >= ((int64_t)1 << 32)) { set_error("n >= 2^32 not supported"); return MORE3D_E_RANGE; }
@@ -126,17 +141,23 @@ extern "C" int more3d_voxel_downsample(const double* xyz, int64_t n, double voxe
     init_device_pool();
     ProfScope prof("voxel_downsample", s);
 
-    const int nparts = 592;
-    double* part = nullptr;
-    M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
-    vx_bbox_partial<<<nparts, VX_THREADS, 0, s>>>(xyz, n, part);
-    vx_bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
-    count_launches(2);
-    M3D_CHECK_LAUNCH();
     double bb[6];
-    M3D_CUDA(cudaMemcpyAsync(bb, part + 6 * nparts, sizeof(bb), cudaMemcpyDeviceToHost, s));
-    M3D_CUDA(cudaStreamSynchronize(s));
-    dev_free(part, s);
+    if (bounds_h) {
+        // the bounding box of the WHOLE cloud, supplied by a caller that holds one shard of it: every shard then
+        // bins on the same voxel lattice and produces the same voxel indices as the unsharded call
+        for (int a = 0; a < 6; ++a) bb[a] = bounds_h[a];
+    } else {
+        const int nparts = 592;
+        double* part = nullptr;
+        M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
+        vx_bbox_partial<<<nparts, VX_THREADS, 0, s>>>(xyz, n, part);
+        vx_bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
+        count_launches(2);
+        M3D_CHECK_LAUNCH();
+        M3D_CUDA(cudaMemcpyAsync(bb, part + 6 * nparts, sizeof(bb), cudaMemcpyDeviceToHost, s));
+        M3D_CUDA(cudaStreamSynchronize(s));
+        dev_free(part, s);
+    }
     for (int a = 0; a < 6; ++a)
         if (!isfinite(bb[a])) { set_error("non-finite coordinates in cloud"); return MORE3D_E_INVALID; }
 

@@ -321,3 +321,74 @@ class StripSaliency:
         cur.wait_stream(down)
         cur.synchronize()
         return res
+
+
+# ------------------------------------------------------------------------------------------------
+# voxel grid across ranks: voxel-aligned x-strips, owner = the voxel's strip, no halo
+# ------------------------------------------------------------------------------------------------
+def voxel_downsample_strips(comm, pts_own, voxel_size, gid_own=None):
+    """open3d voxel_down_sample (Downsample.py:86-89) of a cloud that is spread over the ranks of `comm`
+    (distributed_levelset.DistComm / ThreadComm), in any partition.
+
+    One all-reduce makes the bounding box -- hence the voxel lattice -- global; the x range of the lattice is cut into
+    `world` voxel-aligned strips; every point travels once to the rank that owns its voxel (for a cloud that is
+    already in x-strips only the points next to a strip border move); each rank then reduces its own voxels with
+    the single-GPU kernels on the global lattice.  No halo and no collective on the reduction itself: a voxel's
+    members all sit on one rank.  Members are accumulated in the order of their global point ids (`gid_own`,
+    default: rank-major numbering), so the union of the ranks' outputs equals the single-GPU output bit for bit.
+
+    Returns (means (V, 3) f64, voxel indices (V, 3) int64) of this rank's voxels, device tensors."""
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pts = torch.as_tensor(pts_own, dtype=torch.float64).to(dev).contiguous()
+    n = int(pts.shape[0])
+    world, rank = comm.world, comm.rank
+    voxel = float(voxel_size)
+    if not (voxel > 0 and np.isfinite(voxel)):
+        raise ValueError("voxel_size must be > 0")
+    # global bounding box: one MAX all-reduce over (max, -min)
+    big = torch.finfo(torch.float64).max
+    if n:
+        ext = torch.cat([pts.amax(0), -pts.amin(0)])
+    else:
+        ext = torch.full((6,), -big, dtype=torch.float64, device=dev)
+    comm.allreduce_max(ext)
+    e = ext.cpu().numpy()
+    gmax, gmin = e[:3], -e[3:]
+    bounds = (C.c_double * 6)(*[float(v) for v in gmin], *[float(v) for v in gmax])
+    vmin_x = float(gmin[0]) - voxel * 0.5                         # min_bound - voxel_size * 0.5 (as more3d_voxel_downsample)
+    nx = int(np.floor((float(gmax[0]) - vmin_x) / voxel)) + 2
+    # counts per (sender, receiver) so that everybody knows every message size: one SUM all-reduce
+    if gid_own is None:
+        cnt = torch.zeros(world, dtype=torch.float64, device=dev)
+        cnt[rank] = n
+        comm.allreduce_sum(cnt)
+        start = int(cnt[:rank].sum().item())
+        gid = torch.arange(start, start + n, dtype=torch.int64, device=dev)
+    else:
+        gid = torch.as_tensor(gid_own, dtype=torch.int64).to(dev)
+    ix = torch.floor((pts[:, 0] - vmin_x) / voxel).to(torch.int64) if n else torch.zeros(0, dtype=torch.int64, device=dev)
+    owner = torch.clamp((ix * world) // max(nx, 1), 0, world - 1)
+    sel = {p: torch.nonzero(owner == p).flatten() for p in range(world)}
+    m = torch.zeros((world, world), dtype=torch.float64, device=dev)
+    for p in range(world):
+        m[rank, p] = sel[p].numel()
+    comm.allreduce_sum(m)
+    mh = m.cpu().numpy().astype(np.int64)
+    peers = [p for p in range(world) if p != rank]
+    got_xyz = comm.exchange({p: pts[sel[p]] for p in peers}, {p: (int(mh[p, rank]), 3) for p in peers}, torch.float64, dev)
+    got_gid = comm.exchange({p: gid[sel[p]] for p in peers}, {p: (int(mh[p, rank]),) for p in peers}, torch.int64, dev)
+    mine = torch.cat([pts[sel[rank]]] + [got_xyz[p] for p in peers])
+    mine_gid = torch.cat([gid[sel[rank]]] + [got_gid[p] for p in peers])
+    nl = int(mine.shape[0])
+    if nl == 0:
+        return torch.zeros((0, 3), dtype=torch.float64, device=dev), torch.zeros((0, 3), dtype=torch.int64, device=dev)
+    mine = mine[torch.argsort(mine_gid, stable=True)].contiguous()   # the whole cloud's point order
+    with torch.cuda.device(dev):
+        out = torch.empty((nl, 3), dtype=torch.float64, device=dev)
+        keys = torch.empty((nl, 3), dtype=torch.int64, device=dev)
+        nout = C.c_int64(0)
+        check(lib.more3d_voxel_downsample_bounds(ptr(mine), nl, voxel, bounds, ptr(out), ptr(keys), None,
+                                                 C.byref(nout), stream_ptr()))
+    v = int(nout.value)
+    return out[:v], keys[:v]
