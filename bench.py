@@ -7,8 +7,9 @@ normalise/blend) on a synthetic 10 M-point terrain at 3 neighbourhood radii (BAS
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # weak scaling
 
 A "step" = one pass of the whole pipeline over the cloud (all 3 radii).  `value` = points/s with the
-cloud resident in HBM; `e2e` = the same through the public API with HOST buffers (H2D of the cloud
-and D2H of the three saliency columns inside the timed region).
+cloud resident in HBM; `e2e` = the same through the public tile API (`multiscale_saliency_tiles`) with
+HOST buffers: every step's cloud is copied H2D from pinned memory and its three saliency columns D2H
+inside the timed region, the copies of neighbouring steps overlapping the kernels.
 """
 import argparse
 import json
