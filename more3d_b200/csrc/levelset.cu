@@ -482,6 +482,9 @@ __device__ __forceinline__ double lmv_force(const LsGraph& g, int64_t i, const d
 }
 
 // R + delta (C + F), phi update, increment statistics                      (:404-408, :414-418, :433-437, :614-616)
+// KT > 0: the neighbour count is a compile-time constant (the common k = 5..8), the gather loop is fully unrolled and
+// all of a point's index / operator / neighbour-record loads are in flight together; KT = 0: any k
+template <int KT>
 __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, double* __restrict__ phi,
                                                         const uint8_t* __restrict__ idx2,
                                                         const double* __restrict__ laplace, const double* __restrict__ dphi,
@@ -502,9 +505,11 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, d
             const double2* own = reinterpret_cast<const double2*>(aux + 4 * i);
             const double2 o0 = own[0], o1 = own[1];
             double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
-            for (int j = 0; j < g.k; ++j) {
+            const int kk = KT > 0 ? KT : g.k;
+#pragma unroll
+            for (int j = 0; j < kk; ++j) {
                 const int64_t q = g.nbr[(int64_t)j * g.n + i];
-                const double e0 = g.E[((int64_t)j) * g.n + i], e1 = g.E[((int64_t)(g.k + j)) * g.n + i];
+                const double e0 = g.E[((int64_t)j) * g.n + i], e1 = g.E[((int64_t)(kk + j)) * g.n + i];
                 const double2* nb2 = reinterpret_cast<const double2*>(aux + 4 * q);
                 const double2 v0 = nb2[0], v1 = nb2[1];
                 const double d0 = v0.x - o0.x, d1 = v0.y - o0.y, d2 = v1.x - o1.x, d3 = v1.y - o1.y;
@@ -636,6 +641,20 @@ __global__ void __launch_bounds__(LS_THREADS) ls_extract_prune(LsGraph g, const 
 }  // namespace m3d
 
 using namespace m3d;
+
+static void launch_step_b(const LsGraph& g, const LsParams& p, double* phi, const uint8_t* idx2, const double* laplace,
+                          const double* dphi, const double* aux, const double* zeta, const double* region,
+                          const double* stats, double* phi_new, double* part, cudaStream_t s) {
+#define M3D_STEP_B(KT_) ls_step_b<KT_><<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, phi_new, part)
+    switch (g.k) {
+        case 5: M3D_STEP_B(5); break;
+        case 6: M3D_STEP_B(6); break;
+        case 7: M3D_STEP_B(7); break;
+        case 8: M3D_STEP_B(8); break;
+        default: M3D_STEP_B(0); break;
+    }
+#undef M3D_STEP_B
+}
 
 struct more3d_ls_graph {   // typedef'd in include/more3d_b200.h
     int64_t n;
@@ -818,7 +837,7 @@ static int ls_run_impl(const more3d_ls_graph* G, int model, double* phi, const d
                 ls_reduce_final<<<1, RF_THREADS, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c);
             }
         }
-        ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, bufA, part);
+        launch_step_b(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, bufA, part, s);
         ls_reduce_final<<<1, RF_THREADS, 0, s>>>(part, STEPB_BLOCKS, 2, incs + 2 * it);
         if (!alias_last_active) M3D_CUDA(cudaMemcpyAsync(last_active, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // :617
         ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, bufA, active, azc, bufB, outside);
@@ -916,8 +935,8 @@ extern "C" int more3d_ls_phase(const more3d_ls_graph* G, int phase, const more3d
         count_launches(2 * st->channels);
         break;
     case 3:   // update -> bufA (= phi + increment), incs[0..1] = local sum inc^2, count
-        ls_step_b<<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, st->phi, st->idx2, st->laplace, st->dphi, st->aux, st->zeta,
-                                                      st->region, st->model == 1 ? st->stats : nullptr, st->bufA, st->part);
+        launch_step_b(g, p, st->phi, st->idx2, st->laplace, st->dphi, st->aux, st->zeta, st->region,
+                      st->model == 1 ? st->stats : nullptr, st->bufA, st->part, s);
         ls_reduce_final<<<1, RF_THREADS, 0, s>>>(st->part, STEPB_BLOCKS, 2, st->incs);
         count_launches(2);
         break;
