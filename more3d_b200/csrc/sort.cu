@@ -257,13 +257,19 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict_
         k[j] = ok ? keys[p] : K(0);
         v[j] = ok ? vals[p] : 0u;
     }
+    // digits and their match masks once for both phases; the RS_ITEMS matches are independent of each other, so
+    // they pipeline instead of each waiting behind the counter update of the previous round
+    unsigned dg[RS_ITEMS], pm[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const bool ok = (wbase + j * 32 + lane) < n;
+        dg[j] = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
+        pm[j] = __match_any_sync(0xffffffffu, dg[j]);
+    }
     // phase A: per-warp digit counts
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        bool ok = (wbase + j * 32 + lane) < n;
-        unsigned d = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (ok && (peers & lt) == 0u) wcnt[warp][d] += __popc(peers);
+        if (dg[j] < 256u && (pm[j] & lt) == 0u) wcnt[warp][dg[j]] += __popc(pm[j]);
         __syncwarp();
     }
     __syncthreads();
@@ -286,9 +292,8 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict_
     // phase B: tile-local ranks, keys and values go to their sorted slot of the tile
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        bool ok = (wbase + j * 32 + lane) < n;
-        unsigned d = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
+        const bool ok = dg[j] < 256u;
+        const unsigned d = dg[j], peers = pm[j];
         uint32_t pos = 0;
         if (ok) pos = wcnt[warp][d] + __popc(peers & lt);
         __syncwarp();
