@@ -266,10 +266,15 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict_
         dg[j] = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
         pm[j] = __match_any_sync(0xffffffffu, dg[j]);
     }
-    // phase A: per-warp digit counts
+    // phase A: per-warp digit counts; every key also takes its rank among the warp's EARLIER keys of its digit
+    // (running count before this round + equal-digit lanes below it), so phase B needs no second serial pass
+    uint32_t rk[RS_ITEMS];
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        if (dg[j] < 256u && (pm[j] & lt) == 0u) wcnt[warp][dg[j]] += __popc(pm[j]);
+        const bool ok = dg[j] < 256u;
+        rk[j] = ok ? wcnt[warp][dg[j]] + __popc(pm[j] & lt) : 0u;
+        __syncwarp();
+        if (ok && (pm[j] & lt) == 0u) wcnt[warp][dg[j]] += __popc(pm[j]);
         __syncwarp();
     }
     __syncthreads();
@@ -289,17 +294,11 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict_
         for (int w = 0; w < RS_WARPS; ++w) wcnt[w][d] += ts;
     }
     __syncthreads();
-    // phase B: tile-local ranks, keys and values go to their sorted slot of the tile
+    // phase B: keys and values go to their sorted slot of the tile
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        const bool ok = dg[j] < 256u;
-        const unsigned d = dg[j], peers = pm[j];
-        uint32_t pos = 0;
-        if (ok) pos = wcnt[warp][d] + __popc(peers & lt);
-        __syncwarp();
-        if (ok && (peers & lt) == 0u) wcnt[warp][d] += __popc(peers);
-        __syncwarp();
-        if (ok) {
+        if (dg[j] < 256u) {
+            const uint32_t pos = wcnt[warp][dg[j]] + rk[j];      // tile slot of the digit run + warps below + rank
             keys_s[pos] = k[j];
             vals_s[pos] = v[j];
         }
