@@ -163,6 +163,12 @@ int more3d_voxel_downsample_bounds(const double* xyz, int64_t n, double voxel, c
  * cloud size (sklearn _binary_tree.pxi.tp:872-873).  build(): idx_array n int64; idx_start / idx_end
  * n_nodes int64; is_leaf n_nodes int32; radius n_nodes f64 (node_data of BallTree.get_arrays()). */
 int more3d_balltree_shape(int64_t n, int leaf_size, int64_t* n_levels_h, int64_t* n_nodes_h);
+/* getSmallestNodesOfSize(lod) (BallTreePointSet.py:128-157, :256-276) on the node tables of more3d_balltree_build:
+ * the first node on every branch with radius < lod, or the leaf.  cells: capacity n_nodes int64, in the
+ * reference's depth-first left-before-right order (= the order of the cells' ranges in idx_array); starts:
+ * capacity n_nodes + 1 int64, idx_start of every cell followed by n; *count_h = number of cells. */
+int more3d_lod_select(const int64_t* idx_start, const int32_t* is_leaf, const double* radius, int64_t n_nodes,
+                      int64_t n, double lod, int64_t* cells, int64_t* starts, int64_t* count_h, void* stream);
 int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size, int64_t* idx_array,
                           int64_t* idx_start, int64_t* idx_end, int32_t* is_leaf, double* radius,
                           void* stream);

@@ -87,11 +87,9 @@ def saliency_downsample(pts, saliency, lod, leaf_size=40, zero_thresh=1e-4, lite
     sal64 = sal.to(device=dev.device, dtype=torch.float64).contiguous().reshape(-1)
     if s_thresh is None:
         s_thresh = threshold_otsu(sal)                                      # :54
-    cells = np.atleast_1d(btP.getSmallestNodesOfSize(lod))                  # :47
-    starts = np.append(tree.idx_start[cells], n).astype(np.int64)
-    ncells = len(cells)
+    cells_dev, cs = tree.smallest_nodes_dev(lod)                            # btP.getSmallestNodesOfSize(LOD), :47
+    ncells = int(cells_dev.shape[0])
     with torch.cuda.device(dev.device):
-        cs = torch.from_numpy(starts).to(dev.device)
         keep = torch.empty(n, dtype=torch.uint8, device=dev.device)
         keep_all = torch.empty(ncells, dtype=torch.uint8, device=dev.device)
         mean = torch.empty((ncells, 3), dtype=torch.float64, device=dev.device)
@@ -117,7 +115,8 @@ def saliency_downsample(pts, saliency, lod, leaf_size=40, zero_thresh=1e-4, lite
         out = out.cpu().numpy()
     if return_details:
         det = dict(idx=out_idx if return_device else out_idx.cpu().numpy(),
-                   cell=out_cell if return_device else out_cell.cpu().numpy(), cells=cells, s_thresh=s_thresh,
+                   cell=out_cell if return_device else out_cell.cpu().numpy(), cells=cells_dev.cpu().numpy(),
+                   s_thresh=s_thresh,
                    keep_all=keep_all.cpu().numpy().astype(bool))
         return out, det
     return out

@@ -41,6 +41,7 @@ SIGNATURES = {
     "more3d_voxel_downsample_bounds": [_vp, _i64, _f64, C.POINTER(_f64), _vp, _vp, _vp, C.POINTER(_i64), _vp],
     "more3d_balltree_shape": [_i64, _i32, C.POINTER(_i64), C.POINTER(_i64)],
     "more3d_balltree_build": [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "more3d_lod_select": [_vp, _vp, _vp, _i64, _i64, _f64, _vp, _vp, C.POINTER(_i64), _vp],
     "more3d_lod_cell_rule": [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp],
     "more3d_lod_assemble": [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp],
     "more3d_select_flagged": [_vp, _i64, _vp, C.POINTER(_i64), _vp],

@@ -372,3 +372,73 @@ extern "C" int more3d_lod_cell_rule(const double* xyz, const double* saliency, c
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// getSmallestNodesOfSize (Downsampling/BallTreePointSet.py:128-157, :256-276) on the device
+// ------------------------------------------------------------------------------------------
+namespace m3d {
+// A node is a level-of-detail cell iff it stops the descent (radius < lod or leaf) and none of its ancestors
+// does.  One thread per node walks up its <= n_levels ancestors (heap layout: parent of i is (i - 1) / 2).
+__global__ void __launch_bounds__(LT_THREADS) lod_cell_flags(const int32_t* __restrict__ is_leaf,
+                                                             const double* __restrict__ radius, int64_t n_nodes,
+                                                             double lod, uint32_t* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    bool sel = (radius[i] < lod) || (is_leaf[i] == 1);
+    for (int64_t a = i; sel && a > 0;) {
+        a = (a - 1) >> 1;
+        if ((radius[a] < lod) || (is_leaf[a] == 1)) sel = false;      // an ancestor already stopped (or is a leaf:
+    }                                                                 // the node was never visited by the build)
+    flag[i] = sel ? 1u : 0u;
+}
+__global__ void __launch_bounds__(LT_THREADS) lod_cell_compact(const uint32_t* __restrict__ pos, int64_t n_nodes,
+                                                               const int64_t* __restrict__ idx_start,
+                                                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    if (pos[i + 1] != pos[i]) {             // exclusive scan of the flags: a step marks a selected node
+        keys[pos[i]] = (uint32_t)idx_start[i];
+        vals[pos[i]] = (uint32_t)i;
+    }
+}
+__global__ void __launch_bounds__(LT_THREADS) lod_cell_emit(const uint32_t* __restrict__ keys,
+                                                            const uint32_t* __restrict__ vals, int64_t m, int64_t n,
+                                                            int64_t* __restrict__ cells, int64_t* __restrict__ starts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) { cells[i] = (int64_t)vals[i]; starts[i] = (int64_t)keys[i]; }
+    if (i == m) starts[m] = n;
+}
+}  // namespace m3d
+
+extern "C" int more3d_lod_select(const int64_t* idx_start, const int32_t* is_leaf, const double* radius,
+                                 int64_t n_nodes, int64_t n, double lod, int64_t* cells, int64_t* starts,
+                                 int64_t* count_h, void* stream) {
+    M3D_REQUIRE(idx_start && is_leaf && radius && cells && starts && count_h, "NULL argument");
+    M3D_REQUIRE(n_nodes > 0 && n > 0, "empty tree");
+    if (n >= ((int64_t)1 << 32) || n_nodes >= ((int64_t)1 << 32)) { set_error("n >= 2^32 not supported"); return MORE3D_E_RANGE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    init_device_pool();
+    ProfScope prof("lod_select", s);
+    uint32_t *pos = nullptr, *k1 = nullptr, *k2 = nullptr, *v1 = nullptr, *v2 = nullptr, *ks = nullptr, *vs = nullptr;
+    M3D_TRY(dev_alloc(&pos, (size_t)n_nodes + 1, s));
+    const unsigned nb = (unsigned)((n_nodes + LT_THREADS - 1) / LT_THREADS);
+    lod_cell_flags<<<nb, LT_THREADS, 0, s>>>(is_leaf, radius, n_nodes, lod, pos);
+    M3D_TRY(exclusive_scan_u32(pos, pos, n_nodes, s));
+    uint32_t m32 = 0;
+    M3D_CUDA(cudaMemcpyAsync(&m32, pos + n_nodes, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    const int64_t m = (int64_t)m32;
+    M3D_TRY(dev_alloc(&k1, (size_t)m, s)); M3D_TRY(dev_alloc(&k2, (size_t)m, s));
+    M3D_TRY(dev_alloc(&v1, (size_t)m, s)); M3D_TRY(dev_alloc(&v2, (size_t)m, s));
+    lod_cell_compact<<<nb, LT_THREADS, 0, s>>>(pos, n_nodes, idx_start, k1, v1);
+    int bits = 1;
+    while (bits < 32 && ((int64_t)1 << bits) < n) ++bits;
+    // depth-first, left-before-right order of the reference == order of the cells' ranges in idx_array
+    M3D_TRY(radix_sort_pairs_u32(k1, v1, k2, v2, m, bits, &ks, &vs, s));
+    lod_cell_emit<<<(unsigned)((m + 1 + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(ks, vs, m, n, cells, starts);
+    count_launches(3);
+    M3D_CHECK_LAUNCH();
+    dev_free(pos, s); dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s);
+    *count_h = m;
+    return MORE3D_OK;
+}

@@ -31,7 +31,9 @@ class LodTree:
             rad = torch.empty(self.n_nodes, dtype=torch.float64, device=dev)
             check(lib.more3d_balltree_build(ptr(xyz_dev), self.n, self.leaf_size, ptr(self.idx_array_dev), ptr(start),
                                             ptr(end), ptr(leaf), ptr(rad), stream_ptr()))
-        # node tables are small (<= a few million rows): host copies drive the hierarchy queries
+        # node tables are small (<= a few million rows): host copies drive the hierarchy getters, the device
+        # copies the level-of-detail selection (smallest_nodes_dev)
+        self._start_dev, self._leaf_dev, self._rad_dev = start, leaf, rad
         self.idx_start = start.cpu().numpy()
         self.idx_end = end.cpu().numpy()
         self.is_leaf = leaf.cpu().numpy()
@@ -89,18 +91,24 @@ class LodTree:
     def points_of_node(self, i):
         return self.idx_array[self.idx_start[i]:self.idx_end[i]]
 
+    def smallest_nodes_dev(self, radius):
+        """getSmallestNodesOfSize on the device: (cells int64 [m], starts int64 [m + 1] = idx_start of every cell
+        followed by n), both device tensors, cells in the reference's depth-first left-before-right order."""
+        lib = _lib.load()
+        dev = self._start_dev.device
+        with torch.cuda.device(dev):
+            cells = torch.empty(self.n_nodes, dtype=torch.int64, device=dev)
+            starts = torch.empty(self.n_nodes + 1, dtype=torch.int64, device=dev)
+            m = C.c_int64(0)
+            check(lib.more3d_lod_select(ptr(self._start_dev), ptr(self._leaf_dev), ptr(self._rad_dev), self.n_nodes,
+                                        self.n, float(radius), ptr(cells), ptr(starts), C.byref(m), stream_ptr()))
+        m = int(m.value)
+        return cells[:m], starts[:m + 1]
+
     def smallest_nodes_of_size(self, radius):
         """First node on every branch with radius < `radius` or leaf, in the reference's depth-first,
-        left-before-right order (BallTreePointSet.py:128-147) -- level-synchronous and vectorised."""
-        stop = (self.node_radius < radius) | (self.is_leaf == 1)
-        reach = np.zeros(self.n_nodes, bool)     # reached by the descent (all ancestors kept descending)
-        reach[0] = True
-        for lev in range(1, self.n_levels):
-            a, b = (1 << lev) - 1, min((1 << (lev + 1)) - 1, self.n_nodes)
-            p = (np.arange(a, b) - 1) // 2
-            reach[a:b] = reach[p] & ~stop[p]
-        sel = np.nonzero(reach & stop & self.exists)[0]
-        sel = sel[np.argsort(self.idx_start[sel], kind="stable")]   # DFS order == order of the ranges
+        left-before-right order (BallTreePointSet.py:128-147)."""
+        sel = self.smallest_nodes_dev(radius)[0].cpu().numpy()
         if sel.size == 1:
             return int(sel[0])       # the reference returns a bare index when the root itself qualifies
         return sel
