@@ -300,24 +300,33 @@ class StripSaliency:
         cur = torch.cuda.current_stream(self.dev)
         up = torch.cuda.Stream(device=self.dev)
         down = torch.cuda.Stream(device=self.dev)
+        # two staging buffers filled alternately (no allocation between the strips, see pipeline.multiscale_saliency_tiles)
+        bufs = [torch.empty_like(self.resident) for _ in range(min(2, max(k, 1)))]
+        freed = [None] * len(bufs)
 
-        def upload():
+        def upload(i):
+            slot = i % len(bufs)
             with torch.cuda.stream(up):
-                d = self.host.to(self.dev, non_blocking=True)
+                if freed[slot] is not None:
+                    up.wait_event(freed[slot])
+                else:
+                    up.wait_stream(cur)
+                bufs[slot].copy_(self.host, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(up)
-            return d, ev
+            return bufs[slot], ev
 
         res = None
-        nxt = upload()
+        nxt = upload(0)
         for i in range(k):
             d, ev = nxt
             if i + 1 < k:
-                nxt = upload()
+                nxt = upload(i + 1)
             cur.wait_event(ev)
-            d.record_stream(cur)
             res = self._run(d, self.out_host, copy_stream=down)[0]
-            del d
+            done = torch.cuda.Event()
+            done.record(cur)
+            freed[i % len(bufs)] = done
         cur.wait_stream(down)
         cur.synchronize()
         return res

@@ -70,27 +70,39 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
     cur = torch.cuda.current_stream(dev)
     up = torch.cuda.Stream(device=dev)
     down = torch.cuda.Stream(device=dev)
+    tiles = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64))
+             for t in tiles]                     # numpy input: pageable memory, its copy is then synchronous
+    # two device staging buffers, filled alternately: no allocation (and no allocator-induced synchronisation)
+    # happens between the tiles, and a buffer is overwritten only after the kernels that read it were issued
+    nmax = max(int(t.shape[0]) for t in tiles)
+    bufs = [torch.empty((nmax, 3), dtype=torch.float64, device=dev) for _ in range(min(2, len(tiles)))]
+    freed = [None] * len(bufs)
 
-    def upload(t):
-        if not isinstance(t, torch.Tensor):      # numpy input: pageable memory, the copy is then synchronous
-            t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64))
+    def upload(k):
+        t, slot = tiles[k], k % len(bufs)
         with torch.cuda.stream(up):
-            d = t.to(dev, dtype=torch.float64, non_blocking=True)
+            if freed[slot] is not None:
+                up.wait_event(freed[slot])
+            else:
+                up.wait_stream(cur)              # first use: the buffer was allocated on the compute stream
+            d = bufs[slot][:int(t.shape[0])]
+            d.copy_(t, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(up)
         return d, ev
 
     results = []
-    nxt = upload(tiles[0])
+    nxt = upload(0)
     for k in range(len(tiles)):
         d, ev = nxt
         if k + 1 < len(tiles):
-            nxt = upload(tiles[k + 1])        # enqueued before tile k's kernels: overlaps them
+            nxt = upload(k + 1)                # enqueued before tile k's kernels: overlaps them
         cur.wait_event(ev)
-        d.record_stream(cur)                   # allocated on the upload stream, consumed on the compute stream
         results.append(multiscale_saliency(d, radii, out_host=None if out_hosts is None else out_hosts[k],
                                            copy_stream=down, **params))
-        del d
+        done = torch.cuda.Event()
+        done.record(cur)
+        freed[k % len(bufs)] = done
     cur.wait_stream(down)
     cur.synchronize()
     return results
