@@ -80,3 +80,64 @@ def test_no_cpu_fallback_without_gpu():
         BallTreePointSet(np.zeros((10, 3)))
     with pytest.raises(ValueError):
         BallTreePointSet([[0, 0, 0]])                  # "Wrong input object.", BallTreePointSet.py:40-42
+
+
+def header_prototypes():
+    """name -> list of parameter type strings, parsed from the header"""
+    src = open(os.path.join(ROOT, "include", "more3d_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\s*\*)\s+(more3d_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        protos[m.group(1)] = params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every binding in more3d_b200/_lib.py passes as many arguments as the header declares, and passes a
+    pointer / integer / double where the header has one (a mismatch would corrupt the call silently)."""
+    from more3d_b200 import _lib
+    protos = header_prototypes()
+    assert len(protos) >= 50
+    bad = []
+    for name, argtypes in _lib.SIGNATURES.items():
+        params = protos.get(name)
+        if params is None:
+            bad.append((name, "not in header"))
+            continue
+        if len(params) != len(argtypes):
+            bad.append((name, "header %d args, binding %d" % (len(params), len(argtypes))))
+            continue
+        for i, (p, t) in enumerate(zip(params, argtypes)):
+            is_ptr = "*" in p
+            if is_ptr != (t is ctypes.c_void_p or t is ctypes.c_char_p or hasattr(t, "contents")):
+                bad.append((name, "arg %d: header %r vs %r" % (i, p, t)))
+            elif not is_ptr and re.match(r"(const\s+)?double\b", p) and t is not ctypes.c_double:
+                bad.append((name, "arg %d: header %r vs %r" % (i, p, t)))
+            elif not is_ptr and re.match(r"(const\s+)?int64_t\b", p) and t is not ctypes.c_int64:
+                bad.append((name, "arg %d: header %r vs %r" % (i, p, t)))
+            elif not is_ptr and re.match(r"(const\s+)?int\b", p) and t is not ctypes.c_int:
+                bad.append((name, "arg %d: header %r vs %r" % (i, p, t)))
+    assert not bad, bad
+
+
+def test_ls_state_struct_matches_the_ctypes_mirror():
+    """more3d_ls_state (header) and distributed_levelset._State (ctypes) list the same fields in the same order."""
+    from more3d_b200.distributed_levelset import _State
+    src = open(os.path.join(ROOT, "include", "more3d_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} more3d_ls_state;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names, kinds = [], []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ptr = "*" in decl
+        base = re.match(r"(const\s+)?(\w+)", decl).group(2)
+        for n in re.split(r",", decl[decl.index(base) + len(base):]):
+            names.append(n.replace("*", "").strip())
+            kinds.append("ptr" if ptr else base)
+    got = [(n, "ptr" if t is ctypes.c_void_p else {ctypes.c_int64: "int64_t", ctypes.c_double: "double",
+                                                     ctypes.c_int: "int"}[t]) for n, t in _State._fields_]
+    assert got == list(zip(names, kinds))
