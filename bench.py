@@ -186,7 +186,7 @@ def run_ours(args, rank, world, local_rank):
             # memory and its three saliency columns D2H inside the timed region, the copies of neighbouring tiles
             # overlapping the kernels (the same synthetic tile is sent k times)
             return multiscale_saliency_tiles([host] * k, RADII, out_hosts=[out_host] * k, curvature_weight=CW,
-                                             **PARAMS)
+                                             keep_results=False, **PARAMS)
 
         # neighbour counts for the algorithmic-bytes figure (outside the timed region)
         res = multiscale_saliency(resident, RADII, curvature_weight=CW, keep=True, **PARAMS)

@@ -57,12 +57,14 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
     return out
 
 
-def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, device=None, **params):
+def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, device=None, keep_results=True,
+                              **params):
     """The pipeline over a sequence of host-resident tiles (pinned (N,3) float64 tensors), tile after tile on one
     GPU, with the transfers taken off the critical path: tile k+1 is uploaded on a copy stream while tile k is
     computed, and the saliency columns of tile k travel back (into ``out_hosts[k]``, {radius: pinned float32 tensor})
-    while tile k+1 is computed.  Returns the per-tile results of :func:`multiscale_saliency`; all copies have
-    completed on return."""
+    while tile k+1 is computed.  Returns the per-tile results of :func:`multiscale_saliency` (device tensors;
+    ``keep_results=False`` returns None per tile so that a long stream does not hold every tile's columns in HBM --
+    the results are then in ``out_hosts`` only); all copies have completed on return."""
     tiles = list(host_tiles)
     if not tiles:
         return []
@@ -98,8 +100,10 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
         if k + 1 < len(tiles):
             nxt = upload(k + 1)                # enqueued before tile k's kernels: overlaps them
         cur.wait_event(ev)
-        results.append(multiscale_saliency(d, radii, out_host=None if out_hosts is None else out_hosts[k],
-                                           copy_stream=down, **params))
+        res = multiscale_saliency(d, radii, out_host=None if out_hosts is None else out_hosts[k],
+                                  copy_stream=down, **params)
+        results.append(res if keep_results else None)
+        del res
         done = torch.cuda.Event()
         done.record(cur)
         freed[k % len(bufs)] = done
