@@ -37,6 +37,13 @@ def workload_name(n):
         n, "/".join(str(r) for r in RADII))
 
 
+def config_dict(n, world):
+    """The `config` object of the JSON line -- the SAME for our arm and the reference arm."""
+    return {"workload": workload_name(n), "points_per_gpu": n, "radii": list(RADII),
+            "l2": "inputs (240 MB cloud + 320..640 MB records per radius) exceed the 126 MB L2",
+            "parallelism": "x-strips with 2*r_max ghost halos over NCCL" if world > 1 else "single GPU"}
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
@@ -115,18 +122,21 @@ def ncu_traffic():
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """The reference's CPU path (oracle port: sklearn BallTree + per-point processors) on all host cores."""
+    """The reference's own CPU implementation of the path on all host cores: the UNMODIFIED reference from
+    oracle/_ref (sklearn BallTree.query_radius + verbatim Curvature_Kernel / Saliency_Kernel callbacks) when that
+    was built, else the oracle port.  Each step is a bounded sample of Q query points per radius against the
+    full cloud's tree, extrapolated x N/Q (Q = 50 000)."""
     if rank != 0:
         return
     from more3d_b200 import synthetic
-    from oracle.cpu_bench import CpuSaliencyBaseline, host_cores
+    from oracle.cpu_bench import CpuSaliencyBaseline, host_cores, describe
     n = args.n
     pts = synthetic.terrain(n, seed=2)
     cores = host_cores()
     base = CpuSaliencyBaseline(pts, RADII, PARAMS, workers=cores, seed=1)
-    q = args.cpu_q * cores
+    q = args.cpu_q
     for _ in range(args.warmup):
-        base.step(max(q // 4, cores))
+        base.step(max(q // 8, cores))
     times = []
     for _ in range(args.steps):
         total, raw = base.step(q)
@@ -134,14 +144,14 @@ def run_reference(args, rank, world):
     base.close()
     t = float(np.mean(times))
     value = n / t
-    sample = ("oracle port (sklearn BallTree.query_radius + per-point PCA/Curvature_Kernel/Saliency_Kernel restatement); "
-              "tree over all %d points built once (%.1f s, included in every step), %d random query points per radius per step "
-              "on %d worker processes, extrapolated x N/Q" % (n, base.t_tree, q, cores))
+    sample = ("%s; tree over all %d points built once (%.1f s, included in every step), %d random query points per radius "
+              "per step on %d worker processes, extrapolated x N/Q = %.0f" % (describe(base.kind), n, base.t_tree, q, cores,
+                                                                           n / float(q)))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "points": n, "radii": list(RADII)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_dict(n, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": base.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -269,6 +279,18 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": (tr or {}).get(dom), "algorithmic_bytes_per_step": alg[dom],
                 "kernel_share_of_step": kern[dom]["ms_per_step"] / (ms / args.steps)}
 
+    # ---- configs[4]: strong scaling of ONE 500 M-point tile (r = 0.5), the same global cloud for every N ----
+    strong = None
+    if args.strong_points > 0:
+        if distributed:
+            del job
+        else:
+            del resident, host, out_host
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        strong = strong_leg(args, rank, world, dev)
+
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -277,29 +299,115 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "points_per_gpu": n, "radii": list(RADII),
-                       "l2": "inputs (240 MB cloud + 320..640 MB records per radius) exceed the 126 MB L2",
-                       "parallelism": "x-strips with 2*r_max ghost halos over NCCL" if distributed else "single GPU"},
+            "config": config_dict(n, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern}
     if not distributed:
         line["nonzero_fraction_dk_dn"] = {str(r): nonzero[r] for r in RADII}
+    if strong is not None:
+        line["strong"] = strong
 
     if args.cpu_baseline and not distributed:
-        from oracle.cpu_bench import CpuSaliencyBaseline
-        base = CpuSaliencyBaseline(pts, RADII, PARAMS, workers=1, normals=gpu_normals, K=gpu_K, seed=1)
+        # the reference's CPU path on the host cores beside the GPU number (same run, same cloud): the UNMODIFIED
+        # reference when oracle/_ref was built, else the oracle port; bounded sample, extrapolated x N/Q
+        from oracle.cpu_bench import CpuSaliencyBaseline, host_cores, describe
+        cores = host_cores()
+        base = CpuSaliencyBaseline(pts, RADII, PARAMS, workers=cores, normals=gpu_normals, K=gpu_K, seed=1)
         total, raw = base.step(args.cpu_q)
+        base.close()
         line["cpu_baseline"] = {
-            "value": n / total, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": ("oracle port (sklearn BallTree.query_radius + per-point PCA/Curvature_Kernel/Saliency_Kernel "
-                       "restatement, scipy constants hoisted); tree over all %d points (%.1f s) + %d random query points "
-                       "per radius (%.1f s), extrapolated x N/Q; 1 core" % (n, base.t_tree, args.cpu_q, raw))}
+            "value": n / total, "unit": UNIT, "cores": cores, "kind": base.kind,
+            "sample": ("%s; tree over all %d points (%.1f s) + %d random query points per radius (%.1f s on %d worker "
+                       "processes), extrapolated x N/Q = %.0f" % (describe(base.kind), n, base.t_tree, args.cpu_q, raw, cores,
+                                                                  n / float(args.cpu_q)))}
+        del base
     else:
         line["cpu_baseline"] = None
+
+    if args.configs and not distributed:
+        # BASELINE.json configs[0], [2], [3] at full size on this GPU, each with its algorithmic-bytes fraction, a
+        # bounded CPU leg and a parity spot-check (tools/bench_configs.py)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        try:
+            del pts, gpu_normals, gpu_K
+        except NameError:
+            pass
+        line["configs"] = {}
+        for key in ("0", "2", "3"):
+            try:
+                line["configs"][key] = bench_configs.run_all((key,), small=args.small_configs, peak=peak)[key]
+            except Exception as e:  # a failing sub-record must not lose the headline line
+                line["configs"][key] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
     print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def strong_leg(args, rank, world, dev):
+    """BASELINE.json configs[4]: the saliency pipeline at r = 0.5 on ONE tile of `--strong-points` points, cut
+    into `world` x-strips (radius-halo exchange + min/max + histogram all-reduce over NCCL).  The tile is the
+    counter-based synthetic terrain (point i is a function of (seed, i), generated in HBM), so every N processes
+    the SAME global cloud: `checksum` (sum of neighbour counts, sum of the saliency bit patterns) must not depend
+    on N.  Timing as the main line: CUDA events, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from more3d_b200 import synthetic
+    from more3d_b200.pipeline import multiscale_saliency
+    total, r = int(args.strong_points), 0.5
+    if total % world or synthetic.HASH_SLABS % world:
+        return {"skipped": "strong_points / slab count not divisible by the number of GPUs"}
+    per = total // world
+    lx, ly = synthetic.hash_tile_extent(total)
+    own = synthetic.hash_terrain_device(5, rank * per, per, total, device=dev)
+    distributed = world > 1
+    if distributed:
+        from more3d_b200.distributed import StripSaliency
+        x_lo = rank * lx / world - 0.5 * lx
+        job = StripSaliency(per, rank, world, dev, (r,), PARAMS, CW, cloud=own, x_range=(x_lo, x_lo + lx / world),
+                            host_buffers=False)
+        step = job.step_resident
+        cs = torch.tensor(list(job.checksum[r]), dtype=torch.int64, device=dev)
+        dist.all_reduce(cs)
+    else:
+        res = multiscale_saliency(own, (r,), curvature_weight=CW, keep=True, **PARAMS)
+        cs = torch.stack([res[r]["_pcount"].long().sum(), res[r]["_saliency"].view(torch.int32).long().sum()])
+        del res
+
+        def step():
+            return multiscale_saliency(own, (r,), curvature_weight=CW, **PARAMS)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = max(min(args.steps, 3), 1)
+    a.record()
+    for _ in range(k):
+        step()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    if distributed:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    cs = [int(v) for v in cs.cpu().tolist()]
+    out = {"workload": "configs[4]: %d-point synthetic tile, DM_saliency pipeline at r=0.5, x-strips over %d GPU(s)" % (total, world),
+           "points": total, "n_gpus": world, "scaling": "strong", "steps": k, "ms_per_step": ms / k,
+           "points_per_s": total * k / (ms * 1e-3),
+           "checksum": {"sum_pcount": cs[0], "sum_saliency_f32_bits_mod_2^64": cs[1]},
+           "hbm_allocated_GB_rank0": torch.cuda.max_memory_allocated() / 1e9}
+    del own
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -309,7 +417,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", dest="n", type=int, default=10_000_000, help="points per GPU")
-    ap.add_argument("--cpu-q", type=int, default=2000, help="CPU-baseline sample: query points per radius (per core)")
+    ap.add_argument("--cpu-q", type=int, default=50000,
+                    help="CPU legs: query points per radius per step, split over the host cores (BASELINE.md section 3: 50 000)")
+    ap.add_argument("--strong-points", type=int, default=500_000_000,
+                    help="size of the configs[4] strong-scaling tile (0 = skip the leg)")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="skip the configs[0]/[2]/[3] sub-records (N = 1 only)")
+    ap.add_argument("--small-configs", action="store_true", help="sub-records at reduced sizes (smoke runs)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--radii", default=None, help="comma-separated radii (default 0.5,0.75,1.0 = configs[1]); "
                                                   "'--points 62500000 --radii 0.5' on 8 GPUs is configs[4] (500 M-point tile)")

@@ -318,6 +318,14 @@ int more3d_band_select(const double* xyz, int64_t n, int axis, double lo, double
 int more3d_gather_rows(const void* src, const int64_t* idx, int64_t m, int ncols, int elem_bytes,
                        void* dst, void* stream);
 
+/* ---- synthetic input (bench / test infrastructure; no reference equivalent) ----------------------------
+ * Counter-based open-terrain generator of SURVEY.md section 8d's model: point i of a `total`-point tile of
+ * lx x ly metres is a pure function of (seed, i); ids are slab-major along x (slab = i * slabs / total), so an id
+ * range is an x-strip.  Writes points [id_start, id_start + count) as count*3 f64 (x, y centred on the tile,
+ * z - 1000 m).  numpy twin: more3d_b200/synthetic.py:hash_terrain_host. */
+int more3d_synth_terrain(uint64_t seed, int64_t id_start, int64_t count, int64_t total, double lx, double ly,
+                         int slabs, double noise, double* out_xyz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

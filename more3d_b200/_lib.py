@@ -65,6 +65,7 @@ SIGNATURES = {
     "more3d_compare_terms": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "more3d_band_select": [_vp, _i64, _i32, _f64, _f64, _vp, C.POINTER(_i64), _vp],
     "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "more3d_synth_terrain": [C.c_uint64, _i64, _i64, _i64, _f64, _f64, _i32, _f64, _vp, _vp],
 }
 
 

@@ -255,24 +255,41 @@ def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=N
 class StripSaliency:
     """bench.py's weak-scaling job: rank k owns an n-point strip of a (world * W) x W tile."""
 
-    def __init__(self, n, rank, world, device, radii, params, curvature_weight, seed=2):
+    def __init__(self, n, rank, world, device, radii, params, curvature_weight, seed=2, cloud=None, x_range=None,
+                 host_buffers=True):
+        """Default: rank k generates its own n-point strip on the host (weak scaling).  With `cloud` (an (n, 3) f64
+        device tensor holding this rank's strip of a larger tile) and `x_range` = (x_lo, x_hi) the job runs on that
+        strip instead (bench.py's strong-scaling leg); `host_buffers=False` skips the pinned e2e buffers."""
         from . import synthetic
-        self.n, self.rank, self.world, self.dev = n, rank, world, device
+        self.rank, self.world, self.dev = rank, world, device
         self.radii, self.params, self.cw = tuple(radii), dict(params), curvature_weight
-        W = float(np.sqrt(n / synthetic.DENSITY))
-        self.W = W
-        pts = synthetic.terrain(n, seed=seed + rank, extent=(W, W), origin=(rank * W, 0.0),
-                                centre=(0.5 * world * W, 0.5 * W))
-        self.x_lo = rank * W - 0.5 * world * W
-        self.x_hi = self.x_lo + W
         self.halo = 2.0 * max(radii) * CELL_MARGIN
-        self.host = torch.from_numpy(pts).pin_memory()
-        self.resident = self.host.to(device)
-        self.out_host = {r: torch.empty(n, dtype=torch.float32).pin_memory() for r in radii}
-        self.h2d_bytes = self.host.numel() * 8
-        self.d2h_bytes = n * 4 * len(radii)
-        _, pc = self._run(self.resident, None)
+        if cloud is None:
+            W = float(np.sqrt(n / synthetic.DENSITY))
+            self.W = W
+            pts = synthetic.terrain(n, seed=seed + rank, extent=(W, W), origin=(rank * W, 0.0),
+                                    centre=(0.5 * world * W, 0.5 * W))
+            self.x_lo = rank * W - 0.5 * world * W
+            self.x_hi = self.x_lo + W
+            self.host = torch.from_numpy(pts).pin_memory()
+            self.resident = self.host.to(device)
+        else:
+            self.resident = cloud
+            n = int(cloud.shape[0])
+            self.x_lo, self.x_hi = float(x_range[0]), float(x_range[1])
+            self.host = None
+        self.n = n
+        if host_buffers and self.host is not None:
+            self.out_host = {r: torch.empty(n, dtype=torch.float32).pin_memory() for r in radii}
+            self.h2d_bytes = self.host.numel() * 8
+            self.d2h_bytes = n * 4 * len(radii)
+        else:
+            self.out_host, self.h2d_bytes, self.d2h_bytes = None, 0, 0
+        out, pc = self._run(self.resident, None)
         self.sum_m = {r: float(pc[r].tensor().double().sum()) for r in radii}
+        # partition-independent checksums of the owned points: sum of the neighbour counts and of the saliency
+        # columns' float32 BIT PATTERNS (mod 2^64) -- equal across 1/2/4/8-GPU partitions iff every value is
+        self.checksum = {r: (int(pc[r].tensor().long().sum()), int(out[r].view(torch.int32).long().sum())) for r in radii}
 
     def _run(self, own, out_host, copy_stream=None):
         left = gather_rows(own, band_select(own, 0, -np.inf, self.x_lo + self.halo))

@@ -98,3 +98,86 @@ def sphere_cap(n, seed, radius=50.0, cap=0.2):
     pts = np.stack([radius * sin_t * np.cos(ph), radius * sin_t * np.sin(ph),
                     radius * cos_t - radius - 1000.0], -1)
     return np.ascontiguousarray(pts)
+
+
+# ------------------------------------------------------------------------------------------------
+# Counter-based terrain: point i of a tile is a pure function of (seed, i) -- no sequential RNG stream -- so
+# any rank can generate any id range of a 50 M / 500 M-point tile, on the DEVICE (`more3d_synth_terrain`,
+# csrc/synth.cu; milliseconds instead of minutes of host numpy), and every partition of the ids over 1/2/4/8
+# GPUs is the SAME global cloud (bench.py's strong-scaling leg compares checksums across partitions).
+# The tile's x range is cut into `slabs` equal slabs; ids are slab-major (slab = i * slabs // total), uniform
+# inside the slab, so an id range [k * total / G, (k + 1) * total / G) is exactly the k-th of G x-strips when
+# G divides `slabs`.  Same relief / noise / entity model as `terrain` above.
+# `hash_terrain_host` is the numpy twin of the kernel (integer hashing identical; sin/cos/exp/log differ by
+# a few ulp between libm and CUDA, so z agrees to ~1e-12 m, x and y bit for bit).
+# ------------------------------------------------------------------------------------------------
+HASH_SLABS = 4000
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def _u01(seed, ids, stream):
+    """53-bit uniform in [0, 1) from (seed, id, stream)."""
+    with np.errstate(over="ignore"):
+        k = _splitmix64(_splitmix64(np.uint64(seed) ^ (np.uint64(stream) * np.uint64(0xD1B54A32D192ED03))) ^ ids.astype(np.uint64))
+    return (k >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def hash_tile_extent(total, density=DENSITY, aspect=1.0):
+    """(Lx, Ly) of a tile of `total` points at `density`, Lx = aspect * Ly."""
+    area = total / density
+    ly = float(np.sqrt(area / aspect))
+    return aspect * ly, ly
+
+
+def hash_terrain_host(seed, id_start, count, total, extent=None, noise=0.02, slabs=HASH_SLABS):
+    """numpy twin of more3d_synth_terrain: points [id_start, id_start + count) of the `total`-point tile."""
+    lx, ly = hash_tile_extent(total) if extent is None else map(float, extent)
+    ids = np.arange(id_start, id_start + count, dtype=np.uint64)
+    # slab = floor(id * slabs / total) without 128-bit products: total / slabs points per slab when divisible
+    slab = ((ids.astype(np.float64) + 0.5) * (slabs / float(total))).astype(np.int64)
+    x = (slab + _u01(seed, ids, 1)) * (lx / slabs)
+    y = _u01(seed, ids, 2) * ly
+    z = np.zeros(count)
+    for o in range(7):
+        f = float(2 ** o)
+        z += 2.0 * 2.0 ** (-0.8 * o) * np.sin(f * x / 40.0 + o) * np.cos(f * y / 37.0 + 2 * o)
+    u1, u2 = _u01(seed, ids, 3), _u01(seed, ids, 4)
+    z += noise * np.sqrt(-2.0 * np.log(1.0 - u1)) * np.cos(2.0 * np.pi * u2)
+    B = 50.0
+    bx, by = np.floor(x / B), np.floor(y / B)
+    bid = (bx.astype(np.int64) * 1000003 + by.astype(np.int64)).astype(np.uint64)
+    cx = bx * B + 10.0 + 30.0 * _u01(seed, bid, 5)
+    cy = by * B + 10.0 + 30.0 * _u01(seed, bid, 6)
+    amp = np.where(_u01(seed, bid, 7) < 0.5, -0.4, 0.4)
+    sig = 1.0 + _u01(seed, bid, 8)
+    z += amp * np.exp(-0.5 * ((x - cx) ** 2 + (y - cy) ** 2) / (sig * sig))
+    pts = np.empty((count, 3))
+    pts[:, 0] = x - 0.5 * lx
+    pts[:, 1] = y - 0.5 * ly
+    pts[:, 2] = z - 1000.0
+    return pts
+
+
+def hash_terrain_device(seed, id_start, count, total, extent=None, noise=0.02, slabs=HASH_SLABS, device=None, out=None):
+    """Points [id_start, id_start + count) of the tile, generated on the GPU: (count, 3) float64 CUDA tensor."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    _lib.require_cuda()
+    lx, ly = hash_tile_extent(total) if extent is None else map(float, extent)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if out is None:
+        out = torch.empty((int(count), 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().more3d_synth_terrain(C.c_uint64(int(seed)), int(id_start), int(count), int(total),
+                                                    float(lx), float(ly), int(slabs), float(noise), _lib.ptr(out),
+                                                    _lib.stream_ptr()))
+    return out

@@ -1,11 +1,20 @@
 """CPU-baseline timing of the reference path (test/bench infrastructure, NOT product code).
 
-Executed only by bench.py's ``cpu_baseline`` leg and its ``--impl reference`` arm.  It times the
-oracle port of the reference path (oracle/ref_path.py: sklearn BallTree + the per-point processors)
-on a BOUNDED sample of query points against the FULL cloud's tree and extrapolates x N/Q, because the
-full 10 M-point job takes hours on host cores.  The port hoists the scipy inverse-CDF
-constants out of the per-point loop (the reference re-evaluates them per point, DM_saliency.py:99,
-:282), so it is the reference's path at its most favourable.
+Executed only by bench.py's ``cpu_baseline`` leg and its ``--impl reference`` arm.  Two kinds:
+
+``kind="reference"`` -- the UNMODIFIED reference (oracle/_ref bytecode, oracle/ref_verbatim.py): the tree call the
+    reference makes (``sklearn.neighbors.BallTree(points, leaf_size=40)`` + ``query_radius``,
+    BallTreePointSet.py:35, :339-345) and the verbatim ``Curvature_Kernel.process`` / ``Saliency_Kernel.process``
+    callbacks (DM_saliency.py:88-157, :219-324), scipy inverse CDFs evaluated per point as the reference does.
+    ``BallTreePointSet.__init__`` itself is not used at bench sizes: its O(nodes^2) Python hierarchy
+    reconstruction (:45-53) takes hours at 10 M points and is not part of the saliency path.
+``kind="port"`` -- oracle/ref_path.py, the numpy restatement (scipy constants hoisted: the reference's path at
+    its most favourable); the fallback when oracle/_ref is absent.
+
+Both run on a BOUNDED uniform random sample of Q query points per radius against the FULL cloud's tree and
+extrapolate x N/Q (the full 10 M-point job takes hours on host cores).  The PCA
+normals the reference takes as a precondition (OPALS Normals module, DM_saliency.py:329-330) are computed -- and
+timed -- with the oracle's centroid-PCA for the sampled points.
 """
 import multiprocessing as mp
 import os
@@ -14,19 +23,24 @@ import time
 import numpy as np
 
 from . import ref_path as rp
+from . import ref_verbatim as rv
 
 _G = {}
 
 
 def _pass1_chunk(args):
     r, sub = args
-    pts, tree, eps, min_points = _G["pts"], _G["tree"], _G["eps"], _G["min_points"]
-    nb = tree.query_radius(pts[sub], r)
+    pts, tree, p = _G["pts"], _G["tree"], _G["params"]
+    nb = tree.query_radius(pts[sub], r)                       # BallTreePointSet.py:345
+    nrm = np.empty((len(sub), 3))
+    for t, (i, j) in enumerate(zip(sub, nb)):
+        nrm[t], _ = rp.pca_point(pts[i], pts[j])
+    if _G["kind"] == "reference":
+        K, _, _ = rv.run_curvature(pts, nrm, nb, p["alpha"], p["roughness"], p["min_points"], queries=sub)
+        return K
     out = np.zeros(len(sub))
     for t, (i, j) in enumerate(zip(sub, nb)):
-        n, _ = rp.pca_point(pts[i], pts[j])
-        k, _, _ = rp.curvature_point(pts[i], n, pts[j], eps, min_points)
-        out[t] = k
+        out[t], _, _ = rp.curvature_point(pts[i], nrm[t], pts[j], _G["eps"], p["min_points"])
     return out
 
 
@@ -35,8 +49,12 @@ def _pass2_chunk(args):
     pts, tree, nrm, K = _G["pts"], _G["tree"], _G["normals"], _G["K"]
     table, p = _G["table"], _G["params"]
     nb = tree.query_radius(pts[sub], r)
-    out = np.zeros(len(sub))
     rho = r / np.sqrt(2.0)
+    if _G["kind"] == "reference":
+        dk, dn = rv.run_dk_dn(pts, nrm, K, nb, rho, rho, p["sigma_normal"], p["sigma_curvature"], p["alpha"],
+                              p["min_points"], queries=sub)
+        return dk + dn
+    out = np.zeros(len(sub))
     for t, (i, j) in enumerate(zip(sub, nb)):
         dk, dn = rp.saliency_point(pts[i], nrm[i], K[i], pts[j], nrm[j], K[j], rho, p["sigma_normal"],
                                    p["sigma_curvature"], table, p["min_points"])
@@ -55,15 +73,31 @@ def _run(fn, r, sub, workers, pool):
     return time.perf_counter() - t0
 
 
-class CpuSaliencyBaseline:
-    """Tree built once over the full cloud; ``step`` times one bounded sample of the 3-radius job."""
+def best_kind():
+    return "reference" if rv.available() else "port"
 
-    def __init__(self, pts, radii, params, workers=1, normals=None, K=None, seed=0):
+
+def describe(kind):
+    if kind == "reference":
+        return ("UNMODIFIED reference (%s): sklearn BallTree(leaf_size=40).query_radius as called at "
+                "BallTreePointSet.py:35,:345 + verbatim Curvature_Kernel.process / Saliency_Kernel.process "
+                "(DM_saliency.py:88-157, :219-324) per point; precondition normals by centroid-PCA" % rv.origin())
+    return ("oracle port (sklearn BallTree.query_radius + per-point PCA/Curvature_Kernel/Saliency_Kernel numpy "
+            "restatement, scipy constants hoisted)")
+
+
+class CpuSaliencyBaseline:
+    """Tree built once over the full cloud; ``step`` times one bounded sample of the multi-radius job."""
+
+    def __init__(self, pts, radii, params, workers=1, normals=None, K=None, seed=0, kind=None):
         self.pts = np.ascontiguousarray(pts, np.float64)
         self.n = self.pts.shape[0]
         self.radii = tuple(radii)
         self.params = dict(params)
         self.workers = int(workers)
+        self.kind = kind or best_kind()
+        if self.kind == "reference":
+            rv.load_reference()                            # import cost outside the timed region
         t0 = time.perf_counter()
         self.tree = rp.build_tree(self.pts, 40)           # BallTreePointSet.py:35
         self.t_tree = time.perf_counter() - t0
@@ -78,10 +112,9 @@ class CpuSaliencyBaseline:
         self.normals = np.ascontiguousarray(normals, np.float64)
         self.K = np.asarray(K, np.float32).astype(np.float64)
         self.rng = rng
-        _G.update(pts=self.pts, tree=self.tree, normals=self.normals, K=self.K,
+        _G.update(pts=self.pts, tree=self.tree, normals=self.normals, K=self.K, kind=self.kind,
                   eps=rp.curvature_epsilon(params["alpha"], params["roughness"]),
-                  table=rp.chi2_table(params["alpha"], 8192), params=self.params,
-                  min_points=params["min_points"])
+                  table=rp.chi2_table(params["alpha"], 8192), params=self.params)
         self.pool = None
         if self.workers > 1:
             self.pool = mp.get_context("fork").Pool(self.workers)   # tree/arrays shared copy-on-write
@@ -93,10 +126,11 @@ class CpuSaliencyBaseline:
             self.pool = None
 
     def step(self, q_per_radius):
-        """One bounded sample.  Returns (extrapolated seconds for the whole N-point 3-radius job
+        """One bounded sample.  Returns (extrapolated seconds for the whole N-point multi-radius job
         including the one-off tree build, raw sample seconds)."""
         total = self.t_tree
         raw = 0.0
+        q_per_radius = int(min(q_per_radius, self.n))
         for r in self.radii:
             sub = self.rng.choice(self.n, q_per_radius, replace=False)
             t1 = _run(_pass1_chunk, r, sub, self.workers, self.pool)

@@ -12,6 +12,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "fullsize: GPU parity test at a BASELINE.json size (minutes, tens of GB of HBM)")
 
 
 def pytest_collection_modifyitems(config, items):

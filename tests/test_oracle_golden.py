@@ -202,3 +202,45 @@ def test_levelset_oracle_lmv(golden_dir, tag):
     np.testing.assert_allclose(st["phi"], g["phi12_" + tag], rtol=1e-9, atol=1e-11)
     if not alias:
         assert np.array_equal(st["last_active"], g["last12_" + tag])
+
+
+def test_verbatim_reference_bytecode_reproduces_the_goldens(golden_dir):
+    """oracle/_ref (the UNMODIFIED reference byte-compiled by oracle/build_ref.py) is what the GPU-box tests and
+    bench.py's reference arm execute: it must reproduce the goldens that were generated from the sources."""
+    from oracle import ref_verbatim as rv
+    if not rv.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    g = np.load(os.path.join(golden_dir, "terrain_r05.npz"))
+    pts = g["points"]
+    off, idx = g["nbr_off"], g["nbr_idx"]
+    nb = [idx[off[i]:off[i + 1]].astype(np.int64) for i in range(len(off) - 1)]
+    sub = np.arange(0, len(pts), 3)
+    K, pc, nrm = rv.run_curvature(pts, g["normals_in"][sub], [nb[i] for i in sub], float(g["alpha"]), float(g["roughness"]),
+                                  int(g["min_points"]), queries=sub)
+    assert np.array_equal(K, g["K"][sub]) and np.array_equal(pc, g["pcount"][sub])
+    assert np.array_equal(nrm, g["normals"][sub], equal_nan=True)
+    dk, dn = rv.run_dk_dn(pts, g["normals"], g["K"], [nb[i] for i in sub], float(g["rho"]), float(g["rho"]), float(g["sigma_n"]),
+                          float(g["sigma_k"]), float(g["alpha"]), int(g["min_points"]), queries=sub)
+    assert np.array_equal(dk, g["dk"][sub]) and np.array_equal(dn, g["dn"][sub])
+    bt_mod, _, ls_mod = rv.load_reference()
+    bt = bt_mod.BallTreePointSet(pts[:500], leaf_size=40)
+    assert bt.numberOfNodes >= 1 and hasattr(ls_mod, "Solver")
+
+
+def test_cpu_bench_kinds_agree():
+    """bench.py's CPU legs: the verbatim reference and the oracle port time the same work (same outputs)."""
+    from more3d_b200 import synthetic
+    from oracle import cpu_bench, ref_verbatim as rv
+    pts = synthetic.terrain(20000, seed=4)
+    P = dict(roughness=0.02, alpha=0.05, sigma_normal=0.01, sigma_curvature=0.01, min_points=4)
+    kinds = ["port"] + (["reference"] if rv.available() else [])
+    outs = {}
+    for kind in kinds:
+        b = cpu_bench.CpuSaliencyBaseline(pts, (0.5,), P, workers=1, seed=1, kind=kind)
+        sub = np.arange(0, 20000, 200)
+        outs[kind] = (cpu_bench._pass1_chunk((0.5, sub)), cpu_bench._pass2_chunk((0.5, sub)))
+        total, raw = b.step(50)
+        assert total > raw > 0
+    if "reference" in outs:
+        np.testing.assert_allclose(outs["port"][0], outs["reference"][0], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(outs["port"][1], outs["reference"][1], rtol=1e-4, atol=1e-7)
