@@ -13,6 +13,14 @@ namespace m3d {
 
 constexpr int BB_THREADS = 256;
 
+__device__ __forceinline__ PointRec load_rec_plain(const PointRec* __restrict__ rec, int64_t j) {
+    PointRec r;
+    double w;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(w) : "l"(rec + j));
+    r.idx = __double_as_longlong(w);
+    return r;
+}
+
 __global__ void __launch_bounds__(BB_THREADS) bbox_partial(const double* __restrict__ xyz, int64_t n,
                                                            double* __restrict__ part) {
     // v[0..2] = min x,y,z   v[3..5] = max x,y,z (stored negated so one fmin reduction serves both)
@@ -71,6 +79,71 @@ __global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz,
     keys[i] = key;
     vals[i] = (uint32_t)i;
     atomicAdd(&col_count[key], 1u);
+}
+
+// K1 (thin grids): column key per point AND the point's arrival rank in its column -- the value the counting
+// atomic returns.  Arrival order is arbitrary; column_fixup below turns it into (column, original index) order.
+__global__ void __launch_bounds__(256) cell_keys_rank(const double* __restrict__ xyz, int64_t n, double ox,
+                                                      double oy, double inv, int nx, int ny,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
+                                                      uint32_t* __restrict__ col_count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ix = cell_coord(xyz[3 * i], ox, inv, nx);
+    int iy = cell_coord(xyz[3 * i + 1], oy, inv, ny);
+    ix = min(max(ix, 0), nx - 1);
+    iy = min(max(iy, 0), ny - 1);
+    const uint32_t key = (uint32_t)iy * (uint32_t)nx + (uint32_t)ix;
+    keys[i] = key;
+    ranks[i] = atomicAdd(&col_count[key], 1u);
+}
+
+// K2 (thin grids): counting-sort scatter.  Reads the cloud coalesced, writes one full 32-B sector per point at
+// col_start[key] + arrival rank: the points of a column are now contiguous, in arrival order.
+__global__ void __launch_bounds__(256) scatter_records(const double* __restrict__ xyz, int64_t n,
+                                                       const uint32_t* __restrict__ keys,
+                                                       const uint32_t* __restrict__ ranks,
+                                                       const uint32_t* __restrict__ col_start,
+                                                       PointRec* __restrict__ tmp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PointRec r;
+    r.x = xyz[3 * i]; r.y = xyz[3 * i + 1]; r.z = xyz[3 * i + 2];
+    r.idx = (long long)i;
+    tmp[(size_t)__ldg(col_start + keys[i]) + ranks[i]] = r;
+}
+
+// K3 (thin grids): one thread per scattered record.  Its final slot is the column start plus the number of column
+// members with a smaller original index (columns hold a handful of points: a short loop over L1-resident
+// records), which makes the order (column key, original index) -- exactly what a stable sort by key gives, for
+// any arrival order.  The same loop finds the np.unique flag (a bit-equal point with a smaller index,
+// DM_saliency.py:247); the fp32 record and the order table are written alongside.
+__global__ void __launch_bounds__(256) column_fixup(const PointRec* __restrict__ tmp,
+                                                    const uint32_t* __restrict__ col_start, int64_t n, double ox,
+                                                    double oy, double oz, double inv, int nx, int ny,
+                                                    PointRec* __restrict__ rec, float4* __restrict__ rec32,
+                                                    uint32_t* __restrict__ order, uint8_t* __restrict__ dup) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const PointRec p = load_rec_plain(tmp, t);
+    const int ix = min(max(cell_coord(p.x, ox, inv, nx), 0), nx - 1);
+    const int iy = min(max(cell_coord(p.y, oy, inv, ny), 0), ny - 1);
+    const size_t col = (size_t)iy * nx + ix;
+    const uint32_t b = __ldg(col_start + col), e = __ldg(col_start + col + 1);
+    uint32_t rank = 0;
+    uint8_t f = 0;
+    for (uint32_t j = b; j < e; ++j) {
+        const PointRec q = load_rec_plain(tmp, j);
+        if (q.idx < p.idx) {
+            ++rank;
+            if (q.x == p.x && q.y == p.y && q.z == p.z) f = 1;
+        }
+    }
+    const size_t dst = (size_t)b + rank;
+    rec[dst] = p;
+    rec32[dst] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), 0.0f);
+    order[dst] = (uint32_t)p.idx;
+    dup[dst] = f;
 }
 
 __global__ void __launch_bounds__(256) col_max_pop(const uint32_t* __restrict__ col_start, size_t ncols,
@@ -221,6 +294,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
     const size_t ncols = (size_t)g->nx * g->ny;
 
     uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    PointRec* tmp = nullptr;
     int rc = MORE3D_OK;
 #define G_TRY(e) do { rc = (e); if (rc != MORE3D_OK) goto fail; } while (0)
 #define G_CUDA(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); rc = (_e == cudaErrorMemoryAllocation) ? MORE3D_E_NOMEM : MORE3D_E_CUDA; goto fail; } } while (0)
@@ -232,16 +306,12 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         G_CUDA(cudaMallocAsync((void**)&g->rec32, (size_t)n * sizeof(float4), s));
         G_TRY(dev_alloc(&keys, (size_t)n, s));
         G_TRY(dev_alloc(&vals, (size_t)n, s));
-        G_TRY(dev_alloc(&keys2, (size_t)n, s));
-        G_TRY(dev_alloc(&vals2, (size_t)n, s));
         G_CUDA(cudaMemsetAsync(g->col_start, 0, (ncols + 1) * sizeof(uint32_t), s));
         const unsigned nb = (unsigned)((n + 255) / 256);
-        cell_keys<<<nb, 256, 0, s>>>(xyz, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, keys, vals,
-                                     g->col_start);
+        // keys + arrival ranks (vals holds the ranks on the thin path, the point indices on the tall one)
+        cell_keys_rank<<<nb, 256, 0, s>>>(xyz, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, keys, vals, g->col_start);
         G_CUDA(cudaGetLastError());
         G_TRY(exclusive_scan_u32(g->col_start, g->col_start, (int64_t)ncols, s));
-        int bits = 1;
-        while (((size_t)1 << bits) < ncols) ++bits;
         // thin or tall?  (one more 4-byte read-back per build)
         uint32_t* d_max = nullptr;
         G_TRY(dev_alloc(&d_max, 1, s));
@@ -251,11 +321,15 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         G_CUDA(cudaStreamSynchronize(s));
         dev_free(d_max, s);
         g->tall = g->max_col_pop > M3D_TALL_COLUMN ? 1 : 0;
-        uint32_t *ks = nullptr, *vs = nullptr;
         if (g->tall) {
-            // order = (column, z, original index): stable sort by z first, then by column key
+            // order = (column, z, original index): stable radix sort by z first, then by column key
+            int bits = 1;
+            while (((size_t)1 << bits) < ncols) ++bits;
+            uint32_t *ks = nullptr, *vs = nullptr;
             uint64_t *zk = nullptr, *zk2 = nullptr, *zs = nullptr;
             uint32_t* vz = nullptr;
+            G_TRY(dev_alloc(&keys2, (size_t)n, s));
+            G_TRY(dev_alloc(&vals2, (size_t)n, s));
             G_TRY(dev_alloc(&zk, (size_t)n, s));
             G_TRY(dev_alloc(&zk2, (size_t)n, s));
             z_keys<<<nb, 256, 0, s>>>(xyz, n, zk, vals);
@@ -265,24 +339,27 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
             uint32_t* vother = (vz == vals) ? vals2 : vals;
             gather_u32<<<nb, 256, 0, s>>>(keys, vz, n, keys2);          // column key of the z-ordered points
             G_TRY(radix_sort_pairs_u32(keys2, vz, keys, vother, n, bits, &ks, &vs, s));
-            count_launches(2);
-        } else {
-            G_TRY(radix_sort_pairs_u32(keys, vals, keys2, vals2, n, bits, &ks, &vs, s));
-        }
-        G_CUDA(cudaMemcpyAsync(g->order, vs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-        gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec, g->ox, g->oy, g->oz, g->rec32);
-        if (g->tall)
+            G_CUDA(cudaMemcpyAsync(g->order, vs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec, g->ox, g->oy, g->oz, g->rec32);
             dup_flags_tall<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, g->dup);
-        else
-            dup_flags<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, g->dup);
-        count_launches(4);  // cell_keys, col_max_pop, gather_records, dup_flags
+            count_launches(6);  // cell_keys_rank, col_max_pop, z_keys, gather_u32, gather_records, dup_flags_tall
+        } else {
+            // counting sort: the column table is already the histogram of the WHOLE key, so one scatter places every
+            // point in its column (arrival order) and one fix-up pass orders each column by original index -- the
+            // order a stable sort by key produces, with no radix passes at all
+            G_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * sizeof(PointRec), s));
+            scatter_records<<<nb, 256, 0, s>>>(xyz, n, keys, vals, g->col_start, tmp);
+            column_fixup<<<nb, 256, 0, s>>>(tmp, g->col_start, n, g->ox, g->oy, g->oz, g->inv_cell, g->nx, g->ny,
+                                            g->rec, g->rec32, g->order, g->dup);
+            count_launches(4);  // cell_keys_rank, col_max_pop, scatter_records, column_fixup
+        }
         G_CUDA(cudaGetLastError());
     }
-    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s);
+    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s); dev_free(tmp, s);
     *out = g;
     return MORE3D_OK;
 fail:
-    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s);
+    dev_free(keys, s); dev_free(vals, s); dev_free(keys2, s); dev_free(vals2, s); dev_free(tmp, s);
     more3d_grid_destroy(g);
     return rc;
 #undef G_TRY

@@ -15,6 +15,7 @@
 // implementation-defined order, so radii agree to a few ulp, not bit for bit.
 #include <vector>
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace m3d {
 
@@ -32,12 +33,16 @@ struct Lists {
     uint32_t* p[3];
 };
 
-// one thread per node of the level: choose the split dimension from the sorted lists' end points
+// one thread per node of the level: choose the split dimension from the sorted lists' end points, and say how many
+// of the node's positions count as "left" in this level's partition (floor(cnt / 2) for a split node, all of
+// them for a node that stays as it is) -- the exclusive scan of these counts is the number of lefts before each
+// node's first position, known BEFORE the partition runs because a median split is size-deterministic
 __global__ void __launch_bounds__(LT_THREADS) lt_split_dim(const double* __restrict__ xyz, Lists L,
                                                            const int64_t* __restrict__ nstart,
                                                            const int64_t* __restrict__ nend,
                                                            const int32_t* __restrict__ is_leaf, int64_t first,
-                                                           int64_t count, int8_t* __restrict__ split_dim) {
+                                                           int64_t count, int8_t* __restrict__ split_dim,
+                                                           uint32_t* __restrict__ left_count) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const int64_t node = first + k;
@@ -54,6 +59,7 @@ __global__ void __launch_bounds__(LT_THREADS) lt_split_dim(const double* __restr
         }
     }
     split_dim[k] = best;
+    left_count[k] = (uint32_t)(best < 0 ? (e - b) : (e - b) / 2);
 }
 
 // per position: mark the side (0 = left child, 1 = right child) of the point sitting at rank t - start
@@ -66,6 +72,7 @@ __global__ void __launch_bounds__(LT_THREADS) lt_mark_sides(Lists L, int64_t n, 
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int64_t node = pos_node[t];
+    if (node < first) return;             // a node that became a leaf above this level
     const int d = split_dim[node - first];
     if (d < 0) return;    // leaf: stays where it is
     const int64_t b = nstart[node], e = nend[node];
@@ -73,36 +80,78 @@ __global__ void __launch_bounds__(LT_THREADS) lt_mark_sides(Lists L, int64_t n, 
     side[L.p[d][t]] = (uint8_t)((t - b) >= n_mid);
 }
 
-__global__ void __launch_bounds__(LT_THREADS) lt_left_flags(const uint32_t* __restrict__ list, int64_t n,
-                                                            const uint32_t* __restrict__ pos_node, int64_t first,
+// Stable segmented partition of the three lists in ONE launch and ONE pass over each (blockIdx.y = list): the
+// left flags are scanned with a chained look-back across the tiles of the list; the rank of a left inside its node
+// is the global count of lefts before it minus the (precomputed) count before the node's first position, so no
+// segmented scan and no second read of the flags is needed.  side[] is a 1-byte table indexed by point id
+// (n bytes: L2-resident up to ~100 M points).
+constexpr int LTP_ITEMS = 8;
+constexpr int LTP_TILE = LT_THREADS * LTP_ITEMS;
+__global__ void __launch_bounds__(LT_THREADS) lt_partition3(Lists L, Lists O, int64_t n,
+                                                            const uint32_t* __restrict__ pos_node,
+                                                            const int64_t* __restrict__ nstart,
+                                                            const int64_t* __restrict__ nend, int64_t first,
                                                             const int8_t* __restrict__ split_dim,
                                                             const uint8_t* __restrict__ side,
-                                                            uint32_t* __restrict__ flag) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int64_t node = pos_node[t];
-    flag[t] = (split_dim[node - first] < 0 || side[list[t]] == 0) ? 1u : 0u;
-}
-
-// stable segmented partition of one list: lefts keep their order at the front of the node's range
-__global__ void __launch_bounds__(LT_THREADS) lt_partition(const uint32_t* __restrict__ list, int64_t n,
-                                                           const uint32_t* __restrict__ pos_node,
-                                                           const int64_t* __restrict__ nstart,
-                                                           const int64_t* __restrict__ nend, int64_t first,
-                                                           const int8_t* __restrict__ split_dim,
-                                                           const uint8_t* __restrict__ side,
-                                                           const uint32_t* __restrict__ scan,
-                                                           uint32_t* __restrict__ out) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int64_t node = pos_node[t];
-    const uint32_t pt = list[t];
-    if (split_dim[node - first] < 0) { out[t] = pt; return; }
-    const int64_t b = nstart[node], e = nend[node];
-    const int64_t n_mid = (e - b) / 2;
-    const int64_t lrank = (int64_t)scan[t] - (int64_t)scan[b];
-    const int64_t dst = (side[pt] == 0) ? b + lrank : b + n_mid + ((t - b) - lrank);
-    out[dst] = pt;
+                                                            const uint32_t* __restrict__ node_lp,
+                                                            uint64_t* desc, unsigned* ticket, int ntiles) {
+    __shared__ uint64_t sm[33];
+    __shared__ uint64_t s_prefix;
+    __shared__ unsigned s_tile;
+    const int d = blockIdx.y;
+    const uint32_t* __restrict__ list = L.p[d];
+    uint32_t* __restrict__ out = O.p[d];
+    volatile uint64_t* vd = desc + (size_t)d * ntiles;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket + d, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t base = (int64_t)tile * LTP_TILE + (int64_t)threadIdx.x * LTP_ITEMS;
+    uint32_t pt[LTP_ITEMS], nd[LTP_ITEMS];
+    uint8_t fl[LTP_ITEMS];           // bit 0: counts as left, bit 1: its node is split at this level, bit 2: side
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < LTP_ITEMS; ++i) {
+        const int64_t t = base + i;
+        fl[i] = 0;
+        if (t < n) {
+            pt[i] = list[t];
+            nd[i] = pos_node[t];
+            const bool split = (int64_t)nd[i] >= first && split_dim[(int64_t)nd[i] - first] >= 0;
+            const uint8_t sd = split ? side[pt[i]] : (uint8_t)0;
+            fl[i] = (uint8_t)((sd == 0 ? 1 : 0) | (split ? 2 : 0) | (sd ? 4 : 0));
+            s += fl[i] & 1u;
+        }
+    }
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan<uint64_t>(s, &total, sm);
+    if (threadIdx.x == 0) {
+        vd[tile] = (tile == 0 ? LB_PREFIX : LB_AGG) | total;
+        if (tile == 0) s_prefix = 0;
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        const uint64_t p = lookback_prefix(vd, tile, threadIdx.x);
+        if (threadIdx.x == 0) {
+            vd[tile] = LB_PREFIX | (p + total);
+            s_prefix = p;
+        }
+    }
+    __syncthreads();
+    ex += s_prefix;
+#pragma unroll
+    for (int i = 0; i < LTP_ITEMS; ++i) {
+        const int64_t t = base + i;
+        if (t < n) {
+            int64_t dst = t;
+            if (fl[i] & 2u) {
+                const int64_t b = nstart[nd[i]], e = nend[nd[i]];
+                const int64_t n_mid = (e - b) / 2;
+                const int64_t lrank = (int64_t)ex - (int64_t)node_lp[(int64_t)nd[i] - first];
+                dst = (fl[i] & 4u) ? b + n_mid + ((t - b) - lrank) : b + lrank;
+            }
+            out[dst] = pt[i];
+        }
+        ex += fl[i] & 1u;
+    }
 }
 
 __global__ void __launch_bounds__(LT_THREADS) lt_descend(int64_t n, uint32_t* __restrict__ pos_node,
@@ -112,7 +161,7 @@ __global__ void __launch_bounds__(LT_THREADS) lt_descend(int64_t n, uint32_t* __
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int64_t node = pos_node[t];
-    if (split_dim[node - first] < 0) return;
+    if (node < first || split_dim[node - first] < 0) return;
     const int64_t b = nstart[node], e = nend[node];
     pos_node[t] = (uint32_t)((t - b) < (e - b) / 2 ? 2 * node + 1 : 2 * node + 2);
 }
@@ -229,7 +278,8 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     const unsigned nb = (unsigned)((n + LT_THREADS - 1) / LT_THREADS);
     uint64_t *k1 = nullptr, *k2 = nullptr, *ks = nullptr;
     uint32_t *v1 = nullptr, *v2 = nullptr, *vs = nullptr;
-    uint32_t *lists[3] = {nullptr, nullptr, nullptr}, *alt = nullptr, *pos_node = nullptr, *scan = nullptr;
+    uint32_t *lists[3] = {nullptr, nullptr, nullptr}, *alts[3] = {nullptr, nullptr, nullptr}, *pos_node = nullptr, *node_lp = nullptr;
+    uint64_t* lb_desc = nullptr;
     uint8_t* side = nullptr;
     int8_t* split_dim = nullptr;
     double* sums = nullptr;
@@ -237,9 +287,10 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     M3D_TRY(dev_alloc(&k1, (size_t)n, s)); M3D_TRY(dev_alloc(&k2, (size_t)n, s));
     M3D_TRY(dev_alloc(&v1, (size_t)n, s)); M3D_TRY(dev_alloc(&v2, (size_t)n, s));
     for (int d = 0; d < 3; ++d) M3D_TRY(dev_alloc(&lists[d], (size_t)n, s));
-    M3D_TRY(dev_alloc(&alt, (size_t)n, s));
+    for (int d = 0; d < 3; ++d) M3D_TRY(dev_alloc(&alts[d], (size_t)n, s));
     M3D_TRY(dev_alloc(&pos_node, (size_t)n, s));
-    M3D_TRY(dev_alloc(&scan, (size_t)n + 1, s));
+    M3D_TRY(dev_alloc(&node_lp, (size_t)((n_nodes + 1) / 2 + 2), s));
+    M3D_TRY(dev_alloc(&lb_desc, (size_t)3 * ((n + LTP_TILE - 1) / LTP_TILE) + 4, s));
     M3D_TRY(dev_alloc(&side, (size_t)n, s));
     M3D_TRY(dev_alloc(&split_dim, (size_t)((n_nodes + 1) / 2 + 1), s));
     M3D_TRY(dev_alloc(&sums, (size_t)3 * n_nodes, s));
@@ -255,24 +306,23 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     M3D_CUDA(cudaMemsetAsync(pos_node, 0, (size_t)n * 4, s));
     M3D_CUDA(cudaMemsetAsync(side, 0, (size_t)n, s));
 
+    const int ntiles = (int)((n + LTP_TILE - 1) / LTP_TILE);
     for (int64_t lev = 0; lev + 1 < n_levels; ++lev) {
         const int64_t first = ((int64_t)1 << lev) - 1, count = (int64_t)1 << lev;
         Lists L; L.p[0] = lists[0]; L.p[1] = lists[1]; L.p[2] = lists[2];
+        Lists O; O.p[0] = alts[0]; O.p[1] = alts[1]; O.p[2] = alts[2];
         lt_split_dim<<<(unsigned)((count + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(
-            xyz, L, idx_start, idx_end, is_leaf, first, count, split_dim);
+            xyz, L, idx_start, idx_end, is_leaf, first, count, split_dim, node_lp);
+        M3D_TRY(exclusive_scan_u32(node_lp, node_lp, count, s));
         lt_mark_sides<<<nb, LT_THREADS, 0, s>>>(L, n, pos_node, idx_start, idx_end, first, split_dim, side);
-        count_launches(2);
-        for (int d = 0; d < 3; ++d) {
-            lt_left_flags<<<nb, LT_THREADS, 0, s>>>(lists[d], n, pos_node, first, split_dim, side, scan);
-            M3D_TRY(exclusive_scan_u32(scan, scan, n, s));
-            lt_partition<<<nb, LT_THREADS, 0, s>>>(lists[d], n, pos_node, idx_start, idx_end, first, split_dim,
-                                                   side, scan, alt);
-            count_launches(2);
-            uint32_t* tmp = lists[d]; lists[d] = alt; alt = tmp;
-        }
+        M3D_CUDA(cudaMemsetAsync(lb_desc, 0, ((size_t)3 * ntiles + 4) * sizeof(uint64_t), s));
+        lt_partition3<<<dim3((unsigned)ntiles, 3), LT_THREADS, 0, s>>>(L, O, n, pos_node, idx_start, idx_end, first, split_dim,
+                                                                       side, node_lp, lb_desc, (unsigned*)(lb_desc + (size_t)3 * ntiles),
+                                                                       ntiles);
         lt_descend<<<nb, LT_THREADS, 0, s>>>(n, pos_node, idx_start, idx_end, first, split_dim);
-        count_launches(1);
+        count_launches(4);
         M3D_CHECK_LAUNCH();
+        for (int d = 0; d < 3; ++d) { uint32_t* tmp = lists[d]; lists[d] = alts[d]; alts[d] = tmp; }
     }
 
     // centroids bottom-up, radii top-down
@@ -295,7 +345,8 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     M3D_CHECK_LAUNCH();
     dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s);
     for (int d = 0; d < 3; ++d) dev_free(lists[d], s);
-    dev_free(alt, s); dev_free(pos_node, s); dev_free(scan, s); dev_free(side, s); dev_free(split_dim, s);
+    for (int d = 0; d < 3; ++d) dev_free(alts[d], s);
+    dev_free(pos_node, s); dev_free(node_lp, s); dev_free(lb_desc, s); dev_free(side, s); dev_free(split_dim, s);
     dev_free(sums, s); dev_free(r2, s);
     return MORE3D_OK;
 }

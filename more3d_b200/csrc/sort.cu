@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace m3d {
 
@@ -87,89 +88,51 @@ static void prof_collect() {
 }
 
 // ------------------------------------------------------------------------------------------
-// exclusive scan: tile sums -> single-block scan of the sums -> tile scan + offset
+// exclusive scan: ONE pass over the data (chained scan with decoupled look-back).  Every CTA takes a tile
+// ticket, scans its 2048 elements, publishes its aggregate in a 64-bit descriptor (status in the two top bits,
+// value below: one store makes both visible together) and adds up the descriptors of the tiles before it until
+// it meets one that already carries an inclusive prefix.  Tickets are handed out in launch order, so a tile only
+// ever waits for CTAs that are already running.
 // ------------------------------------------------------------------------------------------
-constexpr int SC_THREADS = 256;
-constexpr int SC_ITEMS = 8;
-constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
-
-template <typename T>
-__device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* smem /* 32 entries */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        T t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) smem[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        T w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : T(0);
-        T winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            T t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        smem[lane] = winc - w;  // exclusive warp offsets
-        if (lane == 31) smem[32] = winc;
-    }
-    __syncthreads();
-    T res = smem[warp] + inc - v;
-    if (total) *total = smem[32];
-    __syncthreads();
-    return res;
-}
-
 template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(SC_THREADS) scan_tile_sums(const Tin* __restrict__ in, int64_t n,
-                                                             Tout* __restrict__ sums) {
-    __shared__ Tout sm[33];
-    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
-    Tout s = 0;
-#pragma unroll
-    for (int i = 0; i < SC_ITEMS; ++i)
-        if (base + i < n) s += (Tout)in[base + i];
-    Tout total;
-    block_exclusive_scan<Tout>(s, &total, sm);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-
-template <typename Tout>
-__global__ void __launch_bounds__(1024) scan_sums_single(Tout* __restrict__ sums, int64_t m,
-                                                         Tout* __restrict__ grand_total) {
-    __shared__ Tout sm[33];
-    Tout carry = 0;
-    for (int64_t base = 0; base < m; base += 1024) {
-        int64_t i = base + threadIdx.x;
-        Tout v = (i < m) ? sums[i] : Tout(0);
-        Tout total;
-        Tout ex = block_exclusive_scan<Tout>(v, &total, sm);
-        if (i < m) sums[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) *grand_total = carry;
-}
-
-template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(SC_THREADS) scan_tile_apply(const Tin* in, int64_t n,
-                                                              const Tout* __restrict__ sums, Tout* out) {
-    __shared__ Tout sm[33];
-    int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
-    Tout v[SC_ITEMS];
-    Tout s = 0;
+__global__ void __launch_bounds__(SC_THREADS) scan_lookback(const Tin* in, Tout* out, int64_t n, uint64_t* desc,
+                                                            unsigned* ticket, int ntiles) {
+    __shared__ uint64_t sm[33];
+    __shared__ uint64_t s_prefix;
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t base = (int64_t)tile * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    uint64_t v[SC_ITEMS];
+    uint64_t s = 0;
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; ++i) {
-        v[i] = (base + i < n) ? (Tout)in[base + i] : Tout(0);
+        v[i] = (base + i < n) ? (uint64_t)in[base + i] : 0ull;
         s += v[i];
     }
-    Tout ex = block_exclusive_scan<Tout>(s, nullptr, sm) + sums[blockIdx.x];
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan<uint64_t>(s, &total, sm);
+    volatile uint64_t* vd = desc;
+    if (threadIdx.x == 0) {
+        vd[tile] = (tile == 0 ? LB_PREFIX : LB_AGG) | total;
+        if (tile == 0) s_prefix = 0;
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        const uint64_t p = lookback_prefix(vd, tile, threadIdx.x);
+        if (threadIdx.x == 0) {
+            vd[tile] = LB_PREFIX | (p + total);
+            s_prefix = p;
+        }
+    }
+    __syncthreads();
+    ex += s_prefix;
 #pragma unroll
     for (int i = 0; i < SC_ITEMS; ++i) {
-        if (base + i < n) out[base + i] = ex;
+        if (base + i < n) out[base + i] = (Tout)ex;
         ex += v[i];
     }
+    if (tile == ntiles - 1 && threadIdx.x == 0) out[n] = (Tout)(s_prefix + total);
 }
 
 template <typename Tin, typename Tout>
@@ -178,15 +141,14 @@ static int exclusive_scan_impl(const Tin* in, Tout* out, int64_t n, cudaStream_t
         M3D_CUDA(cudaMemsetAsync(out, 0, sizeof(Tout), s));
         return MORE3D_OK;
     }
-    int64_t tiles = (n + SC_TILE - 1) / SC_TILE;
-    Tout* sums = nullptr;
-    M3D_TRY(dev_alloc(&sums, (size_t)tiles, s));
-    scan_tile_sums<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, n, sums);
-    scan_sums_single<Tout><<<1, 1024, 0, s>>>(sums, tiles, out + n);
-    scan_tile_apply<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, n, sums, out);
-    count_launches(3);
+    const int64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    uint64_t* desc = nullptr;
+    M3D_TRY(dev_alloc(&desc, (size_t)tiles + 1, s));
+    M3D_CUDA(cudaMemsetAsync(desc, 0, ((size_t)tiles + 1) * sizeof(uint64_t), s));
+    scan_lookback<Tin, Tout><<<(unsigned)tiles, SC_THREADS, 0, s>>>(in, out, n, desc, (unsigned*)(desc + tiles), (int)tiles);
+    count_launches(1);
     M3D_CHECK_LAUNCH();
-    dev_free(sums, s);
+    dev_free(desc, s);
     return MORE3D_OK;
 }
 
@@ -198,79 +160,97 @@ int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaSt
 }
 
 // ------------------------------------------------------------------------------------------
-// radix sort
+// radix sort: stable LSD, 8-bit digits, ONE kernel per digit ("onesweep": the per-tile digit counts are chained
+// through decoupled look-back descriptors instead of a histogram + scan + scatter triple), one up-front kernel
+// that builds the global digit histograms of ALL passes in a single read of the keys.
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;                     // keys per thread (8: 4 CTAs per SM; the kernel is latency-bound, 16 was slower)
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per CTA
-constexpr int RS_WTILE = RS_TILE / RS_WARPS;    // 256 consecutive keys per warp
+constexpr int RS_MAX_PASSES = 8;
+constexpr uint32_t RS_AGG = 1u << 30, RS_PREFIX = 2u << 30, RS_VAL = (1u << 30) - 1u;
 
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) rs_hist(const K* __restrict__ keys, int64_t n, int shift,
-                                                      uint32_t* __restrict__ hist, int nblocks) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_all(const K* __restrict__ keys, int64_t n, int npass,
+                                                          uint32_t* __restrict__ hist /* npass x 256, zeroed */) {
+    __shared__ uint32_t h[RS_MAX_PASSES][256];
+    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
-        int64_t p = base + i;
-        if (p < n) atomicAdd(&h[(unsigned)(keys[p] >> shift) & 255u], 1u);
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
+    const int64_t n_round = ((n + 31) / 32) * 32;               // whole warps stay in the loop (match needs them)
+    for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n_round; i += stride) {
+        const bool ok = i < n;
+        const K k = ok ? keys[i] : K(0);
+        for (int p = 0; p < npass; ++p) {
+            // warp-aggregated: equal digits of the warp's 32 keys cost one shared atomic (the high digits of grid
+            // and voxel keys take a handful of values, a plain atomic per key would serialise on one bank)
+            const unsigned d = ok ? ((unsigned)(k >> (8 * p)) & 255u) : 256u;
+            const unsigned m = __match_any_sync(0xffffffffu, d);
+            if (ok && (m & ((1u << lane) - 1u)) == 0u) atomicAdd(&h[p][d], (uint32_t)__popc(m));
+        }
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
+    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) {
+        const uint32_t c = (&h[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
 }
 
-// Stable scatter: warp w owns RS_WTILE consecutive keys of the tile, walks them in RS_ITEMS rounds of 32;
-// __match_any_sync gives each key its rank among equal digits of the round, per-warp running counters give the
-// rank among the earlier keys of the tile.  The tile is first sorted by digit INTO SHARED MEMORY and then
-// written out linearly: consecutive threads hold consecutive keys of one digit run, so the global stores are
-// contiguous runs (avg 16 keys = 64 B per digit and tile) instead of 4-byte scatters to 256 places.
-template <typename K>
-__global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict__ keys,
-                                                         const uint32_t* __restrict__ vals,
-                                                         K* __restrict__ keys_out,
-                                                         uint32_t* __restrict__ vals_out, int64_t n,
-                                                         int shift, const uint32_t* __restrict__ hist_ex,
-                                                         int nblocks) {
+// one CTA per pass: exclusive scan of its 256 bins (in place)
+__global__ void __launch_bounds__(256) rs_scan_bins(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sm[33];
+    uint32_t* h = hist + 256 * blockIdx.x;
+    const uint32_t c = h[threadIdx.x];
+    h[threadIdx.x] = block_exclusive_scan<uint32_t>(c, nullptr, sm);
+}
+
+// One tile per CTA (ticket order).  Warp w owns ITEMS * 32 consecutive keys of the tile and walks them in ITEMS
+// rounds of 32; __match_any_sync gives each key its rank among equal digits of the round, per-warp running counters
+// its rank among the warp's earlier keys -- a stable rank.  Thread d then owns digit d: it publishes the tile's
+// count of d, looks back over the earlier tiles' descriptors for the number of keys with digit d before this tile,
+// and the tile -- sorted by digit in shared memory -- is written out as contiguous runs.
+template <typename K, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep(const K* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                          K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                          int64_t n, int shift, const uint32_t* __restrict__ bins,
+                                                          uint32_t* desc, unsigned* ticket) {
+    constexpr int TILE = RS_THREADS * ITEMS;
+    constexpr int WTILE = 32 * ITEMS;
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    K* keys_s = reinterpret_cast<K*>(rs_smem);                                   // RS_TILE keys
-    uint32_t* vals_s = reinterpret_cast<uint32_t*>(keys_s + RS_TILE);             // RS_TILE values
-    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(vals_s + RS_TILE);   // RS_WARPS x 256
-    uint32_t* tile_start = &wcnt[0][0] + RS_WARPS * 256;                          // 256: first tile slot of a digit
-    uint32_t* gbase = tile_start + 256;                                           // 256: first global slot
-    uint32_t* scan_sm = gbase + 256;                                              // 33
+    K* keys_s = reinterpret_cast<K*>(rs_smem);                                    // TILE keys
+    uint32_t* vals_s = reinterpret_cast<uint32_t*>(keys_s + TILE);                 // TILE values
+    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(vals_s + TILE);    // RS_WARPS x 256
+    uint32_t* gbase = &wcnt[0][0] + RS_WARPS * 256;                                // 256: global slot of tile slot 0 of a digit run
+    uint32_t* scan_sm = gbase + 256;                                               // 33
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
     __syncthreads();
+    const int tile = (int)s_tile;
 
-    const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
-    const int64_t wbase = tbase + (int64_t)warp * RS_WTILE;
-    K k[RS_ITEMS];
-    uint32_t v[RS_ITEMS];
+    const int64_t tbase = (int64_t)tile * TILE;
+    const int64_t wbase = tbase + (int64_t)warp * WTILE;
+    K k[ITEMS];
+    uint32_t v[ITEMS];
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        int64_t p = wbase + j * 32 + lane;
-        bool ok = p < n;
+    for (int j = 0; j < ITEMS; ++j) {
+        const int64_t p = wbase + j * 32 + lane;
+        const bool ok = p < n;
         k[j] = ok ? keys[p] : K(0);
         v[j] = ok ? vals[p] : 0u;
     }
-    // digits and their match masks once for both phases; the RS_ITEMS matches are independent of each other, so
-    // they pipeline instead of each waiting behind the counter update of the previous round
-    unsigned dg[RS_ITEMS], pm[RS_ITEMS];
+    unsigned dg[ITEMS], pm[ITEMS];
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
+    for (int j = 0; j < ITEMS; ++j) {
         const bool ok = (wbase + j * 32 + lane) < n;
         dg[j] = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
         pm[j] = __match_any_sync(0xffffffffu, dg[j]);
     }
-    // phase A: per-warp digit counts; every key also takes its rank among the warp's EARLIER keys of its digit
-    // (running count before this round + equal-digit lanes below it), so phase B needs no second serial pass
-    uint32_t rk[RS_ITEMS];
+    uint32_t rk[ITEMS];
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
+    for (int j = 0; j < ITEMS; ++j) {
         const bool ok = dg[j] < 256u;
         rk[j] = ok ? wcnt[warp][dg[j]] + __popc(pm[j] & lt) : 0u;
         __syncwarp();
@@ -283,20 +263,28 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict_
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
-            uint32_t c = wcnt[w][d];
+            const uint32_t c = wcnt[w][d];
             wcnt[w][d] = run;           // keys of digit d in lower warps
             run += c;
         }
+        volatile uint32_t* vd = desc;
+        vd[(size_t)tile * 256 + d] = (tile == 0 ? RS_PREFIX : RS_AGG) | run;
         const uint32_t ts = block_exclusive_scan<uint32_t>(run, nullptr, scan_sm);   // digits below d in the tile
-        tile_start[d] = ts;
-        gbase[d] = hist_ex[(size_t)d * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) wcnt[w][d] += ts;
+        uint32_t excl = 0;
+        for (int j = tile - 1; j >= 0; --j) {
+            uint32_t e;
+            do { e = vd[(size_t)j * 256 + d]; } while ((e >> 30) == 0u);
+            excl += e & RS_VAL;
+            if ((e >> 30) == 2u) break;
+        }
+        if (tile > 0) vd[(size_t)tile * 256 + d] = RS_PREFIX | (excl + run);
+        gbase[d] = bins[d] + excl - ts;
     }
     __syncthreads();
-    // phase B: keys and values go to their sorted slot of the tile
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
+    for (int j = 0; j < ITEMS; ++j) {
         if (dg[j] < 256u) {
             const uint32_t pos = wcnt[warp][dg[j]] + rk[j];      // tile slot of the digit run + warps below + rank
             keys_s[pos] = k[j];
@@ -304,51 +292,61 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter(const K* __restrict_
         }
     }
     __syncthreads();
-    // phase C: linear write-out
-    const int tile_n = (int)min((int64_t)RS_TILE, n - tbase);
+    const int tile_n = (int)min((int64_t)TILE, n - tbase);
     for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
         const K kk = keys_s[i];
         const unsigned d = (unsigned)(kk >> shift) & 255u;
-        const uint32_t g = gbase[d] + ((uint32_t)i - tile_start[d]);
+        const uint32_t g = gbase[d] + (uint32_t)i;
         keys_out[g] = kk;
         vals_out[g] = vals_s[i];
     }
 }
 
-template <typename K>
-static size_t rs_scatter_smem() {
-    return (size_t)RS_TILE * (sizeof(K) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + 256 + 33) * sizeof(uint32_t);
-}
+template <typename K> struct RsItems { static constexpr int value = 16; };
+template <> struct RsItems<uint64_t> { static constexpr int value = 12; };
 
 template <typename K>
 static int radix_sort_impl(K* keys, uint32_t* vals, K* keys_alt, uint32_t* vals_alt, int64_t n,
                            int key_bits, K** keys_sorted, uint32_t** vals_sorted, cudaStream_t s) {
+    constexpr int ITEMS = RsItems<K>::value;
+    constexpr int TILE = RS_THREADS * ITEMS;
     *keys_sorted = keys;
     *vals_sorted = vals;
     if (n <= 1 || key_bits <= 0) return MORE3D_OK;
-    if (n >= (int64_t)1 << 32) {
-        set_error("radix sort: n >= 2^32 not supported");
+    if (n >= (int64_t)1 << 30) {
+        set_error("radix sort: n >= 2^30 not supported");
         return MORE3D_E_RANGE;
     }
-    const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
-    const size_t smem = rs_scatter_smem<K>();
-    M3D_CUDA(cudaFuncSetAttribute(rs_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t* hist = nullptr;
-    M3D_TRY(dev_alloc(&hist, (size_t)256 * nblocks + 1, s));
+    const int npass = (key_bits + 7) / 8;
+    const int ntiles = (int)((n + TILE - 1) / TILE);
+    const size_t smem = (size_t)TILE * (sizeof(K) + sizeof(uint32_t)) + (size_t)(RS_WARPS * 256 + 256 + 33) * sizeof(uint32_t);
+    M3D_CUDA(cudaFuncSetAttribute(rs_onesweep<K, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // [npass x 256 bins][ticket + pad][ntiles x 256 descriptors]
+    uint32_t* work = nullptr;
+    const size_t n_bins = (size_t)npass * 256, n_desc = (size_t)ntiles * 256;
+    M3D_TRY(dev_alloc(&work, n_bins + 4 + n_desc, s));
+    uint32_t* bins = work;
+    unsigned* ticket = work + n_bins;
+    uint32_t* desc = work + n_bins + 4;
+    M3D_CUDA(cudaMemsetAsync(work, 0, (n_bins + 4) * sizeof(uint32_t), s));
+    int hb = (int)((n + (int64_t)RS_THREADS * 16 - 1) / ((int64_t)RS_THREADS * 16));
+    if (hb > 148 * 8) hb = 148 * 8;
+    rs_hist_all<K><<<hb, RS_THREADS, 0, s>>>(keys, n, npass, bins);
+    rs_scan_bins<<<npass, 256, 0, s>>>(bins);
+    count_launches(2);
     K* kin = keys;
     K* kout = keys_alt;
     uint32_t* vin = vals;
     uint32_t* vout = vals_alt;
-    for (int shift = 0; shift < key_bits; shift += 8) {
-        rs_hist<K><<<nblocks, RS_THREADS, 0, s>>>(kin, n, shift, hist, nblocks);
-        M3D_TRY(exclusive_scan_u32(hist, hist, (int64_t)256 * nblocks, s));
-        rs_scatter<K><<<nblocks, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
-        count_launches(2);
+    for (int p = 0; p < npass; ++p) {
+        M3D_CUDA(cudaMemsetAsync(ticket, 0, (4 + n_desc) * sizeof(uint32_t), s));
+        rs_onesweep<K, ITEMS><<<ntiles, RS_THREADS, smem, s>>>(kin, vin, kout, vout, n, 8 * p, bins + 256 * p, desc, ticket);
+        count_launches(1);
         M3D_CHECK_LAUNCH();
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
-    dev_free(hist, s);
+    dev_free(work, s);
     *keys_sorted = kin;
     *vals_sorted = vin;
     return MORE3D_OK;

@@ -60,17 +60,19 @@ __device__ __forceinline__ void voxel_index(const double* __restrict__ xyz, int6
         k[a] = (long long)floor(__ddiv_rn(__dsub_rn(xyz[3 * i + a], vg.vmin[a]), vg.voxel));
 }
 
+template <typename K>
 __global__ void __launch_bounds__(VX_THREADS) vx_keys(const double* __restrict__ xyz, int64_t n, VoxelGeom vg,
-                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                      K* __restrict__ keys, uint32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long k[3];
     voxel_index(xyz, i, vg, k);
-    keys[i] = (uint64_t)((k[0] * vg.ny + k[1]) * vg.nz + k[2]);
+    keys[i] = (K)((k[0] * vg.ny + k[1]) * vg.nz + k[2]);
     vals[i] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(VX_THREADS) vx_heads(const uint64_t* __restrict__ keys, int64_t n,
+template <typename K>
+__global__ void __launch_bounds__(VX_THREADS) vx_heads(const K* __restrict__ keys, int64_t n,
                                                        uint32_t* __restrict__ head) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -78,7 +80,8 @@ __global__ void __launch_bounds__(VX_THREADS) vx_heads(const uint64_t* __restric
 }
 
 // seg[i] = exclusive scan of head + head[i] - 1 = voxel row of sorted position i; starts[row] = i at heads
-__global__ void __launch_bounds__(VX_THREADS) vx_starts(const uint64_t* __restrict__ keys,
+template <typename K>
+__global__ void __launch_bounds__(VX_THREADS) vx_starts(const K* __restrict__ keys,
                                                         const uint32_t* __restrict__ scan, int64_t n,
                                                         uint32_t* __restrict__ starts) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,28 +90,46 @@ __global__ void __launch_bounds__(VX_THREADS) vx_starts(const uint64_t* __restri
     if (i == n - 1) starts[scan[n]] = (uint32_t)n;
 }
 
+// One WARP per voxel.  The members' coordinates are gathered 32 at a time (parallel, latency-hidden loads) and then
+// added ONE AFTER THE OTHER in original point order through lane shuffles, so the fp64 sums are exactly those of the
+// sequential host loop (np.add.at / open3d's per-voxel accumulator) -- a tree reduction would round differently.
+template <typename K>
 __global__ void __launch_bounds__(VX_THREADS) vx_means(const double* __restrict__ xyz,
-                                                       const uint64_t* __restrict__ keys,
+                                                       const K* __restrict__ keys,
                                                        const uint32_t* __restrict__ order,
                                                        const uint32_t* __restrict__ starts, int64_t nvox,
                                                        VoxelGeom vg, double* __restrict__ out_xyz,
                                                        int64_t* __restrict__ out_keys,
                                                        int32_t* __restrict__ voxel_of_point) {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nvox) return;
-    const uint32_t b = starts[v], e = starts[v + 1];
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (uint32_t t = b; t < e; ++t) {                 // original point order inside the voxel
-        const int64_t o = order[t];
-        sx += xyz[3 * o]; sy += xyz[3 * o + 1]; sz += xyz[3 * o + 2];
-        if (voxel_of_point) voxel_of_point[o] = (int32_t)v;
-    }
-    const double cnt = (double)(e - b);
-    out_xyz[3 * v] = sx / cnt; out_xyz[3 * v + 1] = sy / cnt; out_xyz[3 * v + 2] = sz / cnt;
-    if (out_keys) {
-        const long long key = (long long)keys[b];
-        const long long kz = key % vg.nz, kxy = key / vg.nz;
-        out_keys[3 * v] = kxy / vg.ny; out_keys[3 * v + 1] = kxy % vg.ny; out_keys[3 * v + 2] = kz;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = (((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; v < nvox; v += warps) {
+        const uint32_t b = starts[v], e = starts[v + 1];
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (uint32_t t0 = b; t0 < e; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            double x = 0.0, y = 0.0, z = 0.0;
+            if (t < e) {
+                const int64_t o = order[t];
+                x = xyz[3 * o]; y = xyz[3 * o + 1]; z = xyz[3 * o + 2];
+                if (voxel_of_point) voxel_of_point[o] = (int32_t)v;
+            }
+            const int cnt = (int)min(32u, e - t0);
+            for (int l = 0; l < cnt; ++l) {            // original point order inside the voxel
+                sx += __shfl_sync(0xffffffffu, x, l);
+                sy += __shfl_sync(0xffffffffu, y, l);
+                sz += __shfl_sync(0xffffffffu, z, l);
+            }
+        }
+        if (lane == 0) {
+            const double cnt = (double)(e - b);
+            out_xyz[3 * v] = sx / cnt; out_xyz[3 * v + 1] = sy / cnt; out_xyz[3 * v + 2] = sz / cnt;
+            if (out_keys) {
+                const long long key = (long long)keys[b];
+                const long long kz = key % vg.nz, kxy = key / vg.nz;
+                out_keys[3 * v] = kxy / vg.ny; out_keys[3 * v + 1] = kxy % vg.ny; out_keys[3 * v + 2] = kz;
+            }
+        }
     }
 }
 
@@ -118,6 +139,56 @@ using namespace m3d;
 
 static int voxel_downsample_impl(const double* xyz, int64_t n, double voxel, const double* bounds_h, double* out_xyz,
                                  int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h, void* stream);
+
+
+template <typename K>
+static int sort_pairs(K* k1, uint32_t* v1, K* k2, uint32_t* v2, int64_t n, int bits, K** ks, uint32_t** vs, cudaStream_t s);
+template <>
+int sort_pairs<uint32_t>(uint32_t* k1, uint32_t* v1, uint32_t* k2, uint32_t* v2, int64_t n, int bits, uint32_t** ks, uint32_t** vs, cudaStream_t s) {
+    return radix_sort_pairs_u32(k1, v1, k2, v2, n, bits, ks, vs, s);
+}
+template <>
+int sort_pairs<uint64_t>(uint64_t* k1, uint32_t* v1, uint64_t* k2, uint32_t* v2, int64_t n, int bits, uint64_t** ks, uint32_t** vs, cudaStream_t s) {
+    return radix_sort_pairs_u64(k1, v1, k2, v2, n, bits, ks, vs, s);
+}
+
+template <typename K>
+static int voxel_reduce(const double* xyz, int64_t n, const VoxelGeom& vg, int bits, double* out_xyz, int64_t* out_keys,
+                        int32_t* voxel_of_point, int64_t* nout_h, cudaStream_t s) {
+    K *k1 = nullptr, *k2 = nullptr, *ks = nullptr;
+    uint32_t *v1 = nullptr, *v2 = nullptr, *vs = nullptr, *head = nullptr, *starts = nullptr;
+    M3D_TRY(dev_alloc(&k1, (size_t)n, s));
+    M3D_TRY(dev_alloc(&k2, (size_t)n, s));
+    M3D_TRY(dev_alloc(&v1, (size_t)n, s));
+    M3D_TRY(dev_alloc(&v2, (size_t)n, s));
+    M3D_TRY(dev_alloc(&head, (size_t)n + 1, s));
+    M3D_TRY(dev_alloc(&starts, (size_t)n + 1, s));
+    const unsigned nb = (unsigned)((n + VX_THREADS - 1) / VX_THREADS);
+    vx_keys<K><<<nb, VX_THREADS, 0, s>>>(xyz, n, vg, k1, v1);
+    count_launches(1);
+    {
+        ProfScope p2("voxel_sort", s);
+        M3D_TRY(sort_pairs<K>(k1, v1, k2, v2, n, bits, &ks, &vs, s));
+    }
+    vx_heads<K><<<nb, VX_THREADS, 0, s>>>(ks, n, head);
+    M3D_TRY(exclusive_scan_u32(head, head, n, s));
+    vx_starts<K><<<nb, VX_THREADS, 0, s>>>(ks, head, n, starts);
+    count_launches(2);
+    M3D_CHECK_LAUNCH();
+    uint32_t nvox = 0;
+    M3D_CUDA(cudaMemcpyAsync(&nvox, head + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    {
+        ProfScope p3("voxel_means", s);
+        vx_means<K><<<(unsigned)min((int64_t)(((int64_t)nvox * 32 + VX_THREADS - 1) / VX_THREADS), (int64_t)148 * 64), VX_THREADS, 0, s>>>(
+            xyz, ks, vs, starts, (int64_t)nvox, vg, out_xyz, out_keys, voxel_of_point);
+    }
+    count_launches(1);
+    M3D_CHECK_LAUNCH();
+    dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s); dev_free(head, s); dev_free(starts, s);
+    *nout_h = (int64_t)nvox;
+    return MORE3D_OK;
+}
 
 extern "C" int more3d_voxel_downsample(const double* xyz, int64_t n, double voxel, double* out_xyz,
                                        int64_t* out_keys, int32_t* voxel_of_point, int64_t* nout_h,
@@ -180,37 +251,8 @@ static int voxel_downsample_impl(const double* xyz, int64_t n, double voxel, con
         while (bits < 63 && ldexp(1.0, bits) < total) ++bits;
     }
 
-    uint64_t *k1 = nullptr, *k2 = nullptr, *ks = nullptr;
-    uint32_t *v1 = nullptr, *v2 = nullptr, *vs = nullptr, *head = nullptr, *starts = nullptr;
-    M3D_TRY(dev_alloc(&k1, (size_t)n, s));
-    M3D_TRY(dev_alloc(&k2, (size_t)n, s));
-    M3D_TRY(dev_alloc(&v1, (size_t)n, s));
-    M3D_TRY(dev_alloc(&v2, (size_t)n, s));
-    M3D_TRY(dev_alloc(&head, (size_t)n + 1, s));
-    M3D_TRY(dev_alloc(&starts, (size_t)n + 1, s));
-    const unsigned nb = (unsigned)((n + VX_THREADS - 1) / VX_THREADS);
-    vx_keys<<<nb, VX_THREADS, 0, s>>>(xyz, n, vg, k1, v1);
-    count_launches(1);
-    {
-        ProfScope p2("voxel_sort", s);
-        M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, bits, &ks, &vs, s));
-    }
-    vx_heads<<<nb, VX_THREADS, 0, s>>>(ks, n, head);
-    M3D_TRY(exclusive_scan_u32(head, head, n, s));
-    vx_starts<<<nb, VX_THREADS, 0, s>>>(ks, head, n, starts);
-    count_launches(2);
-    M3D_CHECK_LAUNCH();
-    uint32_t nvox = 0;
-    M3D_CUDA(cudaMemcpyAsync(&nvox, head + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    M3D_CUDA(cudaStreamSynchronize(s));
-    {
-        ProfScope p3("voxel_means", s);
-        vx_means<<<(unsigned)((nvox + VX_THREADS - 1) / VX_THREADS), VX_THREADS, 0, s>>>(
-            xyz, ks, vs, starts, (int64_t)nvox, vg, out_xyz, out_keys, voxel_of_point);
-    }
-    count_launches(1);
-    M3D_CHECK_LAUNCH();
-    dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s); dev_free(head, s); dev_free(starts, s);
-    *nout_h = (int64_t)nvox;
-    return MORE3D_OK;
+    // 32-bit keys whenever the voxel lattice has fewer than 2^32 cells (terrain tiles always do): 8 instead of
+    // 12 bytes per pair and pass through the radix sort
+    if (bits <= 32) return voxel_reduce<uint32_t>(xyz, n, vg, bits, out_xyz, out_keys, voxel_of_point, nout_h, s);
+    return voxel_reduce<uint64_t>(xyz, n, vg, bits, out_xyz, out_keys, voxel_of_point, nout_h, s);
 }

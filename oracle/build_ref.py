@@ -4,7 +4,7 @@
 
 The reference is pure Python, so "compiling it from the sources where they lie" means byte-compiling the
 three modules of the hot path (``py_compile``, CPython 3.12 of this image -- the GPU box runs the same image)
-into ``oracle/_ref/*.pyc``.  No reference SOURCE is copied: ``oracle/_ref/`` holds bytecode only, is listed in
+into ``oracle/_ref/*.bin`` (CPython bytecode files; named .bin because snapshot tools commonly drop ``*.pyc``).  No reference SOURCE is copied: ``oracle/_ref/`` holds bytecode only, is listed in
 ``.gitignore`` (stays out of history) and NOT in ``.gpurunignore`` (travels to the GPU box like the built
 ``.so``).  ``oracle/ref_verbatim.py`` loads these modules (falling back to the sources under /root/reference
 when they are present and ``_ref`` is not) behind two in-process stubs for the absent ``open3d`` / ``opals``.
@@ -39,7 +39,7 @@ def build(verbose=True):
                 "modules": {}}
     for name, rel in MODULES.items():
         src = os.path.join(REF, rel)
-        dst = os.path.join(OUT, name + ".pyc")
+        dst = os.path.join(OUT, name + ".bin")
         # dfile: the path tracebacks will show -- the reference's own file:line
         py_compile.compile(src, cfile=dst, dfile="reference/" + rel, doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)

@@ -34,13 +34,13 @@ _MODS = {}
 
 def available():
     """True when the verbatim reference can be loaded here (prebuilt bytecode or the source tree)."""
-    return all(os.path.exists(os.path.join(REF_BUILT, m + ".pyc")) for m in _SRC_REL) or \
+    return all(os.path.exists(os.path.join(REF_BUILT, m + ".bin")) for m in _SRC_REL) or \
         all(os.path.exists(os.path.join(REF_SRC, r)) for r in _SRC_REL.values())
 
 
 def origin():
     """Where the reference modules are loaded from (goes into bench.py's `sample` string)."""
-    if all(os.path.exists(os.path.join(REF_BUILT, m + ".pyc")) for m in _SRC_REL):
+    if all(os.path.exists(os.path.join(REF_BUILT, m + ".bin")) for m in _SRC_REL):
         return "oracle/_ref bytecode of the unmodified reference"
     return "reference sources at " + REF_SRC
 
@@ -76,7 +76,7 @@ def _load(name):
     if name in _MODS:
         return _MODS[name]
     install_stubs()
-    pyc = os.path.join(REF_BUILT, name + ".pyc")
+    pyc = os.path.join(REF_BUILT, name + ".bin")
     src = os.path.join(REF_SRC, _SRC_REL[name])
     qual = "more3d_reference_" + name      # never shadows the product modules of the same name
     if os.path.exists(pyc):

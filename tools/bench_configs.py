@@ -274,7 +274,7 @@ def run_all(which=("0", "2", "3"), small=False, peak=6545.9):
                            cpu_points=200_000 if small else 1_000_000)
     if "3" in which:
         out["3"] = config3(500_000 if small else 20_000_000, 40 if small else 200, peak=peak,
-                           cpu_points=100_000 if small else 1_000_000)
+                           cpu_points=50_000 if small else 250_000)
     return out
 
 
