@@ -48,6 +48,16 @@ int more3d_profile_names(char* buf_h, int len);
  * (x, y, z, original index) records.  `cell` is the column width; a query of radius r scans a
  * stencil of ceil(r / cell) columns either side.  xyz: n*3 float64, row-major (x0 y0 z0 x1 ...). */
 int more3d_grid_create(const double* xyz, int64_t n, double cell, void* stream, more3d_grid** out);
+/* Generalised build (no reference equivalent; multi-GPU strips).  The cloud is the concatenation of 1 to 3 device
+ * segments -- a strip's left ghosts, its own points, its right ghosts -- indexed in place (no concatenated copy);
+ * a point's original index is its position in that concatenation.
+ * lattice_h (host, may be NULL) = {origin_x, origin_y} of a column lattice SHARED with other grids: columns are then
+ * floor((x - origin_x) / cell) of that lattice (shifted by an integer), so every strip of a tile bins, orders and
+ * sums exactly like a single grid over the whole tile built with the same origin and cell (the cell is not widened
+ * in this mode).  bounds_h (host, may be NULL) = {min x, y, z, max x, y, z} of the segments when the caller already
+ * has them: skips the bounding-box reduction and its host synchronisation. */
+int more3d_grid_create_segments(const double* const* seg_xyz_h, const int64_t* seg_n_h, int nseg, double cell,
+                                const double* lattice_h, const double* bounds_h, void* stream, more3d_grid** out);
 int more3d_grid_destroy(more3d_grid* g);
 /* info[0]=n, info[1]=nx, info[2]=ny (host ints); geom[0]=cell, geom[1]=origin_x, geom[2]=origin_y */
 int more3d_grid_info(const more3d_grid* g, int64_t* info_h, double* geom_h);
@@ -98,15 +108,19 @@ int more3d_normals_curvature(const more3d_grid* g, double r, double eps, int min
 
 /* ---- dk / dn centre-surround differences ---------------------------------------------------------
  * Saliency_Kernel.process for every point (DM_saliency.py:219-324).  chi2_table[df] =
- * chi2.ppf(alpha, df) for df = 0..table_len-1, computed by the caller with scipy (:282); a
- * neighbourhood with more active neighbours than table_len-1 returns MORE3D_E_RANGE.
+ * chi2.ppf(alpha, df) for df = 0..table_len-1, computed by the caller with scipy (:282).  A neighbourhood with
+ * more active neighbours than table_len-1 is an overflow: with status == NULL the call synchronises the stream
+ * and returns MORE3D_E_RANGE; with status != NULL (device int32, zeroed by the caller) nothing synchronises --
+ * the kernel raises *status to (largest active count + 1), i.e. the table length that would have sufficed, and the
+ * caller reads it whenever it likes (once per pipeline) and repeats the pass with a longer table.
+ * NaN outputs (dk = |0/0| when no neighbour is active, :316) stay in the columns but are kept out of minmax.
  * normals and K may BOTH be NULL: the call then uses the sorted feature records the grid cached during the
  * last more3d_normals_curvature on it (valid only while those outputs are unmodified) and skips the gather.
  * dk, dn: n float32 (_dk, _dn; :491-492).  minmax (may be NULL): 4 float32 {min_dk, max_dk, min_dn,
  * max_dn} over this call's outputs, reduced on the device (the Histo pass of DM_saliency, :562-568). */
 int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
                  double sigma_normal, double sigma_curvature, const double* chi2_table, int table_len,
-                 int min_points, float* dk, float* dn, float* minmax, void* stream);
+                 int min_points, float* dk, float* dn, float* minmax, int32_t* status, void* stream);
 
 /* ---- grid-order variants of the two neighbourhood passes ------------------------------------------
  * Same arithmetic, same values; every per-point output is written at the point's position in the grid's
@@ -116,14 +130,16 @@ int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const fl
  * column back in the caller's order (DM_nonparam_curvature -> DM_dk_dn -> DM_saliency, DM_saliency.py:326-583)
  * runs these, blends in grid order (more3d_saliency_blend is order-agnostic) and unpermutes one column (more3d_unpermute).
  * more3d_dk_dn_gridorder always uses the feature records cached by the last
- * more3d_normals_curvature[_gridorder] on the grid.  n_owned: only points whose ORIGINAL index is < n_owned
- * enter `minmax` (a strip's own points come first, its ghosts after them); <= 0 means all points. */
+ * more3d_normals_curvature[_gridorder] on the grid.  own_lo, n_owned: only points whose ORIGINAL index lies in
+ * [own_lo, own_lo + n_owned) enter `minmax` (a strip's own points sit between its left and right ghosts,
+ * more3d_grid_create_segments); n_owned <= 0 means all points. */
 int more3d_normals_curvature_gridorder(const more3d_grid* g, double r, double eps, int min_points,
                                        double* normals, double* lam_ratio, float* K, int32_t* pcount,
                                        void* stream);
 int more3d_dk_dn_gridorder(const more3d_grid* g, double r, double rho, double sigma_normal,
                            double sigma_curvature, const double* chi2_table, int table_len, int min_points,
-                           int64_t n_owned, float* dk, float* dn, float* minmax, void* stream);
+                           int64_t own_lo, int64_t n_owned, float* dk, float* dn, float* minmax, int32_t* status,
+                           void* stream);
 /* dst[order[i]] = src[i], order as returned by more3d_grid_order (the grid itself is not needed any more);
  * elem_bytes in {4, 8, 24} (f32 / i32 column, f64 column, n x 3 f64 normals). */
 int more3d_unpermute(const int32_t* order, int64_t n, const void* src_gridorder, void* dst, int elem_bytes,
@@ -317,6 +333,19 @@ int more3d_band_select(const double* xyz, int64_t n, int axis, double lo, double
                        int64_t* count_h, void* stream);
 int more3d_gather_rows(const void* src, const int64_t* idx, int64_t m, int ncols, int elem_bytes,
                        void* dst, void* stream);
+
+/* strip_pack: ONE pass over a strip's cloud that packs both halo bands -- the points with x < left_below into
+ * left_out and those with x >= right_from into right_out (cap rows of 3 f64 each, original order kept) -- and reduces
+ * the strip's bounding box.  info (device, 8 f64) = {min x, y, z, max x, y, z, rows in left band, rows in right band};
+ * a band count above cap means rows were dropped.  Nothing synchronises: the caller ships info with its collective.
+ * histogram256_range: numpy.histogram(v, bins=256, range=(lo, hi)) with lohi = {lo, hi} in DEVICE memory (the
+ * all-reduced extrema, f32 or f64 per lohi_bytes; Downsample.py:54 -> skimage threshold_otsu), hist = 256 int64.
+ * negate_odd: v[i] = -v[i] for odd i (rows of {min, max}: one MIN all-reduce then serves minima and maxima). */
+int more3d_strip_pack(const double* xyz, int64_t n, double left_below, double right_from, double* left_out,
+                      double* right_out, int64_t cap, double* info, void* stream);
+int more3d_histogram256_range(const void* v, int elem_bytes, int64_t n, const void* lohi, int lohi_bytes,
+                              int64_t* hist, void* stream);
+int more3d_negate_odd(float* v, int64_t n, void* stream);
 
 /* ---- synthetic input (bench / test infrastructure; no reference equivalent) ----------------------------
  * Counter-based open-terrain generator of SURVEY.md section 8d's model: point i of a `total`-point tile of

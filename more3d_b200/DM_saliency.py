@@ -60,6 +60,11 @@ class PointCloudDM:
         self._normals = None if normals is None else as_device_points(normals, self.device).clone()
         self._grids = {}
         self._minmax = None
+        # chi2-table overflow words of dk/dn passes that have not been checked yet (defer_checks: the pipeline reads
+        # them once at its end instead of synchronising after every radius)
+        self.defer_checks = False
+        self._pending = []
+        self._status = None
 
     @property
     def normals(self):
@@ -129,12 +134,61 @@ class PointCloudDM:
         want = cell_for_radius(radius)
         best = None
         for g in self._grids.values():
-            if g.cell <= want * (1 + 1e-12) and want / g.cell <= 2.05 and (best is None or g.cell > best.cell):
+            # keyed on the REQUESTED cell: on a wide tile the library widens the columns (g.cell > requested), such a
+            # grid still serves every radius it was asked for -- the stencil half-width follows g.cell
+            c = g.requested_cell
+            if c <= want * (1 + 1e-12) and want / c <= 2.05 and (best is None or c > best.requested_cell):
                 best = g
         if best is None:
             best = UniformGrid(self.xyz, want)
             self._grids[float(radius)] = best
         return best
+
+    def status_word(self):
+        """A zeroed device int32 for the next dk/dn pass's overflow report (slot len(_pending) of one small tensor)."""
+        if self._status is None or len(self._pending) >= int(self._status.numel()):
+            self._status = torch.zeros(64, dtype=torch.int32, device=self.device)
+            self._pending = []
+        i = len(self._pending)
+        return self._status[i:i + 1]
+
+    def _need(self, host_words):
+        need = 0
+        for v, length in zip(host_words, self._pending):
+            if int(v) > length:
+                need = max(need, int(v))
+        self._pending = []
+        self._status = None
+        return need
+
+    def check_pending(self):
+        """Read the deferred overflow words (one synchronisation).  Returns 0 if every dk/dn pass since the last
+        check had a long enough chi2 table, else the table length that would have sufficed."""
+        if not self._pending:
+            return 0
+        return self._need(self._status[:len(self._pending)].cpu().tolist())
+
+    def check_pending_async(self, side_stream):
+        """Like check_pending, but the words travel on `side_stream` behind everything queued so far on the current
+        stream; returns a callable that waits for that copy only (not for work queued later) and gives the answer."""
+        if not self._pending:
+            return lambda: 0
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        words = self._status[:len(self._pending)]
+        host = torch.empty(len(self._pending), dtype=torch.int32).pin_memory()
+        with torch.cuda.stream(side_stream):
+            side_stream.wait_event(ev)
+            host.copy_(words, non_blocking=True)
+            words.record_stream(side_stream)
+            done = torch.cuda.Event()
+            done.record(side_stream)
+
+        def result():
+            done.synchronize()
+            return self._need(host.tolist())
+        return result
 
     def drop_grids(self):
         for g in self._grids.values():
@@ -252,25 +306,33 @@ class Saliency_Kernel(_KernelPointEx):
         # feature records are current, and dk/dn can stay in grid order too
         cached = isinstance(rn, GridColumn) and isinstance(rk, GridColumn) and rn.grid is g and rk.grid is g \
             and getattr(g, "_feat_cols", None) == (rn, rk) and rn.clean() and rk.clean()
-        length = 1024
+        length = int(getattr(dm, "chi2_table_len", 1024))
         while True:
             table = _chi2_table(self._alpha, length, dm.device)
-            try:
-                if cached:
-                    dk, dn, minmax = g.dk_dn_gridorder(radius, self._rho_neighbourhood, self._sigma_normal,
-                                                       self._sigma_curvature, table, self._minPoints_neighbourhood)
-                else:
-                    dk, dn, minmax = g.dk_dn(radius, dm.normals, dm.attrs["_nonparam_K"], self._rho_neighbourhood,
-                                             self._sigma_normal, self._sigma_curvature, table,
-                                             self._minPoints_neighbourhood)
+            status = dm.status_word()
+            if cached:
+                dk, dn, minmax = g.dk_dn_gridorder(radius, self._rho_neighbourhood, self._sigma_normal,
+                                                   self._sigma_curvature, table, self._minPoints_neighbourhood,
+                                                   status=status)
+            else:
+                dk, dn, minmax = g.dk_dn(radius, dm.normals, dm.attrs["_nonparam_K"], self._rho_neighbourhood,
+                                         self._sigma_normal, self._sigma_curvature, table,
+                                         self._minPoints_neighbourhood, status=status)
+            if dm.defer_checks:
+                dm._pending.append(length)                       # read by PointCloudDM.check_pending()
                 break
-            except _lib.More3DError as e:
-                if "error -4" not in str(e) or length >= (1 << 22):
-                    raise
-                length *= 8
+            need = int(status.item())         # a neighbourhood with more active neighbours than the table covers
+            dm._pending, dm._status = [], None
+            if need <= length:
+                break
+            if need > (1 << 24):
+                raise _lib.More3DError("dk/dn: %d active neighbours in one neighbourhood" % (need - 1), _lib.E_RANGE)
+            length = max(8 * length, need)
         dm.attrs["_dk"] = dk
         dm.attrs["_dn"] = dn
-        dm._minmax = minmax
+        # the fused extrema are valid for exactly these two column objects in their present state
+        ver = lambda c: c.data._version if isinstance(c, GridColumn) else c._version
+        dm._minmax = (minmax, dk, dn, ver(dk), ver(dn))
         return True
 
 
@@ -349,7 +411,17 @@ def DM_saliency(inFile, curvature_weight=.5, verbose=False, **kwargs):
                    and rdk.clean() and rdn.clean()) else None
     dk, dn = (rdk.data, rdn.data) if grid is not None else (dm.attrs["_dk"], dm.attrs["_dn"])
     with torch.cuda.device(dm.device):
-        minmax = dm._minmax
+        minmax = None
+        mm = dm._minmax
+        if mm is not None and mm[1] is rdk and mm[2] is rdn:
+            # reuse the extrema the dk/dn pass reduced, unless a column was edited in place since (the reference
+            # recomputes them from the stored columns on every call, DM_saliency.py:562-568)
+            ver = lambda c: c.data._version if isinstance(c, GridColumn) else c._version
+            fresh = ver(rdk) == mm[3] and ver(rdn) == mm[4]
+            if fresh and isinstance(rdk, GridColumn):
+                fresh = rdk.clean() and rdn.clean()
+            if fresh:
+                minmax = mm[0]
         if minmax is None:
             minmax = torch.empty(4, dtype=torch.float32, device=dm.device)
             check(lib.more3d_minmax4(ptr(dk), ptr(dn), dm.n, ptr(minmax), stream_ptr()))

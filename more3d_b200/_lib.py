@@ -20,6 +20,8 @@ SIGNATURES = {
     "more3d_profile_get": [C.c_char_p, C.POINTER(_f64), C.POINTER(_i64)],
     "more3d_profile_names": [C.c_char_p, _i32],
     "more3d_grid_create": [_vp, _i64, _f64, _vp, C.POINTER(_vp)],
+    "more3d_grid_create_segments": [C.POINTER(_vp), C.POINTER(_i64), _i32, _f64, C.POINTER(_f64), C.POINTER(_f64), _vp,
+                                    C.POINTER(_vp)],
     "more3d_grid_destroy": [_vp],
     "more3d_grid_info": [_vp, C.POINTER(_i64), C.POINTER(_f64)],
     "more3d_grid_order": [_vp, _vp, _vp],
@@ -30,9 +32,9 @@ SIGNATURES = {
     "more3d_normals_pca": [_vp, _f64, _vp, _vp, _vp, _vp],
     "more3d_nonparam_curvature": [_vp, _f64, _vp, _f64, _i32, _vp, _vp, _vp],
     "more3d_normals_curvature": [_vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
-    "more3d_dk_dn": [_vp, _f64, _vp, _vp, _f64, _f64, _f64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "more3d_dk_dn": [_vp, _f64, _vp, _vp, _f64, _f64, _f64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "more3d_normals_curvature_gridorder": [_vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
-    "more3d_dk_dn_gridorder": [_vp, _f64, _f64, _f64, _f64, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp],
+    "more3d_dk_dn_gridorder": [_vp, _f64, _f64, _f64, _f64, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     "more3d_unpermute": [_vp, _i64, _vp, _vp, _i32, _vp],
     "more3d_minmax4": [_vp, _vp, _i64, _vp, _vp],
     "more3d_saliency_blend": [_vp, _vp, _i64, _vp, _f64, _vp, _vp, _vp],
@@ -65,12 +67,22 @@ SIGNATURES = {
     "more3d_compare_terms": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "more3d_band_select": [_vp, _i64, _i32, _f64, _f64, _vp, C.POINTER(_i64), _vp],
     "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "more3d_strip_pack": [_vp, _i64, _f64, _f64, _vp, _vp, _i64, _vp, _vp],
+    "more3d_histogram256_range": [_vp, _i32, _i64, _vp, _i32, _vp, _vp],
+    "more3d_negate_odd": [_vp, _i64, _vp],
     "more3d_synth_terrain": [C.c_uint64, _i64, _i64, _i64, _f64, _f64, _i32, _f64, _vp, _vp],
 }
 
 
 class More3DError(RuntimeError):
-    pass
+    """Raised for every non-zero return code of the C-ABI; ``rc`` is that code (MORE3D_E_*)."""
+
+    def __init__(self, msg, rc=None):
+        super().__init__(msg)
+        self.rc = rc
+
+
+E_INVALID, E_CUDA, E_NOMEM, E_RANGE = -1, -2, -3, -4
 
 
 def load(build_if_needed=True):
@@ -110,7 +122,7 @@ def load(build_if_needed=True):
 def check(rc):
     if rc != 0:
         msg = load().more3d_last_error().decode("utf-8", "replace")
-        raise More3DError("libmore3d_b200 error %d: %s" % (rc, msg))
+        raise More3DError("libmore3d_b200 error %d: %s" % (rc, msg), rc)
 
 
 def ptr(t):

@@ -95,7 +95,10 @@ struct __align__(32) FeatRec {
 struct more3d_grid {
     int64_t n;
     int nx, ny;
-    double cell, inv_cell, ox, oy;
+    double cell, inv_cell, ox, oy;   // ox, oy: position of local column (0, 0) -- origin of the fp32 records
+    double lox, loy;                 // origin of the column LATTICE: column of x = floor((x - lox) / cell) - x0.  A single
+    int x0, y0;                      // grid has lox = ox, x0 = 0; strips of one tile share the tile's lattice, so every
+                                     // strip bins (and therefore orders and sums) exactly like the whole-tile grid
     int device;
     int tall;               // 1: some xy column holds more than M3D_TALL_COLUMN points -> columns are z-sorted
                             //    and the kernels bracket each column by z (vertical structures); 0: thin columns
@@ -139,12 +142,11 @@ __device__ __forceinline__ double dist2_rule(double dx, double dy, double dz) {
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-__device__ __forceinline__ int cell_coord(double v, double o, double inv, int n) {
+__device__ __forceinline__ int cell_coord(double v, double o, double inv, int shift) {
     double f = floor((v - o) * inv);
     // clamp far-away queries before the int conversion (ix +- stencil must not overflow int32)
     f = fmin(fmax(f, -1.0e9), 1.0e9);
-    (void)n;
-    return (int)f;
+    return (int)f - shift;
 }
 
 // order-preserving double -> uint64 mapping (radix-sortable); -0.0 and +0.0 map to the same key

@@ -153,7 +153,8 @@ struct DkDnParams {
     double zk100_thr;   // largest x with fl(100 * x) <= 0.04 (rounding is monotone, so |100*dk| <= 0.04 <=> |dk| <= x)
     int min_points, s, table_len;
     int grid_order;     // 1: dk / dn are written at the grid position
-    long long n_owned;  // only points with original index < n_owned enter the fused min/max (strip + ghosts)
+    long long own_lo, own_hi;  // only points with original index in [own_lo, own_hi) enter the fused min/max (a strip's
+                               // own points sit between its left and right ghosts)
     Filter32 flt;
 };
 
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
         });
         if (!(pflags & 2LL) && m >= prm.min_points) {                         // :225-229, :240-244
             if (nact >= prm.table_len) {
-                atomicExch(err, 1);
+                atomicMax(err, nact + 1);       // the table length that would have sufficed
             } else {
                 const double chi_t = chi2_table[nact];                        // :282
                 const double imu = 1.0 / (double)mu;
@@ -269,18 +270,21 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
                 dkf = (float)dk; dnf = (float)dn;
             }
         }
-        const int64_t orig = (prm.grid_order && prm.n_owned >= g.n)
+        const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
+        const int64_t orig = (prm.grid_order && all_owned)
                                  ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
         const int64_t o = prm.grid_order ? i : orig;
         dk_out[o] = dkf;
         dn_out[o] = dnf;
-        owned = orig < prm.n_owned;
+        owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
     }
     if (mm) {
         // fused Histo min/max (DM_saliency.py:562-568): warp shuffle, then one atomic per warp
-        const bool cnt = live && owned;
-        unsigned lo_k = cnt ? f32_ordered(dkf) : 0xffffffffu, hi_k = cnt ? f32_ordered(dkf) : 0u;
-        unsigned lo_n = cnt ? f32_ordered(dnf) : 0xffffffffu, hi_n = cnt ? f32_ordered(dnf) : 0u;
+        // NaN (a neighbourhood whose active weights sum to 0 gives dk = |0/0|, DM_saliency.py:316) stays in the column
+        // but is kept out of the extrema -- declared choice: one NaN must not poison every normalised value
+        const bool ck = live && owned && !isnan(dkf), cn = live && owned && !isnan(dnf);
+        unsigned lo_k = ck ? f32_ordered(dkf) : 0xffffffffu, hi_k = ck ? f32_ordered(dkf) : 0u;
+        unsigned lo_n = cn ? f32_ordered(dnf) : 0xffffffffu, hi_n = cn ? f32_ordered(dnf) : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo_k = min(lo_k, __shfl_xor_sync(0xffffffffu, lo_k, o));
@@ -359,8 +363,8 @@ extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double e
 
 static int run_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
                      double sigma_normal, double sigma_curvature, const double* chi2_table,
-                     int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream,
-                     int grid_order, int64_t n_owned) {
+                     int table_len, int min_points, float* dk, float* dn, float* minmax, int32_t* status, void* stream,
+                     int grid_order, int64_t own_lo, int64_t n_owned) {
     M3D_REQUIRE(g != nullptr, "grid is NULL");
     M3D_REQUIRE(r >= 0 && isfinite(r), "radius must be finite and >= 0");
     M3D_REQUIRE(chi2_table && dk && dn, "NULL argument");
@@ -375,8 +379,12 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     if (cached) feat = g->feat;
     else M3D_TRY(dev_alloc(&feat, (size_t)g->n, s));
     M3D_TRY(dev_alloc(&mm, 4, s));
-    M3D_TRY(dev_alloc(&err, 1, s));
-    M3D_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+    if (status) {
+        err = status;       // the caller's status word: raised on overflow, never cleared, read when the caller likes
+    } else {
+        M3D_TRY(dev_alloc(&err, 1, s));
+        M3D_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+    }
     const unsigned nb = (unsigned)((g->n + 255) / 256);
     GridView v = make_view(g);
     if (!cached) {
@@ -391,7 +399,8 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     prm.flt = make_filter(g, r);
     prm.zk100_thr = zk100_threshold();
     prm.grid_order = grid_order;
-    prm.n_owned = (n_owned <= 0 || n_owned > g->n) ? g->n : n_owned;
+    prm.own_lo = (n_owned <= 0) ? 0 : own_lo;
+    prm.own_hi = (n_owned <= 0) ? g->n : own_lo + n_owned;
     {
         ProfScope prof("dkdn", s);
         if (g->tall) dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
@@ -401,12 +410,15 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     count_launches(minmax ? 4 : 3);
     M3D_CHECK_LAUNCH();
     int err_h = 0;
-    M3D_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, s));
-    M3D_CUDA(cudaStreamSynchronize(s));
+    if (!status) {          // no status word: the call itself reports the overflow (one stream synchronisation)
+        M3D_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+        M3D_CUDA(cudaStreamSynchronize(s));
+        dev_free(err, s);
+    }
     if (!cached) dev_free(feat, s);
-    dev_free(mm, s); dev_free(err, s);
+    dev_free(mm, s);
     if (err_h) {
-        set_error("dk/dn: a neighbourhood has more active neighbours than chi2_table covers (table_len=%d)", table_len);
+        set_error("dk/dn: a neighbourhood has %d active neighbours, chi2_table covers %d (table_len)", err_h - 1, table_len - 1);
         return MORE3D_E_RANGE;
     }
     return MORE3D_OK;
@@ -414,9 +426,10 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
 
 extern "C" int more3d_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
                             double sigma_normal, double sigma_curvature, const double* chi2_table,
-                            int table_len, int min_points, float* dk, float* dn, float* minmax, void* stream) {
+                            int table_len, int min_points, float* dk, float* dn, float* minmax, int32_t* status,
+                            void* stream) {
     return run_dk_dn(g, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, table_len, min_points,
-                     dk, dn, minmax, stream, 0, 0);
+                     dk, dn, minmax, status, stream, 0, 0, 0);
 }
 
 // Grid-order variants: every per-point output is written at the point's position in the grid's sorted order
@@ -431,8 +444,8 @@ extern "C" int more3d_normals_curvature_gridorder(const more3d_grid* g, double r
 
 extern "C" int more3d_dk_dn_gridorder(const more3d_grid* g, double r, double rho, double sigma_normal,
                                       double sigma_curvature, const double* chi2_table, int table_len,
-                                      int min_points, int64_t n_owned, float* dk, float* dn, float* minmax,
-                                      void* stream) {
+                                      int min_points, int64_t own_lo, int64_t n_owned, float* dk, float* dn,
+                                      float* minmax, int32_t* status, void* stream) {
     return run_dk_dn(g, r, nullptr, nullptr, rho, sigma_normal, sigma_curvature, chi2_table, table_len, min_points,
-                     dk, dn, minmax, stream, 1, n_owned);
+                     dk, dn, minmax, status, stream, 1, own_lo, n_owned);
 }

@@ -21,15 +21,29 @@ __device__ __forceinline__ PointRec load_rec_plain(const PointRec* __restrict__ 
     return r;
 }
 
-__global__ void __launch_bounds__(BB_THREADS) bbox_partial(const double* __restrict__ xyz, int64_t n,
+// The cloud of a grid is the concatenation of up to three device segments (a strip's left ghosts, its own points,
+// its right ghosts): the kernels that read the caller's coordinates index the segments directly, nothing is
+// concatenated in memory.  end[k] = number of points in segments 0..k.
+struct Segs {
+    const double* p[3];
+    int64_t end[3];
+};
+__device__ __forceinline__ const double* seg_point(const Segs& sg, int64_t i) {
+    if (i < sg.end[0]) return sg.p[0] + 3 * i;
+    if (i < sg.end[1]) return sg.p[1] + 3 * (i - sg.end[0]);
+    return sg.p[2] + 3 * (i - sg.end[1]);
+}
+
+__global__ void __launch_bounds__(BB_THREADS) bbox_partial(Segs sg, int64_t n,
                                                            double* __restrict__ part) {
     // v[0..2] = min x,y,z   v[3..5] = max x,y,z (stored negated so one fmin reduction serves both)
     double v[6] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
+        const double* __restrict__ q = seg_point(sg, i);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double c = xyz[3 * i + a];
+            const double c = q[a];
             v[a] = fmin(v[a], c);
             v[3 + a] = fmin(v[3 + a], -c);
         }
@@ -64,18 +78,29 @@ __global__ void bbox_final(const double* __restrict__ part, int nparts, double* 
         for (int a = 0; a < 6; ++a) out[a] = (a < 3) ? v[a] : -v[a];
 }
 
+// the column lattice as the build kernels need it: column of (x, y) = (floor((x - lox) * inv) - x0, ...), clamped
+struct Lattice {
+    double lox, loy, inv;
+    int x0, y0, nx, ny;
+    __device__ __forceinline__ uint32_t key(double x, double y) const {
+        const int ix = min(max(cell_coord(x, lox, inv, x0), 0), nx - 1);
+        const int iy = min(max(cell_coord(y, loy, inv, y0), 0), ny - 1);
+        return (uint32_t)iy * (uint32_t)nx + (uint32_t)ix;
+    }
+};
+static Lattice make_lattice(const more3d_grid* g) {
+    Lattice l;
+    l.lox = g->lox; l.loy = g->loy; l.inv = g->inv_cell; l.x0 = g->x0; l.y0 = g->y0; l.nx = g->nx; l.ny = g->ny;
+    return l;
+}
+
 // K1: column key per point + column population (spread-address REDG)
-__global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz, int64_t n, double ox,
-                                                 double oy, double inv, int nx, int ny,
+__global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz, int64_t n, Lattice lat,
                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                  uint32_t* __restrict__ col_count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int ix = cell_coord(xyz[3 * i], ox, inv, nx);
-    int iy = cell_coord(xyz[3 * i + 1], oy, inv, ny);
-    ix = min(max(ix, 0), nx - 1);
-    iy = min(max(iy, 0), ny - 1);
-    uint32_t key = (uint32_t)iy * (uint32_t)nx + (uint32_t)ix;
+    const uint32_t key = lat.key(xyz[3 * i], xyz[3 * i + 1]);
     keys[i] = key;
     vals[i] = (uint32_t)i;
     atomicAdd(&col_count[key], 1u);
@@ -83,32 +108,29 @@ __global__ void __launch_bounds__(256) cell_keys(const double* __restrict__ xyz,
 
 // K1 (thin grids): column key per point AND the point's arrival rank in its column -- the value the counting
 // atomic returns.  Arrival order is arbitrary; column_fixup below turns it into (column, original index) order.
-__global__ void __launch_bounds__(256) cell_keys_rank(const double* __restrict__ xyz, int64_t n, double ox,
-                                                      double oy, double inv, int nx, int ny,
+__global__ void __launch_bounds__(256) cell_keys_rank(Segs sg, int64_t n, Lattice lat,
                                                       uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks,
                                                       uint32_t* __restrict__ col_count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int ix = cell_coord(xyz[3 * i], ox, inv, nx);
-    int iy = cell_coord(xyz[3 * i + 1], oy, inv, ny);
-    ix = min(max(ix, 0), nx - 1);
-    iy = min(max(iy, 0), ny - 1);
-    const uint32_t key = (uint32_t)iy * (uint32_t)nx + (uint32_t)ix;
+    const double* __restrict__ q = seg_point(sg, i);
+    const uint32_t key = lat.key(q[0], q[1]);
     keys[i] = key;
     ranks[i] = atomicAdd(&col_count[key], 1u);
 }
 
 // K2 (thin grids): counting-sort scatter.  Reads the cloud coalesced, writes one full 32-B sector per point at
 // col_start[key] + arrival rank: the points of a column are now contiguous, in arrival order.
-__global__ void __launch_bounds__(256) scatter_records(const double* __restrict__ xyz, int64_t n,
+__global__ void __launch_bounds__(256) scatter_records(Segs sg, int64_t n,
                                                        const uint32_t* __restrict__ keys,
                                                        const uint32_t* __restrict__ ranks,
                                                        const uint32_t* __restrict__ col_start,
                                                        PointRec* __restrict__ tmp) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double* __restrict__ q = seg_point(sg, i);
     PointRec r;
-    r.x = xyz[3 * i]; r.y = xyz[3 * i + 1]; r.z = xyz[3 * i + 2];
+    r.x = q[0]; r.y = q[1]; r.z = q[2];
     r.idx = (long long)i;
     tmp[(size_t)__ldg(col_start + keys[i]) + ranks[i]] = r;
 }
@@ -119,16 +141,14 @@ __global__ void __launch_bounds__(256) scatter_records(const double* __restrict_
 // any arrival order.  The same loop finds the np.unique flag (a bit-equal point with a smaller index,
 // DM_saliency.py:247); the fp32 record and the order table are written alongside.
 __global__ void __launch_bounds__(256) column_fixup(const PointRec* __restrict__ tmp,
-                                                    const uint32_t* __restrict__ col_start, int64_t n, double ox,
-                                                    double oy, double oz, double inv, int nx, int ny,
+                                                    const uint32_t* __restrict__ col_start, int64_t n, Lattice lat,
+                                                    double ox, double oy, double oz,
                                                     PointRec* __restrict__ rec, float4* __restrict__ rec32,
                                                     uint32_t* __restrict__ order, uint8_t* __restrict__ dup) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const PointRec p = load_rec_plain(tmp, t);
-    const int ix = min(max(cell_coord(p.x, ox, inv, nx), 0), nx - 1);
-    const int iy = min(max(cell_coord(p.y, oy, inv, ny), 0), ny - 1);
-    const size_t col = (size_t)iy * nx + ix;
+    const size_t col = lat.key(p.x, p.y);
     const uint32_t b = __ldg(col_start + col), e = __ldg(col_start + col + 1);
     uint32_t rank = 0;
     uint8_t f = 0;
@@ -156,11 +176,11 @@ __global__ void __launch_bounds__(256) col_max_pop(const uint32_t* __restrict__ 
 }
 
 // tall clouds: z pre-sort keys, and the column keys re-read in z order for the second (stable) sort
-__global__ void __launch_bounds__(256) z_keys(const double* __restrict__ xyz, int64_t n, uint64_t* __restrict__ zk,
+__global__ void __launch_bounds__(256) z_keys(Segs sg, int64_t n, uint64_t* __restrict__ zk,
                                               uint32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    zk[i] = sortable_key(xyz[3 * i + 2]);
+    zk[i] = sortable_key(seg_point(sg, i)[2]);
     vals[i] = (uint32_t)i;
 }
 __global__ void __launch_bounds__(256) gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx,
@@ -170,55 +190,34 @@ __global__ void __launch_bounds__(256) gather_u32(const uint32_t* __restrict__ s
 }
 
 // K2 tail: gather the sorted records
-__global__ void __launch_bounds__(256) gather_records(const double* __restrict__ xyz,
+__global__ void __launch_bounds__(256) gather_records(Segs sg,
                                                       const uint32_t* __restrict__ order, int64_t n,
                                                       PointRec* __restrict__ rec, double ox, double oy,
                                                       double oz, float4* __restrict__ rec32) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t o = order[i];
+    const double* __restrict__ q = seg_point(sg, (int64_t)o);
     PointRec r;
-    r.x = xyz[3 * (int64_t)o];
-    r.y = xyz[3 * (int64_t)o + 1];
-    r.z = xyz[3 * (int64_t)o + 2];
+    r.x = q[0];
+    r.y = q[1];
+    r.z = q[2];
     r.idx = (long long)o;
     rec[i] = r;
     // fp32 copy relative to the grid origin: |error| <= 2^-24 * extent per coordinate (delta32)
     rec32[i] = make_float4((float)(r.x - ox), (float)(r.y - oy), (float)(r.z - oz), 0.0f);
 }
 
-// coincident-point flags: the np.unique(axis=1) of Saliency_Kernel.process (DM_saliency.py:247)
-// keeps one representative of every set of bit-equal positions; coincident points share a column.
-__global__ void __launch_bounds__(256) dup_flags(const PointRec* __restrict__ rec,
-                                                 const uint32_t* __restrict__ col_start, int64_t n,
-                                                 double ox, double oy, double inv, int nx, int ny,
-                                                 uint8_t* __restrict__ dup) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    PointRec p = rec[i];
-    int ix = min(max(cell_coord(p.x, ox, inv, nx), 0), nx - 1);
-    int iy = min(max(cell_coord(p.y, oy, inv, ny), 0), ny - 1);
-    uint32_t b = col_start[(size_t)iy * nx + ix];
-    uint8_t f = 0;
-    for (int64_t j = b; j < i; ++j) {
-        PointRec q = rec[j];
-        if (q.x == p.x && q.y == p.y && q.z == p.z) { f = 1; break; }
-    }
-    dup[i] = f;
-}
-
-// z-sorted columns: coincident points are adjacent (equal z, then original index), so only the run of
-// equal z before i has to be looked at
+// coincident-point flags of the tall path: the np.unique(axis=1) of Saliency_Kernel.process (DM_saliency.py:247)
+// keeps one representative of every set of bit-equal positions.  z-sorted columns: coincident points are adjacent
+// (equal z, then original index), so only the run of equal z before i has to be looked at
 __global__ void __launch_bounds__(256) dup_flags_tall(const PointRec* __restrict__ rec,
-                                                      const uint32_t* __restrict__ col_start, int64_t n, double ox,
-                                                      double oy, double inv, int nx, int ny,
+                                                      const uint32_t* __restrict__ col_start, int64_t n, Lattice lat,
                                                       uint8_t* __restrict__ dup) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PointRec p = rec[i];
-    int ix = min(max(cell_coord(p.x, ox, inv, nx), 0), nx - 1);
-    int iy = min(max(cell_coord(p.y, oy, inv, ny), 0), ny - 1);
-    const int64_t b = col_start[(size_t)iy * nx + ix];
+    const int64_t b = col_start[lat.key(p.x, p.y)];
     uint8_t f = 0;
     for (int64_t j = i - 1; j >= b; --j) {
         PointRec q = rec[j];
@@ -234,10 +233,28 @@ using namespace m3d;
 
 extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, void* stream,
                                   more3d_grid** out) {
+    const double* seg[1] = {xyz};
+    const int64_t cnt[1] = {n};
+    return more3d_grid_create_segments(seg, cnt, 1, cell, nullptr, nullptr, stream, out);
+}
+
+extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const int64_t* seg_n_h, int nseg, double cell,
+                                           const double* lattice_h, const double* bounds_h, void* stream,
+                                           more3d_grid** out) {
     M3D_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
-    M3D_REQUIRE(n > 0 && xyz != nullptr, "empty cloud");
+    M3D_REQUIRE(seg_xyz_h != nullptr && seg_n_h != nullptr && nseg >= 1 && nseg <= 3, "1 to 3 segments");
     M3D_REQUIRE(cell > 0 && isfinite(cell), "cell must be > 0");
+    Segs sg;
+    int64_t n = 0;
+    for (int k = 0; k < 3; ++k) {
+        const int64_t c = k < nseg ? seg_n_h[k] : 0;
+        M3D_REQUIRE(c >= 0 && (c == 0 || seg_xyz_h[k] != nullptr), "bad segment");
+        sg.p[k] = k < nseg ? seg_xyz_h[k] : nullptr;
+        n += c;
+        sg.end[k] = n;
+    }
+    M3D_REQUIRE(n > 0, "empty cloud");
     if (n >= ((int64_t)1 << 31)) {
         set_error("n >= 2^31 points per grid not supported");
         return MORE3D_E_RANGE;
@@ -246,18 +263,22 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
     init_device_pool();
     ProfScope prof("grid_build", s);
 
-    // bounding box (host needs it to size the table: one small sync per build)
-    const int nparts = 592;  // 4 CTAs per SM on 148 SMs
-    double* part = nullptr;
-    M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
-    bbox_partial<<<nparts, BB_THREADS, 0, s>>>(xyz, n, part);
-    bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
-    count_launches(2);
-    M3D_CHECK_LAUNCH();
+    // bounding box (the host needs it to size the table): given by the caller, or reduced here (one small sync)
     double b6[6];
-    M3D_CUDA(cudaMemcpyAsync(b6, part + 6 * nparts, sizeof(b6), cudaMemcpyDeviceToHost, s));
-    M3D_CUDA(cudaStreamSynchronize(s));
-    dev_free(part, s);
+    if (bounds_h) {
+        for (int a = 0; a < 6; ++a) b6[a] = bounds_h[a];
+    } else {
+        const int nparts = 592;  // 4 CTAs per SM on 148 SMs
+        double* part = nullptr;
+        M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
+        bbox_partial<<<nparts, BB_THREADS, 0, s>>>(sg, n, part);
+        bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
+        count_launches(2);
+        M3D_CHECK_LAUNCH();
+        M3D_CUDA(cudaMemcpyAsync(b6, part + 6 * nparts, sizeof(b6), cudaMemcpyDeviceToHost, s));
+        M3D_CUDA(cudaStreamSynchronize(s));
+        dev_free(part, s);
+    }
     const double bb[4] = {b6[0], b6[1], b6[3], b6[4]};   // min x, min y, max x, max y
     if (!(isfinite(b6[0]) && isfinite(b6[1]) && isfinite(b6[2]) && isfinite(b6[3]) && isfinite(b6[4]) &&
           isfinite(b6[5]))) {
@@ -265,18 +286,41 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         return MORE3D_E_INVALID;
     }
 
-    // widen the cell until the column table fits (stencils stay correct for any cell >= requested):
-    // at most 16000 x 16000 columns (2^28 entries = 1 GiB)
     double ex = bb[2] - bb[0], ey = bb[3] - bb[1];
-    double c = fmax(cell, fmax(ex, ey) / 16000.0);
     more3d_grid* g = new more3d_grid();
     g->n = n;
+    double c;
+    if (lattice_h) {
+        // columns of a lattice shared with other grids (the strips of one tile): origin and cell are given, this
+        // grid covers the integer column range its own bounding box needs (one spare column either side)
+        c = cell;
+        const double inv = 1.0 / c;
+        g->lox = lattice_h[0];
+        g->loy = lattice_h[1];
+        const double fx0 = floor((bb[0] - g->lox) * inv) - 1.0, fx1 = floor((bb[2] - g->lox) * inv) + 1.0;
+        const double fy0 = floor((bb[1] - g->loy) * inv) - 1.0, fy1 = floor((bb[3] - g->loy) * inv) + 1.0;
+        if (!(fabs(fx0) < 1e9 && fabs(fx1) < 1e9 && fabs(fy0) < 1e9 && fabs(fy1) < 1e9) ||
+            (fx1 - fx0 + 1.0) * (fy1 - fy0 + 1.0) > 268435456.0) {
+            delete g;
+            set_error("column table of the shared lattice exceeds 2^28 entries: use a wider cell for every strip");
+            return MORE3D_E_RANGE;
+        }
+        g->x0 = (int)fx0; g->y0 = (int)fy0;
+        g->nx = (int)(fx1 - fx0) + 1; g->ny = (int)(fy1 - fy0) + 1;
+        g->ox = g->lox + (double)g->x0 * c;
+        g->oy = g->loy + (double)g->y0 * c;
+    } else {
+        // widen the cell until the column table fits (stencils stay correct for any cell >= requested):
+        // at most 16000 x 16000 columns (2^28 entries = 1 GiB)
+        c = fmax(cell, fmax(ex, ey) / 16000.0);
+        g->ox = bb[0] - c;
+        g->oy = bb[1] - c;
+        g->lox = g->ox; g->loy = g->oy; g->x0 = 0; g->y0 = 0;
+        g->nx = (int)floor(ex / c) + 3;
+        g->ny = (int)floor(ey / c) + 3;
+    }
     g->cell = c;
     g->inv_cell = 1.0 / c;
-    g->ox = bb[0] - c;
-    g->oy = bb[1] - c;
-    g->nx = (int)floor(ex / c) + 3;
-    g->ny = (int)floor(ey / c) + 3;
     cudaGetDevice(&g->device);
     g->stream = s;
     g->oz = b6[2];
@@ -308,8 +352,9 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
         G_TRY(dev_alloc(&vals, (size_t)n, s));
         G_CUDA(cudaMemsetAsync(g->col_start, 0, (ncols + 1) * sizeof(uint32_t), s));
         const unsigned nb = (unsigned)((n + 255) / 256);
+        const Lattice lat = make_lattice(g);
         // keys + arrival ranks (vals holds the ranks on the thin path, the point indices on the tall one)
-        cell_keys_rank<<<nb, 256, 0, s>>>(xyz, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, keys, vals, g->col_start);
+        cell_keys_rank<<<nb, 256, 0, s>>>(sg, n, lat, keys, vals, g->col_start);
         G_CUDA(cudaGetLastError());
         G_TRY(exclusive_scan_u32(g->col_start, g->col_start, (int64_t)ncols, s));
         // thin or tall?  (one more 4-byte read-back per build)
@@ -332,7 +377,7 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
             G_TRY(dev_alloc(&vals2, (size_t)n, s));
             G_TRY(dev_alloc(&zk, (size_t)n, s));
             G_TRY(dev_alloc(&zk2, (size_t)n, s));
-            z_keys<<<nb, 256, 0, s>>>(xyz, n, zk, vals);
+            z_keys<<<nb, 256, 0, s>>>(sg, n, zk, vals);
             rc = radix_sort_pairs_u64(zk, vals, zk2, vals2, n, 64, &zs, &vz, s);
             dev_free(zk, s); dev_free(zk2, s);
             if (rc != MORE3D_OK) goto fail;
@@ -340,17 +385,17 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
             gather_u32<<<nb, 256, 0, s>>>(keys, vz, n, keys2);          // column key of the z-ordered points
             G_TRY(radix_sort_pairs_u32(keys2, vz, keys, vother, n, bits, &ks, &vs, s));
             G_CUDA(cudaMemcpyAsync(g->order, vs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-            gather_records<<<nb, 256, 0, s>>>(xyz, g->order, n, g->rec, g->ox, g->oy, g->oz, g->rec32);
-            dup_flags_tall<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, g->ox, g->oy, g->inv_cell, g->nx, g->ny, g->dup);
+            gather_records<<<nb, 256, 0, s>>>(sg, g->order, n, g->rec, g->ox, g->oy, g->oz, g->rec32);
+            dup_flags_tall<<<nb, 256, 0, s>>>(g->rec, g->col_start, n, lat, g->dup);
             count_launches(6);  // cell_keys_rank, col_max_pop, z_keys, gather_u32, gather_records, dup_flags_tall
         } else {
             // counting sort: the column table is already the histogram of the WHOLE key, so one scatter places every
             // point in its column (arrival order) and one fix-up pass orders each column by original index -- the
             // order a stable sort by key produces, with no radix passes at all
             G_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * sizeof(PointRec), s));
-            scatter_records<<<nb, 256, 0, s>>>(xyz, n, keys, vals, g->col_start, tmp);
-            column_fixup<<<nb, 256, 0, s>>>(tmp, g->col_start, n, g->ox, g->oy, g->oz, g->inv_cell, g->nx, g->ny,
-                                            g->rec, g->rec32, g->order, g->dup);
+            scatter_records<<<nb, 256, 0, s>>>(sg, n, keys, vals, g->col_start, tmp);
+            column_fixup<<<nb, 256, 0, s>>>(tmp, g->col_start, n, lat, g->ox, g->oy, g->oz, g->rec, g->rec32, g->order,
+                                            g->dup);
             count_launches(4);  // cell_keys_rank, col_max_pop, scatter_records, column_fixup
         }
         G_CUDA(cudaGetLastError());
@@ -377,7 +422,7 @@ int m3d::sort_queries_by_column(const more3d_grid* g, const double* q, int64_t n
     M3D_TRY(dev_alloc(&vals2, (size_t)nq, s));
     M3D_TRY(dev_alloc(&cnt, ncols + 1, s));      // cell_keys also counts; the counts are not used here
     M3D_CUDA(cudaMemsetAsync(cnt, 0, (ncols + 1) * sizeof(uint32_t), s));
-    cell_keys<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(q, nq, g->ox, g->oy, g->inv_cell, g->nx, g->ny, keys, vals, cnt);
+    cell_keys<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(q, nq, make_lattice(g), keys, vals, cnt);
     count_launches(1);
     int bits = 1;
     while (((size_t)1 << bits) < ncols) ++bits;

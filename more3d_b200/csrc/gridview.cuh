@@ -12,8 +12,12 @@ struct GridView {
     int64_t n;
     int nx, ny;
     double ox, oy, oz, inv;
+    double lox, loy;      // lattice origin and integer column shift (see more3d_grid)
+    int x0, y0;
     double lim32;
     int tall;
+    __device__ __forceinline__ int col_x(double x) const { return cell_coord(x, lox, inv, x0); }
+    __device__ __forceinline__ int col_y(double y) const { return cell_coord(y, loy, inv, y0); }
 };
 
 static inline GridView make_view(const more3d_grid* g) {
@@ -21,6 +25,7 @@ static inline GridView make_view(const more3d_grid* g) {
     v.rec = g->rec; v.rec32 = g->rec32; v.col_start = g->col_start; v.dup = g->dup; v.n = g->n;
     v.nx = g->nx; v.ny = g->ny; v.ox = g->ox; v.oy = g->oy; v.oz = g->oz; v.inv = g->inv_cell;
     v.lim32 = g->lim32;
+    v.lox = g->lox; v.loy = g->loy; v.x0 = g->x0; v.y0 = g->y0;
     v.tall = g->tall;
     return v;
 }
@@ -82,8 +87,8 @@ __device__ __forceinline__ PointRec load_rec(const PointRec* __restrict__ rec, i
 // range of sorted records.  f(j) is called with the sorted position of every candidate.
 template <typename F>
 __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx, double qy, int s, F&& f) {
-    const int ix = cell_coord(qx, g.ox, g.inv, g.nx);
-    const int iy = cell_coord(qy, g.oy, g.inv, g.ny);
+    const int ix = g.col_x(qx);
+    const int iy = g.col_y(qy);
     const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
     const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
     if (x0 > x1 || y0 > y1) return;
@@ -108,8 +113,8 @@ __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx,
 template <typename F>
 __device__ __forceinline__ void for_each_candidate_tall(const GridView& g, double qx, double qy, double qz, double r,
                                                      int s, F&& f) {
-    const int ix = cell_coord(qx, g.ox, g.inv, g.nx);
-    const int iy = cell_coord(qy, g.oy, g.inv, g.ny);
+    const int ix = g.col_x(qx);
+    const int iy = g.col_y(qy);
     const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
     const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
     const double zlo = qz - r * (1.0 + 1e-12), zhi = qz + r * (1.0 + 1e-12);
@@ -159,8 +164,8 @@ __device__ __forceinline__ void walk_candidates_pipelined(const GridView& g, dou
         for_each_candidate_tall(g, qx, qy, qz, r, s, [&](int64_t j) { process(load(j)); });
         return;
     }
-    const int ix = cell_coord(qx, g.ox, g.inv, g.nx);
-    const int iy = cell_coord(qy, g.oy, g.inv, g.ny);
+    const int ix = g.col_x(qx);
+    const int iy = g.col_y(qy);
     const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
     const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
     if (x0 > x1 || y0 > y1) return;

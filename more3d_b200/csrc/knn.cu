@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const double* __re
     }
     KnnList<KMAX> L;
     L.init(k);
-    const int ix = min(max(cell_coord(px, g.ox, g.inv, g.nx), -1), g.nx);
-    const int iy = min(max(cell_coord(py, g.oy, g.inv, g.ny), -1), g.ny);
+    const int ix = min(max(g.col_x(px), -1), g.nx);
+    const int iy = min(max(g.col_y(py), -1), g.ny);
 
     auto scan_range = [&](int y, int xa, int xb) {   // columns [xa, xb] of row y, clipped
         if (y < 0 || y >= g.ny) return;

@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(256) minmax4_kernel(const float* __restrict__ 
     unsigned lk = 0xffffffffu, hk = 0u, ln = 0xffffffffu, hn = 0u;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned a = f32_ordered(dk[i]), b = f32_ordered(dn[i]);
-        lk = min(lk, a); hk = max(hk, a); ln = min(ln, b); hn = max(hn, b);
+        const float fk = dk[i], fn = dn[i];       // NaN stays out of the extrema (see dkdn_kernel)
+        if (!isnan(fk)) { const unsigned a = f32_ordered(fk); lk = min(lk, a); hk = max(hk, a); }
+        if (!isnan(fn)) { const unsigned b = f32_ordered(fn); ln = min(ln, b); hn = max(hn, b); }
     }
     warp_minmax_atomic(lk, hk, mm);
     warp_minmax_atomic(ln, hn, mm + 2);
@@ -50,8 +51,10 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk
         const float ndn = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)dn[i], min_n), diff_n), min_n);  // :578
         const float sv = (float)__dadd_rn(__dmul_rn(nw, (double)ndn), __dmul_rn(cw, (double)ndk));      // :579-580
         sal[i] = sv;
-        const unsigned u = f32_ordered(sv);
-        lo = min(lo, u); hi = max(hi, u);
+        if (!isnan(sv)) {
+            const unsigned u = f32_ordered(sv);
+            lo = min(lo, u); hi = max(hi, u);
+        }
     }
     if (smm) warp_minmax_atomic(lo, hi, smm);
 }

@@ -60,4 +60,17 @@ __device__ __forceinline__ uint64_t lookback_prefix(const volatile uint64_t* des
 }
 
 
+// lanes of the warp whose 8-bit digit equals this lane's (invalid lanes match nobody): eight ballots instead of
+// __match_any_sync, whose cost on sm_100 grows with the number of DISTINCT values in the warp (it resolves one
+// value per internal round; low radix digits are all different)
+__device__ __forceinline__ unsigned match_digit(unsigned d, bool valid) {
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? m : ~m;
+    }
+    return valid ? peers : 0u;
+}
+
 }  // namespace m3d

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_all(const K* __restrict__ 
         for (int p = 0; p < npass; ++p) {
             // warp-aggregated: equal digits of the warp's 32 keys cost one shared atomic (the high digits of grid
             // and voxel keys take a handful of values, a plain atomic per key would serialise on one bank)
-            const unsigned d = ok ? ((unsigned)(k >> (8 * p)) & 255u) : 256u;
-            const unsigned m = __match_any_sync(0xffffffffu, d);
+            const unsigned d = (unsigned)(k >> (8 * p)) & 255u;
+            const unsigned m = match_digit(d, ok);
             if (ok && (m & ((1u << lane) - 1u)) == 0u) atomicAdd(&h[p][d], (uint32_t)__popc(m));
         }
     }
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep(const K* __restrict__ 
     for (int j = 0; j < ITEMS; ++j) {
         const bool ok = (wbase + j * 32 + lane) < n;
         dg[j] = ok ? ((unsigned)(k[j] >> shift) & 255u) : 256u;
-        pm[j] = __match_any_sync(0xffffffffu, dg[j]);
+        pm[j] = match_digit(dg[j], ok);
     }
     uint32_t rk[ITEMS];
 #pragma unroll

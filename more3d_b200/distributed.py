@@ -184,76 +184,213 @@ def cuda_histogram(values, edges):
 class _OwnedRows:
     """The owned rows of a grid-order column, brought back to point order only when read."""
 
-    def __init__(self, col, n):
-        self.col, self.n = col, n
+    def __init__(self, col, lo, n):
+        self.col, self.lo, self.n = col, lo, n
 
     def tensor(self):
-        return self.col.tensor()[:self.n]
+        return self.col.tensor()[self.lo:self.lo + self.n]
+
+
+def strip_pack(own, left_below, right_from, cap):
+    """Both halo bands of a strip and its bounding box in ONE pass, nothing synchronised (more3d_strip_pack):
+    returns (left (cap, 3), right (cap, 3), info (8,) f64 = bbox6 + the two row counts), all on the device."""
+    lib = _lib.load()
+    dev = own.device
+    with torch.cuda.device(dev):
+        left = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+        right = torch.empty((cap, 3), dtype=torch.float64, device=dev)
+        info = torch.empty(8, dtype=torch.float64, device=dev)
+        check(lib.more3d_strip_pack(ptr(own), int(own.shape[0]), float(left_below), float(right_from), ptr(left),
+                                    ptr(right), int(cap), ptr(info), stream_ptr()))
+    return left, right, info
+
+
+class StripStep:
+    """The multi-radius saliency of ONE strip, in phases, so that the caller places the collectives between them:
+
+        step = StripStep(own, left, right, radii, params, lattice, bounds)
+        step.features()            # grid + per radius: normals / curvature -> dk / dn;  step.minmax (R, 4) local extrema
+        ... all-reduce step.minmax (MIN / MAX) ...
+        step.blend(weight)         # normalise + blend with the GLOBAL extrema;          step.sal_minmax (R, 2) local
+        ... all-reduce step.sal_minmax ...
+        step.histograms()          # 256-bin histograms over the global range;           step.hist (R, 256) local
+        ... all-reduce step.hist (SUM) ...
+
+    One grid serves all radii; its cloud is [left ghosts, own points, right ghosts] indexed in place; with the
+    tile's `lattice` every per-point result is bit-identical to the single-grid result of the whole tile.  Nothing
+    in here synchronises the host except the grid build's column-population read-back."""
+
+    def __init__(self, own, left, right, radii, params, lattice=None, bounds=None, chi2_table_len=1024):
+        self.radii = tuple(sorted(radii))
+        self.params = dict(params)
+        self.dev = own.device
+        self.n_own = int(own.shape[0])
+        self.n_left = 0 if left is None else int(left.shape[0])
+        self.own, self.left, self.right = own, left, right
+        self.lattice, self.bounds = lattice, bounds
+        self.table_len = int(chi2_table_len)
+        R = len(self.radii)
+        self.minmax = torch.empty((R, 4), dtype=torch.float32, device=self.dev)
+        self.sal_minmax = torch.empty((R, 4), dtype=torch.float32, device=self.dev)   # rows {min, max, min, max}
+        self.status = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        self.hist = None
+        self.grid = None
+
+    def features(self):
+        from .DM_saliency import Curvature_Kernel, _chi2_table
+        p = self.params
+        ck = Curvature_Kernel()
+        ck.setArgs(alpha=p["alpha"], roughness=p["roughness"], min_points=p["min_points"])
+        eps = ck.epsilon()
+        self.grid = g = UniformGrid(self.own, cell_for_radius(self.radii[0]), left=self.left, right=self.right,
+                                    lattice=self.lattice, bounds=self.bounds)
+        table = _chi2_table(p["alpha"], self.table_len, self.dev)
+        self.dk, self.dn, self.pcount = {}, {}, {}
+        for i, r in enumerate(self.radii):
+            if cell_for_radius(r) / g.requested_cell > 2.05:
+                raise ValueError("radii of one strip step must lie within a factor 2 (one shared grid)")
+            rho = r / np.sqrt(2.0)
+            _, _, _, pcount = g.normals_curvature_gridorder(r, eps, p["min_points"])
+            dk, dn, _ = g.dk_dn_gridorder(r, rho, p["sigma_normal"], p["sigma_curvature"], table, p["min_points"],
+                                          own_lo=self.n_left, n_owned=self.n_own, status=self.status[i:i + 1],
+                                          minmax=self.minmax[i])
+            self.dk[r], self.dn[r] = dk, dn
+            self.pcount[r] = _OwnedRows(pcount, self.n_left, self.n_own)
+        return self.minmax
+
+    def blend(self, curvature_weight):
+        lib = _lib.load()
+        self.sal_grid = {}
+        n = self.grid.n
+        with torch.cuda.device(self.dev):
+            for i, r in enumerate(self.radii):
+                sal = torch.empty(n, dtype=torch.float32, device=self.dev)      # blend is elementwise: grid order
+                # the local saliency extrema must cover the OWNED rows only: ghosts are other strips' points, and a
+                # ghost near the halo's outer edge has an incomplete neighbourhood
+                check(lib.more3d_saliency_blend(ptr(self.dk[r].data), ptr(self.dn[r].data), n, ptr(self.minmax[i]),
+                                                float(curvature_weight), ptr(sal), None, stream_ptr()))
+                self.sal_grid[r] = GridColumn(self.dk[r], sal)
+        return None
+
+    def saliency(self, r):
+        """(n_own,) f32 saliency of the owned points, in the caller's point order."""
+        return self.sal_grid[r].tensor()[self.n_left:self.n_left + self.n_own]
+
+    def owned_minmax(self):
+        """Local extrema of the owned points' saliency, rows {min, max, min, max} f32 -- input of the second
+        all-reduce."""
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            for i, r in enumerate(self.radii):
+                v = self.saliency(r)
+                check(lib.more3d_minmax4(ptr(v), ptr(v), self.n_own, ptr(self.sal_minmax[i]), stream_ptr()))
+        return self.sal_minmax
+
+    def histograms(self):
+        """256-bin histograms of the owned saliency over the (global) ranges in sal_minmax, (R, 256) int64."""
+        lib = _lib.load()
+        R = len(self.radii)
+        with torch.cuda.device(self.dev):
+            self.hist = torch.empty((R, 256), dtype=torch.int64, device=self.dev)
+            for i, r in enumerate(self.radii):
+                v = self.saliency(r)
+                check(lib.more3d_histogram256_range(ptr(v), 4, self.n_own, ptr(self.sal_minmax[i]), 4, ptr(self.hist[i]),
+                                                    stream_ptr()))
+        return self.hist
+
+    def result(self):
+        """What outlives the step: the overflow words and the Otsu inputs (a few KB)."""
+        return _StepResult(self.radii, self.status, self.table_len, self.sal_minmax, self.hist)
+
+    def overflow(self):
+        return self.result().overflow()
+
+    def close(self):
+        if self.grid is not None:
+            self.grid.close()
+            self.grid = None
+
+
+class _StepResult:
+    def __init__(self, radii, status, table_len, sal_minmax, hist):
+        self.radii, self.status, self.table_len, self.sal_minmax, self.hist = radii, status, table_len, sal_minmax, hist
+
+    def overflow(self):
+        """0, or the chi2-table length that would have sufficed (reads the status words: synchronises)."""
+        need = int(self.status.cpu().numpy().max())
+        return need if need > self.table_len else 0
+
+    def otsu(self):
+        """Per-radius Otsu thresholds from the (globally reduced) histograms: the step's ONE host read."""
+        lohi = self.sal_minmax.cpu().numpy().astype(np.float64)
+        h = self.hist.cpu().numpy()
+        out = {}
+        for i, r in enumerate(self.radii):
+            lo, hi = float(lohi[i, 0]), float(lohi[i, 1])
+            out[r] = lo if lo == hi else otsu_from_counts(h[i], np.linspace(lo, hi, 257))
+        return out
+
+
+def allreduce_minmax_rows(mm, group=None):
+    """Rows of {min, max, min, max} f32 made global in place with ONE collective: MIN over (min, -max); the sign
+    flips are one tiny library kernel each (more3d_negate_odd)."""
+    lib = _lib.load()
+    with torch.cuda.device(mm.device):
+        check(lib.more3d_negate_odd(ptr(mm), int(mm.numel()), stream_ptr()))
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=group)
+        check(lib.more3d_negate_odd(ptr(mm), int(mm.numel()), stream_ptr()))
+    return mm
 
 
 def strip_saliency(own, ghosts, radii, params, curvature_weight, reduce_minmax=None, out_host=None,
-                   copy_stream=None):
-    """Saliency of the OWNED points of one strip.  own: (n,3) device f64; ghosts: (g,3) device f64
-    (points of the neighbouring strips within 2*r_max).  reduce_minmax(minmax) makes the extrema
-    global (None for a single strip).  Returns {r: saliency (n,) f32} (+ '_pcount' sums in .sum_m)."""
-    from .DM_saliency import Curvature_Kernel, _chi2_table
-    lib = _lib.load()
-    n = int(own.shape[0])
-    local = torch.cat([own, ghosts], dim=0) if ghosts.shape[0] else own
-    dev = local.device
-    ck = Curvature_Kernel()
-    ck.setArgs(alpha=params["alpha"], roughness=params["roughness"], min_points=params["min_points"])
-    eps = ck.epsilon()
+                   copy_stream=None, left=None, lattice=None, bounds=None):
+    """Saliency of the OWNED points of one strip.  own: (n,3) device f64; ghosts: (g,3) device f64 = the points
+    received from the RIGHT neighbour (or all ghosts, when `left` is None and bit-identity with the whole-tile result
+    is not required); left: those from the left neighbour.  reduce_minmax(minmax_row) makes one radius' dk/dn
+    extrema global (None for a single strip).  Returns ({r: saliency (n,) f32}, {r: owned _pcount rows})."""
+    step = StripStep(own, left, ghosts if ghosts is not None and ghosts.shape[0] else None, radii, params,
+                     lattice=lattice, bounds=bounds)
+    step.features()
+    if reduce_minmax is not None:
+        for i, r in enumerate(step.radii):
+            reduce_minmax(step.minmax[i])
+    step.blend(curvature_weight)
     out = {}
-    sum_m = {}
-    g = None
-    for r in sorted(radii):
-        rho = r / np.sqrt(2.0)
-        want = cell_for_radius(r)
-        if g is None or not (g.cell <= want * (1 + 1e-12) and want / g.cell <= 2.05):
-            if g is not None:
-                g.close()
-            g = UniformGrid(local, want)       # shared by the wider radii (see PointCloudDM.grid)
-        # grid-order columns (coalesced writes); dk/dn's fused min/max covers the owned points only
-        _, _, _, pcount = g.normals_curvature_gridorder(r, eps, params["min_points"])
-        length = 1024
-        while True:
-            try:
-                dk, dn, minmax = g.dk_dn_gridorder(r, rho, params["sigma_normal"], params["sigma_curvature"],
-                                                   _chi2_table(params["alpha"], length, dev), params["min_points"],
-                                                   n_owned=n)
-                break
-            except _lib.More3DError as e:
-                if "error -4" not in str(e) or length >= (1 << 22):
-                    raise
-                length *= 8
-        with torch.cuda.device(dev):
-            if reduce_minmax is not None:
-                reduce_minmax(minmax)
-            nl = int(local.shape[0])
-            sal_g = torch.empty(nl, dtype=torch.float32, device=dev)      # blend is elementwise: grid order
-            check(lib.more3d_saliency_blend(ptr(dk.data), ptr(dn.data), nl, ptr(minmax), float(curvature_weight),
-                                            ptr(sal_g), None, stream_ptr()))
-            sal = GridColumn(dk, sal_g).tensor()[:n]                      # back to point order, owned rows
+    for r in step.radii:
+        sal = step.saliency(r)
         if out_host is not None:
-            if copy_stream is None:
-                out_host[r].copy_(sal, non_blocking=True)
-            else:                                   # D2H on a side stream: overlaps the next radius' kernels
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev)
-                    out_host[r].copy_(sal, non_blocking=True)
-                    sal.record_stream(copy_stream)
+            _copy_out(sal, out_host[r], copy_stream, own.device)
         out[r] = sal
-        sum_m[r] = _OwnedRows(pcount, n)
-    if g is not None:
-        g.close()
-    return out, sum_m
+    need = step.overflow()
+    pc = step.pcount
+    step.close()
+    if need:
+        raise _lib.More3DError("dk/dn: chi2 table too short (%d needed)" % need, _lib.E_RANGE)
+    return out, pc
+
+
+def _copy_out(sal, host, copy_stream, dev):
+    if copy_stream is None:
+        host.copy_(sal, non_blocking=True)
+        return
+    ev = torch.cuda.Event()                     # D2H on a side stream: overlaps the kernels queued next
+    ev.record(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(copy_stream):
+        copy_stream.wait_event(ev)
+        host.copy_(sal, non_blocking=True)
+        sal.record_stream(copy_stream)
 
 
 class StripSaliency:
-    """bench.py's weak-scaling job: rank k owns an n-point strip of a (world * W) x W tile."""
+    """bench.py's multi-GPU job: rank k owns an n-point x-strip of a tile.
+
+    One step = pack both halo bands + bounding box (one kernel) -> ONE all-gather of 8 doubles per rank (global
+    bounding box = the shared column lattice, and the neighbours' halo sizes; the step's only host read before the
+    grid build) -> point-to-point halo exchange -> StripStep: grid over [left ghosts, own, right ghosts] on the
+    tile's lattice, 3 radii of normals / curvature / dk / dn -> ONE all-reduce of all radii's dk/dn extrema ->
+    blend -> ONE all-reduce of the saliency extrema -> histograms -> ONE all-reduce of the 256-bin histograms (the
+    global Otsu input, Downsample.py:54).  Three small collectives per step instead of five per radius; the Otsu
+    thresholds are read lazily (`otsu`)."""
 
     def __init__(self, n, rank, world, device, radii, params, curvature_weight, seed=2, cloud=None, x_range=None,
                  host_buffers=True):
@@ -262,7 +399,7 @@ class StripSaliency:
         strip instead (bench.py's strong-scaling leg); `host_buffers=False` skips the pinned e2e buffers."""
         from . import synthetic
         self.rank, self.world, self.dev = rank, world, device
-        self.radii, self.params, self.cw = tuple(radii), dict(params), curvature_weight
+        self.radii, self.params, self.cw = tuple(sorted(radii)), dict(params), curvature_weight
         self.halo = 2.0 * max(radii) * CELL_MARGIN
         if cloud is None:
             W = float(np.sqrt(n / synthetic.DENSITY))
@@ -285,23 +422,78 @@ class StripSaliency:
             self.d2h_bytes = n * 4 * len(radii)
         else:
             self.out_host, self.h2d_bytes, self.d2h_bytes = None, 0, 0
+        # halo capacity: expected band population from the strip's mean density, with slack; a band that does not
+        # fit raises (the count is checked every step)
+        self.cap = int(1.5 * n * self.halo / max(self.x_hi - self.x_lo, 1e-9)) + 4096
+        self._last = None
         out, pc = self._run(self.resident, None)
-        self.sum_m = {r: float(pc[r].tensor().double().sum()) for r in radii}
+        self.sum_m = {r: float(pc[r].tensor().double().sum()) for r in self.radii}
         # partition-independent checksums of the owned points: sum of the neighbour counts and of the saliency
         # columns' float32 BIT PATTERNS (mod 2^64) -- equal across 1/2/4/8-GPU partitions iff every value is
-        self.checksum = {r: (int(pc[r].tensor().long().sum()), int(out[r].view(torch.int32).long().sum())) for r in radii}
+        self.checksum = {r: (int(pc[r].tensor().long().sum()), int(out[r].view(torch.int32).long().sum())) for r in self.radii}
 
     def _run(self, own, out_host, copy_stream=None):
-        left = gather_rows(own, band_select(own, 0, -np.inf, self.x_lo + self.halo))
-        right = gather_rows(own, band_select(own, 0, self.x_hi - self.halo, np.inf))
-        from_left, from_right = exchange_halos(left, right, self.rank, self.world)
-        ghosts = torch.cat([from_left, from_right], dim=0)
-        out, pc = strip_saliency(own, ghosts, self.radii, self.params, self.cw,
-                                 reduce_minmax=allreduce_minmax, out_host=out_host, copy_stream=copy_stream)
-        # the global saliency histogram (256 bins, one all-reduce) and its Otsu threshold, per radius
-        job = DeviceOtsu([out[r] for r in self.radii])         # all radii queued behind the saliency kernels ...
-        self.otsu = dict(zip(self.radii, job.results()))       # ... and read with one wait at the end of the step
+        rank, world = self.rank, self.world
+        left_below = self.x_lo + self.halo if rank > 0 else -np.inf
+        right_from = self.x_hi - self.halo if rank < world - 1 else np.inf
+        send_l, send_r, info = strip_pack(own, left_below, right_from, self.cap)
+        allinfo = torch.empty((world, 8), dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(allinfo, info)
+        ai = allinfo.cpu().numpy()                       # the step's host read: global box + every halo size
+        cnt = ai[:, 6:8].astype(np.int64)
+        if cnt.max() > self.cap:
+            raise _lib.More3DError("halo band holds %d points, capacity %d" % (int(cnt.max()), self.cap), _lib.E_RANGE)
+        gmin, gmax = ai[:, 0:3].min(axis=0), ai[:, 3:6].max(axis=0)
+        n_from_l = int(cnt[rank - 1, 1]) if rank > 0 else 0
+        n_from_r = int(cnt[rank + 1, 0]) if rank < world - 1 else 0
+        from_l = torch.empty((n_from_l, 3), dtype=torch.float64, device=self.dev)
+        from_r = torch.empty((n_from_r, 3), dtype=torch.float64, device=self.dev)
+        ops = []
+        if rank > 0:
+            if cnt[rank, 0]:
+                ops.append(dist.P2POp(dist.isend, send_l[:int(cnt[rank, 0])], rank - 1))
+            if n_from_l:
+                ops.append(dist.P2POp(dist.irecv, from_l, rank - 1))
+        if rank < world - 1:
+            if cnt[rank, 1]:
+                ops.append(dist.P2POp(dist.isend, send_r[:int(cnt[rank, 1])], rank + 1))
+            if n_from_r:
+                ops.append(dist.P2POp(dist.irecv, from_r, rank + 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        # the tile's column lattice (the origin a single grid over the whole tile would use) and this strip's box:
+        # its own points' box widened by the halo in x, the tile's range in y and z
+        cell = cell_for_radius(self.radii[0])
+        lattice = (float(gmin[0]) - cell, float(gmin[1]) - cell)
+        bounds = (max(min(float(ai[rank, 0]), self.x_lo) - self.halo, float(gmin[0])), float(gmin[1]), float(gmin[2]),
+                  min(max(float(ai[rank, 3]), self.x_hi) + self.halo, float(gmax[0])), float(gmax[1]), float(gmax[2]))
+        step = StripStep(own, from_l if n_from_l else None, from_r if n_from_r else None, self.radii, self.params,
+                         lattice=lattice, bounds=bounds)
+        allreduce_minmax_rows(step.features())
+        step.blend(self.cw)
+        out = {}
+        for r in self.radii:
+            out[r] = step.saliency(r)
+            if out_host is not None:
+                _copy_out(out[r], out_host[r], copy_stream, self.dev)
+        allreduce_minmax_rows(step.owned_minmax())
+        dist.all_reduce(step.histograms(), op=dist.ReduceOp.SUM)
+        pc = step.pcount
+        res = step.result()
+        step.close()
+        if self._last is not None:
+            # the previous step's overflow words: read now, one step late, so that no step waits for its own
+            need = self._last.overflow()
+            if need:
+                raise _lib.More3DError("dk/dn: chi2 table too short (%d needed)" % need, _lib.E_RANGE)
+        self._last = res
         return out, pc
+
+    @property
+    def otsu(self):
+        """{radius: global Otsu threshold of the saliency column} of the last step (host read)."""
+        return self._last.otsu()
 
     def step_resident(self):
         return self._run(self.resident, None)[0]
@@ -313,7 +505,7 @@ class StripSaliency:
 
     def steps_e2e(self, k):
         """k strips one after the other from pinned host memory; the upload of strip i+1 runs on a copy stream
-        while strip i is computed (the D2H of the saliency columns is issued per radius by strip_saliency)."""
+        while strip i is computed (the D2H of the saliency columns is issued per radius by the step)."""
         cur = torch.cuda.current_stream(self.dev)
         up = torch.cuda.Stream(device=self.dev)
         down = torch.cuda.Stream(device=self.dev)

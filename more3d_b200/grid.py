@@ -82,16 +82,31 @@ class GridColumn:
 class UniformGrid:
     """Spatial index replacing the reference's ball tree (BallTreePointSet.py:35)."""
 
-    def __init__(self, xyz, cell):
+    def __init__(self, xyz, cell, left=None, right=None, lattice=None, bounds=None):
+        """xyz: (N,3) cloud.  Strips (multi-GPU): `left` / `right` are the ghost points received from the two
+        neighbours -- the grid indexes the three tensors in place as one cloud [left, xyz, right] (no concatenated
+        copy); `lattice` = (origin_x, origin_y) of the column lattice shared by all strips of the tile (bit-identical
+        binning, ordering and sums to the whole-tile grid); `bounds` = (min x, y, z, max x, y, z) if already known."""
         self.lib = _lib.load()
         self.xyz = as_device_points(xyz)
-        self.n = int(self.xyz.shape[0])
+        self.device = self.xyz.device
+        segs = [t for t in (left, self.xyz, right) if t is not None and int(t.shape[0]) > 0]
+        segs = [as_device_points(t, self.device) for t in segs]
+        self._segs = segs                                   # the grid reads them during the build only
+        self.n_left = int(left.shape[0]) if left is not None else 0
+        self.n_own = int(self.xyz.shape[0])
+        self.n = sum(int(t.shape[0]) for t in segs)
         if self.n == 0:
             raise ValueError("empty cloud")
-        self.device = self.xyz.device
+        self.requested_cell = float(cell)
         h = C.c_void_p()
+        ptrs = (C.c_void_p * len(segs))(*[t.data_ptr() for t in segs])
+        cnts = (C.c_int64 * len(segs))(*[int(t.shape[0]) for t in segs])
+        lat = None if lattice is None else (C.c_double * 2)(float(lattice[0]), float(lattice[1]))
+        bnd = None if bounds is None else (C.c_double * 6)(*[float(v) for v in bounds])
         with torch.cuda.device(self.device):
-            check(self.lib.more3d_grid_create(ptr(self.xyz), self.n, float(cell), stream_ptr(), C.byref(h)))
+            check(self.lib.more3d_grid_create_segments(ptrs, cnts, len(segs), float(cell), lat, bnd, stream_ptr(),
+                                                       C.byref(h)))
         self._h = h
         info = (C.c_int64 * 3)()
         geom = (C.c_double * 3)()
@@ -205,17 +220,21 @@ class UniformGrid:
             self._feat_cols = (cols[0], cols[2])     # the cached feature records hold exactly these two
             return cols
 
-    def dk_dn_gridorder(self, r, rho, sigma_normal, sigma_curvature, chi2_table, min_points, n_owned=0):
+    def dk_dn_gridorder(self, r, rho, sigma_normal, sigma_curvature, chi2_table, min_points, own_lo=0, n_owned=0,
+                        status=None, minmax=None):
         """dk / dn from the feature records cached by the last normals_curvature[_gridorder]; GridColumns.
-        n_owned > 0: minmax covers the points with original index < n_owned only (strip + ghosts)."""
+        n_owned > 0: minmax covers the points with original index in [own_lo, own_lo + n_owned) only (a strip's own
+        points between its ghosts).  status: device int32 word for the chi2-table overflow (no synchronisation; see
+        more3d_dk_dn) -- None makes the call itself check and raise.  minmax: optional (4,) f32 device slice to fill."""
         with torch.cuda.device(self.device):
             dk = self._new((self.n,), torch.float32)
             dn = self._new((self.n,), torch.float32)
-            minmax = self._new((4,), torch.float32)
+            if minmax is None:
+                minmax = self._new((4,), torch.float32)
             check(self.lib.more3d_dk_dn_gridorder(self._h, float(r), float(rho), float(sigma_normal),
                                                   float(sigma_curvature), ptr(chi2_table), int(chi2_table.numel()),
-                                                  int(min_points), int(n_owned), ptr(dk), ptr(dn), ptr(minmax),
-                                                  stream_ptr()))
+                                                  int(min_points), int(own_lo), int(n_owned), ptr(dk), ptr(dn),
+                                                  ptr(minmax), ptr(status), stream_ptr()))
             return GridColumn(self, dk), GridColumn(self, dn), minmax
 
     def order_tensor(self):
@@ -226,7 +245,7 @@ class UniformGrid:
                 o = self._order = self.order()
         return o
 
-    def dk_dn(self, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, min_points):
+    def dk_dn(self, r, normals, K, rho, sigma_normal, sigma_curvature, chi2_table, min_points, status=None):
         """chi2_table: device f64 tensor, chi2.ppf(alpha, df) for df = 0..len-1."""
         with torch.cuda.device(self.device):
             dk = self._new((self.n,), torch.float32)
@@ -238,5 +257,5 @@ class UniformGrid:
                 normals = K = None      # untouched since the fused pass: use the grid's cached feature records
             check(self.lib.more3d_dk_dn(self._h, float(r), ptr(normals), ptr(K), float(rho), float(sigma_normal),
                                         float(sigma_curvature), ptr(chi2_table), int(chi2_table.numel()),
-                                        int(min_points), ptr(dk), ptr(dn), ptr(minmax), stream_ptr()))
+                                        int(min_points), ptr(dk), ptr(dn), ptr(minmax), ptr(status), stream_ptr()))
             return dk, dn, minmax

@@ -16,7 +16,7 @@ DEFAULTS = dict(roughness=0.02, alpha=0.05, sigma_normal=0.01, sigma_curvature=0
 
 def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, sigma_normal=0.01,
                         sigma_curvature=0.01, curvature_weight=0.5, min_points=4, keep=False,
-                        out_host=None, copy_stream=None):
+                        out_host=None, copy_stream=None, chi2_table_len=1024, deferred=None):
     """Run the saliency pipeline at each radius (rho = r / sqrt(2)).
 
     xyz: (N,3) float64, numpy (host; copied to the device here) or a CUDA tensor.
@@ -24,8 +24,14 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
     ``out_host``: optional {radius: pinned float32 host tensor} to receive the result (D2H copy).
     ``copy_stream``: the stream those D2H copies run on; when given, the caller waits for it (the compute stream
     does not, so the next tile's kernels start while the last column of this one is still travelling).
+    The chi2-table overflow words of the dk/dn passes are read ONCE, after the last radius was queued (no host
+    synchronisation between the radii); on overflow the pipeline is repeated with a table of the reported length.
+    ``deferred``: a list -- the check is then left to the caller: a callable returning 0 or the needed table length
+    is appended instead (tile streaming checks tile k while tile k + 1 computes).
     """
     dm = PointCloudDM(xyz)
+    dm.defer_checks = True
+    dm.chi2_table_len = int(chi2_table_len)
     out = {}
     own_copy_stream = copy_stream is None
     if out_host is not None and copy_stream is None:
@@ -54,6 +60,15 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
     if out_host is not None and own_copy_stream:
         torch.cuda.current_stream(dm.device).wait_stream(copy_stream)
     dm.drop_grids()
+    if deferred is not None:
+        side = copy_stream if copy_stream is not None else torch.cuda.Stream(device=dm.device)
+        deferred.append(dm.check_pending_async(side))
+        return out
+    need = dm.check_pending()
+    if need:
+        return multiscale_saliency(xyz, radii, roughness, alpha, sigma_normal, sigma_curvature, curvature_weight,
+                                   min_points, keep, out_host, None if own_copy_stream else copy_stream,
+                                   chi2_table_len=max(need, 8 * int(chi2_table_len)))
     return out
 
 
@@ -94,19 +109,40 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
         return d, ev
 
     results = []
+    checks = []
+    redo = []
+
+    def settle(j):
+        # the overflow word of tile j is read while a later tile computes; a tile whose chi2 table was too short (rare:
+        # > 1023 active neighbours in one neighbourhood) is repeated at the end with the reported length
+        need = checks[j]()
+        if need:
+            redo.append((j, need))
+
     nxt = upload(0)
     for k in range(len(tiles)):
         d, ev = nxt
         if k + 1 < len(tiles):
             nxt = upload(k + 1)                # enqueued before tile k's kernels: overlaps them
         cur.wait_event(ev)
+        pend = []
         res = multiscale_saliency(d, radii, out_host=None if out_hosts is None else out_hosts[k],
-                                  copy_stream=down, **params)
+                                  copy_stream=down, deferred=pend, **params)
+        checks.append(pend[0])
         results.append(res if keep_results else None)
         del res
         done = torch.cuda.Event()
         done.record(cur)
         freed[k % len(bufs)] = done
+        if k > 0:
+            settle(k - 1)
+    settle(len(tiles) - 1)
     cur.wait_stream(down)
     cur.synchronize()
+    for j, need in redo:
+        res = multiscale_saliency(tiles[j].to(dev), radii, out_host=None if out_hosts is None else out_hosts[j],
+                                  chi2_table_len=need, **params)
+        cur.synchronize()
+        if keep_results:
+            results[j] = res
     return results

@@ -23,47 +23,116 @@ def test_band_select_is_stable_and_exact():
 
 
 @pytest.mark.parametrize("G", [2, 4])
-def test_logical_strips_match_untiled(G):
+def test_logical_strips_bit_identical_to_untiled(G):
+    """G logical ranks on one GPU, phase by phase as StripSaliency runs them (the all-reduces are replaced by the
+    same reductions on the host): strips on the tile's column lattice, cloud = [left ghosts, own, right ghosts].
+    Every per-point value of every strip is BIT-IDENTICAL to the single-grid result of the whole tile, and the
+    histogram chain gives the whole column's Otsu threshold."""
     import torch
     from more3d_b200 import synthetic
-    from more3d_b200.grid import CELL_MARGIN
-    from more3d_b200.distributed import band_select, gather_rows, strip_saliency, strip_bounds
+    from more3d_b200.grid import CELL_MARGIN, cell_for_radius
+    from more3d_b200.distributed import StripStep, strip_pack
     from more3d_b200.pipeline import multiscale_saliency
+    from oracle import ref_path as rp
     pts = synthetic.terrain(120000, seed=8)
     whole = multiscale_saliency(pts, RADII, curvature_weight=0.5, keep=True, **PARAMS)
-    d = torch.from_numpy(pts).cuda()
-    edges = strip_bounds(pts[:, 0].min(), pts[:, 0].max(), G)
-    edges[0], edges[-1] = -np.inf, np.inf
+    cell = cell_for_radius(min(RADII))
+    lo = pts.min(axis=0)
+    lattice = (lo[0] - cell, lo[1] - cell)                  # the origin more3d_grid_create gives the whole-tile grid
+    col = np.floor((pts[:, 0] - lattice[0]) * (1.0 / cell)).astype(np.int64)
+    cuts = [int(round(k * (col.max() + 1) / G)) for k in range(G + 1)]
+    owner = np.searchsorted(np.array(cuts[1:-1]), col, side="right")     # strips are cut on column boundaries
     halo = 2.0 * max(RADII) * CELL_MARGIN
-    owned, ghosts = [], []
+    d = torch.from_numpy(pts).cuda()
+    steps, own_idx = [], []
     for k in range(G):
-        oi = band_select(d, 0, edges[k], edges[k + 1])
-        gi = torch.cat([band_select(d, 0, edges[k] - halo, edges[k]), band_select(d, 0, edges[k + 1], edges[k + 1] + halo)])
-        owned.append(oi)
-        ghosts.append(gi)
-    # pass 1: local extrema; pass 2: blend with the global extrema (what the all-reduce delivers)
-    local_mm = {r: [] for r in RADII}
-    for k in range(G):
-        it = iter(RADII)
-        strip_saliency(gather_rows(d, owned[k]), gather_rows(d, ghosts[k]), RADII, PARAMS, 0.5,
-                       reduce_minmax=lambda mm: local_mm[next(it)].append(mm.clone()))
-    glob = {}
-    for r in RADII:
-        st = torch.stack(local_mm[r])
-        glob[r] = torch.stack([st[:, 0].min(), st[:, 1].max(), st[:, 2].min(), st[:, 3].max()])
-    for r in RADII:
-        assert torch.equal(glob[r].cpu(), whole[r]["_dkdn_minmax"].cpu())
-    for k in range(G):
-        it = iter(RADII)
-        out, pc = strip_saliency(gather_rows(d, owned[k]), gather_rows(d, ghosts[k]), RADII, PARAMS, 0.5,
-                                 reduce_minmax=lambda mm: mm.copy_(glob[next(it)]))
-        oi = owned[k].cpu().numpy()
+        oi = np.flatnonzero(owner == k)
+        x_lo, x_hi = lattice[0] + cuts[k] * cell, lattice[0] + cuts[k + 1] * cell
+        li = np.flatnonzero((owner < k) & (pts[:, 0] >= x_lo - halo))
+        ri = np.flatnonzero((owner > k) & (pts[:, 0] < x_hi + halo))
+        own = d[torch.from_numpy(oi).cuda()].contiguous()
+        # the halo bands the neighbours would pack (more3d_strip_pack): stable, exact
+        if k > 0:
+            prev = d[torch.from_numpy(np.flatnonzero(owner == k - 1)).cuda()].contiguous()
+            _, band, info = strip_pack(prev, -np.inf, x_lo - halo, 100000)
+            m = int(info[7].item())
+            want = pts[np.flatnonzero((owner == k - 1) & (pts[:, 0] >= x_lo - halo))]
+            assert np.array_equal(band[:m].cpu().numpy(), want)
+            box = info[:6].cpu().numpy()
+            prev_pts = pts[owner == k - 1]
+            assert np.array_equal(box, np.concatenate([prev_pts.min(axis=0), prev_pts.max(axis=0)]))
+        left = d[torch.from_numpy(li).cuda()].contiguous() if len(li) else None
+        right = d[torch.from_numpy(ri).cuda()].contiguous() if len(ri) else None
+        st = StripStep(own, left, right, RADII, PARAMS, lattice=lattice)
+        st.features()
+        steps.append(st)
+        own_idx.append(oi)
+    mm = torch.stack([st.minmax for st in steps])           # (G, R, 4): what the MIN / MAX all-reduce sees
+    glob = torch.stack([mm[:, :, 0].amin(0), mm[:, :, 1].amax(0), mm[:, :, 2].amin(0), mm[:, :, 3].amax(0)], dim=1)
+    for i, r in enumerate(sorted(RADII)):
+        assert torch.equal(glob[i].cpu(), whole[r]["_dkdn_minmax"].cpu())
+    for st in steps:
+        st.minmax.copy_(glob)
+        st.blend(0.5)
+    for st, oi in zip(steps, own_idx):
+        sl = slice(st.n_left, st.n_left + st.n_own)
         for r in RADII:
-            assert np.array_equal(pc[r].tensor().cpu().numpy(), whole[r]["_pcount"].cpu().numpy()[oi])   # integer: exact
-            a = out[r].cpu().numpy().astype(np.float64)
-            b = whole[r]["_saliency"].cpu().numpy()[oi].astype(np.float64)
-            bad = np.abs(a - b) > 1e-5 * np.abs(b) + 1e-7
-            assert bad.sum() <= 2, (k, r, bad.sum())       # threshold straddlers under a different sum order
+            assert np.array_equal(st.pcount[r].tensor().cpu().numpy(), whole[r]["_pcount"].cpu().numpy()[oi])
+            for name, col_ in (("_dk", st.dk[r]), ("_dn", st.dn[r])):
+                assert np.array_equal(col_.tensor()[sl].cpu().numpy(), whole[r][name].cpu().numpy()[oi], equal_nan=True)
+            assert np.array_equal(st.saliency(r).cpu().numpy(), whole[r]["_saliency"].cpu().numpy()[oi], equal_nan=True)
+    smm = torch.stack([st.owned_minmax() for st in steps])
+    gs = torch.stack([smm[:, :, 0].amin(0), smm[:, :, 1].amax(0), smm[:, :, 2].amin(0), smm[:, :, 3].amax(0)], dim=1)
+    hist = 0
+    for st in steps:
+        st.sal_minmax.copy_(gs)
+        hist = hist + st.histograms()
+    for st in steps:
+        st.hist = hist
+    thr = steps[0].result().otsu()
+    for r in RADII:
+        assert thr[r] == rp.otsu_threshold(whole[r]["_saliency"].cpu().numpy())
+    assert all(st.overflow() == 0 for st in steps)
+    [st.close() for st in steps]
+
+
+def test_strip_saliency_wrapper_and_overflow_report():
+    """strip_saliency (own + one ghost tensor, strip-local lattice) stays within tolerance of the untiled result, and
+    a chi2 table that is too short is reported through the status word, not by a string-matched exception."""
+    import torch
+    from more3d_b200 import synthetic, _lib
+    from more3d_b200.grid import CELL_MARGIN
+    from more3d_b200.distributed import band_select, gather_rows, strip_saliency, StripStep
+    from more3d_b200.pipeline import multiscale_saliency
+    pts = synthetic.terrain(60000, seed=9)
+    whole = multiscale_saliency(pts, RADII, curvature_weight=0.5, keep=True, **PARAMS)
+    d = torch.from_numpy(pts).cuda()
+    mid = float(np.median(pts[:, 0]))
+    halo = 2.0 * max(RADII) * CELL_MARGIN
+    oi = band_select(d, 0, -np.inf, mid)
+    gi = band_select(d, 0, mid, mid + halo)
+    glob = {r: whole[r]["_dkdn_minmax"] for r in RADII}
+    it = iter(sorted(RADII))
+    out, pc = strip_saliency(gather_rows(d, oi), gather_rows(d, gi), RADII, PARAMS, 0.5,
+                             reduce_minmax=lambda mm: mm.copy_(glob[next(it)]))
+    o = oi.cpu().numpy()
+    for r in RADII:
+        assert np.array_equal(pc[r].tensor().cpu().numpy(), whole[r]["_pcount"].cpu().numpy()[o])
+        a = out[r].cpu().numpy().astype(np.float64)
+        b = whole[r]["_saliency"].cpu().numpy()[o].astype(np.float64)
+        assert (np.abs(a - b) > 1e-5 * np.abs(b) + 1e-7).sum() <= 2       # another sum order: threshold straddlers
+    st = StripStep(gather_rows(d, oi), None, gather_rows(d, gi), RADII, PARAMS, chi2_table_len=16)
+    st.features()
+    need = st.overflow()
+    assert need > 16 and need <= int(whole[max(RADII)]["_pcount"].max()) + 1
+    st.close()
+    with pytest.raises(_lib.More3DError) as e:
+        from more3d_b200.DM_saliency import _chi2_table
+        from more3d_b200.grid import UniformGrid, cell_for_radius
+        g = UniformGrid(d, cell_for_radius(0.5))
+        g.normals_curvature_gridorder(0.5, 0.04, 4)
+        g.dk_dn_gridorder(0.5, 0.35, 0.01, 0.01, _chi2_table(0.05, 8, d.device), 4)      # no status word: raises
+    assert e.value.rc == _lib.E_RANGE
 
 
 def test_device_otsu_matches_oracle():
