@@ -21,6 +21,29 @@ namespace m3d {
 
 constexpr int LT_THREADS = 256;
 
+// node ranges of sklearn's recursive halving (neighbors/_binary_tree.pxi.tp:1033-1083) computed per node by walking
+// down from the root: the path to heap node i is the binary representation of i + 1 below its leading one
+// (0 = left child, 1 = right child); a left child takes floor(cnt / 2) positions, its sibling the rest.
+// A node that is never visited by the recursive build (its parent is a leaf) gets the empty range [0, 0).
+__global__ void __launch_bounds__(LT_THREADS) lt_node_ranges(int64_t n, int64_t n_nodes, int64_t* __restrict__ nstart,
+                                                             int64_t* __restrict__ nend, int32_t* __restrict__ is_leaf) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const unsigned long long path = (unsigned long long)(i + 1);
+    const int depth = 63 - __clzll(path);
+    int64_t b = 0, e = n;
+    bool visited = true;
+    for (int k = depth - 1; k >= 0; --k) {
+        // the node at the current position is internal only if it has children in the heap and >= 2 points
+        if (e - b < 2) { visited = false; break; }
+        const int64_t mid = b + (e - b) / 2;
+        if ((path >> k) & 1ull) b = mid; else e = mid;
+    }
+    if (!visited) { nstart[i] = 0; nend[i] = 0; is_leaf[i] = 0; return; }
+    nstart[i] = b; nend[i] = e;
+    is_leaf[i] = (2 * i + 1 >= n_nodes || e - b < 2) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(LT_THREADS) lt_keys(const double* __restrict__ xyz, int64_t n, int d,
                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,25 +278,11 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     init_device_pool();
     ProfScope prof("balltree_build", s);
 
-    // node ranges are analytic: recursive halving (host, n_nodes <= a few million)
-    std::vector<int64_t> hs((size_t)n_nodes, 0), he((size_t)n_nodes, 0);
-    std::vector<int32_t> hl((size_t)n_nodes, 0);
-    hs[0] = 0; he[0] = n;
-    for (int64_t i = 0; i < n_nodes; ++i) {
-        const int64_t cnt = he[i] - hs[i];
-        if (i > 0) {
-            const int64_t par = (i - 1) / 2;
-            if (hl[par] || he[par] - hs[par] < 2) { hs[i] = he[i] = 0; continue; }   // never visited by sklearn
-        }
-        if (2 * i + 1 >= n_nodes || cnt < 2) { hl[i] = 1; continue; }               // :1060-1070
-        const int64_t n_mid = cnt / 2;
-        hs[2 * i + 1] = hs[i]; he[2 * i + 1] = hs[i] + n_mid;
-        hs[2 * i + 2] = hs[i] + n_mid; he[2 * i + 2] = he[i];
-    }
-    M3D_CUDA(cudaMemcpyAsync(idx_start, hs.data(), (size_t)n_nodes * 8, cudaMemcpyHostToDevice, s));
-    M3D_CUDA(cudaMemcpyAsync(idx_end, he.data(), (size_t)n_nodes * 8, cudaMemcpyHostToDevice, s));
-    M3D_CUDA(cudaMemcpyAsync(is_leaf, hl.data(), (size_t)n_nodes * 4, cudaMemcpyHostToDevice, s));
-    M3D_CUDA(cudaStreamSynchronize(s));   // the host vectors go out of scope below
+    // node ranges are analytic (recursive halving): one thread per node, no host tables
+    lt_node_ranges<<<(unsigned)((n_nodes + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(n, n_nodes, idx_start, idx_end,
+                                                                                       is_leaf);
+    count_launches(1);
+    M3D_CHECK_LAUNCH();
 
     const unsigned nb = (unsigned)((n + LT_THREADS - 1) / LT_THREADS);
     uint64_t *k1 = nullptr, *k2 = nullptr, *ks = nullptr;

@@ -31,23 +31,35 @@ class LodTree:
             rad = torch.empty(self.n_nodes, dtype=torch.float64, device=dev)
             check(lib.more3d_balltree_build(ptr(xyz_dev), self.n, self.leaf_size, ptr(self.idx_array_dev), ptr(start),
                                             ptr(end), ptr(leaf), ptr(rad), stream_ptr()))
-        # node tables are small (<= a few million rows): host copies drive the hierarchy getters, the device
-        # copies the level-of-detail selection (smallest_nodes_dev)
-        self._start_dev, self._leaf_dev, self._rad_dev = start, leaf, rad
-        self.idx_start = start.cpu().numpy()
-        self.idx_end = end.cpu().numpy()
-        self.is_leaf = leaf.cpu().numpy()
-        self.node_radius = rad.cpu().numpy()
+        # node tables: the device copies drive the level-of-detail selection (smallest_nodes_dev); the host copies
+        # behind the hierarchy getters are made on first use (2 M nodes at 50 M points: tens of ms of copies and numpy)
+        self._start_dev, self._end_dev, self._leaf_dev, self._rad_dev = start, end, leaf, rad
+        self._host = None
         self._idx_array = None
-        # a node exists (was visited by the recursive build) iff it is the root or its parent is internal
-        ids = np.arange(self.n_nodes)
-        par = (ids - 1) // 2
-        self.exists = np.ones(self.n_nodes, bool)
-        for lev in range(1, self.n_levels):
-            a, b = (1 << lev) - 1, min((1 << (lev + 1)) - 1, self.n_nodes)
-            p = par[a:b]
-            self.exists[a:b] = self.exists[p] & (self.is_leaf[p] == 0)
-        self.levels = np.floor(np.log2(ids + 1)).astype(np.int64)
+
+    def _tables(self):
+        if self._host is None:
+            h = {"idx_start": self._start_dev.cpu().numpy(), "idx_end": self._end_dev.cpu().numpy(),
+                 "is_leaf": self._leaf_dev.cpu().numpy(), "node_radius": self._rad_dev.cpu().numpy()}
+            # a node exists (was visited by the recursive build) iff it is the root or its parent is internal
+            ids = np.arange(self.n_nodes)
+            par = (ids - 1) // 2
+            exists = np.ones(self.n_nodes, bool)
+            for lev in range(1, self.n_levels):
+                a, b = (1 << lev) - 1, min((1 << (lev + 1)) - 1, self.n_nodes)
+                p = par[a:b]
+                exists[a:b] = exists[p] & (h["is_leaf"][p] == 0)
+            h["exists"] = exists
+            h["levels"] = np.floor(np.log2(ids + 1)).astype(np.int64)
+            self._host = h
+        return self._host
+
+    idx_start = property(lambda self: self._tables()["idx_start"])
+    idx_end = property(lambda self: self._tables()["idx_end"])
+    is_leaf = property(lambda self: self._tables()["is_leaf"])
+    node_radius = property(lambda self: self._tables()["node_radius"])
+    exists = property(lambda self: self._tables()["exists"])
+    levels = property(lambda self: self._tables()["levels"])
 
     @property
     def idx_array(self):

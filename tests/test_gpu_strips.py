@@ -91,7 +91,11 @@ def test_logical_strips_bit_identical_to_untiled(G):
         st.hist = hist
     thr = steps[0].result().otsu()
     for r in RADII:
-        assert thr[r] == rp.otsu_threshold(whole[r]["_saliency"].cpu().numpy())
+        sal = whole[r]["_saliency"].cpu().numpy()
+        # a point whose active weights sum to 0 carries dk = NaN (DM_saliency.py:316) and hence a NaN saliency; the
+        # extrema and the histogram leave it out (declared choice), so does the oracle call here
+        assert np.isnan(sal).sum() <= 3
+        assert thr[r] == rp.otsu_threshold(sal[~np.isnan(sal)])
     assert all(st.overflow() == 0 for st in steps)
     [st.close() for st in steps]
 
