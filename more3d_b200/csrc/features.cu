@@ -2,6 +2,7 @@
 // curvature, and the dk/dn centre-surround pass.
 // Replaces Curvature_Kernel.process (DM_saliency.py:88-157), Saliency_Kernel.process (:219-324) and the
 // normals precondition (DM_saliency.py:329-330).
+#include <stdlib.h>
 #include "gridview.cuh"
 #include "eig3.cuh"
 
@@ -166,81 +167,78 @@ static double zk100_threshold() {
     return x;
 }
 
-template <bool TALL>
-__global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
-                                                   DkDnParams prm, const double* __restrict__ chi2_table,
-                                                   float* __restrict__ dk_out, float* __restrict__ dn_out,
-                                                   unsigned* __restrict__ mm /* ordered min/max x4 */,
-                                                   int* __restrict__ err) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float dkf = 0.0f, dnf = 0.0f;
-    const bool live = i < g.n;
-    bool owned = false;
-    if (live) {
-        const D4 pa = ld_d4(feat + i, 0), pb = ld_d4(feat + i, 1);   // (x y z K) (nx ny nz flags)
-        const double px = pa.x, py = pa.y, pz = pa.z;
-        const long long pflags = __double_as_longlong(pa.w) & 3LL;
-        const double Kp = __longlong_as_double(__double_as_longlong(pa.w) & ~3LL);
-        const double pnx = pb.x, pny = pb.y, pnz = pb.z;
-        int m = 0, mu = 0, nact = 0, zn = 0, zk = 0, zk100 = 0;
-        double s1n = 0, s2n = 0, s1k = 0, s2k = 0, wn = 0, wk = 0, wsum = 0;
-        // Branch-free candidate body: every lane evaluates the whole expression and the accept / np.unique
-        // decisions enter as selects.  With 32 lanes at independent positions of their rows some lane accepts at
-        // practically every step, so a branch saves no issue slots -- it only serialises two dependent loads per
-        // candidate (ncu: 45 % of the stall samples sat on the first use of each load).  Without control flow both
-        // 32-B halves of the unrolled candidates are requested up front.
-        walk_candidates_pipelined<TALL>(g, px, py, pz, prm.r, prm.s, [&](int64_t j) {
-            D4x2 c;
-            c.a = ld_d4(feat + j, 0);
-            c.b = ld_d4(feat + j, 1);
-            return c;
-        }, [&](const D4x2& c) {
-            const D4& qa = c.a;
-            const D4& qb = c.b;
-            const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);   // :256-257
-            const long long kb = __double_as_longlong(qa.w);
-            const bool in = d2 <= prm.r2;
-            const bool u = in & !((int)kb & 1);                               // np.unique, :247
-            double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);         // :261
-            double dk = Kp - __longlong_as_double(kb & ~3LL);                 // :262
-            dn = u ? dn : 0.0;
-            dk = u ? dk : 0.0;
-            // opaque to the optimiser: keeps |.| as an operand modifier of the consumers instead of a
-            // second, separately masked copy of each value
-            asm("" : "+d"(dn));
-            asm("" : "+d"(dk));
-            // ring weight on the squared distance (:272-275): d/rho2 below rho2, 2 - d/rho2 above,
-            // 0 at equality, clamped at 0.  (-1/rho2)*d + 2 == 2 - (1/rho2)*d bit for bit.
-            const double t = __dmul_rn(prm.inv_rho2, d2);
-            double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
-            const bool keep = u & (d2 != prm.rho2) & !(w < 0.0);
-            w = keep ? w : 0.0;
-            s1n += dn; s2n += dn * dn;
-            s1k += dk; s2k += dk * dk;
-            // counters as predicated adds (one instruction each): m, mu, then with act = w > 0.01 (:279)
-            // nact, zn (|dn| < 0.016, :286), zk (|dk| <= 0.04, :287), zk100 (|100 dk| <= 0.04, :290)
-            asm("{ .reg .pred pin, pu, pa, q;\n"
-                "  setp.ne.u32 pin, %6, 0;\n"
-                "  setp.ne.u32 pu, %7, 0;\n"
-                "  @pin add.s32 %0, %0, 1;\n"
-                "  @pu add.s32 %1, %1, 1;\n"
-                "  setp.gt.f64 pa, %8, %11;\n"
-                "  @pa add.s32 %2, %2, 1;\n"
-                "  .reg .f64 an, ak;\n"
-                "  abs.f64 an, %9;\n"
-                "  abs.f64 ak, %10;\n"
-                "  setp.lt.and.f64 q, an, %12, pa;\n"
-                "  @q add.s32 %3, %3, 1;\n"
-                "  setp.le.and.f64 q, ak, %13, pa;\n"
-                "  @q add.s32 %4, %4, 1;\n"
-                "  setp.le.and.f64 q, ak, %14, pa;\n"
-                "  @q add.s32 %5, %5, 1;\n"
-                "}"
-                : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zn), "+r"(zk), "+r"(zk100)
-                : "r"((unsigned)in), "r"((unsigned)u), "d"(w), "d"(dn), "d"(dk), "d"(0.01), "d"(0.016), "d"(0.04),
-                  "d"(prm.zk100_thr));
-            wn += fabs(dn) * w; wk += dk * w; wsum += w;                      // :300, :316
-        });
+// One query point's state of Saliency_Kernel.process: init() from its own record, add() per candidate, finish().
+// Shared by the global-memory walk (dkdn_kernel) and the shared-memory staged walk (dkdn_smem_kernel): the two produce
+// bit-identical results because they execute the same expression on the same candidates in the same order.
+struct DkdnAcc {
+    double px, py, pz, Kp, pnx, pny, pnz;
+    long long pflags;
+    int m, mu, nact, zn, zk, zk100;
+    double s1n, s2n, s1k, s2k, wn, wk, wsum;
+
+    __device__ __forceinline__ void init(const D4& pa, const D4& pb) {   // (x y z K) (nx ny nz flags)
+        px = pa.x; py = pa.y; pz = pa.z;
+        pflags = __double_as_longlong(pa.w) & 3LL;
+        Kp = __longlong_as_double(__double_as_longlong(pa.w) & ~3LL);
+        pnx = pb.x; pny = pb.y; pnz = pb.z;
+        m = mu = nact = zn = zk = zk100 = 0;
+        s1n = s2n = s1k = s2k = wn = wk = wsum = 0.0;
+    }
+
+    // Branch-free candidate body: every lane evaluates the whole expression and the accept / np.unique
+    // decisions enter as selects.  With 32 lanes at independent positions of their rows some lane accepts at
+    // practically every step, so a branch saves no issue slots -- it only serialises two dependent loads per
+    // candidate (ncu: 45 % of the stall samples sat on the first use of each load).  Without control flow both
+    // 32-B halves of the unrolled candidates are requested up front.
+    __device__ __forceinline__ void add(const D4& qa, const D4& qb, const DkDnParams& prm) {
+        const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);   // :256-257
+        const long long kb = __double_as_longlong(qa.w);
+        const bool in = d2 <= prm.r2;
+        const bool u = in & !((int)kb & 1);                               // np.unique, :247
+        double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);         // :261
+        double dk = Kp - __longlong_as_double(kb & ~3LL);                 // :262
+        dn = u ? dn : 0.0;
+        dk = u ? dk : 0.0;
+        // opaque to the optimiser: keeps |.| as an operand modifier of the consumers instead of a
+        // second, separately masked copy of each value
+        asm("" : "+d"(dn));
+        asm("" : "+d"(dk));
+        // ring weight on the squared distance (:272-275): d/rho2 below rho2, 2 - d/rho2 above,
+        // 0 at equality, clamped at 0.  (-1/rho2)*d + 2 == 2 - (1/rho2)*d bit for bit.
+        const double t = __dmul_rn(prm.inv_rho2, d2);
+        double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
+        const bool keep = u & (d2 != prm.rho2) & !(w < 0.0);
+        w = keep ? w : 0.0;
+        s1n += dn; s2n += dn * dn;
+        s1k += dk; s2k += dk * dk;
+        // counters as predicated adds (one instruction each): m, mu, then with act = w > 0.01 (:279)
+        // nact, zn (|dn| < 0.016, :286), zk (|dk| <= 0.04, :287), zk100 (|100 dk| <= 0.04, :290)
+        asm("{ .reg .pred pin, pu, pa, q;\n"
+            "  setp.ne.u32 pin, %6, 0;\n"
+            "  setp.ne.u32 pu, %7, 0;\n"
+            "  @pin add.s32 %0, %0, 1;\n"
+            "  @pu add.s32 %1, %1, 1;\n"
+            "  setp.gt.f64 pa, %8, %11;\n"
+            "  @pa add.s32 %2, %2, 1;\n"
+            "  .reg .f64 an, ak;\n"
+            "  abs.f64 an, %9;\n"
+            "  abs.f64 ak, %10;\n"
+            "  setp.lt.and.f64 q, an, %12, pa;\n"
+            "  @q add.s32 %3, %3, 1;\n"
+            "  setp.le.and.f64 q, ak, %13, pa;\n"
+            "  @q add.s32 %4, %4, 1;\n"
+            "  setp.le.and.f64 q, ak, %14, pa;\n"
+            "  @q add.s32 %5, %5, 1;\n"
+            "}"
+            : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zn), "+r"(zk), "+r"(zk100)
+            : "r"((unsigned)in), "r"((unsigned)u), "d"(w), "d"(dn), "d"(dk), "d"(0.01), "d"(0.016), "d"(0.04),
+              "d"(prm.zk100_thr));
+        wn += fabs(dn) * w; wk += dk * w; wsum += w;                      // :300, :316
+    }
+
+    __device__ __forceinline__ void finish(const DkDnParams& prm, const double* __restrict__ chi2_table, int* err,
+                                           float& dkf, float& dnf) {
+        dkf = 0.0f; dnf = 0.0f;
         if (!(pflags & 2LL) && m >= prm.min_points) {                         // :225-229, :240-244
             if (nact >= prm.table_len) {
                 atomicMax(err, nact + 1);       // the table length that would have sufficed
@@ -270,6 +268,47 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
                 dkf = (float)dk; dnf = (float)dn;
             }
         }
+    }
+};
+
+// fused Histo min/max (DM_saliency.py:562-568): warp shuffle, then one atomic per warp.
+// NaN (a neighbourhood whose active weights sum to 0 gives dk = |0/0|, DM_saliency.py:316) stays in the column
+// but is kept out of the extrema -- declared choice: one NaN must not poison every normalised value
+__device__ __forceinline__ void dkdn_minmax(unsigned lo_k, unsigned hi_k, unsigned lo_n, unsigned hi_n,
+                                            unsigned* __restrict__ mm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_k = min(lo_k, __shfl_xor_sync(0xffffffffu, lo_k, o));
+        hi_k = max(hi_k, __shfl_xor_sync(0xffffffffu, hi_k, o));
+        lo_n = min(lo_n, __shfl_xor_sync(0xffffffffu, lo_n, o));
+        hi_n = max(hi_n, __shfl_xor_sync(0xffffffffu, hi_n, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k);
+        atomicMin(mm + 2, lo_n); atomicMax(mm + 3, hi_n);
+    }
+}
+
+template <bool TALL>
+__global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                   DkDnParams prm, const double* __restrict__ chi2_table,
+                                                   float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                   unsigned* __restrict__ mm /* ordered min/max x4 */,
+                                                   int* __restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float dkf = 0.0f, dnf = 0.0f;
+    const bool live = i < g.n;
+    bool owned = false;
+    if (live) {
+        DkdnAcc acc;
+        acc.init(ld_d4(feat + i, 0), ld_d4(feat + i, 1));
+        walk_candidates_pipelined<TALL>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
+            D4x2 c;
+            c.a = ld_d4(feat + j, 0);
+            c.b = ld_d4(feat + j, 1);
+            return c;
+        }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
+        acc.finish(prm, chi2_table, err, dkf, dnf);
         const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
         const int64_t orig = (prm.grid_order && all_owned)
                                  ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
@@ -279,24 +318,129 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
         owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
     }
     if (mm) {
-        // fused Histo min/max (DM_saliency.py:562-568): warp shuffle, then one atomic per warp
-        // NaN (a neighbourhood whose active weights sum to 0 gives dk = |0/0|, DM_saliency.py:316) stays in the column
-        // but is kept out of the extrema -- declared choice: one NaN must not poison every normalised value
         const bool ck = live && owned && !isnan(dkf), cn = live && owned && !isnan(dnf);
-        unsigned lo_k = ck ? f32_ordered(dkf) : 0xffffffffu, hi_k = ck ? f32_ordered(dkf) : 0u;
-        unsigned lo_n = cn ? f32_ordered(dnf) : 0xffffffffu, hi_n = cn ? f32_ordered(dnf) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo_k = min(lo_k, __shfl_xor_sync(0xffffffffu, lo_k, o));
-            hi_k = max(hi_k, __shfl_xor_sync(0xffffffffu, hi_k, o));
-            lo_n = min(lo_n, __shfl_xor_sync(0xffffffffu, lo_n, o));
-            hi_n = max(hi_n, __shfl_xor_sync(0xffffffffu, hi_n, o));
+        dkdn_minmax(ck ? f32_ordered(dkf) : 0xffffffffu, ck ? f32_ordered(dkf) : 0u,
+                    cn ? f32_ordered(dnf) : 0xffffffffu, cn ? f32_ordered(dnf) : 0u, mm);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6, shared-memory staged variant (BASELINE.json north_star: "shared-memory staging of candidate cells and
+// warp-cooperative, vectorised float4 point loads").  One CTA per block of CB columns of one grid row: the CTA's
+// queries are the points of those columns (a contiguous run of sorted positions), their candidates the (2s+1)
+// contiguous record ranges of the block's stencil rows widened by s columns.  All threads copy those ranges with
+// coalesced 16-byte loads into shared memory, split into four arrays of 16-byte quarter records so that lanes at
+// neighbouring records hit different banks and lanes at the same record are served by one broadcast; every thread
+// then walks ITS OWN sub-range of every row out of shared memory -- same candidates, same order, same arithmetic as
+// dkdn_kernel, hence bit-identical outputs.  A block whose ranges exceed the staging capacity walks global memory.
+// ------------------------------------------------------------------------------------------
+constexpr int SMW_THREADS = 128;
+constexpr int SMW_MAX_ROWS = 13;       // s <= 6
+
+__device__ __forceinline__ D4 lds_d4(const double2* __restrict__ lo, const double2* __restrict__ hi, uint32_t j) {
+    const double2 a = lo[j], b = hi[j];
+    D4 r;
+    r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+
+__global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                                DkDnParams prm, const double* __restrict__ chi2_table,
+                                                                float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                                unsigned* __restrict__ mm, int* __restrict__ err,
+                                                                int cb, int nbx, int cap) {
+    extern __shared__ __align__(16) unsigned char smw[];
+    double2* q0 = reinterpret_cast<double2*>(smw);          // (x, y)
+    double2* q1 = q0 + cap;                                 // (z, K | flags)
+    double2* q2 = q1 + cap;                                 // (nx, ny)
+    double2* q3 = q2 + cap;                                 // (nz, pad)
+    uint32_t* cs = reinterpret_cast<uint32_t*>(q3 + cap);   // rows x csw: staged offsets of the widened columns
+    __shared__ uint32_t row_b[SMW_MAX_ROWS], row_off[SMW_MAX_ROWS + 1];
+
+    const int iy = blockIdx.x / nbx, bx = blockIdx.x - iy * nbx;
+    const int c0 = bx * cb, c1 = min(c0 + cb, g.nx);
+    const uint32_t qa = __ldg(g.col_start + (size_t)iy * g.nx + c0), qb = __ldg(g.col_start + (size_t)iy * g.nx + c1);
+    if (qa == qb) return;                                   // no query in this block (uniform for the CTA)
+    const int s = prm.s;
+    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1), nrows = y1 - y0 + 1;
+    const int xs0 = max(c0 - s, 0), xs1 = min(c1 - 1 + s, g.nx - 1), csw = cb + 2 * s + 1;
+    if ((int)threadIdx.x < nrows) {
+        const uint32_t* row = g.col_start + (size_t)(y0 + threadIdx.x) * g.nx;
+        row_b[threadIdx.x] = __ldg(row + xs0);
+        row_off[threadIdx.x + 1] = __ldg(row + xs1 + 1) - row_b[threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int r = 0; r < nrows; ++r) { const uint32_t len = row_off[r + 1]; row_off[r] = run; run += len; }
+        row_off[nrows] = run;
+    }
+    __syncthreads();
+    const uint32_t total = row_off[nrows];
+    const bool staged = total <= (uint32_t)cap;
+    if (staged) {
+        // column offsets of the widened block, as positions in the staged arrays
+        for (int t = threadIdx.x; t < nrows * csw; t += blockDim.x) {
+            const int r = t / csw, c = t - r * csw;
+            const int x = min(xs0 + c, xs1 + 1);
+            cs[t] = __ldg(g.col_start + (size_t)(y0 + r) * g.nx + x) - row_b[r] + row_off[r];
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k);
-            atomicMin(mm + 2, lo_n); atomicMax(mm + 3, hi_n);
+        // warp-cooperative copy: consecutive threads take consecutive 16-byte quarters of the contiguous range
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(feat);
+        for (int r = 0; r < nrows; ++r) {
+            const uint32_t len4 = (row_off[r + 1] - row_off[r]) * 4u;
+            const size_t gbase = (size_t)row_b[r] * 4u;
+            const uint32_t sbase = row_off[r];
+            for (uint32_t t = threadIdx.x; t < len4; t += blockDim.x) {
+                const double2 v = __ldg(src + gbase + t);
+                const uint32_t rec = t >> 2, k = t & 3u;
+                double2* dst = k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3));
+                dst[sbase + rec] = v;
+            }
         }
     }
+    __syncthreads();
+
+    unsigned lo_k = 0xffffffffu, hi_k = 0u, lo_n = 0xffffffffu, hi_n = 0u;
+    const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
+    const int ry = iy - y0;
+    for (uint32_t q = qa + threadIdx.x; q < qb; q += blockDim.x) {
+        DkdnAcc acc;
+        float dkf, dnf;
+        if (staged) {
+            const uint32_t o = row_off[ry] + (q - row_b[ry]);
+            acc.init(lds_d4(q0, q1, o), lds_d4(q2, q3, o));
+            const int ix = min(max(g.col_x(acc.px), c0), c1 - 1);
+            const int xa = max(ix - s, 0) - xs0, xb = min(ix + s, g.nx - 1) - xs0 + 1;
+            for (int r = 0; r < nrows; ++r) {
+                const uint32_t b = cs[r * csw + xa], e = cs[r * csw + xb];
+                run_range_pipelined(b, e, [&](int64_t j) {
+                    D4x2 c;
+                    c.a = lds_d4(q0, q1, (uint32_t)j);
+                    c.b = lds_d4(q2, q3, (uint32_t)j);
+                    return c;
+                }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
+            }
+        } else {
+            acc.init(ld_d4(feat + q, 0), ld_d4(feat + q, 1));
+            walk_candidates_pipelined<false>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
+                D4x2 c;
+                c.a = ld_d4(feat + j, 0);
+                c.b = ld_d4(feat + j, 1);
+                return c;
+            }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
+        }
+        acc.finish(prm, chi2_table, err, dkf, dnf);
+        const int64_t orig = (prm.grid_order && all_owned)
+                                 ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + q) + 3));
+        const int64_t o = prm.grid_order ? (int64_t)q : orig;
+        dk_out[o] = dkf;
+        dn_out[o] = dnf;
+        const bool owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
+        if (owned && !isnan(dkf)) { const unsigned u = f32_ordered(dkf); lo_k = min(lo_k, u); hi_k = max(hi_k, u); }
+        if (owned && !isnan(dnf)) { const unsigned u = f32_ordered(dnf); lo_n = min(lo_n, u); hi_n = max(hi_n, u); }
+    }
+    if (mm) dkdn_minmax(lo_k, hi_k, lo_n, hi_n, mm);
 }
 
 __global__ void minmax_init(unsigned* mm) {
@@ -361,6 +505,19 @@ extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double e
     return launch_moments(g, MODE_FUSED, r, eps, min_points, normals, lam_ratio, K, pcount, (cudaStream_t)stream);
 }
 
+// kernel variant of the dk/dn pass: 0 = global-memory walk (default), 1 = shared-memory staged walk.
+// MORE3D_DKDN_VARIANT / MORE3D_SMEM_CAP in the environment select it for A/B measurements (read once).
+static int dkdn_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MORE3D_DKDN_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+static int smem_walk_cap() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MORE3D_SMEM_CAP"); v = e ? atoi(e) : 640; if (v < 64) v = 64; if (v > 3000) v = 3000; }
+    return v;
+}
+
 static int run_dk_dn(const more3d_grid* g, double r, const double* normals, const float* K, double rho,
                      double sigma_normal, double sigma_curvature, const double* chi2_table,
                      int table_len, int min_points, float* dk, float* dn, float* minmax, int32_t* status, void* stream,
@@ -403,8 +560,25 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     prm.own_hi = (n_owned <= 0) ? g->n : own_lo + n_owned;
     {
         ProfScope prof("dkdn", s);
-        if (g->tall) dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
-        else dkdn_kernel<false><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+        const int variant = dkdn_variant();
+        if (g->tall) {
+            dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+        } else if (variant == 1 && prm.s <= (SMW_MAX_ROWS - 1) / 2) {
+            // staging capacity in records and the column-block width that fills ~80 % of it at the grid's mean density
+            const int cap = smem_walk_cap();
+            const double dens = (double)g->n / ((double)g->nx * (double)g->ny);
+            int cb = (int)(0.8 * cap / ((2 * prm.s + 1) * fmax(dens, 1e-3))) - 2 * prm.s;
+            cb = cb < 8 ? 8 : (cb > 96 ? 96 : cb);
+            const int nbx = (g->nx + cb - 1) / cb;
+            const size_t smem = (size_t)cap * 64 + (size_t)SMW_MAX_ROWS * (cb + 2 * prm.s + 1) * sizeof(uint32_t);
+            M3D_CUDA(cudaFuncSetAttribute(dkdn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int threads = ((int)(cb * dens * 1.15) + 31) / 32 * 32;          // one thread per expected query
+            threads = threads < 32 ? 32 : (threads > SMW_THREADS ? SMW_THREADS : threads);
+            dkdn_smem_kernel<<<(unsigned)((size_t)nbx * g->ny), threads, smem, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                                  minmax ? mm : nullptr, err, cb, nbx, cap);
+        } else {
+            dkdn_kernel<false><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+        }
     }
     if (minmax) minmax_finish<<<1, 32, 0, s>>>(mm, minmax);
     count_launches(minmax ? 4 : 3);

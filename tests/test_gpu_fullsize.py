@@ -134,6 +134,7 @@ def test_config1_saliency_10m_sample_vs_verbatim_reference():
         assert (dk[sub] != 0).mean() > 0.02                                                 # not vacuous
         sal_or, _ = rp.saliency_blend(dk, dn, 0.5)                                          # whole columns (global min/max)
         assert np.array_equal(cols["_saliency"].cpu().numpy(), sal_or, equal_nan=True)
+        assert np.isnan(sal_or).mean() < 1e-3                                               # not vacuous
     del res, d
     torch.cuda.empty_cache()
 

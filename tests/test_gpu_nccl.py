@@ -10,7 +10,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RADII = (0.5, 0.75, 1.0)
-PARAMS = dict(roughness=0.02, alpha=0.05, sigma_normal=0.01, sigma_curvature=0.01, min_points=4)
+# sigma_normal 1e-3: on this smooth relief the default 0.01 zeroes every dn, and a constant column normalises to NaN
+# (max == min in DM_saliency.py:577-578) -- the comparison would be vacuous
+PARAMS = dict(roughness=0.02, alpha=0.05, sigma_normal=1e-3, sigma_curvature=0.01, min_points=4)
 TOTAL = 600_000
 
 
@@ -64,6 +66,7 @@ def test_two_ranks_over_nccl_bit_identical_to_untiled():
     for r in RADII:
         sal = whole[r]["_saliency"].cpu().numpy()
         pc = whole[r]["_pcount"].cpu().numpy()
+        assert np.isnan(sal).mean() < 1e-3 and np.unique(sal[~np.isnan(sal)]).size > 100        # not vacuous
         for k in range(world):
             assert np.array_equal(ret[k][0][r], sal[k * per:(k + 1) * per], equal_nan=True)    # bit-identical
             assert ret[k][1][r][0] == int(pc[k * per:(k + 1) * per].sum())
