@@ -10,8 +10,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RADII = (0.5, 0.75, 1.0)
-# sigma_normal 1e-3: on this smooth relief the default 0.01 zeroes every dn, and a constant column normalises to NaN
-# (max == min in DM_saliency.py:577-578) -- the comparison would be vacuous
+# rough tile (noise 0.15 m) + sigma_normal 1e-3: on the smooth default relief every dn is zeroed, and a constant column
+# normalises to NaN (max == min in DM_saliency.py:577-578) -- the comparison would be vacuous
 PARAMS = dict(roughness=0.02, alpha=0.05, sigma_normal=1e-3, sigma_curvature=0.01, min_points=4)
 TOTAL = 600_000
 
@@ -37,7 +37,7 @@ def _worker(rank, world, port, ret):
         from more3d_b200.distributed import StripSaliency
         per = TOTAL // world
         lx, _ = synthetic.hash_tile_extent(TOTAL)
-        own = synthetic.hash_terrain_device(11, rank * per, per, TOTAL, device=dev)
+        own = synthetic.hash_terrain_device(11, rank * per, per, TOTAL, noise=0.15, device=dev)
         x_lo = rank * lx / world - 0.5 * lx
         job = StripSaliency(per, rank, world, dev, RADII, PARAMS, 0.5, cloud=own, x_range=(x_lo, x_lo + lx / world),
                             host_buffers=False)
@@ -60,7 +60,7 @@ def test_two_ranks_over_nccl_bit_identical_to_untiled():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     torch.cuda.set_device(0)
-    whole_pts = synthetic.hash_terrain_device(11, 0, TOTAL, TOTAL)
+    whole_pts = synthetic.hash_terrain_device(11, 0, TOTAL, TOTAL, noise=0.15)
     whole = multiscale_saliency(whole_pts, RADII, curvature_weight=0.5, keep=True, **PARAMS)
     per = TOTAL // world
     for r in RADII:

@@ -5,8 +5,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RADII = (0.5, 1.0)
-# sigma_normal 1e-3: with the default 0.01 every dn of this smooth relief is zeroed by the chi^2 test, and a constant
-# column normalises to NaN ((x - min) / (max - min), DM_saliency.py:577-578): saliency comparisons would be vacuous
+# rough tiles (noise 0.15 m) and sigma_normal 1e-3, as the "rough" goldens: on the smooth default relief every dn is zeroed
+# (chi^2 test / 60 % rule), and a constant column normalises to NaN ((x - min) / (max - min), DM_saliency.py:577-578) --
+# saliency comparisons would be vacuous
+NOISE = 0.15
 PARAMS = dict(roughness=0.02, alpha=0.05, sigma_normal=1e-3, sigma_curvature=0.01, min_points=4)
 
 
@@ -36,7 +38,7 @@ def test_logical_strips_bit_identical_to_untiled(G):
     from more3d_b200.distributed import StripStep, strip_pack
     from more3d_b200.pipeline import multiscale_saliency
     from oracle import ref_path as rp
-    pts = synthetic.terrain(120000, seed=8)
+    pts = synthetic.terrain(120000, seed=8, noise=NOISE)
     whole = multiscale_saliency(pts, RADII, curvature_weight=0.5, keep=True, **PARAMS)
     cell = cell_for_radius(min(RADII))
     lo = pts.min(axis=0)
@@ -110,7 +112,7 @@ def test_strip_saliency_wrapper_and_overflow_report():
     from more3d_b200.grid import CELL_MARGIN
     from more3d_b200.distributed import band_select, gather_rows, strip_saliency, StripStep
     from more3d_b200.pipeline import multiscale_saliency
-    pts = synthetic.terrain(60000, seed=9)
+    pts = synthetic.terrain(60000, seed=9, noise=NOISE)
     whole = multiscale_saliency(pts, RADII, curvature_weight=0.5, keep=True, **PARAMS)
     d = torch.from_numpy(pts).cuda()
     mid = float(np.median(pts[:, 0]))
