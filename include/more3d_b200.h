@@ -311,6 +311,16 @@ int more3d_ls_smooth_raw(const double* u, int cols, const int64_t* nbs, const do
                          const uint8_t* mask, double* out, void* stream);
 int more3d_ls_elementwise(int op, const double* x, double param, int64_t n, double* out, void* stream);
 
+/* ---- cue pre-processing of the level-set driver ("next" row; run_levelsets.py:215-221) -----------------------------
+ * select_kth: exact order statistics -- out[i] (device) = the ranks_h[i]-th smallest of v (0-based, 1 <= nk <= 4), by an
+ * 8-pass radix select on order-preserving keys (no sort); np.percentile's two neighbouring statistics come from one
+ * call.  cue_ops, in place on x (n f64): op 0 = np.abs; op 1 = clip(x, arg_dev[0], arg_dev[1]) (levelsets_func.py:107-109);
+ * op 2 = normalize(x, s = arg) (:100-104: skipped when the column is all zero), out_dev (may be NULL) = {min, max};
+ * op 3 = out_dev[0..1] = {0, numpy `linear` interpolation of arg_dev[0], arg_dev[1] at gamma = arg}: the clip bounds
+ * of `clip(zeta, 0, np.percentile(zeta, pc))` without a host round trip; op 4 = out_dev[0..1] = {min, max} of x. */
+int more3d_select_kth(const double* v, int64_t n, const int64_t* ranks_h, int nk, double* out, void* stream);
+int more3d_cue_ops(int op, double* x, int64_t n, const double* arg_dev, double arg, double* out_dev, void* stream);
+
 /* ---- evaluation terms of Downsampling/downsample_compare.py ("next" row) -----------------------------
  * normals_from_knn: centroid-PCA normal over a kNN table (open3d estimate_normals(KDTreeSearchParamKNN),
  * downsample_compare.py:57, :112-121); fewer than 3 valid neighbours -> (0, 0, 1).  orient_normals: NaN ->

@@ -28,16 +28,24 @@ def threshold_otsu(values, nbins=256):
     if v.dtype not in (torch.float32, torch.float64):
         v = v.double()
     v = v.to(device="cuda").contiguous().reshape(-1)
-    lo, hi = float(v.min()), float(v.max())
-    if lo == hi:
-        return lo
     if nbins != 256:
         raise NotImplementedError("only nbins=256 (the skimage default used by the reference)")
-    edges = np.linspace(lo, hi, nbins + 1)          # numpy.histogram's bin edges for range=(min, max)
+    n = int(v.numel())
     with torch.cuda.device(v.device):
-        de = torch.from_numpy(edges).to(v.device)
+        # extrema -> histogram over numpy.linspace(min, max, 257) entirely on the device, ONE host read at the end
+        if v.dtype == torch.float32:
+            mm = torch.empty(4, dtype=torch.float32, device=v.device)
+            check(lib.more3d_minmax4(ptr(v), ptr(v), n, ptr(mm), stream_ptr()))
+        else:
+            mm = torch.empty(2, dtype=torch.float64, device=v.device)
+            check(lib.more3d_cue_ops(4, ptr(v), n, None, 0.0, ptr(mm), stream_ptr()))
         hist = torch.empty(256, dtype=torch.int64, device=v.device)
-        check(lib.more3d_histogram256(ptr(v), v.element_size(), int(v.numel()), ptr(de), ptr(hist), stream_ptr()))
+        check(lib.more3d_histogram256_range(ptr(v), v.element_size(), n, ptr(mm), v.element_size(), ptr(hist), stream_ptr()))
+        lohi = mm[:2].cpu().numpy().astype(np.float64)
+    lo, hi = float(lohi[0]), float(lohi[1])
+    if lo == hi:
+        return lo
+    edges = np.linspace(lo, hi, nbins + 1)          # numpy.histogram's bin edges for range=(min, max)
     counts = hist.cpu().numpy().astype(np.float64)
     centers = (edges[:-1] + edges[1:]) / 2.0
     with np.errstate(all="ignore"):

@@ -9,8 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmore3d_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
-FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
 
 def sources():
@@ -27,8 +26,24 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """Compile and link in-tree.  Safe under torchrun: one process builds at a time (file lock), the others wait and
+    then find the library fresh; the link goes to a temporary name and is renamed into place, so a concurrent
+    dlopen never sees a half-written file."""
     if not force and not stale():
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():      # another rank built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
@@ -47,8 +62,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -71,8 +71,12 @@ def compare(pts, downsampled, normals_pts=None, rnn=.1, knn=64, rnn_flag=True, u
         ang = torch.empty(Q.shape[0], dtype=torch.float64, device=P.device)
         check(lib.more3d_compare_terms(ptr(P), int(P.shape[0]), ptr(Q), int(Q.shape[0]), ptr(closest), ptr(closest2),
                                        ptr(NP), ptr(NQ), ptr(c2p), ptr(ang), stream_ptr()))
-    s = torch.sort(ang).values
-    m = s.numel()
-    med = 0.5 * (s[(m - 1) // 2] + s[m // 2])                    # np.median
+        # np.median: mean of the two middle ORDER STATISTICS, found by radix select on the device (no sort)
+        m = int(ang.numel())
+        mid = torch.empty(2, dtype=torch.float64, device=P.device)
+        ranks = (C.c_int64 * 2)((m - 1) // 2, m // 2)
+        check(lib.more3d_select_kth(ptr(ang), m, ranks, 2, ptr(mid), stream_ptr()))
+    mid = mid.cpu().numpy()
+    med = (float(mid[0]) + float(mid[1])) / 2.0
     return {"c2c": float(E2.mean() + E.mean() / 2), "c2p": float(c2p.mean()), "dN": float(med),
             "dn_all": ang.cpu().numpy(), "E": E.cpu().numpy(), "E2": E2.cpu().numpy()}

@@ -70,18 +70,64 @@ def dp(s):
     return _elementwise(2, s, 0.0)
 
 
+def _percentile_plan(n, q):
+    """numpy's `linear` percentile (lib/_function_base_impl.py: _compute_virtual_index with alpha = beta = 1):
+    returns (lower rank j, upper rank, interpolation weight gamma)."""
+    quant = np.true_divide(q, 100.0)
+    vi = n * quant + (1.0 + quant * (1.0 - 1.0 - 1.0)) - 1.0
+    j = int(np.floor(vi))
+    j = min(max(j, 0), n - 1)
+    gamma = float(vi - j)
+    return j, min(j + 1, n - 1), gamma
+
+
+def _percentile_bounds_dev(d, q):
+    """device tensor (2,) = {0, np.percentile(d, q)} for a flat f64 device tensor, no host round trip"""
+    lib = _lib.load()
+    n = int(d.numel())
+    j, j1, gamma = _percentile_plan(n, q)
+    with torch.cuda.device(d.device):
+        ab = torch.empty(2, dtype=torch.float64, device=d.device)
+        ranks = (C.c_int64 * 2)(j, j1)
+        check(lib.more3d_select_kth(ptr(d), n, ranks, 2, ptr(ab), stream_ptr()))
+        lohi = torch.empty(2, dtype=torch.float64, device=d.device)
+        check(lib.more3d_cue_ops(3, None, 0, ptr(ab), float(gamma), ptr(lohi), stream_ptr()))
+    return lohi
+
+
+def percentile(array, q):
+    """np.percentile(array, q) (scalar q, default `linear` method) computed on the device: exact order statistics by
+    radix select + numpy's interpolation rule (the clip bound of run_levelsets.py:220)."""
+    a = np.asarray(array, dtype=np.float64)
+    d = _dev(a.reshape(-1))
+    return float(_percentile_bounds_dev(d, q)[1].item())
+
+
+def _inplace_device(array, fn):
+    """run fn(flat f64 device tensor) and write the result back into the caller's numpy array (the reference's
+    cue helpers work in place on host arrays; the arithmetic happens on the GPU)"""
+    a = np.asarray(array)
+    if a.size == 0:
+        return
+    d = _dev(np.ascontiguousarray(a, dtype=np.float64).reshape(-1))
+    fn(d)
+    array[...] = d.cpu().numpy().reshape(a.shape).astype(a.dtype, copy=False)
+
+
 def normalize(array, s=1):
-    """in place, host side: cue pre-processing of the driver script (:100-104)"""
-    if np.any(array != 0):
-        array -= array.min()
-        array /= array.max()
-        array *= s
+    """in place: shift to a zero minimum, scale to a maximum of s; an all-zero array is left alone (:100-104)"""
+    lib = _lib.load()
+    _inplace_device(array, lambda d: check(lib.more3d_cue_ops(2, ptr(d), int(d.numel()), None, float(s), None, stream_ptr())))
 
 
 def clip(array, a, b):
-    """in place, host side (:107-109)"""
-    array[array < a] = a
-    array[array > b] = b
+    """in place: array[array < a] = a; array[array > b] = b (:107-109)"""
+    lib = _lib.load()
+
+    def run(d):
+        lohi = torch.tensor([float(a), float(b)], dtype=torch.float64).to(d.device)
+        check(lib.more3d_cue_ops(1, ptr(d), int(d.numel()), ptr(lohi), 0.0, None, stream_ptr()))
+    _inplace_device(array, run)
 
 
 def _mask_of(idx, n):
@@ -437,6 +483,33 @@ class Solver:
         self._set_active_from_phi()
         self._alias = False
         self._last_active = self._mirror(self._active.get_host().copy())   # last_active[:] = active, :553
+
+    def preprocess_cue(self, num_smooth=0, cue_clip_pc=99.9, scale=1):
+        """The driver's cue pre-processing (run_levelsets.py:211-221) with the cue resident in HBM throughout:
+        `num_smooth` kernel-smoothing passes, zeta = |zeta|, clip(zeta, 0, np.percentile(zeta, cue_clip_pc)),
+        normalize(zeta, scale).  Same values as the host sequence ``smooth / np.abs / clip / normalize`` on
+        ``solver.zeta``; nothing is copied to the host."""
+        lib = _lib.load()
+        z = self._zeta.get_dev(torch.float64)
+        n = int(z.shape[0])
+        cols = 1 if z.ndim == 1 else int(z.shape[1])
+        with torch.cuda.device(z.device):
+            for _ in range(int(num_smooth)):
+                # smooth(zeta, slice(None), neighbors, weights) (:350-358) column by column on the solver's own graph
+                cols_in = [z.reshape(n)] if cols == 1 else [z[:, c].contiguous() for c in range(cols)]
+                cols_out = []
+                for u in cols_in:
+                    o = torch.empty_like(u)
+                    check(lib.more3d_ls_smooth(self.diff._g, ptr(u), None, ptr(o), stream_ptr()))
+                    cols_out.append(o)
+                z = cols_out[0].reshape(z.shape) if cols == 1 else torch.stack(cols_out, dim=1).contiguous()
+            flat = z.reshape(-1)
+            check(lib.more3d_cue_ops(0, ptr(flat), int(flat.numel()), None, 0.0, None, stream_ptr()))
+            lohi = _percentile_bounds_dev(flat, cue_clip_pc)
+            check(lib.more3d_cue_ops(1, ptr(flat), int(flat.numel()), ptr(lohi), 0.0, None, stream_ptr()))
+            check(lib.more3d_cue_ops(2, ptr(flat), int(flat.numel()), None, float(scale), None, stream_ptr()))
+        self._zeta.dev = z
+        self._zeta.dev_written()
 
     def initialize_from_zeta(self, percentile):
         _print('initializing from zeta')

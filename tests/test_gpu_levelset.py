@@ -259,3 +259,134 @@ def test_solver_lmv_against_oracle_other_size():
     assert np.array_equal(solver.active, st["active"])
     np.testing.assert_allclose(solver.phi, st["phi"], rtol=1e-8, atol=1e-10)
     assert np.abs(solver.phi - phi0).max() > 1e-3                                # the flow moved
+
+
+def test_cue_preprocessing_on_device_matches_numpy(g):
+    """f-3: clip / normalize / percentile and the driver's cue pre-processing (run_levelsets.py:211-221) on the device
+    == the reference's host numpy sequence, bit for bit."""
+    from more3d_b200 import levelsets_func as ls
+    rng = np.random.Generator(np.random.PCG64(17))
+    for shape in ((50001,), (20000, 2), (7,)):
+        a = rng.normal(size=shape) * np.exp(rng.normal(size=shape))            # long tails, both signs
+        for q in (0.0, 50.0, 99.9, 37.3, 100.0):
+            assert ls.percentile(a, q) == float(np.percentile(a, q))
+        b = a.copy()
+        want = a.copy()
+        lo, hi = np.percentile(a, 5), np.percentile(a, 99)
+        ls.clip(b, lo, hi)
+        want[want < lo] = lo
+        want[want > hi] = hi
+        assert np.array_equal(b, want)
+        ls.normalize(b, 3)
+        want -= want.min()
+        want /= want.max()
+        want *= 3
+        assert np.array_equal(b, want)
+    z = np.zeros(100)
+    ls.normalize(z)                                                             # all zero: untouched (:101)
+    assert np.all(z == 0)
+    # the whole driver sequence on a solver, cue resident in HBM
+    pts, h = g["points"], float(g["h"])
+    zeta = rng.normal(size=(len(pts), 1)) ** 3
+    solver = ls.Solver(h, zeta, pts, g["neighbors"], (g["t1"], g["t2"]), "chan_vese", weights=g["weights"])
+    solver.preprocess_cue(num_smooth=2, cue_clip_pc=99.0, scale=1)
+    ref = zeta.copy()
+    for _ in range(2):
+        ref = ls.smooth(ref, slice(None), g["neighbors"], g["weights"])
+    ref = np.abs(ref)
+    ref_clip = ref.copy()
+    hi = np.percentile(ref, 99.0)
+    ref_clip[ref_clip > hi] = hi
+    ref_clip -= ref_clip.min()
+    ref_clip /= ref_clip.max()
+    assert np.array_equal(solver.zeta, ref_clip)
+
+
+def test_init_methods_and_save_match_verbatim_reference(g, tmp_path):
+    """initialize_from_seeds / _point / _zeta / _mask and Solver.save(extract=True) against the UNMODIFIED reference
+    Solver (oracle/_ref, CPU numpy) constructed on the same neighbourhoods: phi, active sets, the aliasing of
+    last_active, and the two text files byte for byte."""
+    from more3d_b200 import levelsets_func as ls
+    from oracle import ref_verbatim as rv
+    if not rv.available():
+        pytest.skip("oracle/_ref not built")
+    _, _, ref_ls = rv.load_reference()
+    pts, h = g["points"][:1500].copy(), float(g["h"])
+    # neighbourhoods of the sub-cloud from the reference itself
+    nb, nrm, tang = ref_ls.build_neighborhoods(pts.copy(), h, 7)
+    rng = np.random.Generator(np.random.PCG64(23))
+    zeta = np.abs(rng.normal(size=(len(pts), 1)))
+    ref = ref_ls.Solver(h, zeta.copy(), pts, nb, tang, "chan_vese")
+    our = ls.Solver(h, zeta.copy(), pts, nb, tang, "chan_vese", weights=ref.diff.weights)
+
+    def same(alias):
+        assert np.array_equal(our.phi, ref.phi)
+        assert np.array_equal(our.active, ref.active)
+        assert np.array_equal(our.last_active, ref.last_active)
+        assert (our.last_active is our.active) == alias == (ref.last_active is ref.active)
+
+    np.random.seed(5)
+    ref.initialize_from_seeds(6, 1.5)
+    np.random.seed(5)                                     # the reference draws its seeds from numpy's global stream
+    our.initialize_from_seeds(6, 1.5)
+    assert np.array_equal(our.seeds, ref.seeds)
+    same(True)
+    ref.initialize_from_seeds(3, 1.0, reuse_seeds=True)    # seeds kept
+    our.initialize_from_seeds(3, 1.0, reuse_seeds=True)
+    same(True)
+    p0 = pts[len(pts) // 2] + 0.1
+    ref.initialize_from_point(p0, 2.5)
+    our.initialize_from_point(p0, 2.5)
+    same(True)
+    mask = pts[:, 0] > np.median(pts[:, 0])
+    ref.initialize_from_mask(mask)
+    our.initialize_from_mask(mask)
+    same(False)
+    # initialize_from_zeta indexes a 1-D phi with the mask of the (N, C) cue: IndexError in the reference (:559), and here
+    with pytest.raises(IndexError):
+        ref.initialize_from_zeta(60.0)
+    with pytest.raises(IndexError):
+        our.initialize_from_zeta(60.0)
+    # a few iterations, then the two text files of save(extract=True)
+    kw = dict(stepsize=.005, nu=1e-4, mu=2.5e-3, lambda1=1, lambda2=1, epsilon=1, cap=True, tolerance=0)
+    ref.run(4, **kw)
+    our.run(4, **kw)
+    assert np.array_equal(our.active, ref.active)
+    np.testing.assert_allclose(our.phi, ref.phi, rtol=1e-8, atol=1e-10)
+    our.phi[:] = ref.phi                                   # same state -> the files must be identical
+    origin = np.r_[100.0, -50.0, 7.0]
+    ref.save(str(tmp_path / "ref"), origin=origin, extract=True, extraction_threshold=3)
+    our.save(str(tmp_path / "our"), origin=origin, extract=True, extraction_threshold=3)
+    for suffix in (".txt", "_extract.txt"):
+        assert (tmp_path / ("our" + suffix)).read_bytes() == (tmp_path / ("ref" + suffix)).read_bytes()
+    assert (tmp_path / "our_extract.txt").stat().st_size > 0
+
+
+def test_trajectory_without_handed_over_frames_or_weights_is_quantified(g, capsys):
+    """What a user of the drop-in path actually runs: frames with OUR normal signs and OUR (correctly rounded) Wendland
+    weights, 10 iterations, against the verbatim golden trajectory.  The reference's own trajectory is not
+    reproducible across hosts at the bit level (LAPACK's SVD sign, numpy's SIMD pow), so this pins
+    HOW FAR the two drift: the active sets stay almost identical and phi differs at isolated points only."""
+    from more3d_b200 import levelsets_func as ls
+    pts, h, k = g["points"], float(g["h"]), int(g["k"])
+    report = {}
+    for tag, own_frames, own_weights in (("ref frames, own weights", False, True), ("own frames, ref weights", True, False),
+                                         ("own frames, own weights", True, True)):
+        if own_frames:
+            nb, _, tang = ls.build_neighborhoods(pts.copy(), h, k)
+        else:
+            nb, tang = g["neighbors"], (g["t1"], g["t2"])
+        solver = ls.Solver(h, g["zeta"], pts, nb, tang, "chan_vese", weights=None if own_weights else g["weights"])
+        solver.initialize_from_voxels(2.0)
+        solver.phi[:] = ls.smooth(solver.phi, slice(None), nb, solver.diff.weights)
+        solver.run(10, **RUN)
+        d = np.abs(solver.phi - g["phi10"])
+        a, b = solver.active, g["act10"]
+        jac = (a & b).sum() / max((a | b).sum(), 1)
+        report[tag] = dict(jaccard_active=float(jac), frac_phi_off_1e6=float((d > 1e-6).mean()),
+                           frac_phi_off_1e2=float((d > 1e-2).mean()), median_abs=float(np.median(d)))
+        assert jac >= 0.97, (tag, report[tag])
+        assert (d > 1e-2).mean() <= 0.03, (tag, report[tag])
+        assert np.median(d) <= 1e-9, (tag, report[tag])
+    with capsys.disabled():
+        print("\nlevel-set drift after 10 iterations vs the verbatim golden:", report)

@@ -331,3 +331,44 @@ def test_tile_stream_matches_single_calls():
     assert multiscale_saliency_tiles([], radii) == []
     plain = multiscale_saliency_tiles([tiles[0].numpy()], radii, **kw)           # pageable numpy input works too
     assert np.array_equal(plain[0][0.5].cpu().numpy(), res[0][0.5].cpu().numpy(), equal_nan=True)
+
+
+def test_attribute_container_round_trip(tmp_path, golden_dir):
+    """f-4: the on-disk attribute container (PointCloudDM.save_as / load) carries every column of the reference's ODM
+    layouts (DM_saliency.py:377-384, :486-494) -- NormalX/Y/Z, _nonparam_K, _pcount, _dk, _dn, the normalised pair,
+    _saliency and Classification -- with their storage types, and the pipeline resumes from a reloaded file."""
+    import torch
+    from more3d_b200.DM_saliency import PointCloudDM, DM_nonparam_curvature, DM_dk_dn, DM_saliency, DM_saliency_stats
+    g = load(golden_dir, "rough_r05")
+    r, rho = float(g["radius"]), float(g["rho"])
+    dm = PointCloudDM(g["points"])
+    cls = (np.arange(len(g["points"])) % 7).astype(np.uint8)
+    dm.attrs["Classification"] = torch.from_numpy(cls).cuda()
+    DM_nonparam_curvature(dm, "sphere", roughness=float(g["roughness"]), alpha=float(g["alpha"]),
+                          min_points=int(g["min_points"]), radius=r)
+    path1 = str(tmp_path / "stage1.npz")
+    dm.save_as(path1)
+    # second stage from the FILE, as the reference chains its stages through the ODM (DM_saliency.py:362, :415, :471)
+    dm2 = DM_dk_dn(path1, "sphere", rho, rho, sigma_normal=float(g["sigma_n"]), sigma_curvature=float(g["sigma_k"]),
+                   alpha=float(g["alpha"]), min_points=int(g["min_points"]), radius=r)
+    DM_saliency(dm2, curvature_weight=0.5)
+    path2 = str(tmp_path / "stage2.npz")
+    dm2.save_as(path2)
+    dm3 = PointCloudDM.load(path2)
+    assert np.array_equal(dm3.xyz.cpu().numpy(), g["points"])
+    want_types = {"_nonparam_K": np.float32, "_pcount": np.int32, "_dk": np.float32, "_dn": np.float32,
+                  "_saliency": np.float32, "Classification": np.uint8}
+    for name, t in want_types.items():
+        a = dm3.get(name)
+        assert a.dtype == t, (name, a.dtype)
+        assert np.array_equal(a, dm2.get(name), equal_nan=True)
+    for ax in "XYZ":
+        assert np.array_equal(dm3.get("Normal" + ax), dm2.get("Normal" + ax), equal_nan=True)
+    assert np.array_equal(dm3.get("Classification"), cls)
+    # values are those of the in-memory pipeline / the verbatim golden
+    assert np.array_equal(dm3.get("_pcount"), g["pcount"])
+    bad = ~rel_close(dm3.get("_dk"), g["dk"]) | ~rel_close(dm3.get("_dn"), g["dn"])
+    assert bad.sum() <= 3
+    st = DM_saliency_stats(path2)
+    s = dm3.get("_saliency").astype(np.float64)
+    assert st[0] == s.min() and st[1] == s.max()
