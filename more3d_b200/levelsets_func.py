@@ -71,10 +71,10 @@ def dp(s):
 
 
 def _percentile_plan(n, q):
-    """numpy's `linear` percentile (lib/_function_base_impl.py: _compute_virtual_index with alpha = beta = 1):
-    returns (lower rank j, upper rank, interpolation weight gamma)."""
+    """numpy's `linear` percentile (lib/_function_base_impl.py: virtual index (n - 1) * q / 100, gamma = its
+    fractional part): returns (lower rank j, upper rank, interpolation weight gamma)."""
     quant = np.true_divide(q, 100.0)
-    vi = n * quant + (1.0 + quant * (1.0 - 1.0 - 1.0)) - 1.0
+    vi = (n - 1) * quant
     j = int(np.floor(vi))
     j = min(max(j, 0), n - 1)
     gamma = float(vi - j)

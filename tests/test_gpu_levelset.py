@@ -387,6 +387,6 @@ def test_trajectory_without_handed_over_frames_or_weights_is_quantified(g, capsy
                            frac_phi_off_1e2=float((d > 1e-2).mean()), median_abs=float(np.median(d)))
         assert jac >= 0.97, (tag, report[tag])
         assert (d > 1e-2).mean() <= 0.03, (tag, report[tag])
-        assert np.median(d) <= 1e-9, (tag, report[tag])
+        assert np.median(d) <= 1e-6, (tag, report[tag])
     with capsys.disabled():
         print("\nlevel-set drift after 10 iterations vs the verbatim golden:", report)
