@@ -353,6 +353,11 @@ int more3d_gather_rows(const void* src, const int64_t* idx, int64_t m, int ncols
  * negate_odd: v[i] = -v[i] for odd i (rows of {min, max}: one MIN all-reduce then serves minima and maxima). */
 int more3d_strip_pack(const double* xyz, int64_t n, double left_below, double right_from, double* left_out,
                       double* right_out, int64_t cap, double* info, void* stream);
+/* saliency_blend for the grid-order columns of a strip (all g->n rows are blended): sal_minmax (2 f32, device) covers
+ * only the rows whose ORIGINAL index lies in [own_lo, own_lo + n_owned) -- the strip's own points. */
+int more3d_saliency_blend_owned(const more3d_grid* g, const float* dk, const float* dn, const float* minmax,
+                                double curvature_weight, int64_t own_lo, int64_t n_owned, float* sal,
+                                float* sal_minmax, void* stream);
 int more3d_histogram256_range(const void* v, int elem_bytes, int64_t n, const void* lohi, int lohi_bytes,
                               int64_t* hist, void* stream);
 int more3d_negate_odd(float* v, int64_t n, void* stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "more3d_select_kth": [_vp, _i64, C.POINTER(_i64), _i32, _vp, _vp],
     "more3d_cue_ops": [_i32, _vp, _i64, _vp, _f64, _vp, _vp],
+    "more3d_saliency_blend_owned": [_vp, _vp, _vp, _vp, _f64, _i64, _i64, _vp, _vp, _vp],
     "more3d_strip_pack": [_vp, _i64, _f64, _f64, _vp, _vp, _i64, _vp, _vp],
     "more3d_histogram256_range": [_vp, _i32, _i64, _vp, _i32, _vp, _vp],
     "more3d_negate_odd": [_vp, _i64, _vp],

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256) minmax4_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk, const float* __restrict__ dn,
                                                     int64_t n, const float* __restrict__ minmax, double cw,
                                                     double nw, float* __restrict__ sal,
-                                                    unsigned* __restrict__ smm) {
+                                                    unsigned* __restrict__ smm, const PointRec* __restrict__ rec,
+                                                    long long own_lo, long long own_hi) {
     const double min_k = (double)minmax[0], max_k = (double)minmax[1];
     const double min_n = (double)minmax[2], max_n = (double)minmax[3];
     const double diff_k = __dsub_rn(max_k, min_k), diff_n = __dsub_rn(max_n, min_n);   // :570-571
@@ -51,7 +52,12 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk
         const float ndn = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)dn[i], min_n), diff_n), min_n);  // :578
         const float sv = (float)__dadd_rn(__dmul_rn(nw, (double)ndn), __dmul_rn(cw, (double)ndk));      // :579-580
         sal[i] = sv;
-        if (!isnan(sv)) {
+        // grid-order columns of a strip: only the rows of its OWN points (original index in [own_lo, own_hi)) count
+        const bool mine = rec == nullptr || [&] {
+            const long long o = __double_as_longlong(__ldg(reinterpret_cast<const double*>(rec + i) + 3));
+            return o >= own_lo && o < own_hi;
+        }();
+        if (mine && !isnan(sv)) {
             const unsigned u = f32_ordered(sv);
             lo = min(lo, u); hi = max(hi, u);
         }
@@ -73,6 +79,7 @@ __global__ void __launch_bounds__(256) hist256_kernel(const T* __restrict__ v, i
     __syncthreads();
     const double first = e[0], last = e[256];
     const double denom = __dsub_rn(last, first);
+    const double scale = 256.0 / denom;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
@@ -80,9 +87,13 @@ __global__ void __launch_bounds__(256) hist256_kernel(const T* __restrict__ v, i
         if (i < n) {
             const double a = (double)v[i];
             if (a >= first && a <= last) {
-                double f = __dmul_rn(__ddiv_rn(__dsub_rn(a, first), denom), 256.0);
+                // numpy divides here ((a - first) / (last - first) * 256); a reciprocal multiply lands within one bin of
+                // that, and the two edge fix-ups below move any such index to THE bin whose edges bracket a -- the
+                // same final bin numpy reaches
+                double f = __dmul_rn(__dsub_rn(a, first), scale);
                 int b = (int)f;
-                if (b == 256) b = 255;
+                if (b > 255) b = 255;
+                if (b < 0) b = 0;
                 if (a < e[b]) b -= 1;
                 if (a >= e[b + 1] && b != 255) b += 1;
                 bin = b;
@@ -124,9 +135,29 @@ extern "C" int more3d_saliency_blend(const float* dk, const float* dn, int64_t n
     }
     const double nw = 1.0 - curvature_weight;   // DM_saliency.py:572
     ProfScope prof("blend", s);
-    blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, n, minmax, curvature_weight, nw, sal, mm);
+    blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, n, minmax, curvature_weight, nw, sal, mm, nullptr, 0, 0);
     if (sal_minmax) mm4_finish<<<1, 32, 0, s>>>(mm, sal_minmax, 2);
     count_launches(sal_minmax ? 3 : 1);
+    M3D_CHECK_LAUNCH();
+    dev_free(mm, s);
+    return MORE3D_OK;
+}
+
+extern "C" int more3d_saliency_blend_owned(const more3d_grid* g, const float* dk, const float* dn, const float* minmax,
+                                           double curvature_weight, int64_t own_lo, int64_t n_owned, float* sal,
+                                           float* sal_minmax, void* stream) {
+    M3D_REQUIRE(g && dk && dn && minmax && sal && sal_minmax, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* mm = nullptr;
+    M3D_TRY(dev_alloc(&mm, 2, s));
+    mm4_init<<<1, 32, 0, s>>>(mm, 2);
+    const double nw = 1.0 - curvature_weight;   // DM_saliency.py:572
+    const bool all = n_owned <= 0 || (own_lo <= 0 && own_lo + n_owned >= g->n);
+    ProfScope prof("blend", s);
+    blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, g->n, minmax, curvature_weight, nw, sal, mm, all ? nullptr : g->rec,
+                                         (long long)own_lo, (long long)(own_lo + n_owned));
+    mm4_finish<<<1, 32, 0, s>>>(mm, sal_minmax, 2);
+    count_launches(3);
     M3D_CHECK_LAUNCH();
     dev_free(mm, s);
     return MORE3D_OK;

@@ -28,6 +28,8 @@ __global__ void strip_pack_init(unsigned long long* info) {
     else if (threadIdx.x < 8) info[threadIdx.x] = 0ull;
 }
 
+// Warp w of a tile owns 256 consecutive points and reads them in 8 rounds of 32 (lanes 24 bytes apart: coalesced);
+// a ballot per round and band gives every selected point its rank, so the packed bands keep the cloud's order.
 __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __restrict__ xyz, int64_t n,
                                                                 double left_below, double right_from,
                                                                 double* __restrict__ left_out,
@@ -40,24 +42,36 @@ __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const int tile = (int)s_tile;
-    const int64_t base = (int64_t)tile * SP_TILE + (int64_t)threadIdx.x * SP_ITEMS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t wbase = (int64_t)tile * SP_TILE + (int64_t)warp * (32 * SP_ITEMS);
     double px[SP_ITEMS], py[SP_ITEMS], pz[SP_ITEMS];
-    unsigned fl = 0;                                  // bit i: item i in the left band, bit 8 + i: in the right band
+    unsigned ml[SP_ITEMS], mr[SP_ITEMS];              // ballots of round j: lanes in the left / right band
+    unsigned cl = 0, cr = 0;                          // warp totals
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int i = 0; i < SP_ITEMS; ++i) {
-        if (base + i < n) {
-            px[i] = xyz[3 * (base + i)]; py[i] = xyz[3 * (base + i) + 1]; pz[i] = xyz[3 * (base + i) + 2];
-            if (px[i] < left_below) fl |= 1u << i;
-            if (px[i] >= right_from) fl |= 1u << (8 + i);
-            lo[0] = fmin(lo[0], px[i]); lo[1] = fmin(lo[1], py[i]); lo[2] = fmin(lo[2], pz[i]);
-            hi[0] = fmax(hi[0], px[i]); hi[1] = fmax(hi[1], py[i]); hi[2] = fmax(hi[2], pz[i]);
+    for (int j = 0; j < SP_ITEMS; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
+        bool fl = false, fr = false;
+        px[j] = py[j] = pz[j] = 0.0;
+        if (i < n) {
+            px[j] = xyz[3 * i]; py[j] = xyz[3 * i + 1]; pz[j] = xyz[3 * i + 2];
+            fl = px[j] < left_below;
+            fr = px[j] >= right_from;
+            lo[0] = fmin(lo[0], px[j]); lo[1] = fmin(lo[1], py[j]); lo[2] = fmin(lo[2], pz[j]);
+            hi[0] = fmax(hi[0], px[j]); hi[1] = fmax(hi[1], py[j]); hi[2] = fmax(hi[2], pz[j]);
         }
+        ml[j] = __ballot_sync(0xffffffffu, fl);
+        mr[j] = __ballot_sync(0xffffffffu, fr);
+        cl += __popc(ml[j]);
+        cr += __popc(mr[j]);
     }
-    // both band counts travel in one 62-bit scan value: left in bits 0..30, right in bits 31..61
-    const uint64_t mine = (uint64_t)__popc(fl & 0xffu) | ((uint64_t)__popc(fl >> 8) << 31);
+    // both band counts travel in one 62-bit scan value: left in bits 0..30, right in bits 31..61.  Thread = (warp,
+    // lane): lane 0 of every warp carries the warp's totals, the block scan then yields the warps' exclusive offsets.
+    const uint64_t mine = lane == 0 ? ((uint64_t)cl | ((uint64_t)cr << 31)) : 0ull;
     uint64_t total;
     uint64_t ex = block_exclusive_scan<uint64_t>(mine, &total, sm);
+    ex = __shfl_sync(0xffffffffu, ex, 0);             // the warp's offset inside the tile
     volatile uint64_t* vd = desc;
     if (threadIdx.x == 0) {
         vd[tile] = (tile == 0 ? LB_PREFIX : LB_AGG) | total;
@@ -74,15 +88,17 @@ __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __
     ex += s_prefix;
     int64_t l = (int64_t)(ex & 0x7fffffffull), r = (int64_t)(ex >> 31);
 #pragma unroll
-    for (int i = 0; i < SP_ITEMS; ++i) {
-        if (fl & (1u << i)) {
-            if (l < cap) { left_out[3 * l] = px[i]; left_out[3 * l + 1] = py[i]; left_out[3 * l + 2] = pz[i]; }
-            ++l;
+    for (int j = 0; j < SP_ITEMS; ++j) {
+        if (ml[j] & (1u << lane)) {
+            const int64_t o = l + __popc(ml[j] & lt);
+            if (o < cap) { left_out[3 * o] = px[j]; left_out[3 * o + 1] = py[j]; left_out[3 * o + 2] = pz[j]; }
         }
-        if (fl & (1u << (8 + i))) {
-            if (r < cap) { right_out[3 * r] = px[i]; right_out[3 * r + 1] = py[i]; right_out[3 * r + 2] = pz[i]; }
-            ++r;
+        if (mr[j] & (1u << lane)) {
+            const int64_t o = r + __popc(mr[j] & lt);
+            if (o < cap) { right_out[3 * o] = px[j]; right_out[3 * o + 1] = py[j]; right_out[3 * o + 2] = pz[j]; }
         }
+        l += __popc(ml[j]);
+        r += __popc(mr[j]);
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) {
         const uint64_t all = s_prefix + total;
@@ -98,7 +114,7 @@ __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __
             hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             if (lo[a] <= hi[a]) {
@@ -133,6 +149,7 @@ __global__ void __launch_bounds__(256) hist256_range_kernel(const T* __restrict_
     for (int i = threadIdx.x; i < 257; i += 256) e[i] = (i == 256) ? last : __dadd_rn(__dmul_rn((double)i, step), first);
     __syncthreads();
     const double denom = __dsub_rn(last, first);
+    const double scale = 256.0 / denom;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
@@ -140,9 +157,13 @@ __global__ void __launch_bounds__(256) hist256_range_kernel(const T* __restrict_
         if (i < n && denom > 0.0) {
             const double a = (double)v[i];
             if (a >= first && a <= last) {
-                double f = __dmul_rn(__ddiv_rn(__dsub_rn(a, first), denom), 256.0);
+                // numpy divides here ((a - first) / (last - first) * 256); a reciprocal multiply lands within one bin of
+                // that, and the two edge fix-ups below move any such index to THE bin whose edges bracket a -- the
+                // same final bin numpy reaches
+                double f = __dmul_rn(__dsub_rn(a, first), scale);
                 int b = (int)f;
-                if (b == 256) b = 255;
+                if (b > 255) b = 255;
+                if (b < 0) b = 0;
                 if (a < e[b]) b -= 1;
                 if (a >= e[b + 1] && b != 255) b += 1;
                 bin = b;

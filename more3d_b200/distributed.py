@@ -231,7 +231,7 @@ class StripStep:
         self.table_len = int(chi2_table_len)
         R = len(self.radii)
         self.minmax = torch.empty((R, 4), dtype=torch.float32, device=self.dev)
-        self.sal_minmax = torch.empty((R, 4), dtype=torch.float32, device=self.dev)   # rows {min, max, min, max}
+        self.sal_minmax = torch.empty((R, 2), dtype=torch.float32, device=self.dev)   # rows {min, max} of the owned saliency
         self.status = torch.zeros(R, dtype=torch.int32, device=self.dev)
         self.hist = None
         self.grid = None
@@ -259,31 +259,28 @@ class StripStep:
         return self.minmax
 
     def blend(self, curvature_weight):
+        """normalise + blend every radius with the (global) extrema in self.minmax; fills self.sal_minmax with the
+        extrema of the OWNED rows (rows {min, max}: ready for the MIN all-reduce)."""
         lib = _lib.load()
         self.sal_grid = {}
         n = self.grid.n
         with torch.cuda.device(self.dev):
             for i, r in enumerate(self.radii):
                 sal = torch.empty(n, dtype=torch.float32, device=self.dev)      # blend is elementwise: grid order
-                # the local saliency extrema must cover the OWNED rows only: ghosts are other strips' points, and a
-                # ghost near the halo's outer edge has an incomplete neighbourhood
-                check(lib.more3d_saliency_blend(ptr(self.dk[r].data), ptr(self.dn[r].data), n, ptr(self.minmax[i]),
-                                                float(curvature_weight), ptr(sal), None, stream_ptr()))
+                # ghosts are other strips' points (and near the halo's outer edge their neighbourhoods are incomplete)
+                check(lib.more3d_saliency_blend_owned(self.grid._h, ptr(self.dk[r].data), ptr(self.dn[r].data),
+                                                      ptr(self.minmax[i]), float(curvature_weight), self.n_left,
+                                                      self.n_own, ptr(sal), ptr(self.sal_minmax[i]), stream_ptr()))
                 self.sal_grid[r] = GridColumn(self.dk[r], sal)
-        return None
+        return self.sal_minmax
 
     def saliency(self, r):
         """(n_own,) f32 saliency of the owned points, in the caller's point order."""
         return self.sal_grid[r].tensor()[self.n_left:self.n_left + self.n_own]
 
     def owned_minmax(self):
-        """Local extrema of the owned points' saliency, rows {min, max, min, max} f32 -- input of the second
+        """Local extrema of the owned points' saliency, rows {min, max} f32 (filled by blend) -- input of the second
         all-reduce."""
-        lib = _lib.load()
-        with torch.cuda.device(self.dev):
-            for i, r in enumerate(self.radii):
-                v = self.saliency(r)
-                check(lib.more3d_minmax4(ptr(v), ptr(v), self.n_own, ptr(self.sal_minmax[i]), stream_ptr()))
         return self.sal_minmax
 
     def histograms(self):
@@ -332,7 +329,7 @@ class _StepResult:
 
 
 def allreduce_minmax_rows(mm, group=None):
-    """Rows of {min, max, min, max} f32 made global in place with ONE collective: MIN over (min, -max); the sign
+    """Rows of {min, max[, min, max]} f32 made global in place with ONE collective: MIN over (min, -max); the sign
     flips are one tiny library kernel each (more3d_negate_odd)."""
     lib = _lib.load()
     with torch.cuda.device(mm.device):
