@@ -87,20 +87,26 @@ __global__ void __launch_bounds__(LT_THREADS) lt_split_dim(const double* __restr
 
 // per position: mark the side (0 = left child, 1 = right child) of the point sitting at rank t - start
 // of its node's split-dimension list
+// ... and the node every POSITION belongs to on the next level (the partition keeps a node's range: positions
+// [b, b + n_mid) become its left child, the rest its right child), written to a second table because the partition
+// of this level still reads the current one
 __global__ void __launch_bounds__(LT_THREADS) lt_mark_sides(Lists L, int64_t n, const uint32_t* __restrict__ pos_node,
                                                             const int64_t* __restrict__ nstart,
                                                             const int64_t* __restrict__ nend, int64_t first,
                                                             const int8_t* __restrict__ split_dim,
-                                                            uint8_t* __restrict__ side) {
+                                                            uint8_t* __restrict__ side,
+                                                            uint32_t* __restrict__ pos_node_next) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int64_t node = pos_node[t];
-    if (node < first) return;             // a node that became a leaf above this level
-    const int d = split_dim[node - first];
-    if (d < 0) return;    // leaf: stays where it is
+    int d = -1;
+    if (node >= first) d = split_dim[node - first];     // node < first: became a leaf above this level
+    if (d < 0) { pos_node_next[t] = (uint32_t)node; return; }    // leaf: stays where it is
     const int64_t b = nstart[node], e = nend[node];
     const int64_t n_mid = (e - b) / 2;
-    side[L.p[d][t]] = (uint8_t)((t - b) >= n_mid);
+    const bool right = (t - b) >= n_mid;
+    side[L.p[d][t]] = (uint8_t)right;
+    pos_node_next[t] = (uint32_t)(right ? 2 * node + 2 : 2 * node + 1);
 }
 
 // Stable segmented partition of the three lists in ONE launch and ONE pass over each (blockIdx.y = list): the
@@ -139,8 +145,17 @@ __global__ void __launch_bounds__(LT_THREADS) lt_partition3(Lists L, Lists O, in
         if (t < n) {
             pt[i] = list[t];
             nd[i] = pos_node[t];
-            const bool split = (int64_t)nd[i] >= first && split_dim[(int64_t)nd[i] - first] >= 0;
-            const uint8_t sd = split ? side[pt[i]] : (uint8_t)0;
+            const int sdim = (int64_t)nd[i] >= first ? (int)split_dim[(int64_t)nd[i] - first] : -1;
+            const bool split = sdim >= 0;
+            uint8_t sd = 0;
+            if (split) {
+                if (sdim == d) {            // the node's split list: the side is positional, no gather
+                    const int64_t b = nstart[nd[i]], e = nend[nd[i]];
+                    sd = (uint8_t)((t - b) >= (e - b) / 2);
+                } else {
+                    sd = side[pt[i]];       // 1-byte table indexed by point id (L2-resident)
+                }
+            }
             fl[i] = (uint8_t)((sd == 0 ? 1 : 0) | (split ? 2 : 0) | (sd ? 4 : 0));
             s += fl[i] & 1u;
         }
@@ -175,18 +190,6 @@ __global__ void __launch_bounds__(LT_THREADS) lt_partition3(Lists L, Lists O, in
         }
         ex += fl[i] & 1u;
     }
-}
-
-__global__ void __launch_bounds__(LT_THREADS) lt_descend(int64_t n, uint32_t* __restrict__ pos_node,
-                                                         const int64_t* __restrict__ nstart,
-                                                         const int64_t* __restrict__ nend, int64_t first,
-                                                         const int8_t* __restrict__ split_dim) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int64_t node = pos_node[t];
-    if (node < first || split_dim[node - first] < 0) return;
-    const int64_t b = nstart[node], e = nend[node];
-    pos_node[t] = (uint32_t)((t - b) < (e - b) / 2 ? 2 * node + 1 : 2 * node + 2);
 }
 
 // sums of the deepest visited nodes (thread per node, sequential over its points), then parents
@@ -287,7 +290,7 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     const unsigned nb = (unsigned)((n + LT_THREADS - 1) / LT_THREADS);
     uint64_t *k1 = nullptr, *k2 = nullptr, *ks = nullptr;
     uint32_t *v1 = nullptr, *v2 = nullptr, *vs = nullptr;
-    uint32_t *lists[3] = {nullptr, nullptr, nullptr}, *alts[3] = {nullptr, nullptr, nullptr}, *pos_node = nullptr, *node_lp = nullptr;
+    uint32_t *lists[3] = {nullptr, nullptr, nullptr}, *alts[3] = {nullptr, nullptr, nullptr}, *pos_node = nullptr, *pos_node2 = nullptr, *node_lp = nullptr;
     uint64_t* lb_desc = nullptr;
     uint8_t* side = nullptr;
     int8_t* split_dim = nullptr;
@@ -298,6 +301,7 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     for (int d = 0; d < 3; ++d) M3D_TRY(dev_alloc(&lists[d], (size_t)n, s));
     for (int d = 0; d < 3; ++d) M3D_TRY(dev_alloc(&alts[d], (size_t)n, s));
     M3D_TRY(dev_alloc(&pos_node, (size_t)n, s));
+    M3D_TRY(dev_alloc(&pos_node2, (size_t)n, s));
     M3D_TRY(dev_alloc(&node_lp, (size_t)((n_nodes + 1) / 2 + 2), s));
     M3D_TRY(dev_alloc(&lb_desc, (size_t)3 * ((n + LTP_TILE - 1) / LTP_TILE) + 4, s));
     M3D_TRY(dev_alloc(&side, (size_t)n, s));
@@ -323,15 +327,15 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
         lt_split_dim<<<(unsigned)((count + LT_THREADS - 1) / LT_THREADS), LT_THREADS, 0, s>>>(
             xyz, L, idx_start, idx_end, is_leaf, first, count, split_dim, node_lp);
         M3D_TRY(exclusive_scan_u32(node_lp, node_lp, count, s));
-        lt_mark_sides<<<nb, LT_THREADS, 0, s>>>(L, n, pos_node, idx_start, idx_end, first, split_dim, side);
+        lt_mark_sides<<<nb, LT_THREADS, 0, s>>>(L, n, pos_node, idx_start, idx_end, first, split_dim, side, pos_node2);
         M3D_CUDA(cudaMemsetAsync(lb_desc, 0, ((size_t)3 * ntiles + 4) * sizeof(uint64_t), s));
         lt_partition3<<<dim3((unsigned)ntiles, 3), LT_THREADS, 0, s>>>(L, O, n, pos_node, idx_start, idx_end, first, split_dim,
                                                                        side, node_lp, lb_desc, (unsigned*)(lb_desc + (size_t)3 * ntiles),
                                                                        ntiles);
-        lt_descend<<<nb, LT_THREADS, 0, s>>>(n, pos_node, idx_start, idx_end, first, split_dim);
-        count_launches(4);
+        count_launches(3);
         M3D_CHECK_LAUNCH();
         for (int d = 0; d < 3; ++d) { uint32_t* tmp = lists[d]; lists[d] = alts[d]; alts[d] = tmp; }
+        { uint32_t* tmp = pos_node; pos_node = pos_node2; pos_node2 = tmp; }
     }
 
     // centroids bottom-up, radii top-down
@@ -355,7 +359,7 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     dev_free(k1, s); dev_free(k2, s); dev_free(v1, s); dev_free(v2, s);
     for (int d = 0; d < 3; ++d) dev_free(lists[d], s);
     for (int d = 0; d < 3; ++d) dev_free(alts[d], s);
-    dev_free(pos_node, s); dev_free(node_lp, s); dev_free(lb_desc, s); dev_free(side, s); dev_free(split_dim, s);
+    dev_free(pos_node, s); dev_free(pos_node2, s); dev_free(node_lp, s); dev_free(lb_desc, s); dev_free(side, s); dev_free(split_dim, s);
     dev_free(sums, s); dev_free(r2, s);
     return MORE3D_OK;
 }

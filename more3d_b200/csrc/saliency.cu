@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) minmax4_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk, const float* __restrict__ dn,
                                                     int64_t n, const float* __restrict__ minmax, double cw,
                                                     double nw, float* __restrict__ sal,
-                                                    unsigned* __restrict__ smm, const PointRec* __restrict__ rec,
+                                                    unsigned* __restrict__ smm, const uint32_t* __restrict__ order,
                                                     long long own_lo, long long own_hi) {
     const double min_k = (double)minmax[0], max_k = (double)minmax[1];
     const double min_n = (double)minmax[2], max_n = (double)minmax[3];
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk
         const float sv = (float)__dadd_rn(__dmul_rn(nw, (double)ndn), __dmul_rn(cw, (double)ndk));      // :579-580
         sal[i] = sv;
         // grid-order columns of a strip: only the rows of its OWN points (original index in [own_lo, own_hi)) count
-        const bool mine = rec == nullptr || [&] {
-            const long long o = __double_as_longlong(__ldg(reinterpret_cast<const double*>(rec + i) + 3));
+        const bool mine = order == nullptr || [&] {
+            const long long o = (long long)__ldg(order + i);
             return o >= own_lo && o < own_hi;
         }();
         if (mine && !isnan(sv)) {
@@ -154,7 +154,7 @@ extern "C" int more3d_saliency_blend_owned(const more3d_grid* g, const float* dk
     const double nw = 1.0 - curvature_weight;   // DM_saliency.py:572
     const bool all = n_owned <= 0 || (own_lo <= 0 && own_lo + n_owned >= g->n);
     ProfScope prof("blend", s);
-    blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, g->n, minmax, curvature_weight, nw, sal, mm, all ? nullptr : g->rec,
+    blend_kernel<<<148 * 8, 256, 0, s>>>(dk, dn, g->n, minmax, curvature_weight, nw, sal, mm, all ? nullptr : g->order,
                                          (long long)own_lo, (long long)(own_lo + n_owned));
     mm4_finish<<<1, 32, 0, s>>>(mm, sal_minmax, 2);
     count_launches(3);

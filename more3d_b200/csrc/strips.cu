@@ -118,8 +118,11 @@ __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             if (lo[a] <= hi[a]) {
-                atomicMin(info + a, ord64(lo[a]));
-                atomicMax(info + 3 + a, ord64(hi[a]));
+                // racy pre-read: after the first tiles hardly any warp still improves a bound, and thousands of
+                // same-address atomics would serialise in L2
+                const unsigned long long ol = ord64(lo[a]), oh = ord64(hi[a]);
+                if (ol < *(volatile unsigned long long*)(info + a)) atomicMin(info + a, ol);
+                if (oh > *(volatile unsigned long long*)(info + 3 + a)) atomicMax(info + 3 + a, oh);
             }
         }
     }
