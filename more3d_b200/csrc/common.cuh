@@ -67,6 +67,23 @@ static inline void dev_free(void* p, cudaStream_t s) {
     if (p) cudaFreeAsync(p, s);
 }
 
+// scratch buffers of one C-ABI call: freed (stream-ordered) when the holder goes out of scope, on every return path
+struct Scratch {
+    cudaStream_t s;
+    void* p[40];
+    int n;
+    explicit Scratch(cudaStream_t stream) : s(stream), n(0) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() { for (int i = 0; i < n; ++i) dev_free(p[i], s); }
+    template <typename T>
+    int alloc(T** out, size_t count) {
+        const int rc = dev_alloc(out, count, s);
+        if (rc == MORE3D_OK && n < 40) p[n++] = (void*)*out;
+        return rc;
+    }
+};
+
 // Margin between the grid's column width and the largest radius one stencil step covers: rounding
 // in floor((x - ox) * inv_cell) is ~1e-13 relative, 2^-16 leaves orders of magnitude of slack.
 #define M3D_CELL_MARGIN (1.0 + 1.0 / 65536.0)

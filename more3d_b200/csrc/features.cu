@@ -530,16 +530,17 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     M3D_REQUIRE(!cached || g->feat != nullptr, "no cached feature records: run more3d_normals_curvature on this grid first");
     M3D_REQUIRE(table_len > 0, "chi2 table is empty");
     cudaStream_t s = (cudaStream_t)stream;
+    Scratch sc(s);
     FeatRec* feat = nullptr;
     unsigned* mm = nullptr;
     int* err = nullptr;
     if (cached) feat = g->feat;
-    else M3D_TRY(dev_alloc(&feat, (size_t)g->n, s));
-    M3D_TRY(dev_alloc(&mm, 4, s));
+    else M3D_TRY(sc.alloc(&feat, (size_t)g->n));
+    M3D_TRY(sc.alloc(&mm, 4));
     if (status) {
         err = status;       // the caller's status word: raised on overflow, never cleared, read when the caller likes
     } else {
-        M3D_TRY(dev_alloc(&err, 1, s));
+        M3D_TRY(sc.alloc(&err, 1));
         M3D_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
     }
     const unsigned nb = (unsigned)((g->n + 255) / 256);
@@ -587,10 +588,7 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     if (!status) {          // no status word: the call itself reports the overflow (one stream synchronisation)
         M3D_CUDA(cudaMemcpyAsync(&err_h, err, sizeof(int), cudaMemcpyDeviceToHost, s));
         M3D_CUDA(cudaStreamSynchronize(s));
-        dev_free(err, s);
     }
-    if (!cached) dev_free(feat, s);
-    dev_free(mm, s);
     if (err_h) {
         set_error("dk/dn: a neighbourhood has %d active neighbours, chi2_table covers %d (table_len)", err_h - 1, table_len - 1);
         return MORE3D_E_RANGE;

@@ -331,7 +331,9 @@ __device__ __forceinline__ void block_sum_store(double v[NV], double* __restrict
 // deactivated / newly activated points are re-clamped to +-max_val (Solver.run :603-608, initialize_new :542-545)
 __global__ void __launch_bounds__(LS_THREADS) ls_reclamp(int64_t n, const uint8_t* __restrict__ active,
                                                          const uint8_t* __restrict__ last_active, double max_val,
-                                                         double* __restrict__ phi) {
+                                                         double* __restrict__ phi,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (active[i] != last_active[i]) phi[i] = np_sign(phi[i]) * max_val;
@@ -341,7 +343,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_reclamp(int64_t n, const uint8_
 __global__ void __launch_bounds__(LS_THREADS) ls_step_a(LsGraph g, LsParams p, const double* __restrict__ phi,
                                                         const uint8_t* __restrict__ active, uint8_t* __restrict__ idx2,
                                                         double* __restrict__ laplace, double* __restrict__ dphi /* SoA 3n */,
-                                                        double* __restrict__ aux /* AoS n x 4: dp_, ctmp xyz */) {
+                                                        double* __restrict__ aux /* AoS n x 4: dp_, ctmp xyz */,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     uint8_t on = 0;
@@ -373,7 +377,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_a(LsGraph g, LsParams p, c
 __global__ void __launch_bounds__(LS_THREADS) ls_region_partial(int64_t n, int channels, double eps,
                                                                 const double* __restrict__ phi,
                                                                 const double* __restrict__ zeta, int c,
-                                                                double* __restrict__ part /* RED_BLOCKS x 4 */) {
+                                                                double* __restrict__ part /* RED_BLOCKS x 4 */,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     double v[4] = {0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double H = heaviside(phi[i], eps);
@@ -387,7 +393,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_region_partial(int64_t n, int c
 // thread walking all 9 472 partials of step b took 0.28 ms, 12 % of an iteration.)
 constexpr int RF_THREADS = 256;
 __global__ void __launch_bounds__(RF_THREADS) ls_reduce_final(const double* __restrict__ part, int nblocks, int nv,
-                                                              double* __restrict__ out) {
+                                                              double* __restrict__ out,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     __shared__ double sm[RF_THREADS / 32];
     for (int a = 0; a < nv; ++a) {
         double r = 0;
@@ -410,7 +418,9 @@ __global__ void __launch_bounds__(RF_THREADS) ls_reduce_final(const double* __re
 // means.  The cue is a single channel: the reference's expressions only broadcast for a 1-D zeta.
 // idx_ = idx | neighbours of idx (:463-464); idxd is zeroed by the caller
 __global__ void __launch_bounds__(LS_THREADS) ls_lmv_dilate(LsGraph g, const uint8_t* __restrict__ idx2,
-                                                            uint8_t* __restrict__ idxd) {
+                                                            uint8_t* __restrict__ idxd,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     if (idx2[i]) {
@@ -424,7 +434,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_lmv_stats(LsGraph g, double eps
                                                            const double* __restrict__ zeta,
                                                            const uint8_t* __restrict__ idxd,
                                                            const uint8_t* __restrict__ force /* or NULL */,
-                                                           double* __restrict__ stats /* AoS n x 4 */) {
+                                                           double* __restrict__ stats /* AoS n x 4 */,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     double2* out = reinterpret_cast<double2*>(stats + 4 * i);
@@ -492,7 +504,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, d
                                                         const double* __restrict__ zeta,
                                                         const double* __restrict__ region /* channels x 4 sums */,
                                                         const double* __restrict__ stats /* lmv: n x 4, else NULL */,
-                                                        double* __restrict__ phi_new, double* __restrict__ part /* RED_BLOCKS x 2 */) {
+                                                        double* __restrict__ phi_new, double* __restrict__ part /* RED_BLOCKS x 2 */,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     double v[2] = {0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += (int64_t)gridDim.x * blockDim.x) {
         double out = phi[i];
@@ -555,7 +569,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_b(LsGraph g, LsParams p, d
 // active[active] = zero_crossings(phi, active) (:617-619); cap to +-max_val (:620-624)
 __global__ void __launch_bounds__(LS_THREADS) ls_step_c(LsGraph g, LsParams p, const double* __restrict__ phi_new,
                                                         const uint8_t* __restrict__ active, uint8_t* __restrict__ active_zc,
-                                                        double* __restrict__ phi_cap, uint8_t* __restrict__ outside) {
+                                                        double* __restrict__ phi_cap, uint8_t* __restrict__ outside,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const double u = phi_new[i];
@@ -576,14 +592,18 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_c(LsGraph g, LsParams p, c
 }
 // phi[outside] = smooth(phi, outside)  (Jacobi: reads the clamped field, :625-627)
 __global__ void __launch_bounds__(LS_THREADS) ls_step_d(LsGraph g, const double* __restrict__ phi_cap,
-                                                        const uint8_t* __restrict__ outside, double* __restrict__ phi_s) {
+                                                        const uint8_t* __restrict__ outside, double* __restrict__ phi_s,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     phi_s[i] = outside[i] ? smooth_at(g, i, phi_cap) : phi_cap[i];
 }
 // lonely points: every neighbour has the other sign -> smoothed (:628-631); result is the new phi
 __global__ void __launch_bounds__(LS_THREADS) ls_step_e(LsGraph g, const double* __restrict__ phi_s,
-                                                        double* __restrict__ phi_out) {
+                                                        double* __restrict__ phi_out,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const double u = phi_s[i];
@@ -594,7 +614,9 @@ __global__ void __launch_bounds__(LS_THREADS) ls_step_e(LsGraph g, const double*
 }
 // active[neighbors[active]] = True (:632)
 __global__ void __launch_bounds__(LS_THREADS) ls_step_f(LsGraph g, const uint8_t* __restrict__ active_zc,
-                                                        uint8_t* __restrict__ active) {
+                                                        uint8_t* __restrict__ active,
+        const int* __restrict__ stop = nullptr) {
+    if (stop != nullptr && *stop != 0) return;   // the run has converged (device-side early exit, see ls_run_impl)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     if (active_zc[i]) {
@@ -642,10 +664,25 @@ __global__ void __launch_bounds__(LS_THREADS) ls_extract_prune(LsGraph g, const 
 
 using namespace m3d;
 
+// byte-buffer clears / copies of the iteration as kernels, so that they too stop once the run has converged
+__global__ void __launch_bounds__(LS_THREADS) ls_fill_u8(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t n,
+                                                         const int* __restrict__ stop) {
+    if (stop != nullptr && *stop != 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src ? src[i] : (uint8_t)0;
+}
+// end of iteration `it`: mean(increment^2)^0.5 < tolerance (levelsets_func.py:635-638) raises the stop flag; every later
+// kernel of the queue then returns at once, and `done` says how many iterations really ran
+__global__ void ls_check_tolerance(const double* __restrict__ inc2, double tolerance, int it, int* stop, int* done) {
+    if (*stop != 0) return;
+    *done = it + 1;
+    if (sqrt(inc2[0] / inc2[1]) < tolerance) *stop = 1;
+}
+
 static void launch_step_b(const LsGraph& g, const LsParams& p, double* phi, const uint8_t* idx2, const double* laplace,
                           const double* dphi, const double* aux, const double* zeta, const double* region,
-                          const double* stats, double* phi_new, double* part, cudaStream_t s) {
-#define M3D_STEP_B(KT_) ls_step_b<KT_><<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, phi_new, part)
+                          const double* stats, double* phi_new, double* part, cudaStream_t s, const int* stop = nullptr) {
+#define M3D_STEP_B(KT_) ls_step_b<KT_><<<STEPB_BLOCKS, LS_THREADS, 0, s>>>(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, phi_new, part, stop)
     switch (g.k) {
         case 5: M3D_STEP_B(5); break;
         case 6: M3D_STEP_B(6); break;
@@ -804,57 +841,67 @@ static int ls_run_impl(const more3d_ls_graph* G, int model, double* phi, const d
     p.stepsize = stepsize; p.nu = nu; p.mu = mu; p.lambda1 = lambda1; p.lambda2 = lambda2; p.epsilon = epsilon;
     p.max_val = max_val; p.cap = cap; p.channels = channels; p.model = model;
     ProfScope prof("ls_run", s);
+    Scratch sc(s);
     double* stats = nullptr;
     uint8_t* idxd = nullptr;
-    if (model == 1) { M3D_TRY(dev_alloc(&stats, (size_t)4 * n, s)); M3D_TRY(dev_alloc(&idxd, (size_t)n, s)); }
+    if (model == 1) { M3D_TRY(sc.alloc(&stats, (size_t)4 * n)); M3D_TRY(sc.alloc(&idxd, (size_t)n)); }
     double *laplace = nullptr, *dphi = nullptr, *aux = nullptr, *bufA = nullptr, *bufB = nullptr;
     double *part = nullptr, *region = nullptr, *incs = nullptr;
     uint8_t *idx2 = nullptr, *azc = nullptr, *outside = nullptr;
-    M3D_TRY(dev_alloc(&laplace, (size_t)n, s)); M3D_TRY(dev_alloc(&dphi, (size_t)3 * n, s));
-    M3D_TRY(dev_alloc(&aux, (size_t)4 * n, s));
-    M3D_TRY(dev_alloc(&bufA, (size_t)n, s));    M3D_TRY(dev_alloc(&bufB, (size_t)n, s));
-    M3D_TRY(dev_alloc(&part, (size_t)STEPB_BLOCKS * 4, s));
-    M3D_TRY(dev_alloc(&region, (size_t)4 * channels, s));
-    M3D_TRY(dev_alloc(&incs, (size_t)2 * (iterations + 1), s));
-    M3D_TRY(dev_alloc(&idx2, (size_t)n, s)); M3D_TRY(dev_alloc(&azc, (size_t)n, s)); M3D_TRY(dev_alloc(&outside, (size_t)n, s));
+    M3D_TRY(sc.alloc(&laplace, (size_t)n)); M3D_TRY(sc.alloc(&dphi, (size_t)3 * n));
+    M3D_TRY(sc.alloc(&aux, (size_t)4 * n));
+    M3D_TRY(sc.alloc(&bufA, (size_t)n));    M3D_TRY(sc.alloc(&bufB, (size_t)n));
+    M3D_TRY(sc.alloc(&part, (size_t)STEPB_BLOCKS * 4));
+    M3D_TRY(sc.alloc(&region, (size_t)4 * channels));
+    M3D_TRY(sc.alloc(&incs, (size_t)2 * (iterations + 1)));
+    M3D_TRY(sc.alloc(&idx2, (size_t)n)); M3D_TRY(sc.alloc(&azc, (size_t)n)); M3D_TRY(sc.alloc(&outside, (size_t)n));
     const unsigned nb = (unsigned)((n + LS_THREADS - 1) / LS_THREADS);
     int done = 0, conv = 0;
+    // tolerance > 0 (the reference's default): convergence is decided ON THE DEVICE -- a stop flag raised by the
+    // iteration that meets the tolerance makes every kernel queued after it return at once -- so the whole run is
+    // enqueued without a host round trip per iteration and read back with ONE synchronisation at the end.
+    int* flags = nullptr;                         // {stop, done}
+    M3D_TRY(sc.alloc(&flags, 2));
+    M3D_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), s));
+    const int* stop = tolerance > 0 ? flags : nullptr;
+    const unsigned nbf = 148 * 8;
     for (int it = 0; it < iterations; ++it) {
-        if (!alias_last_active) ls_reclamp<<<nb, LS_THREADS, 0, s>>>(n, active, last_active, max_val, phi);
+        if (!alias_last_active) ls_reclamp<<<nb, LS_THREADS, 0, s>>>(n, active, last_active, max_val, phi, stop);
         if (nu > 0 || mu > 0 || model == 1) {             // _lmv_step differentiates unconditionally, :440-446
-            ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, phi, active, idx2, laplace, dphi, aux);
+            ls_step_a<<<nb, LS_THREADS, 0, s>>>(g, p, phi, active, idx2, laplace, dphi, aux, stop);
         } else {
-            M3D_CUDA(cudaMemcpyAsync(idx2, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // idx stays the active mask
+            ls_fill_u8<<<nbf, LS_THREADS, 0, s>>>(idx2, active, n, stop);      // idx stays the active mask
         }
         if (model == 1) {
-            M3D_CUDA(cudaMemsetAsync(idxd, 0, (size_t)n, s));
-            ls_lmv_dilate<<<nb, LS_THREADS, 0, s>>>(g, idx2, idxd);
-            ls_lmv_stats<<<nb, LS_THREADS, 0, s>>>(g, epsilon, phi, zeta, idxd, nullptr, stats);
-            count_launches(2);
+            ls_fill_u8<<<nbf, LS_THREADS, 0, s>>>(idxd, nullptr, n, stop);
+            ls_lmv_dilate<<<nb, LS_THREADS, 0, s>>>(g, idx2, idxd, stop);
+            ls_lmv_stats<<<nb, LS_THREADS, 0, s>>>(g, epsilon, phi, zeta, idxd, nullptr, stats, stop);
+            count_launches(3);
         } else {
             for (int c = 0; c < channels; ++c) {
-                ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, epsilon, phi, zeta, c, part);
-                ls_reduce_final<<<1, RF_THREADS, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c);
+                ls_region_partial<<<RED_BLOCKS, LS_THREADS, 0, s>>>(n, channels, epsilon, phi, zeta, c, part, stop);
+                ls_reduce_final<<<1, RF_THREADS, 0, s>>>(part, RED_BLOCKS, 4, region + 4 * c, stop);
             }
         }
-        launch_step_b(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, bufA, part, s);
-        ls_reduce_final<<<1, RF_THREADS, 0, s>>>(part, STEPB_BLOCKS, 2, incs + 2 * it);
-        if (!alias_last_active) M3D_CUDA(cudaMemcpyAsync(last_active, active, (size_t)n, cudaMemcpyDeviceToDevice, s));   // :617
-        ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, bufA, active, azc, bufB, outside);
-        ls_step_d<<<nb, LS_THREADS, 0, s>>>(g, bufB, outside, bufA);
-        ls_step_e<<<nb, LS_THREADS, 0, s>>>(g, bufA, phi);
-        M3D_CUDA(cudaMemsetAsync(active, 0, (size_t)n, s));
-        ls_step_f<<<nb, LS_THREADS, 0, s>>>(g, azc, active);
-        count_launches(7 + (model == 1 ? 0 : 2 * channels) + (alias_last_active ? 0 : 1));
+        launch_step_b(g, p, phi, idx2, laplace, dphi, aux, zeta, region, stats, bufA, part, s, stop);
+        ls_reduce_final<<<1, RF_THREADS, 0, s>>>(part, STEPB_BLOCKS, 2, incs + 2 * it, stop);
+        if (!alias_last_active) ls_fill_u8<<<nbf, LS_THREADS, 0, s>>>(last_active, active, n, stop);   // :617
+        ls_step_c<<<nb, LS_THREADS, 0, s>>>(g, p, bufA, active, azc, bufB, outside, stop);
+        ls_step_d<<<nb, LS_THREADS, 0, s>>>(g, bufB, outside, bufA, stop);
+        ls_step_e<<<nb, LS_THREADS, 0, s>>>(g, bufA, phi, stop);
+        ls_fill_u8<<<nbf, LS_THREADS, 0, s>>>(active, nullptr, n, stop);
+        ls_step_f<<<nb, LS_THREADS, 0, s>>>(g, azc, active, stop);
+        if (tolerance > 0) ls_check_tolerance<<<1, 1, 0, s>>>(incs + 2 * it, tolerance, it, flags, flags + 1);   // :635-638
+        count_launches(9 + (model == 1 ? 0 : 2 * channels) + (alias_last_active ? 0 : 2) + (tolerance > 0 ? 1 : 0));
         M3D_CHECK_LAUNCH();
         done = it + 1;
-        if (tolerance > 0) {                               // the reference checks every iteration, :635-638
-            double h2[2];
-            M3D_CUDA(cudaMemcpyAsync(h2, incs + 2 * it, sizeof(h2), cudaMemcpyDeviceToHost, s));
-            M3D_CUDA(cudaStreamSynchronize(s));
-            const double rmsc = sqrt(h2[0] / h2[1]);
-            if (rmsc < tolerance) { conv = 1; break; }
-        }
+    }
+    if (tolerance > 0 && iterations > 0) {
+        int h[2] = {0, 0};
+        M3D_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, s));
+        M3D_CUDA(cudaStreamSynchronize(s));
+        conv = h[0];
+        done = h[1];
     }
     if (rmsc_h && done > 0) {
         double* tmp = new double[(size_t)2 * done];
@@ -866,9 +913,6 @@ static int ls_run_impl(const more3d_ls_graph* G, int model, double* phi, const d
     }
     if (iterations_done_h) *iterations_done_h = done;
     if (converged_h) *converged_h = conv;
-    dev_free(laplace, s); dev_free(dphi, s); dev_free(aux, s); dev_free(bufA, s); dev_free(bufB, s);
-    dev_free(part, s); dev_free(region, s); dev_free(incs, s); dev_free(idx2, s); dev_free(azc, s); dev_free(outside, s);
-    dev_free(stats, s); dev_free(idxd, s);
     return MORE3D_OK;
 }
 

@@ -390,3 +390,36 @@ def test_trajectory_without_handed_over_frames_or_weights_is_quantified(g, capsy
         assert np.median(d) <= 1e-6, (tag, report[tag])
     with capsys.disabled():
         print("\nlevel-set drift after 10 iterations vs the verbatim golden:", report)
+
+
+def test_tolerance_stops_on_the_device_at_the_reference_iteration(g):
+    """tolerance > 0 (the reference's default, levelsets_func.py:598, :635-638): the run stops after the FIRST iteration
+    whose RMS change is below it -- decided by a device-side flag, not a host round trip per iteration -- and leaves
+    exactly the state a tolerance-free run of that many iterations leaves."""
+    from more3d_b200 import levelsets_func as ls
+    pts, h = g["points"], float(g["h"])
+
+    def fresh():
+        s = ls.Solver(h, g["zeta"], pts, g["neighbors"], (g["t1"], g["t2"]), "chan_vese", weights=g["weights"])
+        s.initialize_from_voxels(2.0)
+        s.phi[:] = g["phi_s"]
+        return s
+    kw = dict(RUN)
+    s0 = fresh()
+    s0.run(12, **kw)
+    hist = list(s0.rmsc_history)
+    j = int(np.argmin(hist[:8]))                       # the run must stop right after iteration j
+    tol = hist[j] * (1 + 1e-9)
+    stop_at = next(i for i, v in enumerate(hist) if v < tol)
+    kw["tolerance"] = tol
+    s1 = fresh()
+    assert s1.run(12, **kw) is True
+    assert len(s1.rmsc_history) == stop_at + 1 and s1.rmsc_history == hist[:stop_at + 1]
+    kw["tolerance"] = 0
+    s2 = fresh()
+    assert s2.run(stop_at + 1, **kw) is False
+    assert np.array_equal(s1.phi, s2.phi) and np.array_equal(s1.active, s2.active)
+    kw["tolerance"] = min(hist) * 0.5                  # never reached: all iterations run, not converged
+    s3 = fresh()
+    assert s3.run(12, **kw) is False and len(s3.rmsc_history) == 12
+    assert np.array_equal(s3.phi, s0.phi)
