@@ -25,6 +25,30 @@ from ._lib import check, ptr, stream_ptr
 from .grid import GridColumn, UniformGrid, as_device_points, cell_for_radius
 
 
+# Overflow status words of the dk/dn passes: handed out from one zeroed per-device ring (a word is only ever written on a
+# chi2-table overflow, so the ring needs no re-zeroing kernel per pass; after an overflow the ring is replaced).
+_STATUS_RING = {}
+_RING_WORDS = 4096
+
+
+def _status_words(device, count):
+    key = str(device)
+    ring = _STATUS_RING.get(key)
+    if ring is None or ring[1] + count > _RING_WORDS:
+        if ring is None:
+            ring = [torch.zeros(_RING_WORDS, dtype=torch.int32, device=device), 0]
+            _STATUS_RING[key] = ring
+        else:
+            ring[1] = 0                      # wrap: the oldest words were read long ago (and found zero)
+    t = ring[0][ring[1]:ring[1] + count]
+    ring[1] += count
+    return t
+
+
+def _status_ring_poisoned(device):
+    _STATUS_RING.pop(str(device), None)      # an overflow left a non-zero word: start a fresh ring
+
+
 class _Columns(dict):
     """Attribute table: name -> device tensor in the caller's point order.  A value may be stored as a
     GridColumn (grid order); reading it through the mapping interface un-permutes it once, `raw` does not."""
@@ -147,7 +171,7 @@ class PointCloudDM:
     def status_word(self):
         """A zeroed device int32 for the next dk/dn pass's overflow report (slot len(_pending) of one small tensor)."""
         if self._status is None or len(self._pending) >= int(self._status.numel()):
-            self._status = torch.zeros(64, dtype=torch.int32, device=self.device)
+            self._status = _status_words(self.device, 16)
             self._pending = []
         i = len(self._pending)
         return self._status[i:i + 1]
@@ -155,6 +179,8 @@ class PointCloudDM:
     def _need(self, host_words):
         need = 0
         for v, length in zip(host_words, self._pending):
+            if int(v) != 0:
+                _status_ring_poisoned(self.device)
             if int(v) > length:
                 need = max(need, int(v))
         self._pending = []
@@ -323,6 +349,8 @@ class Saliency_Kernel(_KernelPointEx):
                 break
             need = int(status.item())         # a neighbourhood with more active neighbours than the table covers
             dm._pending, dm._status = [], None
+            if need:
+                _status_ring_poisoned(dm.device)
             if need <= length:
                 break
             if need > (1 << 24):

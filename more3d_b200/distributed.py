@@ -232,7 +232,8 @@ class StripStep:
         R = len(self.radii)
         self.minmax = torch.empty((R, 4), dtype=torch.float32, device=self.dev)
         self.sal_minmax = torch.empty((R, 2), dtype=torch.float32, device=self.dev)   # rows {min, max} of the owned saliency
-        self.status = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        from .DM_saliency import _status_words
+        self.status = _status_words(self.dev, R)
         self.hist = None
         self.grid = None
 
@@ -315,6 +316,9 @@ class _StepResult:
     def overflow(self):
         """0, or the chi2-table length that would have sufficed (reads the status words: synchronises)."""
         need = int(self.status.cpu().numpy().max())
+        if need:
+            from .DM_saliency import _status_ring_poisoned
+            _status_ring_poisoned(self.status.device)
         return need if need > self.table_len else 0
 
     def otsu(self):
