@@ -46,9 +46,8 @@ class BallTreePointSet(object):
 
     def _knn_cell(self, k):
         """Column width giving ~k points per 3x3 block for this cloud's mean planimetric density."""
-        lo = self.__dev.amin(dim=0)
-        hi = self.__dev.amax(dim=0)
-        ext = (hi - lo).cpu().numpy()
+        b = _lib.cloud_bounds(self.__dev)
+        ext = b[3:] - b[:3]
         area = max(float(ext[0]) * float(ext[1]), 1e-300)
         n = self.__points.shape[0]
         cell = np.sqrt(max(k, 8) * area / (4.0 * n))

@@ -475,5 +475,8 @@ def DM_saliency_stats(odm):
     if "_saliency" not in dm.attrs:
         print("no saliency values")
         return 1
-    s = dm.attrs["_saliency"].double()
-    return (float(s.min()), float(s.max()), float(s.mean()), float(s.std(unbiased=False)))
+    sal = dm.attrs["_saliency"].contiguous()
+    with torch.cuda.device(sal.device):
+        out = torch.empty(4, dtype=torch.float64, device=sal.device)
+        check(_lib.load().more3d_column_stats(ptr(sal), int(sal.numel()), ptr(out), stream_ptr()))
+    return tuple(float(v) for v in out.cpu().numpy())

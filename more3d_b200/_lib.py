@@ -67,6 +67,7 @@ SIGNATURES = {
     "more3d_compare_terms": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "more3d_band_select": [_vp, _i64, _i32, _f64, _f64, _vp, C.POINTER(_i64), _vp],
     "more3d_gather_rows": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "more3d_column_stats": [_vp, _i64, _vp, _vp],
     "more3d_select_kth": [_vp, _i64, C.POINTER(_i64), _i32, _vp, _vp],
     "more3d_cue_ops": [_i32, _vp, _i64, _vp, _f64, _vp, _vp],
     "more3d_saliency_blend_owned": [_vp, _vp, _vp, _vp, _f64, _i64, _i64, _vp, _vp, _vp],
@@ -164,6 +165,19 @@ def profile_all():
     check(load().more3d_profile_names(buf, 4096))
     names = [n for n in buf.value.decode().split(",") if n]
     return {n: profile_get(n) for n in names}
+
+
+def cloud_bounds(xyz):
+    """(min x, y, z, max x, y, z) of an (N, 3) f64 device tensor as host floats -- the bounding-box reduction of
+    more3d_strip_pack with both halo bands empty (one kernel, one small read)."""
+    import torch
+    n = int(xyz.shape[0])
+    with torch.cuda.device(xyz.device):
+        info = torch.empty(8, dtype=torch.float64, device=xyz.device)
+        dummy = torch.empty(3, dtype=torch.float64, device=xyz.device)
+        check(load().more3d_strip_pack(ptr(xyz), n, float("-inf"), float("inf"), ptr(dummy), ptr(dummy), 0, ptr(info),
+                                       stream_ptr()))
+    return info[:6].cpu().numpy()
 
 
 def launch_count():

@@ -96,7 +96,8 @@ struct __align__(32) PointRec {
     long long idx;  // original index
 };
 
-// sorted feature record for the dk/dn pass: 64 B
+// sorted feature record for the dk/dn pass: 64 B per point, STORED AS TWO ARRAYS OF 32-BYTE HALVES (first (x, y, z, K)
+// of all points, then (nx, ny, nz, pad) of all points; see ld_d4 / st_feat in features.cu) -- the struct only sizes it
 struct __align__(32) FeatRec {
     double x, y, z;
     double K;        // _nonparam_K (f32 value widened: 29 zero mantissa bits) with two flags in bits 0-1:

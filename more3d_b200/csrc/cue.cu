@@ -134,9 +134,65 @@ __global__ void __launch_bounds__(256) normalize_kernel(double* x, int64_t n, co
         x[i] = __dmul_rn(__ddiv_rn(__dsub_rn(x[i], mn), top), s);
 }
 
+// {min, max, sum} partials, then {min, max, mean}; second pass: sum of squared deviations -> population sigma.
+// Fixed 592-block tree: reproducible run to run.
+__global__ void __launch_bounds__(256) stats_partial(const float* __restrict__ x, int64_t n, const double* __restrict__ mean,
+                                                     double* __restrict__ part) {
+    double lo = INFINITY, hi = -INFINITY, sum = 0.0;
+    const double mu = mean ? mean[2] : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        if (mean) { const double d = v - mu; sum += d * d; }
+        else { lo = fmin(lo, v); hi = fmax(hi, v); sum += v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    __shared__ double sl[8], sh[8], ss[8];
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = lo; sh[threadIdx.x >> 5] = hi; ss[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, sl[w]); hi = fmax(hi, sh[w]); sum += ss[w]; }
+        part[3 * blockIdx.x] = lo; part[3 * blockIdx.x + 1] = hi; part[3 * blockIdx.x + 2] = sum;
+    }
+}
+__global__ void stats_final(const double* __restrict__ part, int nparts, int64_t n, int second, double* __restrict__ out) {
+    double lo = INFINITY, hi = -INFINITY, sum = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 32) { lo = fmin(lo, part[3 * i]); hi = fmax(hi, part[3 * i + 1]); sum += part[3 * i + 2]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (threadIdx.x == 0) {
+        if (second) out[3] = sqrt(sum / (double)n);
+        else { out[0] = lo; out[1] = hi; out[2] = sum / (double)n; }
+    }
+}
+
 }  // namespace m3d
 
 using namespace m3d;
+
+/* out (device, 4 f64) = {min, max, mean, population sigma} of an f32 column (DM_saliency_stats, DM_saliency.py:585-607) */
+extern "C" int more3d_column_stats(const float* x, int64_t n, double* out, void* stream) {
+    M3D_REQUIRE(x && out && n > 0, "NULL / empty argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch sc(s);
+    double* part = nullptr;
+    M3D_TRY(sc.alloc(&part, (size_t)3 * 592));
+    stats_partial<<<592, 256, 0, s>>>(x, n, nullptr, part);
+    stats_final<<<1, 32, 0, s>>>(part, 592, n, 0, out);
+    stats_partial<<<592, 256, 0, s>>>(x, n, out, part);
+    stats_final<<<1, 32, 0, s>>>(part, 592, n, 1, out);
+    count_launches(4);
+    M3D_CHECK_LAUNCH();
+    return MORE3D_OK;
+}
 
 extern "C" int more3d_select_kth(const double* v, int64_t n, const int64_t* ranks_h, int nk, double* out, void* stream) {
     M3D_REQUIRE(v && ranks_h && out && n > 0, "NULL / empty argument");

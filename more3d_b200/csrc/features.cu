@@ -25,6 +25,26 @@ struct CurvParams {
 
 constexpr int WALK_THREADS = 256;
 
+struct D4 { double x, y, z, w; };
+struct D4x2 { D4 a, b; };
+// The feature records live as TWO arrays of 32-byte halves -- half 0 = (x, y, z, K | flags) of all n points, then half 1
+// = (nx, ny, nz, pad) of all n points -- not as n 64-byte structs: at every candidate step the 32 lanes of a warp read
+// ~13 distinct records out of a window of ~32 consecutive ones, and with 32-byte elements that window is 8 cache lines
+// per load instead of 16 (the L1 data pipe, this kernel's highest bound, charges a wavefront per line touched).
+__device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int64_t n, int64_t j, int h) {
+    D4 r;
+    ldg256(reinterpret_cast<const char*>(f) + ((size_t)h * (size_t)n + (size_t)j) * 32, r.x, r.y, r.z, r.w);
+    return r;
+}
+__device__ __forceinline__ void st_feat(FeatRec* __restrict__ f, int64_t n, int64_t i, double x, double y, double z,
+                                        double K, double nx, double ny, double nz) {
+    double4* a = reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + (size_t)i * 32);
+    double4* b = reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + ((size_t)n + (size_t)i) * 32);
+    *a = make_double4(x, y, z, K);
+    *b = make_double4(nx, ny, nz, 0.0);
+}
+
+
 // One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
 // query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
 template <int MODE, bool TALL>
@@ -110,12 +130,9 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, Cu
         // the dk/dn pass's sorted feature record, written here (coalesced) instead of being gathered
         // from the original-order columns by build_feat_kernel; same arithmetic as there
         const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
-        FeatRec f;
-        f.x = p.x; f.y = p.y; f.z = p.z;
-        f.K = __longlong_as_double(__double_as_longlong((double)K) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL));
-        f.nx = nx / nn; f.ny = ny / nn; f.nz = nz / nn;
-        f.pad = 0.0;
-        feat_out[i] = f;
+        st_feat(feat_out, g.n, i, p.x, p.y, p.z,
+                __longlong_as_double(__double_as_longlong((double)K) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL)),
+                nx / nn, ny / nn, nz / nn);
     }
 }
 
@@ -132,21 +149,9 @@ __global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const doubl
     const double nx = normals[3 * o], ny = normals[3 * o + 1], nz = normals[3 * o + 2];
     // n / ||n||, DM_saliency.py:258-259 (norm = sqrt of the sequential sum of squares)
     const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
-    FeatRec f;
-    f.x = p.x; f.y = p.y; f.z = p.z;
-    f.K = __longlong_as_double(__double_as_longlong((double)K[o]) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL));
-    f.nx = nx / nn; f.ny = ny / nn; f.nz = nz / nn;
-    f.pad = 0.0;
-    feat[i] = f;
-}
-
-struct D4 { double x, y, z, w; };
-struct D4x2 { D4 a, b; };
-// half h (0/1) of a 64-B feature record as two LDG.128 through the read-only path
-__device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int h) {
-    D4 r;
-    ldg256(reinterpret_cast<const char*>(f) + 32 * h, r.x, r.y, r.z, r.w);
-    return r;
+    st_feat(feat, g.n, i, p.x, p.y, p.z,
+            __longlong_as_double(__double_as_longlong((double)K[o]) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL)),
+            nx / nn, ny / nn, nz / nn);
 }
 
 struct DkDnParams {
@@ -301,11 +306,11 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
     bool owned = false;
     if (live) {
         DkdnAcc acc;
-        acc.init(ld_d4(feat + i, 0), ld_d4(feat + i, 1));
+        acc.init(ld_d4(feat, g.n, i, 0), ld_d4(feat, g.n, i, 1));
         walk_candidates_pipelined<TALL>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
             D4x2 c;
-            c.a = ld_d4(feat + j, 0);
-            c.b = ld_d4(feat + j, 1);
+            c.a = ld_d4(feat, g.n, j, 0);
+            c.b = ld_d4(feat, g.n, j, 1);
             return c;
         }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
         acc.finish(prm, chi2_table, err, dkf, dnf);
@@ -388,12 +393,13 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
         // warp-cooperative copy: consecutive threads take consecutive 16-byte quarters of the contiguous range
         const double2* __restrict__ src = reinterpret_cast<const double2*>(feat);
         for (int r = 0; r < nrows; ++r) {
-            const uint32_t len4 = (row_off[r + 1] - row_off[r]) * 4u;
-            const size_t gbase = (size_t)row_b[r] * 4u;
+            const uint32_t len2 = (row_off[r + 1] - row_off[r]) * 2u;       // 16-byte quarters per half array
+            const size_t gbase = (size_t)row_b[r] * 2u;
             const uint32_t sbase = row_off[r];
-            for (uint32_t t = threadIdx.x; t < len4; t += blockDim.x) {
-                const double2 v = __ldg(src + gbase + t);
-                const uint32_t rec = t >> 2, k = t & 3u;
+            for (uint32_t t = threadIdx.x; t < 2u * len2; t += blockDim.x) {
+                const uint32_t half = t >= len2 ? 1u : 0u, u = t - half * len2;
+                const double2 v = __ldg(src + (size_t)half * (size_t)g.n * 2u + gbase + u);
+                const uint32_t rec = u >> 1, k = 2u * half + (u & 1u);
                 double2* dst = k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3));
                 dst[sbase + rec] = v;
             }
@@ -422,11 +428,11 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
                 }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
             }
         } else {
-            acc.init(ld_d4(feat + q, 0), ld_d4(feat + q, 1));
+            acc.init(ld_d4(feat, g.n, q, 0), ld_d4(feat, g.n, q, 1));
             walk_candidates_pipelined<false>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
                 D4x2 c;
-                c.a = ld_d4(feat + j, 0);
-                c.b = ld_d4(feat + j, 1);
+                c.a = ld_d4(feat, g.n, j, 0);
+                c.b = ld_d4(feat, g.n, j, 1);
                 return c;
             }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
         }

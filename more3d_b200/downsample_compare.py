@@ -17,7 +17,8 @@ from .grid import UniformGrid, as_device_points, cell_for_radius
 
 
 def _knn_cell(d, k):
-    ext = (d.amax(dim=0) - d.amin(dim=0)).cpu().numpy()
+    b = _lib.cloud_bounds(d)
+    ext = b[3:] - b[:3]
     cell = float(np.sqrt(max(k, 8) * max(float(ext[0]) * float(ext[1]), 1e-300) / (4.0 * d.shape[0])))
     return cell if np.isfinite(cell) and cell > 0 else 1.0
 

@@ -159,8 +159,8 @@ def smooth(u, idx, nbs, w):
 
 
 def _knn_grid(dpts, k):
-    lo, hi = dpts.amin(dim=0), dpts.amax(dim=0)
-    ext = (hi - lo).cpu().numpy()
+    b = _lib.cloud_bounds(dpts)
+    ext = b[3:] - b[:3]
     area = max(float(ext[0]) * float(ext[1]), 1e-300)
     cell = float(np.sqrt(max(k, 8) * area / (4.0 * dpts.shape[0])))
     if not np.isfinite(cell) or cell <= 0:
