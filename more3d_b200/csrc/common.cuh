@@ -131,6 +131,7 @@ struct more3d_grid {
     uint32_t* col_start;    // nx*ny + 1
     uint8_t* dup;           // n (sorted order): 1 if coincident with an earlier sorted point
     m3d::FeatRec* feat;     // n sorted feature records cached by the last more3d_normals_curvature (or NULL)
+    int feat_split;         // 1: stored as two arrays of 32-B halves (fine grids), 0: interleaved 64-B records
 };
 
 namespace m3d {

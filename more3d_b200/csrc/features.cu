@@ -31,17 +31,21 @@ struct D4x2 { D4 a, b; };
 // = (nx, ny, nz, pad) of all n points -- not as n 64-byte structs: at every candidate step the 32 lanes of a warp read
 // ~13 distinct records out of a window of ~32 consecutive ones, and with 32-byte elements that window is 8 cache lines
 // per load instead of 16 (the L1 data pipe, this kernel's highest bound, charges a wavefront per line touched).
+// That pays on fine grids (a 9x9 stencil of quarter-radius columns: 14.83 -> 14.41 ms over the three radii of
+// configs[1]); on a coarse grid (>= 4 points per column: the lanes of a warp sit in ~3 columns and both halves of their
+// few records share cache lines) the interleaved 64-byte layout is 8-12 % faster, so the layout follows the grid's
+// mean column population (feat_split, decided when the grid is built).  n == 0 selects the interleaved layout.
 __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int64_t n, int64_t j, int h) {
     D4 r;
-    ldg256(reinterpret_cast<const char*>(f) + ((size_t)h * (size_t)n + (size_t)j) * 32, r.x, r.y, r.z, r.w);
+    const size_t slot = n ? (size_t)h * (size_t)n + (size_t)j : 2 * (size_t)j + (size_t)h;
+    ldg256(reinterpret_cast<const char*>(f) + slot * 32, r.x, r.y, r.z, r.w);
     return r;
 }
 __device__ __forceinline__ void st_feat(FeatRec* __restrict__ f, int64_t n, int64_t i, double x, double y, double z,
                                         double K, double nx, double ny, double nz) {
-    double4* a = reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + (size_t)i * 32);
-    double4* b = reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + ((size_t)n + (size_t)i) * 32);
-    *a = make_double4(x, y, z, K);
-    *b = make_double4(nx, ny, nz, 0.0);
+    const size_t sa = n ? (size_t)i : 2 * (size_t)i, sb = n ? (size_t)n + (size_t)i : 2 * (size_t)i + 1;
+    *reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + sa * 32) = make_double4(x, y, z, K);
+    *reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + sb * 32) = make_double4(nx, ny, nz, 0.0);
 }
 
 
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, Cu
         // the dk/dn pass's sorted feature record, written here (coalesced) instead of being gathered
         // from the original-order columns by build_feat_kernel; same arithmetic as there
         const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
-        st_feat(feat_out, g.n, i, p.x, p.y, p.z,
+        st_feat(feat_out, g.feat_n, i, p.x, p.y, p.z,
                 __longlong_as_double(__double_as_longlong((double)K) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL)),
                 nx / nn, ny / nn, nz / nn);
     }
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const doubl
     const double nx = normals[3 * o], ny = normals[3 * o + 1], nz = normals[3 * o + 2];
     // n / ||n||, DM_saliency.py:258-259 (norm = sqrt of the sequential sum of squares)
     const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
-    st_feat(feat, g.n, i, p.x, p.y, p.z,
+    st_feat(feat, g.feat_n, i, p.x, p.y, p.z,
             __longlong_as_double(__double_as_longlong((double)K[o]) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL)),
             nx / nn, ny / nn, nz / nn);
 }
@@ -306,11 +310,11 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
     bool owned = false;
     if (live) {
         DkdnAcc acc;
-        acc.init(ld_d4(feat, g.n, i, 0), ld_d4(feat, g.n, i, 1));
+        acc.init(ld_d4(feat, g.feat_n, i, 0), ld_d4(feat, g.feat_n, i, 1));
         walk_candidates_pipelined<TALL>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
             D4x2 c;
-            c.a = ld_d4(feat, g.n, j, 0);
-            c.b = ld_d4(feat, g.n, j, 1);
+            c.a = ld_d4(feat, g.feat_n, j, 0);
+            c.b = ld_d4(feat, g.feat_n, j, 1);
             return c;
         }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
         acc.finish(prm, chi2_table, err, dkf, dnf);
@@ -398,7 +402,8 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
             const uint32_t sbase = row_off[r];
             for (uint32_t t = threadIdx.x; t < 2u * len2; t += blockDim.x) {
                 const uint32_t half = t >= len2 ? 1u : 0u, u = t - half * len2;
-                const double2 v = __ldg(src + (size_t)half * (size_t)g.n * 2u + gbase + u);
+                const double2 v = g.feat_n ? __ldg(src + (size_t)half * (size_t)g.n * 2u + gbase + u)
+                                           : __ldg(src + 2 * (gbase + (u & ~1u)) + 2 * half + (u & 1u));
                 const uint32_t rec = u >> 1, k = 2u * half + (u & 1u);
                 double2* dst = k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3));
                 dst[sbase + rec] = v;
@@ -428,11 +433,11 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
                 }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
             }
         } else {
-            acc.init(ld_d4(feat, g.n, q, 0), ld_d4(feat, g.n, q, 1));
+            acc.init(ld_d4(feat, g.feat_n, q, 0), ld_d4(feat, g.feat_n, q, 1));
             walk_candidates_pipelined<false>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
                 D4x2 c;
-                c.a = ld_d4(feat, g.n, j, 0);
-                c.b = ld_d4(feat, g.n, j, 1);
+                c.a = ld_d4(feat, g.feat_n, j, 0);
+                c.b = ld_d4(feat, g.feat_n, j, 1);
                 return c;
             }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
         }

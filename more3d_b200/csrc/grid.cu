@@ -334,6 +334,7 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
     }
     g->rec32 = nullptr;
     g->feat = nullptr;
+    g->feat_split = ((double)n / ((double)g->nx * (double)g->ny)) < 4.0 ? 1 : 0;
     g->order = nullptr; g->rec = nullptr; g->col_start = nullptr; g->dup = nullptr;
     const size_t ncols = (size_t)g->nx * g->ny;
 

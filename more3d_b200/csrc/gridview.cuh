@@ -16,6 +16,7 @@ struct GridView {
     int x0, y0;
     double lim32;
     int tall;
+    int64_t feat_n;       // n when the feature records are split into two half arrays, 0 when interleaved (features.cu)
     __device__ __forceinline__ int col_x(double x) const { return cell_coord(x, lox, inv, x0); }
     __device__ __forceinline__ int col_y(double y) const { return cell_coord(y, loy, inv, y0); }
 };
@@ -27,6 +28,7 @@ static inline GridView make_view(const more3d_grid* g) {
     v.lim32 = g->lim32;
     v.lox = g->lox; v.loy = g->loy; v.x0 = g->x0; v.y0 = g->y0;
     v.tall = g->tall;
+    v.feat_n = g->feat_split ? g->n : 0;
     return v;
 }
 
