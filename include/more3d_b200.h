@@ -55,9 +55,14 @@ int more3d_grid_create(const double* xyz, int64_t n, double cell, void* stream, 
  * floor((x - origin_x) / cell) of that lattice (shifted by an integer), so every strip of a tile bins, orders and
  * sums exactly like a single grid over the whole tile built with the same origin and cell (the cell is not widened
  * in this mode).  bounds_h (host, may be NULL) = {min x, y, z, max x, y, z} of the segments when the caller already
- * has them: skips the bounding-box reduction and its host synchronisation. */
+ * has them: skips the bounding-box reduction and its host synchronisation.
+ * x_split (1..8): columns are cell / x_split wide along x and `cell` high along y.  A stencil row stays ONE contiguous
+ * range whatever the column width, so narrower columns only trim the row's overhang beyond the query circle
+ * (2 r + cell / x_split instead of 2 r + cell): fewer rejected candidates in every fixed-radius pass.  more3d_knn needs
+ * x_split = 1. */
 int more3d_grid_create_segments(const double* const* seg_xyz_h, const int64_t* seg_n_h, int nseg, double cell,
-                                const double* lattice_h, const double* bounds_h, void* stream, more3d_grid** out);
+                                int x_split, const double* lattice_h, const double* bounds_h, void* stream,
+                                more3d_grid** out);
 int more3d_grid_destroy(more3d_grid* g);
 /* info[0]=n, info[1]=nx, info[2]=ny (host ints); geom[0]=cell, geom[1]=origin_x, geom[2]=origin_y */
 int more3d_grid_info(const more3d_grid* g, int64_t* info_h, double* geom_h);

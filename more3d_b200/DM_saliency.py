@@ -22,7 +22,7 @@ from scipy import stats
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import GridColumn, UniformGrid, as_device_points, cell_for_radius
+from .grid import GridColumn, UniformGrid, X_SPLIT, as_device_points, cell_for_radius
 
 
 # Overflow status words of the dk/dn passes: handed out from one zeroed per-device ring (a word is only ever written on a
@@ -164,7 +164,7 @@ class PointCloudDM:
             if c <= want * (1 + 1e-12) and want / c <= 2.05 and (best is None or c > best.requested_cell):
                 best = g
         if best is None:
-            best = UniformGrid(self.xyz, want)
+            best = UniformGrid(self.xyz, want, x_split=X_SPLIT)
             self._grids[float(radius)] = best
         return best
 

@@ -114,6 +114,9 @@ struct more3d_grid {
     int64_t n;
     int nx, ny;
     double cell, inv_cell, ox, oy;   // ox, oy: position of local column (0, 0) -- origin of the fp32 records
+    double cell_x, inv_x;            // column WIDTH along x (cell / x_split); `cell` is the row height along y.  Narrower
+    int x_split;                     // columns cost nothing per stencil row (a row stays one contiguous range) and trim its
+                                     // overhang beyond the query circle: (2r + cell_x) instead of (2r + cell) per row
     double lox, loy;                 // origin of the column LATTICE: column of x = floor((x - lox) / cell) - x0.  A single
     int x0, y0;                      // grid has lox = ox, x0 = 0; strips of one tile share the tile's lattice, so every
                                      // strip bins (and therefore orders and sums) exactly like the whole-tile grid

@@ -35,9 +35,10 @@ struct D4x2 { D4 a, b; };
 // configs[1]); on a coarse grid (>= 4 points per column: the lanes of a warp sit in ~3 columns and both halves of their
 // few records share cache lines) the interleaved 64-byte layout is 8-12 % faster, so the layout follows the grid's
 // mean column population (feat_split, decided when the grid is built).  n == 0 selects the interleaved layout.
+template <bool SPLIT>
 __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int64_t n, int64_t j, int h) {
-    D4 r;
-    const size_t slot = n ? (size_t)h * (size_t)n + (size_t)j : 2 * (size_t)j + (size_t)h;
+    D4 r;      // the layout is a template parameter: one more select + multiply per load costs 7 % in this issue-bound loop
+    const size_t slot = SPLIT ? (size_t)h * (size_t)n + (size_t)j : 2 * (size_t)j + (size_t)h;
     ldg256(reinterpret_cast<const char*>(f) + slot * 32, r.x, r.y, r.z, r.w);
     return r;
 }
@@ -298,7 +299,7 @@ __device__ __forceinline__ void dkdn_minmax(unsigned lo_k, unsigned hi_k, unsign
     }
 }
 
-template <bool TALL>
+template <bool TALL, bool SPLIT>
 __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                    DkDnParams prm, const double* __restrict__ chi2_table,
                                                    float* __restrict__ dk_out, float* __restrict__ dn_out,
@@ -310,11 +311,11 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
     bool owned = false;
     if (live) {
         DkdnAcc acc;
-        acc.init(ld_d4(feat, g.feat_n, i, 0), ld_d4(feat, g.feat_n, i, 1));
+        acc.init(ld_d4<SPLIT>(feat, g.n, i, 0), ld_d4<SPLIT>(feat, g.n, i, 1));
         walk_candidates_pipelined<TALL>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
             D4x2 c;
-            c.a = ld_d4(feat, g.feat_n, j, 0);
-            c.b = ld_d4(feat, g.feat_n, j, 1);
+            c.a = ld_d4<SPLIT>(feat, g.n, j, 0);
+            c.b = ld_d4<SPLIT>(feat, g.n, j, 1);
             return c;
         }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
         acc.finish(prm, chi2_table, err, dkf, dnf);
@@ -353,6 +354,7 @@ __device__ __forceinline__ D4 lds_d4(const double2* __restrict__ lo, const doubl
     return r;
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                                 DkDnParams prm, const double* __restrict__ chi2_table,
                                                                 float* __restrict__ dk_out, float* __restrict__ dn_out,
@@ -370,8 +372,8 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
     const int c0 = bx * cb, c1 = min(c0 + cb, g.nx);
     const uint32_t qa = __ldg(g.col_start + (size_t)iy * g.nx + c0), qb = __ldg(g.col_start + (size_t)iy * g.nx + c1);
     if (qa == qb) return;                                   // no query in this block (uniform for the CTA)
-    const int s = prm.s;
-    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1), nrows = y1 - y0 + 1;
+    const int s = M3D_SX(prm.s), sy = M3D_SY(prm.s);
+    const int y0 = max(iy - sy, 0), y1 = min(iy + sy, g.ny - 1), nrows = y1 - y0 + 1;
     const int xs0 = max(c0 - s, 0), xs1 = min(c1 - 1 + s, g.nx - 1), csw = cb + 2 * s + 1;
     if ((int)threadIdx.x < nrows) {
         const uint32_t* row = g.col_start + (size_t)(y0 + threadIdx.x) * g.nx;
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
             const uint32_t sbase = row_off[r];
             for (uint32_t t = threadIdx.x; t < 2u * len2; t += blockDim.x) {
                 const uint32_t half = t >= len2 ? 1u : 0u, u = t - half * len2;
-                const double2 v = g.feat_n ? __ldg(src + (size_t)half * (size_t)g.n * 2u + gbase + u)
+                const double2 v = SPLIT ? __ldg(src + (size_t)half * (size_t)g.n * 2u + gbase + u)
                                            : __ldg(src + 2 * (gbase + (u & ~1u)) + 2 * half + (u & 1u));
                 const uint32_t rec = u >> 1, k = 2u * half + (u & 1u);
                 double2* dst = k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3));
@@ -433,11 +435,11 @@ __global__ void __launch_bounds__(SMW_THREADS) dkdn_smem_kernel(GridView g, cons
                 }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
             }
         } else {
-            acc.init(ld_d4(feat, g.feat_n, q, 0), ld_d4(feat, g.feat_n, q, 1));
+            acc.init(ld_d4<SPLIT>(feat, g.n, q, 0), ld_d4<SPLIT>(feat, g.n, q, 1));
             walk_candidates_pipelined<false>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
                 D4x2 c;
-                c.a = ld_d4(feat, g.feat_n, j, 0);
-                c.b = ld_d4(feat, g.feat_n, j, 1);
+                c.a = ld_d4<SPLIT>(feat, g.n, j, 0);
+                c.b = ld_d4<SPLIT>(feat, g.n, j, 1);
                 return c;
             }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
         }
@@ -573,23 +575,31 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     {
         ProfScope prof("dkdn", s);
         const int variant = dkdn_variant();
+        const bool split = g->feat_split != 0;
         if (g->tall) {
-            dkdn_kernel<true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
-        } else if (variant == 1 && prm.s <= (SMW_MAX_ROWS - 1) / 2) {
+            if (split) dkdn_kernel<true, true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+            else dkdn_kernel<true, false><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+        } else if (variant == 1 && M3D_SY(prm.s) <= (SMW_MAX_ROWS - 1) / 2) {
             // staging capacity in records and the column-block width that fills ~80 % of it at the grid's mean density
             const int cap = smem_walk_cap();
             const double dens = (double)g->n / ((double)g->nx * (double)g->ny);
-            int cb = (int)(0.8 * cap / ((2 * prm.s + 1) * fmax(dens, 1e-3))) - 2 * prm.s;
+            const int sxh = M3D_SX(prm.s), syh = M3D_SY(prm.s);
+            int cb = (int)(0.8 * cap / ((2 * syh + 1) * fmax(dens, 1e-3))) - 2 * sxh;
             cb = cb < 8 ? 8 : (cb > 96 ? 96 : cb);
             const int nbx = (g->nx + cb - 1) / cb;
-            const size_t smem = (size_t)cap * 64 + (size_t)SMW_MAX_ROWS * (cb + 2 * prm.s + 1) * sizeof(uint32_t);
-            M3D_CUDA(cudaFuncSetAttribute(dkdn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const size_t smem = (size_t)cap * 64 + (size_t)SMW_MAX_ROWS * (cb + 2 * sxh + 1) * sizeof(uint32_t);
+            M3D_CUDA(cudaFuncSetAttribute(dkdn_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            M3D_CUDA(cudaFuncSetAttribute(dkdn_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int threads = ((int)(cb * dens * 1.15) + 31) / 32 * 32;          // one thread per expected query
             threads = threads < 32 ? 32 : (threads > SMW_THREADS ? SMW_THREADS : threads);
-            dkdn_smem_kernel<<<(unsigned)((size_t)nbx * g->ny), threads, smem, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                                  minmax ? mm : nullptr, err, cb, nbx, cap);
+            if (split) dkdn_smem_kernel<true><<<(unsigned)((size_t)nbx * g->ny), threads, smem, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                                               minmax ? mm : nullptr, err, cb, nbx, cap);
+            else dkdn_smem_kernel<false><<<(unsigned)((size_t)nbx * g->ny), threads, smem, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                                            minmax ? mm : nullptr, err, cb, nbx, cap);
+        } else if (split) {
+            dkdn_kernel<false, true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
         } else {
-            dkdn_kernel<false><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
+            dkdn_kernel<false, false><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
         }
     }
     if (minmax) minmax_finish<<<1, 32, 0, s>>>(mm, minmax);

@@ -80,17 +80,17 @@ __global__ void bbox_final(const double* __restrict__ part, int nparts, double* 
 
 // the column lattice as the build kernels need it: column of (x, y) = (floor((x - lox) * inv) - x0, ...), clamped
 struct Lattice {
-    double lox, loy, inv;
+    double lox, loy, inv, inv_x;
     int x0, y0, nx, ny;
     __device__ __forceinline__ uint32_t key(double x, double y) const {
-        const int ix = min(max(cell_coord(x, lox, inv, x0), 0), nx - 1);
+        const int ix = min(max(cell_coord(x, lox, inv_x, x0), 0), nx - 1);
         const int iy = min(max(cell_coord(y, loy, inv, y0), 0), ny - 1);
         return (uint32_t)iy * (uint32_t)nx + (uint32_t)ix;
     }
 };
 static Lattice make_lattice(const more3d_grid* g) {
     Lattice l;
-    l.lox = g->lox; l.loy = g->loy; l.inv = g->inv_cell; l.x0 = g->x0; l.y0 = g->y0; l.nx = g->nx; l.ny = g->ny;
+    l.lox = g->lox; l.loy = g->loy; l.inv = g->inv_cell; l.inv_x = g->inv_x; l.x0 = g->x0; l.y0 = g->y0; l.nx = g->nx; l.ny = g->ny;
     return l;
 }
 
@@ -235,12 +235,13 @@ extern "C" int more3d_grid_create(const double* xyz, int64_t n, double cell, voi
                                   more3d_grid** out) {
     const double* seg[1] = {xyz};
     const int64_t cnt[1] = {n};
-    return more3d_grid_create_segments(seg, cnt, 1, cell, nullptr, nullptr, stream, out);
+    return more3d_grid_create_segments(seg, cnt, 1, cell, 1, nullptr, nullptr, stream, out);
 }
 
 extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const int64_t* seg_n_h, int nseg, double cell,
-                                           const double* lattice_h, const double* bounds_h, void* stream,
+                                           int x_split, const double* lattice_h, const double* bounds_h, void* stream,
                                            more3d_grid** out) {
+    M3D_REQUIRE(x_split >= 1 && x_split <= 8, "x_split must be 1..8");
     M3D_REQUIRE(out != nullptr, "out is NULL");
     *out = nullptr;
     M3D_REQUIRE(seg_xyz_h != nullptr && seg_n_h != nullptr && nseg >= 1 && nseg <= 3, "1 to 3 segments");
@@ -294,10 +295,10 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         // columns of a lattice shared with other grids (the strips of one tile): origin and cell are given, this
         // grid covers the integer column range its own bounding box needs (one spare column either side)
         c = cell;
-        const double inv = 1.0 / c;
+        const double inv = 1.0 / c, invx = 1.0 / (c / (double)x_split);
         g->lox = lattice_h[0];
         g->loy = lattice_h[1];
-        const double fx0 = floor((bb[0] - g->lox) * inv) - 1.0, fx1 = floor((bb[2] - g->lox) * inv) + 1.0;
+        const double fx0 = floor((bb[0] - g->lox) * invx) - 1.0, fx1 = floor((bb[2] - g->lox) * invx) + 1.0;
         const double fy0 = floor((bb[1] - g->loy) * inv) - 1.0, fy1 = floor((bb[3] - g->loy) * inv) + 1.0;
         if (!(fabs(fx0) < 1e9 && fabs(fx1) < 1e9 && fabs(fy0) < 1e9 && fabs(fy1) < 1e9) ||
             (fx1 - fx0 + 1.0) * (fy1 - fy0 + 1.0) > 268435456.0) {
@@ -307,20 +308,23 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         }
         g->x0 = (int)fx0; g->y0 = (int)fy0;
         g->nx = (int)(fx1 - fx0) + 1; g->ny = (int)(fy1 - fy0) + 1;
-        g->ox = g->lox + (double)g->x0 * c;
+        g->ox = g->lox + (double)g->x0 * (c / (double)x_split);
         g->oy = g->loy + (double)g->y0 * c;
     } else {
         // widen the cell until the column table fits (stencils stay correct for any cell >= requested):
         // at most 16000 x 16000 columns (2^28 entries = 1 GiB)
-        c = fmax(cell, fmax(ex, ey) / 16000.0);
+        c = fmax(cell, fmax(ex * (double)x_split, ey) / 16000.0);
         g->ox = bb[0] - c;
         g->oy = bb[1] - c;
         g->lox = g->ox; g->loy = g->oy; g->x0 = 0; g->y0 = 0;
-        g->nx = (int)floor(ex / c) + 3;
+        g->nx = (int)floor((ex + c) / (c / (double)x_split)) + 2;
         g->ny = (int)floor(ey / c) + 3;
     }
     g->cell = c;
     g->inv_cell = 1.0 / c;
+    g->x_split = x_split;
+    g->cell_x = c / (double)x_split;
+    g->inv_x = 1.0 / g->cell_x;
     cudaGetDevice(&g->device);
     g->stream = s;
     g->oz = b6[2];

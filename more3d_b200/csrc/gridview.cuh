@@ -11,13 +11,14 @@ struct GridView {
     const uint8_t* dup;
     int64_t n;
     int nx, ny;
-    double ox, oy, oz, inv;
+    double ox, oy, oz, inv;   // inv: 1 / row height (y)
+    double inv_x;             // 1 / column width (x)
     double lox, loy;      // lattice origin and integer column shift (see more3d_grid)
     int x0, y0;
     double lim32;
     int tall;
     int64_t feat_n;       // n when the feature records are split into two half arrays, 0 when interleaved (features.cu)
-    __device__ __forceinline__ int col_x(double x) const { return cell_coord(x, lox, inv, x0); }
+    __device__ __forceinline__ int col_x(double x) const { return cell_coord(x, lox, inv_x, x0); }
     __device__ __forceinline__ int col_y(double y) const { return cell_coord(y, loy, inv, y0); }
 };
 
@@ -26,6 +27,7 @@ static inline GridView make_view(const more3d_grid* g) {
     v.rec = g->rec; v.rec32 = g->rec32; v.col_start = g->col_start; v.dup = g->dup; v.n = g->n;
     v.nx = g->nx; v.ny = g->ny; v.ox = g->ox; v.oy = g->oy; v.oz = g->oz; v.inv = g->inv_cell;
     v.lim32 = g->lim32;
+    v.inv_x = g->inv_x;
     v.lox = g->lox; v.loy = g->loy; v.x0 = g->x0; v.y0 = g->y0;
     v.tall = g->tall;
     v.feat_n = g->feat_split ? g->n : 0;
@@ -33,13 +35,19 @@ static inline GridView make_view(const more3d_grid* g) {
 }
 
 // stencil half-width (in columns) that is guaranteed to contain every point within r
+// Returned packed: rows (y) in the low 16 bits, columns (x) in the high 16 bits -- the walkers take one int.
 static inline int stencil_halfwidth(const more3d_grid* g, double r) {
-    double s = ceil(r * M3D_CELL_MARGIN / g->cell);
-    double lim = (double)((g->nx > g->ny) ? g->nx : g->ny);
-    if (s > lim) s = lim;
-    if (s < 1) s = 1;
-    return (int)s;
+    double sy = ceil(r * M3D_CELL_MARGIN / g->cell), sx = ceil(r * M3D_CELL_MARGIN / g->cell_x);
+    if (sy > (double)g->ny) sy = (double)g->ny;
+    if (sx > (double)g->nx) sx = (double)g->nx;
+    if (sy < 1) sy = 1;
+    if (sx < 1) sx = 1;
+    if (sy > 32767.0) sy = 32767.0;         // wider than any table this library builds (<= 2^28 columns)
+    if (sx > 32767.0) sx = 32767.0;
+    return (int)sy | ((int)sx << 16);
 }
+#define M3D_SY(s) ((s) & 0xffff)
+#define M3D_SX(s) ((s) >> 16)
 
 // fp32 distance filter.  With every fp32 record coordinate within delta32 of the exact one, the fp32
 // squared distance of a pair near the sphere surface is within h of the exact fp64 rule's value:
@@ -91,8 +99,8 @@ template <typename F>
 __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx, double qy, int s, F&& f) {
     const int ix = g.col_x(qx);
     const int iy = g.col_y(qy);
-    const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
-    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
+    const int x0 = max(ix - M3D_SX(s), 0), x1 = min(ix + M3D_SX(s), g.nx - 1);
+    const int y0 = max(iy - M3D_SY(s), 0), y1 = min(iy + M3D_SY(s), g.ny - 1);
     if (x0 > x1 || y0 > y1) return;
     // the bounds of row y+1 are requested before row y is walked, so their latency hides behind the row
     const uint32_t* cs = g.col_start + (size_t)y0 * g.nx;
@@ -117,8 +125,8 @@ __device__ __forceinline__ void for_each_candidate_tall(const GridView& g, doubl
                                                      int s, F&& f) {
     const int ix = g.col_x(qx);
     const int iy = g.col_y(qy);
-    const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
-    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
+    const int x0 = max(ix - M3D_SX(s), 0), x1 = min(ix + M3D_SX(s), g.nx - 1);
+    const int y0 = max(iy - M3D_SY(s), 0), y1 = min(iy + M3D_SY(s), g.ny - 1);
     const double zlo = qz - r * (1.0 + 1e-12), zhi = qz + r * (1.0 + 1e-12);
     for (int y = y0; y <= y1; ++y)
         for (int x = x0; x <= x1; ++x) {
@@ -168,8 +176,8 @@ __device__ __forceinline__ void walk_candidates_pipelined(const GridView& g, dou
     }
     const int ix = g.col_x(qx);
     const int iy = g.col_y(qy);
-    const int x0 = max(ix - s, 0), x1 = min(ix + s, g.nx - 1);
-    const int y0 = max(iy - s, 0), y1 = min(iy + s, g.ny - 1);
+    const int x0 = max(ix - M3D_SX(s), 0), x1 = min(ix + M3D_SX(s), g.nx - 1);
+    const int y0 = max(iy - M3D_SY(s), 0), y1 = min(iy + M3D_SY(s), g.ny - 1);
     if (x0 > x1 || y0 > y1) return;
     const uint32_t* cs = g.col_start + (size_t)y0 * g.nx;
     uint32_t nb = __ldg(cs + x0), ne = __ldg(cs + x1 + 1);

@@ -104,6 +104,7 @@ static void launch_knn(const more3d_grid* g, const double* q, int64_t nq, int k,
 
 extern "C" int more3d_knn(const more3d_grid* g, const double* q, int64_t nq, int k, int64_t* idx, double* dist,
                           void* stream) {
+    M3D_REQUIRE(g == nullptr || g->x_split == 1, "more3d_knn needs a grid with square columns (x_split = 1)");
     M3D_REQUIRE(g != nullptr, "grid is NULL");
     M3D_REQUIRE(nq >= 0, "nq < 0");
     M3D_REQUIRE(q != nullptr || nq == g->n, "self query (q == NULL) needs nq == n");

@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import GridColumn, UniformGrid, CELL_MARGIN, cell_for_radius
+from .grid import GridColumn, UniformGrid, CELL_MARGIN, X_SPLIT, cell_for_radius
 
 
 def strip_bounds(x_min, x_max, world):
@@ -244,7 +244,7 @@ class StripStep:
         ck.setArgs(alpha=p["alpha"], roughness=p["roughness"], min_points=p["min_points"])
         eps = ck.epsilon()
         self.grid = g = UniformGrid(self.own, cell_for_radius(self.radii[0]), left=self.left, right=self.right,
-                                    lattice=self.lattice, bounds=self.bounds)
+                                    lattice=self.lattice, bounds=self.bounds, x_split=X_SPLIT)
         table = _chi2_table(p["alpha"], self.table_len, self.dev)
         self.dk, self.dn, self.pcount = {}, {}, {}
         for i, r in enumerate(self.radii):

@@ -19,6 +19,9 @@ CELL_MARGIN = 1.0 + 1.0 / 65536.0
 # more, shorter row ranges.  Measured on B200, 10 M-point terrain: 2 is 17 % faster than 1 over the
 # moments + dk/dn kernels, 3 is no better than 2 (profiles/README.md).
 CELLS_PER_RADIUS = int(os.environ.get("MORE3D_CELLS_PER_RADIUS", "2"))
+# Columns of the fixed-radius grids are this many times narrower along x than they are high along y (see
+# more3d_grid_create_segments): 2 trims 10 / 7 / 6 % of the candidates at r = 0.5 / 0.75 / 1.0 on the shared grid.
+X_SPLIT = int(os.environ.get("MORE3D_X_SPLIT", "2"))
 
 
 def cell_for_radius(radius):
@@ -82,11 +85,12 @@ class GridColumn:
 class UniformGrid:
     """Spatial index replacing the reference's ball tree (BallTreePointSet.py:35)."""
 
-    def __init__(self, xyz, cell, left=None, right=None, lattice=None, bounds=None):
+    def __init__(self, xyz, cell, left=None, right=None, lattice=None, bounds=None, x_split=1):
         """xyz: (N,3) cloud.  Strips (multi-GPU): `left` / `right` are the ghost points received from the two
         neighbours -- the grid indexes the three tensors in place as one cloud [left, xyz, right] (no concatenated
         copy); `lattice` = (origin_x, origin_y) of the column lattice shared by all strips of the tile (bit-identical
-        binning, ordering and sums to the whole-tile grid); `bounds` = (min x, y, z, max x, y, z) if already known."""
+        binning, ordering and sums to the whole-tile grid); `bounds` = (min x, y, z, max x, y, z) if already known;
+        `x_split`: columns cell / x_split wide (fewer rejected candidates per stencil row; kNN needs 1)."""
         self.lib = _lib.load()
         self.xyz = as_device_points(xyz)
         self.device = self.xyz.device
@@ -99,13 +103,14 @@ class UniformGrid:
         if self.n == 0:
             raise ValueError("empty cloud")
         self.requested_cell = float(cell)
+        self.x_split = int(x_split)
         h = C.c_void_p()
         ptrs = (C.c_void_p * len(segs))(*[t.data_ptr() for t in segs])
         cnts = (C.c_int64 * len(segs))(*[int(t.shape[0]) for t in segs])
         lat = None if lattice is None else (C.c_double * 2)(float(lattice[0]), float(lattice[1]))
         bnd = None if bounds is None else (C.c_double * 6)(*[float(v) for v in bounds])
         with torch.cuda.device(self.device):
-            check(self.lib.more3d_grid_create_segments(ptrs, cnts, len(segs), float(cell), lat, bnd, stream_ptr(),
+            check(self.lib.more3d_grid_create_segments(ptrs, cnts, len(segs), float(cell), int(x_split), lat, bnd, stream_ptr(),
                                                        C.byref(h)))
         self._h = h
         info = (C.c_int64 * 3)()
