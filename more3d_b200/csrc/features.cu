@@ -479,6 +479,7 @@ static int launch_moments(const more3d_grid* g, int mode, double r, double eps, 
     prm.grid_order = grid_order;
     const unsigned nb = (unsigned)((g->n + WALK_THREADS - 1) / WALK_THREADS);
     GridView v = make_view(g);
+    set_row_clip(v, g, r);
     ProfScope prof("moments", s);
     if (mode == MODE_NORMALS) {
         if (g->tall) moments_kernel<MODE_NORMALS, true><<<nb, WALK_THREADS, 0, s>>>(v, prm, normals, lam_ratio, nullptr, pcount, nullptr);
@@ -558,6 +559,7 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
     }
     const unsigned nb = (unsigned)((g->n + 255) / 256);
     GridView v = make_view(g);
+    set_row_clip(v, g, r);
     if (!cached) {
         ProfScope prof("build_feat", s);
         build_feat_kernel<<<nb, 256, 0, s>>>(v, normals, K, feat);

@@ -301,9 +301,9 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         const double fx0 = floor((bb[0] - g->lox) * invx) - 1.0, fx1 = floor((bb[2] - g->lox) * invx) + 1.0;
         const double fy0 = floor((bb[1] - g->loy) * inv) - 1.0, fy1 = floor((bb[3] - g->loy) * inv) + 1.0;
         if (!(fabs(fx0) < 1e9 && fabs(fx1) < 1e9 && fabs(fy0) < 1e9 && fabs(fy1) < 1e9) ||
-            (fx1 - fx0 + 1.0) * (fy1 - fy0 + 1.0) > 268435456.0) {
+            (fx1 - fx0 + 1.0) * (fy1 - fy0 + 1.0) > fmax(268435456.0, 2.0 * (double)n)) {
             delete g;
-            set_error("column table of the shared lattice exceeds 2^28 entries: use a wider cell for every strip");
+            set_error("column table of the shared lattice exceeds max(2^28, 2 n) entries: use a wider cell or a smaller x_split for every strip");
             return MORE3D_E_RANGE;
         }
         g->x0 = (int)fx0; g->y0 = (int)fy0;
@@ -311,9 +311,15 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         g->ox = g->lox + (double)g->x0 * (c / (double)x_split);
         g->oy = g->loy + (double)g->y0 * c;
     } else {
-        // widen the cell until the column table fits (stencils stay correct for any cell >= requested):
-        // at most 16000 x 16000 columns (2^28 entries = 1 GiB)
-        c = fmax(cell, fmax(ex * (double)x_split, ey) / 16000.0);
+        // The column table may hold max(2^28, 2 n) entries (1 GiB, or 8 bytes per point on very large tiles).  If the
+        // requested geometry does not fit, first give up the x refinement, then widen the cell (stencils stay correct
+        // for any cell >= requested).
+        double maxcols = fmax(268435456.0, 2.0 * (double)n);
+        if (maxcols > 2147483647.0) maxcols = 2147483647.0;
+        c = cell;
+        auto cols = [&](double cc, int xs) { return (floor((ex + cc) / (cc / (double)xs)) + 2.0) * (floor(ey / cc) + 3.0); };
+        while (x_split > 1 && cols(c, x_split) > maxcols) --x_split;
+        while (cols(c, x_split) > maxcols) c *= 1.05;
         g->ox = bb[0] - c;
         g->oy = bb[1] - c;
         g->lox = g->ox; g->loy = g->oy; g->x0 = 0; g->y0 = 0;

@@ -17,6 +17,7 @@ struct GridView {
     int x0, y0;
     double lim32;
     int tall;
+    unsigned char sxr[16];   // column half-width of the stencil row at |row offset| j (circle-clipped rows), 255 = unclipped
     int64_t feat_n;       // n when the feature records are split into two half arrays, 0 when interleaved (features.cu)
     __device__ __forceinline__ int col_x(double x) const { return cell_coord(x, lox, inv_x, x0); }
     __device__ __forceinline__ int col_y(double y) const { return cell_coord(y, loy, inv, y0); }
@@ -31,6 +32,7 @@ static inline GridView make_view(const more3d_grid* g) {
     v.lox = g->lox; v.loy = g->loy; v.x0 = g->x0; v.y0 = g->y0;
     v.tall = g->tall;
     v.feat_n = g->feat_split ? g->n : 0;
+    for (int j = 0; j < 16; ++j) v.sxr[j] = 255;
     return v;
 }
 
@@ -48,6 +50,28 @@ static inline int stencil_halfwidth(const more3d_grid* g, double r) {
 }
 #define M3D_SY(s) ((s) & 0xffff)
 #define M3D_SX(s) ((s) >> 16)
+
+// Circle-clipped stencil rows, per ROW OFFSET (not per query: every lane of a warp uses the same widths, so nothing
+// diverges and no register is spent).  A point in the row j rows away from the query's row is at least (j - 1) row
+// heights away in y, so it can only be within r if |dx| <= sqrt(r^2 - ((j - 1) cell)^2): the outer rows of a wide stencil
+// (9 rows of quarter-radius cells at r = 1.0 on the shared grid) need 13 and 15 columns instead of 17.
+static inline void set_row_clip(GridView& v, const more3d_grid* g, double r) {
+    const int s = stencil_halfwidth(g, r), sy = M3D_SY(s), sx = M3D_SX(s);
+    for (int j = 0; j < 16; ++j) {
+        int w = sx;
+        if (j >= 2 && j <= sy) {
+            const double dy = (double)(j - 1) * g->cell * (1.0 - 1e-9);
+            const double w2 = r * r - dy * dy;
+            const double dx = w2 > 0.0 ? sqrt(w2) * (1.0 + 1e-9) : 0.0;
+            const double c = ceil(dx * M3D_CELL_MARGIN / g->cell_x);
+            if (c < (double)w) w = (int)c;
+        }
+        v.sxr[j] = (unsigned char)(w > 254 ? 255 : w);
+    }
+}
+__device__ __forceinline__ int row_halfwidth(const GridView& g, int s, int dy) {
+    return min(M3D_SX(s), (int)g.sxr[min(abs(dy), 15)]);
+}
 
 // fp32 distance filter.  With every fp32 record coordinate within delta32 of the exact one, the fp32
 // squared distance of a pair near the sphere surface is within h of the exact fp64 rule's value:
@@ -99,18 +123,19 @@ template <typename F>
 __device__ __forceinline__ void for_each_candidate(const GridView& g, double qx, double qy, int s, F&& f) {
     const int ix = g.col_x(qx);
     const int iy = g.col_y(qy);
-    const int x0 = max(ix - M3D_SX(s), 0), x1 = min(ix + M3D_SX(s), g.nx - 1);
     const int y0 = max(iy - M3D_SY(s), 0), y1 = min(iy + M3D_SY(s), g.ny - 1);
-    if (x0 > x1 || y0 > y1) return;
+    if (ix + M3D_SX(s) < 0 || ix - M3D_SX(s) > g.nx - 1 || y0 > y1) return;
     // the bounds of row y+1 are requested before row y is walked, so their latency hides behind the row
     const uint32_t* cs = g.col_start + (size_t)y0 * g.nx;
-    uint32_t nb = __ldg(cs + x0), ne = __ldg(cs + x1 + 1);
+    int w = row_halfwidth(g, s, y0 - iy);
+    uint32_t nb = __ldg(cs + min(max(ix - w, 0), g.nx)), ne = __ldg(cs + min(max(ix + w + 1, 0), g.nx));
     for (int y = y0; y <= y1; ++y) {
         const uint32_t b = nb, e = ne;
         if (y < y1) {
             cs += g.nx;
-            nb = __ldg(cs + x0);
-            ne = __ldg(cs + x1 + 1);
+            w = row_halfwidth(g, s, y + 1 - iy);
+            nb = __ldg(cs + min(max(ix - w, 0), g.nx));
+            ne = __ldg(cs + min(max(ix + w + 1, 0), g.nx));
         }
         for (uint32_t j = b; j < e; ++j) f((int64_t)j);
     }
@@ -176,17 +201,18 @@ __device__ __forceinline__ void walk_candidates_pipelined(const GridView& g, dou
     }
     const int ix = g.col_x(qx);
     const int iy = g.col_y(qy);
-    const int x0 = max(ix - M3D_SX(s), 0), x1 = min(ix + M3D_SX(s), g.nx - 1);
     const int y0 = max(iy - M3D_SY(s), 0), y1 = min(iy + M3D_SY(s), g.ny - 1);
-    if (x0 > x1 || y0 > y1) return;
+    if (ix + M3D_SX(s) < 0 || ix - M3D_SX(s) > g.nx - 1 || y0 > y1) return;
     const uint32_t* cs = g.col_start + (size_t)y0 * g.nx;
-    uint32_t nb = __ldg(cs + x0), ne = __ldg(cs + x1 + 1);
+    int w = row_halfwidth(g, s, y0 - iy);
+    uint32_t nb = __ldg(cs + min(max(ix - w, 0), g.nx)), ne = __ldg(cs + min(max(ix + w + 1, 0), g.nx));
     for (int y = y0; y <= y1; ++y) {
         const uint32_t b = nb, e = ne;
         if (y < y1) {
             cs += g.nx;
-            nb = __ldg(cs + x0);
-            ne = __ldg(cs + x1 + 1);
+            w = row_halfwidth(g, s, y + 1 - iy);
+            nb = __ldg(cs + min(max(ix - w, 0), g.nx));
+            ne = __ldg(cs + min(max(ix + w + 1, 0), g.nx));
         }
         run_range_pipelined(b, e, load, process);
     }

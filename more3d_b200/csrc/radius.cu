@@ -75,6 +75,7 @@ extern "C" int more3d_radius_count(const more3d_grid* g, const double* q, int64_
     ProfScope prof("radius_count", s);
     const Filter32 flt = make_filter(g, r);
     GridView v = make_view(g);
+    set_row_clip(v, g, r);
     uint32_t* qo = nullptr;
     if (q) M3D_TRY(sort_queries_by_column(g, q, nq, s, &qo));
     if (q) {
@@ -112,6 +113,7 @@ extern "C" int more3d_radius_fill(const more3d_grid* g, const double* q, int64_t
     const int sw = stencil_halfwidth(g, r);
     const unsigned nb = (unsigned)((nq + 255) / 256);
     GridView v = make_view(g);
+    set_row_clip(v, g, r);
     const double r2 = r * r;
     const Filter32 flt = make_filter(g, r);
     ProfScope prof("radius_fill", s);

@@ -20,8 +20,9 @@ CELL_MARGIN = 1.0 + 1.0 / 65536.0
 # moments + dk/dn kernels, 3 is no better than 2 (profiles/README.md).
 CELLS_PER_RADIUS = int(os.environ.get("MORE3D_CELLS_PER_RADIUS", "2"))
 # Columns of the fixed-radius grids are this many times narrower along x than they are high along y (see
-# more3d_grid_create_segments): 2 trims 10 / 7 / 6 % of the candidates at r = 0.5 / 0.75 / 1.0 on the shared grid.
-X_SPLIT = int(os.environ.get("MORE3D_X_SPLIT", "2"))
+# more3d_grid_create_segments): configs[1] takes 22.6 / 21.9 / 21.3 ms per step with 1 / 2 / 4 (the column table grows
+# by the same factor: 4 columns per point at 4).
+X_SPLIT = int(os.environ.get("MORE3D_X_SPLIT", "4"))
 
 
 def cell_for_radius(radius):
