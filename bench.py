@@ -134,7 +134,9 @@ def run_reference(args, rank, world):
     pts = synthetic.terrain(n, seed=2)
     cores = host_cores()
     base = CpuSaliencyBaseline(pts, RADII, PARAMS, workers=cores, seed=1)
-    q = args.cpu_q
+    # Q query points per radius and step (50 000); with many steps the per-step sample shrinks so
+    # that the whole run stays within a few minutes (>= 300 000 sampled queries per radius in total)
+    q = args.cpu_q if args.steps <= 6 else max(10000, min(args.cpu_q, 300000 // args.steps))
     for _ in range(args.warmup):
         base.step(max(q // 8, cores))
     times = []
