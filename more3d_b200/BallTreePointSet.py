@@ -30,6 +30,7 @@ class BallTreePointSet(object):
         self.__leaf_size = int(leaf_size)
         self.__dev = torch.from_numpy(self.__points).cuda()
         self.__grids = {}
+        self.__bounds = None
         self.__tree = None  # LOD-cell hierarchy, built on first use (see lodtree.py)
 
     # ---------------- internals -------------
@@ -46,7 +47,9 @@ class BallTreePointSet(object):
 
     def _knn_cell(self, k):
         """Column width giving ~k points per 3x3 block for this cloud's mean planimetric density."""
-        b = _lib.cloud_bounds(self.__dev)
+        if self.__bounds is None:                       # the cloud is immutable: one reduction per object
+            self.__bounds = _lib.cloud_bounds(self.__dev)
+        b = self.__bounds
         ext = b[3:] - b[:3]
         area = max(float(ext[0]) * float(ext[1]), 1e-300)
         n = self.__points.shape[0]

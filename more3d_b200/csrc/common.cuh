@@ -155,6 +155,8 @@ int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaSt
 // grid.cu: processing order for EXTERNAL query points -- their indices sorted by grid column, so that the 32
 // lanes of a warp walk the same stencil rows (the locality the self-query path gets from the sorted cloud).
 // *order is a stream-ordered allocation of nq uint32 (free with dev_free); NULL for small query sets.
+// bounding box {min x, y, z, max x, y, z} of a cloud, read back to the host (one small synchronisation)
+int cloud_bbox(const double* xyz, int64_t n, double box_h[6], cudaStream_t s);
 int sort_queries_by_column(const more3d_grid* g, const double* q, int64_t nq, cudaStream_t s, uint32_t** order);
 
 // device helpers -------------------------------------------------------------------------------

@@ -422,6 +422,23 @@ fail:
 #undef G_CUDA
 }
 
+int m3d::cloud_bbox(const double* xyz, int64_t n, double box_h[6], cudaStream_t s) {
+    Segs sg;
+    sg.p[0] = xyz; sg.p[1] = sg.p[2] = nullptr;
+    sg.end[0] = sg.end[1] = sg.end[2] = n;
+    const int nparts = 592;
+    double* part = nullptr;
+    M3D_TRY(dev_alloc(&part, (size_t)6 * nparts + 6, s));
+    bbox_partial<<<nparts, BB_THREADS, 0, s>>>(sg, n, part);
+    bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
+    count_launches(2);
+    M3D_CHECK_LAUNCH();
+    M3D_CUDA(cudaMemcpyAsync(box_h, part + 6 * nparts, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    dev_free(part, s);
+    return MORE3D_OK;
+}
+
 int m3d::sort_queries_by_column(const more3d_grid* g, const double* q, int64_t nq, cudaStream_t s, uint32_t** order) {
     *order = nullptr;
     if (nq < 4096 || nq >= ((int64_t)1 << 32)) return MORE3D_OK;

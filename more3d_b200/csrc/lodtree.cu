@@ -13,6 +13,7 @@
 // Node radius = sqrt(max squared distance to the node centroid) (neighbors/_ball_tree.pyx.tp:86-145);
 // the centroid here is a pairwise (children-first) fp64 sum, sklearn's is a sequential one in an
 // implementation-defined order, so radii agree to a few ulp, not bit for bit.
+#include <string.h>
 #include <vector>
 #include "common.cuh"
 #include "scan.cuh"
@@ -44,12 +45,55 @@ __global__ void __launch_bounds__(LT_THREADS) lt_node_ranges(int64_t n, int64_t 
     is_leaf[i] = (2 * i + 1 >= n_nodes || e - b < 2) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(LT_THREADS) lt_keys(const double* __restrict__ xyz, int64_t n, int d,
+// Coordinate order of one axis = order of the keys k = sortable(v) - sortable(v_min): an exact, order-preserving
+// unsigned integer of `bits` significant bits (the axis' bounding interval is known).  The order is produced in two
+// steps instead of bits / 8 radix passes over 64-bit keys: a radix sort of the TOP 32 bits (4 passes over 8-byte pairs),
+// then a fix-up of the short runs of equal top bits (a few points at 40 points / m^2: the top 32 bits resolve a
+// quarter of a millimetre or better) by their low bits -- which are gathered once -- and, last, the point index.
+__global__ void __launch_bounds__(LT_THREADS) lt_keys(const double* __restrict__ xyz, int64_t n, int d, uint64_t base,
                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = sortable_key(xyz[3 * i + d]);
+    keys[i] = sortable_key(xyz[3 * i + d]) - base;
     vals[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(LT_THREADS) lt_keys_hi(const double* __restrict__ xyz, int64_t n, int d, uint64_t base,
+                                                         int shift, uint32_t* __restrict__ hi, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    hi[i] = (uint32_t)((sortable_key(xyz[3 * i + d]) - base) >> shift);
+    vals[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(LT_THREADS) lt_gather_lo(const double* __restrict__ xyz, int64_t n, int d, uint64_t base,
+                                                           int shift, const uint32_t* __restrict__ order,
+                                                           uint32_t* __restrict__ lo) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t k = sortable_key(xyz[3 * (int64_t)order[t] + d]) - base;
+    lo[t] = shift ? (uint32_t)(k & ((1ull << shift) - 1ull)) : 0u;
+}
+// one thread per sorted position: its final slot inside its run of equal top bits = the number of run members with
+// smaller low bits, or equal low bits and an earlier position (the stable sort left ties in index order)
+constexpr int LT_MAX_RUN = 4096;
+__global__ void __launch_bounds__(LT_THREADS) lt_tie_fix(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo,
+                                                         const uint32_t* __restrict__ order, int64_t n,
+                                                         uint32_t* __restrict__ out, int* __restrict__ overflow) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t h = hi[t], l = lo[t];
+    int64_t b = t, e = t + 1;
+    uint32_t rank = 0;
+    while (b > 0 && hi[b - 1] == h) {
+        --b;
+        if (lo[b] <= l) ++rank;
+        if (t - b > LT_MAX_RUN) { *overflow = 1; return; }
+    }
+    while (e < n && hi[e] == h) {
+        if (lo[e] < l) ++rank;
+        ++e;
+        if (e - t > LT_MAX_RUN) { *overflow = 1; return; }
+    }
+    out[b + rank] = order[t];
 }
 
 struct Lists {
@@ -309,13 +353,47 @@ extern "C" int more3d_balltree_build(const double* xyz, int64_t n, int leaf_size
     M3D_TRY(dev_alloc(&sums, (size_t)3 * n_nodes, s));
     M3D_TRY(dev_alloc(&r2, (size_t)n_nodes, s));
 
-    // three lists sorted by (coordinate, index): stable LSD sort of order-preserving 64-bit keys
+    // three lists sorted by (coordinate, index)
+    double box[6];
+    M3D_TRY(cloud_bbox(xyz, n, box, s));                     // one small host read
+    int* overflow = nullptr;
+    M3D_TRY(dev_alloc(&overflow, 1, s));
+    uint32_t* k32 = reinterpret_cast<uint32_t*>(k1);         // the 64-bit key buffers double as 32-bit ones
+    uint32_t* k32b = reinterpret_cast<uint32_t*>(k2);
+    uint32_t* lo32 = k32b + n;                               // second half of k2: the gathered low bits
     for (int d = 0; d < 3; ++d) {
-        lt_keys<<<nb, LT_THREADS, 0, s>>>(xyz, n, d, k1, v1);
-        count_launches(1);
-        M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, 64, &ks, &vs, s));
-        M3D_CUDA(cudaMemcpyAsync(lists[d], vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        auto skey = [](double v) { v = v + 0.0; uint64_t u; memcpy(&u, &v, 8); return (u >> 63) ? ~u : (u | 0x8000000000000000ull); };
+        const uint64_t base = skey(box[d]), range = skey(box[3 + d]) - base;
+        int bits = 0;
+        while (bits < 64 && (range >> bits) != 0) ++bits;
+        if (bits == 0) bits = 1;
+        const int shift = bits > 32 ? bits - 32 : 0;
+        uint32_t *ks32 = nullptr, *vs32 = nullptr;
+        lt_keys_hi<<<nb, LT_THREADS, 0, s>>>(xyz, n, d, base, shift, k32, v1);
+        M3D_TRY(radix_sort_pairs_u32(k32, v1, k32b, v2, n, bits - shift, &ks32, &vs32, s));
+        int ovf = 0;
+        if (shift) {
+            // the sorted top bits may sit in either buffer; the low bits go to the other one's spare half
+            uint32_t* lo_buf = (ks32 == k32b) ? (k32 + n) : lo32;
+            M3D_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), s));
+            lt_gather_lo<<<nb, LT_THREADS, 0, s>>>(xyz, n, d, base, shift, vs32, lo_buf);
+            lt_tie_fix<<<nb, LT_THREADS, 0, s>>>(ks32, lo_buf, vs32, n, lists[d], overflow);
+            M3D_CUDA(cudaMemcpyAsync(&ovf, overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+            M3D_CUDA(cudaStreamSynchronize(s));
+            count_launches(3);
+        } else {
+            M3D_CUDA(cudaMemcpyAsync(lists[d], vs32, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+            count_launches(1);
+        }
+        if (ovf) {
+            // a run of more than LT_MAX_RUN equal top bits (many near-coincident coordinates): full-width radix sort
+            lt_keys<<<nb, LT_THREADS, 0, s>>>(xyz, n, d, base, k1, v1);
+            count_launches(1);
+            M3D_TRY(radix_sort_pairs_u64(k1, v1, k2, v2, n, bits, &ks, &vs, s));
+            M3D_CUDA(cudaMemcpyAsync(lists[d], vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        }
     }
+    dev_free(overflow, s);
     M3D_CUDA(cudaMemsetAsync(pos_node, 0, (size_t)n * 4, s));
     M3D_CUDA(cudaMemsetAsync(side, 0, (size_t)n, s));
 
