@@ -322,7 +322,7 @@ int more3d_ls_elementwise(int op, const double* x, double param, int64_t n, doub
  * call.  cue_ops, in place on x (n f64): op 0 = np.abs; op 1 = clip(x, arg_dev[0], arg_dev[1]) (levelsets_func.py:107-109);
  * op 2 = normalize(x, s = arg) (:100-104: skipped when the column is all zero), out_dev (may be NULL) = {min, max};
  * op 3 = out_dev[0..1] = {0, numpy `linear` interpolation of arg_dev[0], arg_dev[1] at gamma = arg}: the clip bounds
- * of `clip(zeta, 0, np.percentile(zeta, pc))` without a host round trip; op 4 = out_dev[0..1] = {min, max} of x. */
+ * of `clip(zeta, 0, np.percentile(zeta, pc))` without a host round trip; op 4 = out_dev[0..1] = {min, max} of x; op 5 = out_dev[0] = mean of x. */
 /* DM_saliency_stats (DM_saliency.py:585-607): out (device, 4 f64) = {min, max, mean, population sigma} of an f32 column */
 int more3d_column_stats(const float* x, int64_t n, double* out, void* stream);
 int more3d_select_kth(const double* v, int64_t n, const int64_t* ranks_h, int nk, double* out, void* stream);

@@ -46,7 +46,11 @@ __global__ void __launch_bounds__(256) orient_up_kernel(double* __restrict__ nor
     if (i >= n) return;
     double x = normals[3 * i], y = normals[3 * i + 1], z = normals[3 * i + 2];
     if (isnan(x)) { x = 0.0; y = 0.0; z = 1.0; }
-    if (upwards_z && z < 0.0) { x = -x; y = -y; z = -z; }
+    if ((upwards_z & 1) && z < 0.0) { x = -x; y = -y; z = -z; }
+    if (upwards_z & 2) {                       // normals.normalize_normals(), downsample_compare.py:122
+        const double nn = sqrt(x * x + y * y + z * z);
+        if (nn > 0.0) { x /= nn; y /= nn; z /= nn; }
+    }
     normals[3 * i] = x; normals[3 * i + 1] = y; normals[3 * i + 2] = z;
 }
 

@@ -125,6 +125,26 @@ __global__ void minmax_f64_final(const double* __restrict__ part, int nparts, do
     }
     if (threadIdx.x == 0) { out[0] = lo; out[1] = hi; }
 }
+__global__ void __launch_bounds__(256) sum_f64_partial(const double* __restrict__ x, int64_t n, double* __restrict__ part) {
+    double sum = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) sum += x[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ double ss[8];
+    if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) sum += ss[w];
+        part[blockIdx.x] = sum;
+    }
+}
+__global__ void sum_f64_final(const double* __restrict__ part, int nparts, double scale, double* __restrict__ out) {
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 32) sum += part[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (threadIdx.x == 0) out[0] = sum * scale;
+}
 // if np.any(array != 0): array -= array.min(); array /= array.max(); array *= s   (levelsets_func.py:100-104)
 __global__ void __launch_bounds__(256) normalize_kernel(double* x, int64_t n, const double* __restrict__ mm, double s) {
     const double mn = mm[0], mx = mm[1];
@@ -262,8 +282,18 @@ extern "C" int more3d_cue_ops(int op, double* x, int64_t n, const double* arg_de
         dev_free(part, s);
         break;
     }
+    case 5: { // out_dev[0] = mean of x (fixed 592-block tree: reproducible); x is only read
+        M3D_REQUIRE(x && out_dev && n > 0, "NULL / empty argument");
+        double* part = nullptr;
+        M3D_TRY(dev_alloc(&part, (size_t)592, s));
+        sum_f64_partial<<<592, 256, 0, s>>>(x, n, part);
+        sum_f64_final<<<1, 32, 0, s>>>(part, 592, 1.0 / (double)n, out_dev);
+        count_launches(2);
+        dev_free(part, s);
+        break;
+    }
     default:
-        M3D_REQUIRE(false, "op must be 0 (abs), 1 (clip), 2 (normalize), 3 (percentile interpolation) or 4 (min / max)");
+        M3D_REQUIRE(false, "op must be 0 (abs), 1 (clip), 2 (normalize), 3 (percentile interpolation), 4 (min / max) or 5 (mean)");
     }
     M3D_CHECK_LAUNCH();
     return MORE3D_OK;

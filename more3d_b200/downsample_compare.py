@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr, stream_ptr
-from .grid import UniformGrid, as_device_points, cell_for_radius
+from .grid import UniformGrid, X_SPLIT, as_device_points, cell_for_radius
 
 
 def _knn_cell(d, k):
@@ -31,7 +31,7 @@ def estimate_normals(points, radius=None, knn=None, upwards_z=True, return_devic
     n = int(d.shape[0])
     with torch.cuda.device(d.device):
         if radius is not None:
-            g = UniformGrid(d, cell_for_radius(radius))
+            g = UniformGrid(d, cell_for_radius(radius), x_split=X_SPLIT)
             normals, _, _ = g.normals_pca(radius)
             g.close()
         else:
@@ -64,8 +64,8 @@ def compare(pts, downsampled, normals_pts=None, rnn=.1, knn=64, rnn_flag=True, u
         normals_pts = estimate_normals(P, radius=rnn if rnn_flag else None, knn=knn, upwards_z=upwards_z, return_device=True)
     NP = as_device_points(normals_pts)
     NQ = estimate_normals(Q, radius=rnn if rnn_flag else None, knn=knn, upwards_z=upwards_z, return_device=True)
-    NQ = NQ / NQ.norm(dim=1, keepdim=True)                       # normals.normalize_normals(), :122
     with torch.cuda.device(P.device):
+        check(lib.more3d_orient_normals(ptr(NQ), int(NQ.shape[0]), 2, stream_ptr()))   # normals.normalize_normals(), :122
         E, closest = _nearest(P, Q)                              # btP.query(downsampled, 1), :132
         E2, closest2 = _nearest(Q, P)                            # downsampled_bt.query(pts, 1), :136
         c2p = torch.empty(P.shape[0], dtype=torch.float64, device=P.device)
@@ -77,7 +77,13 @@ def compare(pts, downsampled, normals_pts=None, rnn=.1, knn=64, rnn_flag=True, u
         mid = torch.empty(2, dtype=torch.float64, device=P.device)
         ranks = (C.c_int64 * 2)((m - 1) // 2, m // 2)
         check(lib.more3d_select_kth(ptr(ang), m, ranks, 2, ptr(mid), stream_ptr()))
+        # np.average of the three error columns: library reductions (fixed tree), read back together with the median
+        avg = torch.empty(3, dtype=torch.float64, device=P.device)
+        for i, col in enumerate((E, E2, c2p)):
+            col = col.reshape(-1).contiguous()
+            check(lib.more3d_cue_ops(5, ptr(col), int(col.numel()), None, 0.0, ptr(avg[i:i + 1]), stream_ptr()))
     mid = mid.cpu().numpy()
+    avg = avg.cpu().numpy()
     med = (float(mid[0]) + float(mid[1])) / 2.0
-    return {"c2c": float(E2.mean() + E.mean() / 2), "c2p": float(c2p.mean()), "dN": float(med),
+    return {"c2c": float(avg[1] + avg[0] / 2), "c2p": float(avg[2]), "dN": float(med),
             "dn_all": ang.cpu().numpy(), "E": E.cpu().numpy(), "E2": E2.cpu().numpy()}
