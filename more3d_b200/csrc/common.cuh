@@ -159,6 +159,10 @@ int exclusive_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, cudaSt
 int cloud_bbox(const double* xyz, int64_t n, double box_h[6], cudaStream_t s);
 int sort_queries_by_column(const more3d_grid* g, const double* q, int64_t nq, cudaStream_t s, uint32_t** order);
 
+// features.cu: kernel variant of the dk/dn pass (MORE3D_DKDN_VARIANT, read once): 0 = two passes (screen + refine,
+// default), 1 = shared-memory staged one-pass walk, 2 = global-memory one-pass walk
+int dkdn_variant();
+
 // device helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ double dist2_rule(double dx, double dy, double dz) {
     // ((dx*dx)+(dy*dy))+(dz*dz), round-to-nearest each step, never contracted to FMA:

@@ -3,6 +3,7 @@
 // Replaces Curvature_Kernel.process (DM_saliency.py:88-157), Saliency_Kernel.process (:219-324) and the
 // normals precondition (DM_saliency.py:329-330).
 #include <stdlib.h>
+#include <vector>
 #include "gridview.cuh"
 #include "eig3.cuh"
 
@@ -42,11 +43,33 @@ __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int64_t n, in
     ldg256(reinterpret_cast<const char*>(f) + slot * 32, r.x, r.y, r.z, r.w);
     return r;
 }
+// 4th word of a record's first half: [63..32] the float32 bits of _nonparam_K, [31..2] the unit normal quantised to
+// 3 x 10 bits (q = rint(511 c) + 512; a NaN normal is stored as the zero vector), [1..0] the flags (bit 0 = coincident
+// with an earlier point, bit 1 = raw normal was NaN).  The quantised normal only serves the SCREENING pass of dk/dn
+// (dkdn_screen_kernel), which needs a certified bound on n_p . n_q, never its value.
+__device__ __forceinline__ uint32_t q10(double c) {
+    double v = rint(c * 511.0);
+    v = fmin(fmax(v, -511.0), 511.0);          // NaN -> -511 here; the caller replaces NaN normals as a whole
+    return (uint32_t)((int)v + 512);
+}
+__device__ __forceinline__ double feat_kword(float K, int flags, double ux, double uy, double uz) {
+    uint32_t lo = (uint32_t)flags;
+    if (isnan(ux) || isnan(uy) || isnan(uz)) lo |= (512u << 2) | (512u << 12) | (512u << 22);
+    else lo |= (q10(ux) << 2) | (q10(uy) << 12) | (q10(uz) << 22);
+    return __longlong_as_double((long long)(((unsigned long long)__float_as_uint(K) << 32) | lo));
+}
+__device__ __forceinline__ double kword_K(long long kb) { return (double)__uint_as_float((uint32_t)((unsigned long long)kb >> 32)); }
+
+// (nx, ny, nz) is the RAW normal: the record holds n / ||n||, DM_saliency.py:258-259 (norm = sqrt of the sequential
+// sum of squares)
 __device__ __forceinline__ void st_feat(FeatRec* __restrict__ f, int64_t n, int64_t i, double x, double y, double z,
-                                        double K, double nx, double ny, double nz) {
+                                        float K, bool dup, double nx, double ny, double nz) {
+    const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
+    const double ux = nx / nn, uy = ny / nn, uz = nz / nn;
+    const double kw = feat_kword(K, (dup ? 1 : 0) | (isnan(nx) ? 2 : 0), ux, uy, uz);
     const size_t sa = n ? (size_t)i : 2 * (size_t)i, sb = n ? (size_t)n + (size_t)i : 2 * (size_t)i + 1;
-    *reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + sa * 32) = make_double4(x, y, z, K);
-    *reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + sb * 32) = make_double4(nx, ny, nz, 0.0);
+    *reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + sa * 32) = make_double4(x, y, z, kw);
+    *reinterpret_cast<double4*>(reinterpret_cast<char*>(f) + sb * 32) = make_double4(ux, uy, uz, 0.0);
 }
 
 
@@ -134,10 +157,7 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, Cu
     if (MODE == MODE_FUSED && feat_out) {
         // the dk/dn pass's sorted feature record, written here (coalesced) instead of being gathered
         // from the original-order columns by build_feat_kernel; same arithmetic as there
-        const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
-        st_feat(feat_out, g.feat_n, i, p.x, p.y, p.z,
-                __longlong_as_double(__double_as_longlong((double)K) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL)),
-                nx / nn, ny / nn, nz / nn);
+        st_feat(feat_out, g.feat_n, i, p.x, p.y, p.z, K, g.dup[i] != 0, nx, ny, nz);
     }
 }
 
@@ -152,11 +172,7 @@ __global__ void __launch_bounds__(256) build_feat_kernel(GridView g, const doubl
     const PointRec p = load_rec(g.rec, i);
     const int64_t o = p.idx;
     const double nx = normals[3 * o], ny = normals[3 * o + 1], nz = normals[3 * o + 2];
-    // n / ||n||, DM_saliency.py:258-259 (norm = sqrt of the sequential sum of squares)
-    const double nn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
-    st_feat(feat, g.feat_n, i, p.x, p.y, p.z,
-            __longlong_as_double(__double_as_longlong((double)K[o]) | (long long)(g.dup[i] ? 1 : 0) | (isnan(nx) ? 2LL : 0LL)),
-            nx / nn, ny / nn, nz / nn);
+    st_feat(feat, g.feat_n, i, p.x, p.y, p.z, K[o], g.dup[i] != 0, nx, ny, nz);
 }
 
 struct DkDnParams {
@@ -167,6 +183,11 @@ struct DkDnParams {
     long long own_lo, own_hi;  // only points with original index in [own_lo, own_hi) enter the fused min/max (a strip's
                                // own points sit between its left and right ghosts)
     Filter32 flt;
+    // screening pass (dkdn_screen_kernel): a candidate is ACTIVE (w > 0.01, :272-279) iff it is unique, inside and
+    // act_lo <= d2 <= act_hi, d2 != rho2 -- the weight's rounding is monotone on either side of rho2, so the two
+    // thresholds (found by the host with the kernel's own arithmetic) reproduce the comparison bit for bit
+    double act_lo, act_hi;
+    float dot_thr;      // quantised n_p . n_q above this  =>  certainly |1 - n_p . n_q| < 0.016 (:286)
 };
 
 // largest double x >= 0 with fl(x * 100.0) <= 0.04: the rescue test of DM_saliency.py:290 without the multiply
@@ -175,6 +196,28 @@ static double zk100_threshold() {
     while (x * 100.0 <= 0.04) x = nextafter(x, 1.0);
     while (x * 100.0 > 0.04) x = nextafter(x, 0.0);
     return x;
+}
+
+// act_lo = smallest d2 with fl(inv_rho2 * d2) > 0.01, act_hi = largest d2 with fl(2 - fl(inv_rho2 * d2)) > 0.01 (the two
+// branches of the ring weight, DkdnAcc::add).  false if rho is degenerate (the screening pass is then not used).
+static bool act_interval(double rho2, double inv_rho2, double* lo, double* hi) {
+    if (!(rho2 > 0.0) || !isfinite(rho2) || !isfinite(inv_rho2) || !(inv_rho2 > 0.0)) return false;
+    // volatile: every product and difference is rounded to double exactly as __dmul_rn / __dsub_rn do (no contraction)
+    auto w_lo = [&](double x) { volatile double t = inv_rho2 * x; return (double)t; };
+    auto w_hi = [&](double x) { volatile double t = inv_rho2 * x; volatile double u = 2.0 - t; return (double)u; };
+    double x = 0.01 * rho2;
+    int up = 0, down = 0;
+    while (!(w_lo(x) > 0.01) && ++up < 1000) x = nextafter(x, INFINITY);
+    while (x > 0.0 && w_lo(nextafter(x, 0.0)) > 0.01 && ++down < 1000) x = nextafter(x, 0.0);
+    if (up >= 1000 || down >= 1000 || !(x < rho2) || !(w_lo(x) > 0.01)) return false;
+    *lo = x;
+    x = 1.99 * rho2;
+    up = down = 0;
+    while (!(w_hi(x) > 0.01) && ++down < 1000) x = nextafter(x, 0.0);
+    while (w_hi(nextafter(x, INFINITY)) > 0.01 && ++up < 1000) x = nextafter(x, INFINITY);
+    if (up >= 1000 || down >= 1000 || !(x > rho2) || !(w_hi(x) > 0.01)) return false;
+    *hi = x;
+    return true;
 }
 
 // One query point's state of Saliency_Kernel.process: init() from its own record, add() per candidate, finish().
@@ -189,7 +232,7 @@ struct DkdnAcc {
     __device__ __forceinline__ void init(const D4& pa, const D4& pb) {   // (x y z K) (nx ny nz flags)
         px = pa.x; py = pa.y; pz = pa.z;
         pflags = __double_as_longlong(pa.w) & 3LL;
-        Kp = __longlong_as_double(__double_as_longlong(pa.w) & ~3LL);
+        Kp = kword_K(__double_as_longlong(pa.w));
         pnx = pb.x; pny = pb.y; pnz = pb.z;
         m = mu = nact = zn = zk = zk100 = 0;
         s1n = s2n = s1k = s2k = wn = wk = wsum = 0.0;
@@ -206,7 +249,7 @@ struct DkdnAcc {
         const bool in = d2 <= prm.r2;
         const bool u = in & !((int)kb & 1);                               // np.unique, :247
         double dn = 1.0 - (pnx * qb.x + pny * qb.y + pnz * qb.z);         // :261
-        double dk = Kp - __longlong_as_double(kb & ~3LL);                 // :262
+        double dk = Kp - kword_K(kb);                                     // :262
         dn = u ? dn : 0.0;
         dk = u ? dk : 0.0;
         // opaque to the optimiser: keeps |.| as an operand modifier of the consumers instead of a
@@ -332,6 +375,352 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
         dkdn_minmax(ck ? f32_ordered(dkf) : 0xffffffffu, ck ? f32_ordered(dkf) : 0u,
                     cn ? f32_ordered(dnf) : 0xffffffffu, cn ? f32_ordered(dnf) : 0u, mm);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6 in two passes (thin grids, split records; the default).
+//
+// Saliency_Kernel.process returns dk = 0 whenever more than 60 % of the ACTIVE neighbours have |dk| <= 0.04 and dn = 0
+// whenever more than 60 % have |dn| < 0.016 (DM_saliency.py:286-316) -- whatever the chi2 tests say.  On open terrain
+// that settles dn for practically every point and dk for 80-95 % of them, and both conditions are pure COUNTS:
+//
+//   pass 1, dkdn_screen_kernel (every point; thread per point, the same row walk as dkdn_kernel): per candidate only
+//     the exact fp64 accept rule, the active test as two thresholds on d2 (act_interval), |dk| <= T as a float32
+//     interval test on the neighbour's K (dk_interval: exact, K is a float32 column) and a CERTIFIED lower count of
+//     |dn| < 0.016 from the 3 x 10-bit normal packed beside K -- 12 FP64 instructions and ONE 32-byte load per
+//     candidate instead of 35 and two.  A point whose counts settle both outputs writes (0, 0); the others are
+//     appended to a work list (bit 31 of an entry: the normal test did not settle dn).
+//   pass 2, dkdn_refine_kernel (listed points; one WARP per point): the full expression of DkdnAcc on the point's
+//     candidates, lanes striding over the concatenated stencil rows (coalesced 32-byte loads), partial sums combined
+//     by a fixed shuffle tree.  Counters and decisions are the same integers as in the one-pass kernel; the fp64 sums
+//     are added in another (still deterministic, lattice-defined) order, i.e. values agree to rounding.
+// ------------------------------------------------------------------------------------------
+
+// { x float32 : |fl64(Kp - x)| <= T } as a closed float32 interval [lo, hi] (the fp64 difference is monotone in x).
+// ok = false if the few-ulp search did not pin both ends (the point is then refined unconditionally).
+__device__ __forceinline__ bool dk_pred(double Kp, float x, double T) { return fabs(__dsub_rn(Kp, (double)x)) <= T; }
+__device__ __forceinline__ bool dk_interval(double Kp, double T, float& lo, float& hi) {
+    const float inf = __int_as_float(0x7f800000);
+    float l = __double2float_rd(Kp - T), h = __double2float_ru(Kp + T);
+#pragma unroll 1
+    for (int k = 0; k < 4 && !dk_pred(Kp, l, T); ++k) l = nextafterf(l, inf);
+#pragma unroll 1
+    for (int k = 0; k < 4 && dk_pred(Kp, nextafterf(l, -inf), T); ++k) l = nextafterf(l, -inf);
+#pragma unroll 1
+    for (int k = 0; k < 4 && !dk_pred(Kp, h, T); ++k) h = nextafterf(h, -inf);
+#pragma unroll 1
+    for (int k = 0; k < 4 && dk_pred(Kp, nextafterf(h, inf), T); ++k) h = nextafterf(h, inf);
+    lo = l; hi = h;
+    return dk_pred(Kp, l, T) && !dk_pred(Kp, nextafterf(l, -inf), T) && dk_pred(Kp, h, T) &&
+           !dk_pred(Kp, nextafterf(h, inf), T) && l <= h && isfinite(l) && isfinite(h);
+}
+
+struct ScreenAcc {
+    double px, py, pz;
+    float ax, ay, az, bias;                  // n_p * 1024/511 and -1.5 * their sum (see add)
+    float k_lo, k_hi, k100_lo, k100_hi;
+    int m, mu, nact, zn, zk, zk100;
+    float s1, s2;                            // float32 sums of t = max(1 - quantised n_p . n_q, 0) over the unique neighbours
+
+    __device__ __forceinline__ void add(const D4& qa, const DkDnParams& prm) {
+        const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(qa.w);
+        const uint32_t lo = (uint32_t)kb;
+        const float Kq = __uint_as_float((uint32_t)(kb >> 32));
+        // the 10-bit fields dropped into the mantissa of a float in [1, 2): g = 1 + q / 1024, so that the quantised
+        // component (q - 512) / 511 = (g - 1.5) * 1024 / 511 needs no integer conversion; (field & mask) | 1.0f is
+        // one LOP3 each
+        uint32_t bx, by, bz;
+        const uint32_t msk = 0x007FE000u, one = 0x3F800000u;
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bx) : "r"(lo << 11), "r"(msk), "r"(one));
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(by) : "r"(lo << 1), "r"(msk), "r"(one));
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bz) : "r"(lo >> 9), "r"(msk), "r"(one));
+        const float dot = fmaf(__uint_as_float(bx), ax, fmaf(__uint_as_float(by), ay, fmaf(__uint_as_float(bz), az, bias)));
+        const float t = fmaxf(1.0f - dot, 0.0f);
+        // counters as predicated adds: m (inside), mu and the float32 sums (unique & inside), then with
+        // act = unique & inside & act_lo <= d2 <= act_hi & d2 != rho2:
+        // nact, zn (certainly |dn| < 0.016), zk (|dk| <= 0.04), zk100 (|100 dk| <= 0.04)
+        asm("{ .reg .pred pin, pu, pa, q;\n"
+            "  setp.le.f64 pin, %8, %9;\n"
+            "  @pin add.s32 %0, %0, 1;\n"
+            "  setp.eq.and.u32 pu, %13, 0, pin;\n"
+            "  @pu add.s32 %1, %1, 1;\n"
+            "  @pu add.f32 %6, %6, %21;\n"
+            "  @pu fma.rn.f32 %7, %21, %21, %7;\n"
+            "  setp.ge.and.f64 pa, %8, %10, pu;\n"
+            "  setp.le.and.f64 pa, %8, %11, pa;\n"
+            "  setp.ne.and.f64 pa, %8, %12, pa;\n"
+            "  @pa add.s32 %2, %2, 1;\n"
+            "  setp.gt.and.f32 q, %14, %15, pa;\n"
+            "  @q add.s32 %3, %3, 1;\n"
+            "  setp.ge.and.f32 q, %16, %17, pa;\n"
+            "  setp.le.and.f32 q, %16, %18, q;\n"
+            "  @q add.s32 %4, %4, 1;\n"
+            "  setp.ge.and.f32 q, %16, %19, pa;\n"
+            "  setp.le.and.f32 q, %16, %20, q;\n"
+            "  @q add.s32 %5, %5, 1;\n"
+            "}"
+            : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zn), "+r"(zk), "+r"(zk100), "+f"(s1), "+f"(s2)
+            : "d"(d2), "d"(prm.r2), "d"(prm.act_lo), "d"(prm.act_hi), "d"(prm.rho2), "r"(lo & 1u), "f"(dot),
+              "f"(prm.dot_thr), "f"(Kq), "f"(k_lo), "f"(k_hi), "f"(k100_lo), "f"(k100_hi), "f"(t));
+    }
+
+    // Certified: chi_n < chi_t (DM_saliency.py:283, :292), from the quantised normals.  Every t_j is within
+    // delta = 1.8e-3 of the exact dn_j (quantisation sqrt(3) * 0.5 / 511 = 1.70e-3 plus the float32 evaluation; dn_j >= 0,
+    // so clamping t at 0 keeps the bound), std is a seminorm: std(dn) <= std(t) + delta.  The float32 sums of the
+    // non-negative t_j and t_j^2 carry a relative error below eps = (mu + 2) * 2^-23 each, which moves the variance by at
+    // most eps * (var + 3 mean^2).  A NaN anywhere makes the comparison false (not certified).
+    __device__ __forceinline__ bool dn_settled_by_chi2(double chi_t, double sigma_n) const {
+        const double imu = 1.0 / (double)mu, mean = (double)s1 * imu;
+        const double var = fmax((double)s2 * imu - mean * mean, 0.0);
+        const double eps = ((double)mu + 2.0) * (1.0 / 8388608.0);
+        const double std_up = sqrt(var * (1.0 + 2.0 * eps) + 4.0 * eps * mean * mean) + 1.8e-3;
+        return (double)(m - 1) * std_up / sigma_n * 1.001 < chi_t;
+    }
+};
+
+constexpr uint32_t REFINE_NEED_N = 0x80000000u;
+
+__global__ void __launch_bounds__(WALK_THREADS) dkdn_screen_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                          DkDnParams prm, const double* __restrict__ chi2_table,
+                                                          float* __restrict__ dk_out,
+                                                          float* __restrict__ dn_out, unsigned* __restrict__ mm,
+                                                          int* __restrict__ err, uint32_t* __restrict__ list,
+                                                          unsigned* __restrict__ list_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < g.n;
+    bool owned = false, refine = false, need_n = false;
+    if (live) {
+        const D4 pa = ld_d4<true>(feat, g.n, i, 0), pb = ld_d4<true>(feat, g.n, i, 1);
+        ScreenAcc acc;
+        acc.px = pa.x; acc.py = pa.y; acc.pz = pa.z;
+        const long long kb = __double_as_longlong(pa.w);
+        const double Kp = kword_K(kb);
+        const double c = 1024.0 / 511.0;
+        acc.ax = (float)(pb.x * c); acc.ay = (float)(pb.y * c); acc.az = (float)(pb.z * c);
+        acc.bias = (float)(-1.5 * c * (pb.x + pb.y + pb.z));
+        bool ok = dk_interval(Kp, 0.04, acc.k_lo, acc.k_hi);
+        ok = dk_interval(Kp, prm.zk100_thr, acc.k100_lo, acc.k100_hi) && ok;
+        acc.m = acc.mu = acc.nact = acc.zn = acc.zk = acc.zk100 = 0;
+        acc.s1 = acc.s2 = 0.0f;
+        walk_candidates_pipelined<false>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
+            return ld_d4<true>(feat, g.n, j, 0);
+        }, [&](const D4& q) { acc.add(q, prm); });
+        if (!(kb & 2LL) && acc.m >= prm.min_points) {                       // DM_saliency.py:225-229, :240-244
+            if (acc.nact >= prm.table_len) {
+                atomicMax(err, acc.nact + 1);
+            } else {
+                const int zk = (acc.zk == acc.nact) ? acc.zk100 : acc.zk;   // :289-290
+                const double lim = 0.6 * (double)acc.nact;
+                const bool k_zero = ok && (double)zk > lim;                 // :309-311
+                // dn = 0 if chi_n < chi_t or zn > 0.6 nact (:292-294): zn is a certified lower count, the chi2 test a
+                // certified upper bound
+                need_n = !((double)acc.zn > lim) && !acc.dn_settled_by_chi2(__ldg(chi2_table + acc.nact), prm.sigma_n);
+                refine = !k_zero || need_n;
+            }
+        }
+        const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
+        const int64_t orig = (prm.grid_order && all_owned)
+                                 ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+        if (!refine) {
+            const int64_t o = prm.grid_order ? i : orig;
+            dk_out[o] = 0.0f;
+            dn_out[o] = 0.0f;
+        }
+        owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
+    }
+    // work list: one atomic per warp, entries of a warp stay in sorted order
+    const unsigned vote = __ballot_sync(0xffffffffu, refine);
+    if (vote) {
+        const int lane = threadIdx.x & 31, leader = __ffs(vote) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(list_count, (unsigned)__popc(vote));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (refine) list[base + __popc(vote & ((1u << lane) - 1u))] = (uint32_t)i | (need_n ? REFINE_NEED_N : 0u);
+    }
+    if (mm) {
+        const bool c0 = live && owned && !refine;       // refined points enter the extrema in pass 2
+        const unsigned z = f32_ordered(0.0f);
+        dkdn_minmax(c0 ? z : 0xffffffffu, c0 ? z : 0u, c0 ? z : 0xffffffffu, c0 ? z : 0u, mm);
+    }
+}
+
+constexpr int REFINE_WARPS = WALK_THREADS / 32;
+constexpr int REFINE_BATCH = 4;        // candidate records requested per lane before the first is used
+
+// The dk half of DkdnAcc::add (same expressions, same order: bit-identical dk), for the points whose dn the screening
+// pass has settled -- practically all of them: no normal is loaded or multiplied.
+struct DkAcc {
+    double px, py, pz, Kp;
+    int m, mu, nact, zk, zk100;
+    double s1k, s2k, wk, wsum;
+
+    __device__ __forceinline__ void init(const D4& pa) {
+        px = pa.x; py = pa.y; pz = pa.z;
+        Kp = kword_K(__double_as_longlong(pa.w));
+        m = mu = nact = zk = zk100 = 0;
+        s1k = s2k = wk = wsum = 0.0;
+    }
+    __device__ __forceinline__ void add(const D4& qa, const DkDnParams& prm) {
+        const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);
+        const long long kb = __double_as_longlong(qa.w);
+        const bool in = d2 <= prm.r2;
+        const bool u = in & !((int)kb & 1);
+        double dk = Kp - kword_K(kb);
+        dk = u ? dk : 0.0;
+        asm("" : "+d"(dk));
+        const double t = __dmul_rn(prm.inv_rho2, d2);
+        double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
+        const bool keep = u & (d2 != prm.rho2) & !(w < 0.0);
+        w = keep ? w : 0.0;
+        s1k += dk; s2k += dk * dk;
+        asm("{ .reg .pred pin, pu, pa, q;\n"
+            "  setp.ne.u32 pin, %5, 0;\n"
+            "  setp.ne.u32 pu, %6, 0;\n"
+            "  @pin add.s32 %0, %0, 1;\n"
+            "  @pu add.s32 %1, %1, 1;\n"
+            "  setp.gt.f64 pa, %7, %9;\n"
+            "  @pa add.s32 %2, %2, 1;\n"
+            "  .reg .f64 ak;\n"
+            "  abs.f64 ak, %8;\n"
+            "  setp.le.and.f64 q, ak, %10, pa;\n"
+            "  @q add.s32 %3, %3, 1;\n"
+            "  setp.le.and.f64 q, ak, %11, pa;\n"
+            "  @q add.s32 %4, %4, 1;\n"
+            "}"
+            : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zk), "+r"(zk100)
+            : "r"((unsigned)in), "r"((unsigned)u), "d"(w), "d"(dk), "d"(0.01), "d"(0.04), "d"(prm.zk100_thr));
+        wk += dk * w; wsum += w;
+    }
+};
+
+// G lanes stride over the concatenated stencil rows of ONE point; BATCH records are requested before the first is
+// consumed.  rows: s_off[k] = first flattened index of row k (s_off[nrows] = total), s_b[k] = its first record.
+template <int BATCH, int G, typename LD, typename PR>
+__device__ __forceinline__ void refine_walk(const uint32_t* __restrict__ s_b, const uint32_t* __restrict__ s_off,
+                                            uint32_t total, int gl, LD&& load, PR&& process) {
+    int r = 0;
+    for (uint32_t base = gl; base < total; base += (uint32_t)(G * BATCH)) {
+        decltype(load((int64_t)0)) buf[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const uint32_t t = base + (uint32_t)(G * u);
+            if (t < total) {
+                while (t >= s_off[r + 1]) ++r;
+                buf[u] = load((int64_t)s_b[r] + (t - s_off[r]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u)
+            if (base + (uint32_t)(G * u) < total) process(buf[u]);
+    }
+}
+
+// G lanes per listed point, 32 / G points per warp: the per-point work outside the candidate loop (own record, row
+// table, shuffle tree, finish) is shared by the 32 / G points a warp handles at once, and that many independent
+// dependency chains are in flight per warp.
+constexpr int REFINE_G = 8;
+constexpr int REFINE_ROWS = 32;        // stencil rows per point (2 sy + 1 <= 31, checked by the host)
+
+template <int G>
+__global__ void __launch_bounds__(WALK_THREADS, 2) dkdn_refine_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                          DkDnParams prm, const double* __restrict__ chi2_table,
+                                                          float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                          unsigned* __restrict__ mm, int* __restrict__ err,
+                                                          const uint32_t* __restrict__ list,
+                                                          const unsigned* __restrict__ list_count) {
+    constexpr int GP = 32 / G;
+    __shared__ uint32_t s_b[REFINE_WARPS][GP][REFINE_ROWS], s_off[REFINE_WARPS][GP][REFINE_ROWS + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, grp = lane / G, gl = lane % G;
+    uint32_t* sb = s_b[wib][grp];
+    uint32_t* so = s_off[wib][grp];
+    const unsigned count = *list_count;
+    const unsigned stride = gridDim.x * REFINE_WARPS * GP;
+    const int sx = M3D_SX(prm.s), sy = M3D_SY(prm.s);
+    const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
+    unsigned lo_k = 0xffffffffu, hi_k = 0u, lo_n = 0xffffffffu, hi_n = 0u;
+    for (unsigned base = (blockIdx.x * REFINE_WARPS + wib) * GP; base < count; base += stride) {   // warp-uniform
+        const unsigned e = base + grp;
+        const bool valid = e < count;
+        const uint32_t ent = valid ? __ldg(list + e) : 0u;
+        const int64_t i = (int64_t)(ent & ~REFINE_NEED_N);
+        const bool need_n = (ent & REFINE_NEED_N) != 0;
+        const D4 pa = ld_d4<true>(feat, g.n, i, 0);
+        // the stencil rows of the point: the same ranges walk_candidates_pipelined visits
+        const int ix = g.col_x(pa.x), iy = g.col_y(pa.y);
+        const int y0 = max(iy - sy, 0), y1 = min(iy + sy, g.ny - 1);
+        const int nrows = (!valid || ix + sx < 0 || ix - sx > g.nx - 1 || y0 > y1) ? 0 : y1 - y0 + 1;
+        __syncwarp();
+        for (int k = gl; k < nrows; k += G) {
+            const int y = y0 + k, w = row_halfwidth(g, prm.s, y - iy);
+            const uint32_t* cs = g.col_start + (size_t)y * g.nx;
+            const uint32_t b = __ldg(cs + min(max(ix - w, 0), g.nx));
+            sb[k] = b;
+            so[k + 1] = __ldg(cs + min(max(ix + w + 1, 0), g.nx)) - b;
+        }
+        __syncwarp();
+        if (gl == 0) {
+            uint32_t run = 0;
+            so[0] = 0;
+            for (int k = 1; k <= nrows; ++k) { run += so[k]; so[k] = run; }
+        }
+        __syncwarp();
+        const uint32_t total = so[nrows];
+
+        DkdnAcc acc;
+        if (need_n) {                                  // rare: the full expression, normals included
+            acc.init(pa, ld_d4<true>(feat, g.n, i, 1));
+            refine_walk<1, G>(sb, so, total, gl, [&](int64_t j) {
+                D4x2 c;
+                c.a = ld_d4<true>(feat, g.n, j, 0);
+                c.b = ld_d4<true>(feat, g.n, j, 1);
+                return c;
+            }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
+        } else {
+            DkAcc dk;
+            dk.init(pa);
+            refine_walk<REFINE_BATCH, G>(sb, so, total, gl, [&](int64_t j) { return ld_d4<true>(feat, g.n, j, 0); },
+                                         [&](const D4& c) { dk.add(c, prm); });
+            acc.px = dk.px; acc.py = dk.py; acc.pz = dk.pz; acc.Kp = dk.Kp;
+            acc.pnx = acc.pny = acc.pnz = 0.0;
+            acc.pflags = __double_as_longlong(pa.w) & 3LL;
+            acc.m = dk.m; acc.mu = dk.mu; acc.nact = dk.nact; acc.zk = dk.zk; acc.zk100 = dk.zk100; acc.zn = 0;
+            acc.s1k = dk.s1k; acc.s2k = dk.s2k; acc.wk = dk.wk; acc.wsum = dk.wsum;
+            acc.s1n = acc.s2n = acc.wn = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            acc.m += __shfl_xor_sync(0xffffffffu, acc.m, o);
+            acc.mu += __shfl_xor_sync(0xffffffffu, acc.mu, o);
+            acc.nact += __shfl_xor_sync(0xffffffffu, acc.nact, o);
+            acc.zn += __shfl_xor_sync(0xffffffffu, acc.zn, o);
+            acc.zk += __shfl_xor_sync(0xffffffffu, acc.zk, o);
+            acc.zk100 += __shfl_xor_sync(0xffffffffu, acc.zk100, o);
+            acc.s1k += __shfl_xor_sync(0xffffffffu, acc.s1k, o);
+            acc.s2k += __shfl_xor_sync(0xffffffffu, acc.s2k, o);
+            acc.wk += __shfl_xor_sync(0xffffffffu, acc.wk, o);
+            acc.wsum += __shfl_xor_sync(0xffffffffu, acc.wsum, o);
+            acc.s1n += __shfl_xor_sync(0xffffffffu, acc.s1n, o);
+            acc.s2n += __shfl_xor_sync(0xffffffffu, acc.s2n, o);
+            acc.wn += __shfl_xor_sync(0xffffffffu, acc.wn, o);
+        }
+        if (gl == 0 && valid) {
+            float dkf, dnf;
+            acc.finish(prm, chi2_table, err, dkf, dnf);
+            if (!need_n) dnf = 0.0f;
+            const int64_t orig = (prm.grid_order && all_owned)
+                                     ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+            const int64_t o = prm.grid_order ? i : orig;
+            dk_out[o] = dkf;
+            dn_out[o] = dnf;
+            const bool owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
+            if (owned && !isnan(dkf)) { const unsigned u = f32_ordered(dkf); lo_k = min(lo_k, u); hi_k = max(hi_k, u); }
+            if (owned && !isnan(dnf)) { const unsigned u = f32_ordered(dnf); lo_n = min(lo_n, u); hi_n = max(hi_n, u); }
+        }
+    }
+    if (mm && hi_k >= lo_k) { atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k); }
+    if (mm && hi_n >= lo_n) { atomicMin(mm + 2, lo_n); atomicMax(mm + 3, hi_n); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,11 +908,29 @@ extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double e
     return launch_moments(g, MODE_FUSED, r, eps, min_points, normals, lam_ratio, K, pcount, (cudaStream_t)stream);
 }
 
-// kernel variant of the dk/dn pass: 0 = global-memory walk (default), 1 = shared-memory staged walk.
+// kernel variant of the dk/dn pass: 0 = two passes (screening walk + warp-per-point refinement; default on thin grids),
+// 1 = shared-memory staged one-pass walk, 2 = global-memory one-pass walk (always used on tall grids).
 // MORE3D_DKDN_VARIANT / MORE3D_SMEM_CAP in the environment select it for A/B measurements (read once).
-static int dkdn_variant() {
+namespace m3d {
+int dkdn_variant() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MORE3D_DKDN_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+}  // namespace m3d
+// persistent grid of the refinement pass: every SM filled once (queried once per device)
+static int refine_grid_size() {
+    static int v = 0;
+    if (v == 0) {
+        int dev = 0, sms = 148, per = 2;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dkdn_refine_kernel<REFINE_G>, WALK_THREADS, 0) != cudaSuccess || per < 1) {
+            cudaGetLastError();
+            per = 2;
+        }
+        v = sms * per;
+    }
     return v;
 }
 static int smem_walk_cap() {
@@ -598,6 +1005,38 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
                                                                                                minmax ? mm : nullptr, err, cb, nbx, cap);
             else dkdn_smem_kernel<false><<<(unsigned)((size_t)nbx * g->ny), threads, smem, s>>>(v, feat, prm, chi2_table, dk, dn,
                                                                                             minmax ? mm : nullptr, err, cb, nbx, cap);
+        } else if (variant == 0 && split && g->n < (int64_t)REFINE_NEED_N && M3D_SY(prm.s) <= 15 &&
+                   act_interval(prm.rho2, prm.inv_rho2, &prm.act_lo, &prm.act_hi)) {
+            // |n_p . n_q - quantised| <= sqrt(3) * 0.5 / 511 (quantisation) + float32 evaluation < 1.8e-3:
+            // quantised > 0.984 + 1.8e-3  =>  1 - n_p . n_q < 0.016 with a 1e-4 margin over the fp64 rounding
+            prm.dot_thr = 0.98581f;
+            uint32_t* list = nullptr;
+            unsigned* list_count = nullptr;
+            M3D_TRY(sc.alloc(&list, (size_t)g->n));
+            M3D_TRY(sc.alloc(&list_count, 1));
+            M3D_CUDA(cudaMemsetAsync(list_count, 0, sizeof(unsigned), s));
+            {
+                ProfScope p1("dkdn_screen", s);
+                dkdn_screen_kernel<<<nb, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err,
+                                                               list, list_count);
+            }
+            {
+                ProfScope p2("dkdn_refine", s);
+                dkdn_refine_kernel<REFINE_G><<<refine_grid_size(), WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                              minmax ? mm : nullptr, err, list, list_count);
+            }
+            count_launches(1);
+            if (getenv("MORE3D_DKDN_STATS")) {       // debugging aid: synchronises
+                unsigned cnt = 0;
+                cudaMemcpyAsync(&cnt, list_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
+                std::vector<uint32_t> h(cnt);
+                cudaMemcpy(h.data(), list, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+                size_t nn = 0;
+                for (uint32_t e : h) nn += (e >> 31);
+                fprintf(stderr, "[dkdn] r=%g n=%lld refined=%u (%.2f%%) of which need_n=%zu (%.2f%%)\n", r, (long long)g->n, cnt,
+                        100.0 * cnt / (double)g->n, nn, 100.0 * nn / (double)g->n);
+            }
         } else if (split) {
             dkdn_kernel<false, true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
         } else {

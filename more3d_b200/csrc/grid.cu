@@ -377,6 +377,9 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         G_CUDA(cudaStreamSynchronize(s));
         dev_free(d_max, s);
         g->tall = g->max_col_pop > M3D_TALL_COLUMN ? 1 : 0;
+        // thin grids: the two-pass dk/dn reads only the first halves of the feature records in its screening pass, so the
+        // records are always split into two half arrays there (the one-pass kernel keeps the population heuristic)
+        if (!g->tall && dkdn_variant() != 2) g->feat_split = 1;
         if (g->tall) {
             // order = (column, z, original index): stable radix sort by z first, then by column key
             int bits = 1;

@@ -28,7 +28,7 @@ for r in (0.5, 0.75, 1.0):
         multiscale_saliency(d, (r,), **PARAMS)
     prof = _lib.profile_all()
     _lib.profile_enable(False)
-    out[str(r)] = {k: round(v[0] / reps, 4) for k, v in prof.items() if k in ("dkdn", "moments", "grid_build")}
+    out[str(r)] = {k: round(v[0] / reps, 4) for k, v in prof.items() if k in ("dkdn", "dkdn_screen", "dkdn_refine", "moments", "grid_build")}
 res = multiscale_saliency(d, (0.5, 0.75, 1.0), keep=True, **PARAMS)
 arrs = {}
 for r in (0.5, 0.75, 1.0):
@@ -37,6 +37,15 @@ for r in (0.5, 0.75, 1.0):
 if len(sys.argv) > 2 and os.path.exists(sys.argv[2]):
     ref = np.load(sys.argv[2])
     out["bit_identical_to_ref"] = bool(all(np.array_equal(arrs[k], ref[k], equal_nan=True) for k in arrs))
+    # variants that add in another order (the two-pass kernel's refinement): same zeros / NaNs, values to rounding
+    cmp = {}
+    for k in arrs:
+        a, b = arrs[k].astype(np.float64), ref[k].astype(np.float64)
+        same_class = bool(np.array_equal(a == 0, b == 0) and np.array_equal(np.isnan(a), np.isnan(b)))
+        nz = (b != 0) & ~np.isnan(b) & ~np.isnan(a)
+        rel = float(np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz]))) if nz.any() else 0.0
+        cmp[k] = {"same_zero_nan_pattern": same_class, "max_rel_diff": rel, "n_diff": int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))}
+    out["compare"] = cmp
 if len(sys.argv) > 1:
     np.savez(sys.argv[1], **arrs)
 print(json.dumps(out))
