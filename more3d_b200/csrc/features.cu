@@ -3,7 +3,6 @@
 // Replaces Curvature_Kernel.process (DM_saliency.py:88-157), Saliency_Kernel.process (:219-324) and the
 // normals precondition (DM_saliency.py:329-330).
 #include <stdlib.h>
-#include <vector>
 #include "gridview.cuh"
 #include "eig3.cuh"
 
@@ -417,56 +416,60 @@ __device__ __forceinline__ bool dk_interval(double Kp, double T, float& lo, floa
 
 struct ScreenAcc {
     double px, py, pz;
-    float ax, ay, az, bias;                  // n_p * 1024/511 and -1.5 * their sum (see add)
+    float ax, ay, az, c0;                    // t = 1 - quantised n_p . n_q = c0 - sum g_c a_c (see set_normal / add)
     float k_lo, k_hi, k100_lo, k100_hi;
-    int m, mu, nact, zn, zk, zk100;
+    int m, mu, nact, zk, zk100;
     float s1, s2;                            // float32 sums of t = max(1 - quantised n_p . n_q, 0) over the unique neighbours
+
+    // The 10-bit fields of a neighbour's packed normal are read IN PLACE as mantissa bits of a float in [1, 2):
+    // g = 1 + q 2^-k with k = 21, 11 (fields at bits 2-11 and 12-21: one LOP3 each) and 10 (bits 22-31, one shift
+    // more), so the quantised component (q - 512) / 511 = g 2^k / 511 - (2^k + 512) / 511 needs no integer conversion:
+    //   1 - n_p . n_q' = [1 + sum_c n_p,c (2^k_c + 512) / 511] - sum_c g_c (n_p,c 2^k_c / 511) = c0 - sum_c g_c a_c.
+    // float32 error: c0 ~ 4105 n_p,x and a_x g_x carry 2.5e-4 each (the x scale 2^21 / 511), everything else < 1e-5.
+    __device__ __forceinline__ void set_normal(double nx, double ny, double nz) {
+        const double kx = 2097152.0, ky = 2048.0, kz = 1024.0;
+        ax = (float)(nx * kx / 511.0); ay = (float)(ny * ky / 511.0); az = (float)(nz * kz / 511.0);
+        c0 = (float)(1.0 + (nx * (kx + 512.0) + ny * (ky + 512.0) + nz * (kz + 512.0)) / 511.0);
+    }
 
     __device__ __forceinline__ void add(const D4& qa, const DkDnParams& prm) {
         const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);
         const unsigned long long kb = (unsigned long long)__double_as_longlong(qa.w);
         const uint32_t lo = (uint32_t)kb;
         const float Kq = __uint_as_float((uint32_t)(kb >> 32));
-        // the 10-bit fields dropped into the mantissa of a float in [1, 2): g = 1 + q / 1024, so that the quantised
-        // component (q - 512) / 511 = (g - 1.5) * 1024 / 511 needs no integer conversion; (field & mask) | 1.0f is
-        // one LOP3 each
         uint32_t bx, by, bz;
-        const uint32_t msk = 0x007FE000u, one = 0x3F800000u;
-        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bx) : "r"(lo << 11), "r"(msk), "r"(one));
-        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(by) : "r"(lo << 1), "r"(msk), "r"(one));
-        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bz) : "r"(lo >> 9), "r"(msk), "r"(one));
-        const float dot = fmaf(__uint_as_float(bx), ax, fmaf(__uint_as_float(by), ay, fmaf(__uint_as_float(bz), az, bias)));
-        const float t = fmaxf(1.0f - dot, 0.0f);
+        const uint32_t one = 0x3F800000u;
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bx) : "r"(lo), "r"(0x00000FFCu), "r"(one));
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(by) : "r"(lo), "r"(0x003FF000u), "r"(one));
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(bz) : "r"(lo >> 9), "r"(0x007FE000u), "r"(one));
+        const float t = fmaxf(fmaf(-__uint_as_float(bz), az, fmaf(-__uint_as_float(by), ay, fmaf(-__uint_as_float(bx), ax, c0))), 0.0f);
         // counters as predicated adds: m (inside), mu and the float32 sums (unique & inside), then with
-        // act = unique & inside & act_lo <= d2 <= act_hi & d2 != rho2:
-        // nact, zn (certainly |dn| < 0.016), zk (|dk| <= 0.04), zk100 (|100 dk| <= 0.04)
+        // act = unique & inside & act_lo <= d2 <= act_hi & d2 != rho2: nact, zk (|dk| <= 0.04), zk100 (|100 dk| <= 0.04)
         asm("{ .reg .pred pin, pu, pa, q;\n"
-            "  setp.le.f64 pin, %8, %9;\n"
+            "  setp.le.f64 pin, %7, %8;\n"
             "  @pin add.s32 %0, %0, 1;\n"
-            "  setp.eq.and.u32 pu, %13, 0, pin;\n"
+            "  setp.eq.and.u32 pu, %12, 0, pin;\n"
             "  @pu add.s32 %1, %1, 1;\n"
-            "  @pu add.f32 %6, %6, %21;\n"
-            "  @pu fma.rn.f32 %7, %21, %21, %7;\n"
-            "  setp.ge.and.f64 pa, %8, %10, pu;\n"
-            "  setp.le.and.f64 pa, %8, %11, pa;\n"
-            "  setp.ne.and.f64 pa, %8, %12, pa;\n"
+            "  @pu add.f32 %5, %5, %18;\n"
+            "  @pu fma.rn.f32 %6, %18, %18, %6;\n"
+            "  setp.ge.and.f64 pa, %7, %9, pu;\n"
+            "  setp.le.and.f64 pa, %7, %10, pa;\n"
+            "  setp.ne.and.f64 pa, %7, %11, pa;\n"
             "  @pa add.s32 %2, %2, 1;\n"
-            "  setp.gt.and.f32 q, %14, %15, pa;\n"
+            "  setp.ge.and.f32 q, %13, %14, pa;\n"
+            "  setp.le.and.f32 q, %13, %15, q;\n"
             "  @q add.s32 %3, %3, 1;\n"
-            "  setp.ge.and.f32 q, %16, %17, pa;\n"
-            "  setp.le.and.f32 q, %16, %18, q;\n"
+            "  setp.ge.and.f32 q, %13, %16, pa;\n"
+            "  setp.le.and.f32 q, %13, %17, q;\n"
             "  @q add.s32 %4, %4, 1;\n"
-            "  setp.ge.and.f32 q, %16, %19, pa;\n"
-            "  setp.le.and.f32 q, %16, %20, q;\n"
-            "  @q add.s32 %5, %5, 1;\n"
             "}"
-            : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zn), "+r"(zk), "+r"(zk100), "+f"(s1), "+f"(s2)
-            : "d"(d2), "d"(prm.r2), "d"(prm.act_lo), "d"(prm.act_hi), "d"(prm.rho2), "r"(lo & 1u), "f"(dot),
-              "f"(prm.dot_thr), "f"(Kq), "f"(k_lo), "f"(k_hi), "f"(k100_lo), "f"(k100_hi), "f"(t));
+            : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zk), "+r"(zk100), "+f"(s1), "+f"(s2)
+            : "d"(d2), "d"(prm.r2), "d"(prm.act_lo), "d"(prm.act_hi), "d"(prm.rho2), "r"(lo & 1u), "f"(Kq), "f"(k_lo),
+              "f"(k_hi), "f"(k100_lo), "f"(k100_hi), "f"(t));
     }
 
     // Certified: chi_n < chi_t (DM_saliency.py:283, :292), from the quantised normals.  Every t_j is within
-    // delta = 1.8e-3 of the exact dn_j (quantisation sqrt(3) * 0.5 / 511 = 1.70e-3 plus the float32 evaluation; dn_j >= 0,
+    // delta = 2.3e-3 of the exact dn_j (quantisation sqrt(3) * 0.5 / 511 = 1.70e-3 plus 5e-4 of float32 evaluation; dn_j >= 0,
     // so clamping t at 0 keeps the bound), std is a seminorm: std(dn) <= std(t) + delta.  The float32 sums of the
     // non-negative t_j and t_j^2 carry a relative error below eps = (mu + 2) * 2^-23 each, which moves the variance by at
     // most eps * (var + 3 mean^2).  A NaN anywhere makes the comparison false (not certified).
@@ -474,34 +477,34 @@ struct ScreenAcc {
         const double imu = 1.0 / (double)mu, mean = (double)s1 * imu;
         const double var = fmax((double)s2 * imu - mean * mean, 0.0);
         const double eps = ((double)mu + 2.0) * (1.0 / 8388608.0);
-        const double std_up = sqrt(var * (1.0 + 2.0 * eps) + 4.0 * eps * mean * mean) + 1.8e-3;
+        const double std_up = sqrt(var * (1.0 + 2.0 * eps) + 4.0 * eps * mean * mean) + 2.3e-3;
         return (double)(m - 1) * std_up / sigma_n * 1.001 < chi_t;
     }
 };
 
-constexpr uint32_t REFINE_NEED_N = 0x80000000u;
+
 
 __global__ void __launch_bounds__(WALK_THREADS) dkdn_screen_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                           DkDnParams prm, const double* __restrict__ chi2_table,
                                                           float* __restrict__ dk_out,
                                                           float* __restrict__ dn_out, unsigned* __restrict__ mm,
                                                           int* __restrict__ err, uint32_t* __restrict__ list,
+                                                          unsigned long long* __restrict__ aux,
                                                           unsigned* __restrict__ list_count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < g.n;
     bool owned = false, refine = false, need_n = false;
+    unsigned long long counts = 0;      // m, mu, nact and the effective zk of a dk-only entry, 16 bits each
     if (live) {
         const D4 pa = ld_d4<true>(feat, g.n, i, 0), pb = ld_d4<true>(feat, g.n, i, 1);
         ScreenAcc acc;
         acc.px = pa.x; acc.py = pa.y; acc.pz = pa.z;
         const long long kb = __double_as_longlong(pa.w);
         const double Kp = kword_K(kb);
-        const double c = 1024.0 / 511.0;
-        acc.ax = (float)(pb.x * c); acc.ay = (float)(pb.y * c); acc.az = (float)(pb.z * c);
-        acc.bias = (float)(-1.5 * c * (pb.x + pb.y + pb.z));
+        acc.set_normal(pb.x, pb.y, pb.z);
         bool ok = dk_interval(Kp, 0.04, acc.k_lo, acc.k_hi);
         ok = dk_interval(Kp, prm.zk100_thr, acc.k100_lo, acc.k100_hi) && ok;
-        acc.m = acc.mu = acc.nact = acc.zn = acc.zk = acc.zk100 = 0;
+        acc.m = acc.mu = acc.nact = acc.zk = acc.zk100 = 0;
         acc.s1 = acc.s2 = 0.0f;
         walk_candidates_pipelined<false>(g, acc.px, acc.py, acc.pz, prm.r, prm.s, [&](int64_t j) {
             return ld_d4<true>(feat, g.n, j, 0);
@@ -513,10 +516,14 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_screen_kernel(GridView g, c
                 const int zk = (acc.zk == acc.nact) ? acc.zk100 : acc.zk;   // :289-290
                 const double lim = 0.6 * (double)acc.nact;
                 const bool k_zero = ok && (double)zk > lim;                 // :309-311
-                // dn = 0 if chi_n < chi_t or zn > 0.6 nact (:292-294): zn is a certified lower count, the chi2 test a
-                // certified upper bound
-                need_n = !((double)acc.zn > lim) && !acc.dn_settled_by_chi2(__ldg(chi2_table + acc.nact), prm.sigma_n);
+                // dn = 0 if chi_n < chi_t (:292-293): certified upper bound of chi_n from the packed normals
+                need_n = !acc.dn_settled_by_chi2(__ldg(chi2_table + acc.nact), prm.sigma_n);
+                // the refinement of a dk-only point takes its (exact) counters from here; a counter that does not fit
+                // 16 bits sends the point through the whole expression instead
+                if (acc.m >= 65536 || !ok) need_n = true;
                 refine = !k_zero || need_n;
+                counts = (unsigned long long)acc.m | ((unsigned long long)acc.mu << 16) |
+                         ((unsigned long long)acc.nact << 32) | ((unsigned long long)zk << 48);
             }
         }
         const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
@@ -529,14 +536,28 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_screen_kernel(GridView g, c
         }
         owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
     }
-    // work list: one atomic per warp, entries of a warp stay in sorted order
-    const unsigned vote = __ballot_sync(0xffffffffu, refine);
-    if (vote) {
-        const int lane = threadIdx.x & 31, leader = __ffs(vote) - 1;
+    // work lists: one atomic per warp and list, entries of a warp stay in sorted order.  Points whose dn is settled (dk
+    // only) fill the buffer from the front, the rare ones that need the whole expression from the back.
+    const int lane = threadIdx.x & 31;
+    const unsigned vote_k = __ballot_sync(0xffffffffu, refine && !need_n);
+    const unsigned vote_n = __ballot_sync(0xffffffffu, refine && need_n);
+    if (vote_k) {
+        const int leader = __ffs(vote_k) - 1;
         unsigned base = 0;
-        if (lane == leader) base = atomicAdd(list_count, (unsigned)__popc(vote));
+        if (lane == leader) base = atomicAdd(list_count, (unsigned)__popc(vote_k));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (refine) list[base + __popc(vote & ((1u << lane) - 1u))] = (uint32_t)i | (need_n ? REFINE_NEED_N : 0u);
+        if (refine && !need_n) {
+            const unsigned pos = base + __popc(vote_k & ((1u << lane) - 1u));
+            list[pos] = (uint32_t)i;
+            aux[pos] = counts;
+        }
+    }
+    if (vote_n) {
+        const int leader = __ffs(vote_n) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(list_count + 1, (unsigned)__popc(vote_n));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (refine && need_n) list[(size_t)g.n - 1 - (base + __popc(vote_n & ((1u << lane) - 1u)))] = (uint32_t)i;
     }
     if (mm) {
         const bool c0 = live && owned && !refine;       // refined points enter the extrema in pass 2
@@ -546,19 +567,17 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_screen_kernel(GridView g, c
 }
 
 constexpr int REFINE_WARPS = WALK_THREADS / 32;
-constexpr int REFINE_BATCH = 4;        // candidate records requested per lane before the first is used
 
-// The dk half of DkdnAcc::add (same expressions, same order: bit-identical dk), for the points whose dn the screening
-// pass has settled -- practically all of them: no normal is loaded or multiplied.
+// The sums of the dk half of DkdnAcc::add (same expressions, same order: bit-identical dk), for the points whose dn the
+// screening pass has settled -- practically all of them: no normal is loaded or multiplied, and the counters (m, mu,
+// nact, zk) come from the screening pass, which computed them exactly.
 struct DkAcc {
     double px, py, pz, Kp;
-    int m, mu, nact, zk, zk100;
     double s1k, s2k, wk, wsum;
 
     __device__ __forceinline__ void init(const D4& pa) {
         px = pa.x; py = pa.y; pz = pa.z;
         Kp = kword_K(__double_as_longlong(pa.w));
-        m = mu = nact = zk = zk100 = 0;
         s1k = s2k = wk = wsum = 0.0;
     }
     __device__ __forceinline__ void add(const D4& qa, const DkDnParams& prm) {
@@ -568,60 +587,170 @@ struct DkAcc {
         const bool u = in & !((int)kb & 1);
         double dk = Kp - kword_K(kb);
         dk = u ? dk : 0.0;
-        asm("" : "+d"(dk));
         const double t = __dmul_rn(prm.inv_rho2, d2);
         double w = (d2 < prm.rho2) ? t : __dsub_rn(2.0, t);
         const bool keep = u & (d2 != prm.rho2) & !(w < 0.0);
         w = keep ? w : 0.0;
         s1k += dk; s2k += dk * dk;
-        asm("{ .reg .pred pin, pu, pa, q;\n"
-            "  setp.ne.u32 pin, %5, 0;\n"
-            "  setp.ne.u32 pu, %6, 0;\n"
-            "  @pin add.s32 %0, %0, 1;\n"
-            "  @pu add.s32 %1, %1, 1;\n"
-            "  setp.gt.f64 pa, %7, %9;\n"
-            "  @pa add.s32 %2, %2, 1;\n"
-            "  .reg .f64 ak;\n"
-            "  abs.f64 ak, %8;\n"
-            "  setp.le.and.f64 q, ak, %10, pa;\n"
-            "  @q add.s32 %3, %3, 1;\n"
-            "  setp.le.and.f64 q, ak, %11, pa;\n"
-            "  @q add.s32 %4, %4, 1;\n"
-            "}"
-            : "+r"(m), "+r"(mu), "+r"(nact), "+r"(zk), "+r"(zk100)
-            : "r"((unsigned)in), "r"((unsigned)u), "d"(w), "d"(dk), "d"(0.01), "d"(0.04), "d"(prm.zk100_thr));
         wk += dk * w; wsum += w;
     }
 };
 
-// G lanes stride over the concatenated stencil rows of ONE point; BATCH records are requested before the first is
-// consumed.  rows: s_off[k] = first flattened index of row k (s_off[nrows] = total), s_b[k] = its first record.
-template <int BATCH, int G, typename LD, typename PR>
-__device__ __forceinline__ void refine_walk(const uint32_t* __restrict__ s_b, const uint32_t* __restrict__ s_off,
-                                            uint32_t total, int gl, LD&& load, PR&& process) {
-    int r = 0;
-    for (uint32_t base = gl; base < total; base += (uint32_t)(G * BATCH)) {
-        decltype(load((int64_t)0)) buf[BATCH];
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const uint32_t t = base + (uint32_t)(G * u);
-            if (t < total) {
-                while (t >= s_off[r + 1]) ++r;
-                buf[u] = load((int64_t)s_b[r] + (t - s_off[r]));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u)
-            if (base + (uint32_t)(G * u) < total) process(buf[u]);
-    }
-}
-
 // G lanes per listed point, 32 / G points per warp: the per-point work outside the candidate loop (own record, row
 // table, shuffle tree, finish) is shared by the 32 / G points a warp handles at once, and that many independent
-// dependency chains are in flight per warp.
+// dependency chains are in flight per warp.  The G lanes stride over the point's concatenated stencil rows:
+// rows: s_off[k] = first flattened index of row k (s_off[nrows] = total), s_b[k] = its first record.
 constexpr int REFINE_G = 8;
 constexpr int REFINE_ROWS = 32;        // stencil rows per point (2 sy + 1 <= 31, checked by the host)
 
+struct RefineRows {
+    const uint32_t* sb;
+    const uint32_t* so;
+    uint32_t total, next;     // next: first flattened index of row r + 1
+    int64_t delta;            // first record of row r minus its first flattened index
+    int r;
+    __device__ __forceinline__ void start() {
+        r = 0;
+        next = so[1];
+        delta = (int64_t)sb[0] - (int64_t)so[0];
+    }
+    // sorted position of flattened candidate t < total (t must not decrease between calls): the common case costs a
+    // compare and an add, the row table in shared memory is read only when t crosses into another row
+    __device__ __forceinline__ int64_t locate(uint32_t t) {
+        while (t >= next) {
+            ++r;
+            next = so[r + 1];
+            delta = (int64_t)sb[r] - (int64_t)so[r];
+        }
+        return (int64_t)t + delta;
+    }
+};
+
+// the row table of point (px, py) for the G lanes of its group: the same ranges walk_candidates_pipelined visits
+template <int G>
+__device__ __forceinline__ RefineRows refine_rows(const GridView& g, const DkDnParams& prm, bool valid, double px, double py,
+                                                  uint32_t* sb, uint32_t* so, int gl) {
+    const int sx = M3D_SX(prm.s), sy = M3D_SY(prm.s);
+    const int ix = g.col_x(px), iy = g.col_y(py);
+    const int y0 = max(iy - sy, 0), y1 = min(iy + sy, g.ny - 1);
+    const int nrows = (!valid || ix + sx < 0 || ix - sx > g.nx - 1 || y0 > y1) ? 0 : y1 - y0 + 1;
+    __syncwarp();
+    for (int k = gl; k < nrows; k += G) {
+        const int y = y0 + k, w = row_halfwidth(g, prm.s, y - iy);
+        const uint32_t* cs = g.col_start + (size_t)y * g.nx;
+        const uint32_t b = __ldg(cs + min(max(ix - w, 0), g.nx));
+        sb[k] = b;
+        so[k + 1] = __ldg(cs + min(max(ix + w + 1, 0), g.nx)) - b;
+    }
+    __syncwarp();
+    if (gl == 0) {
+        uint32_t run = 0;
+        so[0] = 0;
+        for (int k = 1; k <= nrows; ++k) { run += so[k]; so[k] = run; }
+    }
+    __syncwarp();
+    RefineRows rr;
+    rr.sb = sb; rr.so = so; rr.total = so[nrows];
+    if (nrows == 0) so[1] = 0;                 // start() reads the first row's end
+    __syncwarp();
+    rr.start();
+    return rr;
+}
+
+// pass 2a: the points whose dn is settled -- dk only, no normals.  Candidate records are double-buffered two at a time
+// (the next pair is requested before the current one is consumed).
+template <int G>
+__global__ void __launch_bounds__(WALK_THREADS, 3) dk_refine_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                           DkDnParams prm, const double* __restrict__ chi2_table,
+                                                           float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                           unsigned* __restrict__ mm, int* __restrict__ err,
+                                                           const uint32_t* __restrict__ list,
+                                                           const unsigned long long* __restrict__ aux,
+                                                           const unsigned* __restrict__ list_count) {
+    constexpr int GP = 32 / G;
+    __shared__ uint32_t s_b[REFINE_WARPS][GP][REFINE_ROWS], s_off[REFINE_WARPS][GP][REFINE_ROWS + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, grp = lane / G, gl = lane % G;
+    const unsigned count = list_count[0];
+    const unsigned stride = gridDim.x * REFINE_WARPS * GP;
+    const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
+    unsigned lo_k = 0xffffffffu, hi_k = 0u;
+    bool any = false;
+    unsigned base = (blockIdx.x * REFINE_WARPS + wib) * GP;
+    // the next point's list entry and own record are requested one iteration ahead
+    uint32_t ent_next = (base + grp < count) ? __ldg(list + base + grp) : 0u;
+    D4 pa_next = ld_d4<true>(feat, g.n, (int64_t)ent_next, 0);
+    for (; base < count; base += stride) {                      // warp-uniform
+        const bool valid = base + grp < count;
+        const int64_t i = (int64_t)ent_next;
+        const D4 pa = pa_next;
+        ent_next = (base + stride + grp < count) ? __ldg(list + base + stride + grp) : 0u;
+        RefineRows rr = refine_rows<G>(g, prm, valid, pa.x, pa.y, s_b[wib][grp], s_off[wib][grp], gl);
+        pa_next = ld_d4<true>(feat, g.n, (int64_t)ent_next, 0);
+        DkAcc dk;
+        dk.init(pa);
+        {
+            const uint32_t total = rr.total;
+            uint32_t t = gl;
+            D4 c0, c1, n0, n1;
+            c0 = c1 = n0 = n1 = pa;
+            if (t < total) c0 = ld_d4<true>(feat, g.n, rr.locate(t), 0);
+            if (t + G < total) c1 = ld_d4<true>(feat, g.n, rr.locate(t + G), 0);
+            while (t < total) {
+                if (t + 2 * G < total) n0 = ld_d4<true>(feat, g.n, rr.locate(t + 2 * G), 0);
+                if (t + 3 * G < total) n1 = ld_d4<true>(feat, g.n, rr.locate(t + 3 * G), 0);
+                dk.add(c0, prm);
+                if (t + G < total) dk.add(c1, prm);
+                t += 2 * G;
+                if (t >= total) break;
+                if (t + 2 * G < total) c0 = ld_d4<true>(feat, g.n, rr.locate(t + 2 * G), 0);
+                if (t + 3 * G < total) c1 = ld_d4<true>(feat, g.n, rr.locate(t + 3 * G), 0);
+                dk.add(n0, prm);
+                if (t + G < total) dk.add(n1, prm);
+                t += 2 * G;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            dk.s1k += __shfl_xor_sync(0xffffffffu, dk.s1k, o);
+            dk.s2k += __shfl_xor_sync(0xffffffffu, dk.s2k, o);
+            dk.wk += __shfl_xor_sync(0xffffffffu, dk.wk, o);
+            dk.wsum += __shfl_xor_sync(0xffffffffu, dk.wsum, o);
+        }
+        if (gl == 0 && valid) {
+            // the dk half of DkdnAcc::finish, same expressions (the screening pass has checked the normal, m and nact)
+            const unsigned long long cw = __ldg(aux + base + grp);
+            const int m = (int)(cw & 0xffffu), mu = (int)((cw >> 16) & 0xffffu), nact = (int)((cw >> 32) & 0xffffu),
+                      zk = (int)(cw >> 48);
+            const double chi_t = chi2_table[nact];
+            const double imu = 1.0 / (double)mu;
+            const double mk = dk.s1k * imu;
+            const double std_k = sqrt(fmax(dk.s2k * imu - mk * mk, 0.0));
+            const double sdk = isnan(dk.s1k) ? dk.s1k : std_k;
+            const double chi_k = (double)(m - 1) * sdk / prm.sigma_k;
+            const double lim = 0.6 * (double)nact;
+            double v;
+            if (chi_k < chi_t) v = 0.0;
+            else if ((double)zk > lim) v = 0.0;
+            else v = fabs(dk.wk / dk.wsum);
+            const float dkf = (float)v;
+            const int64_t orig = (prm.grid_order && all_owned)
+                                     ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+            const int64_t o = prm.grid_order ? i : orig;
+            dk_out[o] = dkf;
+            dn_out[o] = 0.0f;
+            const bool owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
+            if (owned) {
+                any = true;
+                if (!isnan(dkf)) { const unsigned u = f32_ordered(dkf); lo_k = min(lo_k, u); hi_k = max(hi_k, u); }
+            }
+        }
+    }
+    if (mm && hi_k >= lo_k) { atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k); }
+    if (mm && any) { const unsigned z = f32_ordered(0.0f); atomicMin(mm + 2, z); atomicMax(mm + 3, z); }
+}
+
+// pass 2b: the (rare) points that need the whole expression, normals included; entries sit at the END of the list
 template <int G>
 __global__ void __launch_bounds__(WALK_THREADS, 2) dkdn_refine_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                           DkDnParams prm, const double* __restrict__ chi2_table,
@@ -632,61 +761,21 @@ __global__ void __launch_bounds__(WALK_THREADS, 2) dkdn_refine_kernel(GridView g
     constexpr int GP = 32 / G;
     __shared__ uint32_t s_b[REFINE_WARPS][GP][REFINE_ROWS], s_off[REFINE_WARPS][GP][REFINE_ROWS + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, grp = lane / G, gl = lane % G;
-    uint32_t* sb = s_b[wib][grp];
-    uint32_t* so = s_off[wib][grp];
-    const unsigned count = *list_count;
+    const unsigned count = list_count[1];
     const unsigned stride = gridDim.x * REFINE_WARPS * GP;
-    const int sx = M3D_SX(prm.s), sy = M3D_SY(prm.s);
     const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
     unsigned lo_k = 0xffffffffu, hi_k = 0u, lo_n = 0xffffffffu, hi_n = 0u;
     for (unsigned base = (blockIdx.x * REFINE_WARPS + wib) * GP; base < count; base += stride) {   // warp-uniform
         const unsigned e = base + grp;
         const bool valid = e < count;
-        const uint32_t ent = valid ? __ldg(list + e) : 0u;
-        const int64_t i = (int64_t)(ent & ~REFINE_NEED_N);
-        const bool need_n = (ent & REFINE_NEED_N) != 0;
+        const int64_t i = valid ? (int64_t)__ldg(list + ((size_t)g.n - 1 - e)) : 0;
         const D4 pa = ld_d4<true>(feat, g.n, i, 0);
-        // the stencil rows of the point: the same ranges walk_candidates_pipelined visits
-        const int ix = g.col_x(pa.x), iy = g.col_y(pa.y);
-        const int y0 = max(iy - sy, 0), y1 = min(iy + sy, g.ny - 1);
-        const int nrows = (!valid || ix + sx < 0 || ix - sx > g.nx - 1 || y0 > y1) ? 0 : y1 - y0 + 1;
-        __syncwarp();
-        for (int k = gl; k < nrows; k += G) {
-            const int y = y0 + k, w = row_halfwidth(g, prm.s, y - iy);
-            const uint32_t* cs = g.col_start + (size_t)y * g.nx;
-            const uint32_t b = __ldg(cs + min(max(ix - w, 0), g.nx));
-            sb[k] = b;
-            so[k + 1] = __ldg(cs + min(max(ix + w + 1, 0), g.nx)) - b;
-        }
-        __syncwarp();
-        if (gl == 0) {
-            uint32_t run = 0;
-            so[0] = 0;
-            for (int k = 1; k <= nrows; ++k) { run += so[k]; so[k] = run; }
-        }
-        __syncwarp();
-        const uint32_t total = so[nrows];
-
+        RefineRows rr = refine_rows<G>(g, prm, valid, pa.x, pa.y, s_b[wib][grp], s_off[wib][grp], gl);
         DkdnAcc acc;
-        if (need_n) {                                  // rare: the full expression, normals included
-            acc.init(pa, ld_d4<true>(feat, g.n, i, 1));
-            refine_walk<1, G>(sb, so, total, gl, [&](int64_t j) {
-                D4x2 c;
-                c.a = ld_d4<true>(feat, g.n, j, 0);
-                c.b = ld_d4<true>(feat, g.n, j, 1);
-                return c;
-            }, [&](const D4x2& c) { acc.add(c.a, c.b, prm); });
-        } else {
-            DkAcc dk;
-            dk.init(pa);
-            refine_walk<REFINE_BATCH, G>(sb, so, total, gl, [&](int64_t j) { return ld_d4<true>(feat, g.n, j, 0); },
-                                         [&](const D4& c) { dk.add(c, prm); });
-            acc.px = dk.px; acc.py = dk.py; acc.pz = dk.pz; acc.Kp = dk.Kp;
-            acc.pnx = acc.pny = acc.pnz = 0.0;
-            acc.pflags = __double_as_longlong(pa.w) & 3LL;
-            acc.m = dk.m; acc.mu = dk.mu; acc.nact = dk.nact; acc.zk = dk.zk; acc.zk100 = dk.zk100; acc.zn = 0;
-            acc.s1k = dk.s1k; acc.s2k = dk.s2k; acc.wk = dk.wk; acc.wsum = dk.wsum;
-            acc.s1n = acc.s2n = acc.wn = 0.0;
+        acc.init(pa, ld_d4<true>(feat, g.n, i, 1));
+        for (uint32_t t = gl; t < rr.total; t += G) {
+            const int64_t j = rr.locate(t);
+            acc.add(ld_d4<true>(feat, g.n, j, 0), ld_d4<true>(feat, g.n, j, 1), prm);
         }
         __syncwarp();
 #pragma unroll
@@ -708,7 +797,6 @@ __global__ void __launch_bounds__(WALK_THREADS, 2) dkdn_refine_kernel(GridView g
         if (gl == 0 && valid) {
             float dkf, dnf;
             acc.finish(prm, chi2_table, err, dkf, dnf);
-            if (!need_n) dnf = 0.0f;
             const int64_t orig = (prm.grid_order && all_owned)
                                      ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
             const int64_t o = prm.grid_order ? i : orig;
@@ -918,20 +1006,17 @@ int dkdn_variant() {
     return v;
 }
 }  // namespace m3d
-// persistent grid of the refinement pass: every SM filled once (queried once per device)
-static int refine_grid_size() {
-    static int v = 0;
-    if (v == 0) {
-        int dev = 0, sms = 148, per = 2;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, dkdn_refine_kernel<REFINE_G>, WALK_THREADS, 0) != cudaSuccess || per < 1) {
-            cudaGetLastError();
-            per = 2;
-        }
-        v = sms * per;
+// persistent grids of the refinement passes: every SM filled once (queried once per device)
+template <typename K>
+static int persistent_grid(K kernel, int fallback_per_sm) {
+    int dev = 0, sms = 148, per = fallback_per_sm;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, WALK_THREADS, 0) != cudaSuccess || per < 1) {
+        cudaGetLastError();
+        per = fallback_per_sm;
     }
-    return v;
+    return sms * per;
 }
 static int smem_walk_cap() {
     static int v = -1;
@@ -1005,37 +1090,40 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
                                                                                                minmax ? mm : nullptr, err, cb, nbx, cap);
             else dkdn_smem_kernel<false><<<(unsigned)((size_t)nbx * g->ny), threads, smem, s>>>(v, feat, prm, chi2_table, dk, dn,
                                                                                             minmax ? mm : nullptr, err, cb, nbx, cap);
-        } else if (variant == 0 && split && g->n < (int64_t)REFINE_NEED_N && M3D_SY(prm.s) <= 15 &&
+        } else if (variant == 0 && split && M3D_SY(prm.s) <= 15 &&
                    act_interval(prm.rho2, prm.inv_rho2, &prm.act_lo, &prm.act_hi)) {
             // |n_p . n_q - quantised| <= sqrt(3) * 0.5 / 511 (quantisation) + float32 evaluation < 1.8e-3:
             // quantised > 0.984 + 1.8e-3  =>  1 - n_p . n_q < 0.016 with a 1e-4 margin over the fp64 rounding
             prm.dot_thr = 0.98581f;
             uint32_t* list = nullptr;
             unsigned* list_count = nullptr;
+            unsigned long long* aux = nullptr;
             M3D_TRY(sc.alloc(&list, (size_t)g->n));
-            M3D_TRY(sc.alloc(&list_count, 1));
-            M3D_CUDA(cudaMemsetAsync(list_count, 0, sizeof(unsigned), s));
+            M3D_TRY(sc.alloc(&aux, (size_t)g->n));
+            M3D_TRY(sc.alloc(&list_count, 2));
+            M3D_CUDA(cudaMemsetAsync(list_count, 0, 2 * sizeof(unsigned), s));
+            static int grid_k = 0, grid_n = 0;
+            if (!grid_k) grid_k = persistent_grid(dk_refine_kernel<REFINE_G>, 3);
+            if (!grid_n) grid_n = persistent_grid(dkdn_refine_kernel<REFINE_G>, 2);
             {
                 ProfScope p1("dkdn_screen", s);
                 dkdn_screen_kernel<<<nb, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err,
-                                                               list, list_count);
+                                                               list, aux, list_count);
             }
             {
                 ProfScope p2("dkdn_refine", s);
-                dkdn_refine_kernel<REFINE_G><<<refine_grid_size(), WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                              minmax ? mm : nullptr, err, list, list_count);
+                dk_refine_kernel<REFINE_G><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                          minmax ? mm : nullptr, err, list, aux, list_count);
+                dkdn_refine_kernel<REFINE_G><<<grid_n, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                            minmax ? mm : nullptr, err, list, list_count);
             }
-            count_launches(1);
+            count_launches(2);
             if (getenv("MORE3D_DKDN_STATS")) {       // debugging aid: synchronises
-                unsigned cnt = 0;
-                cudaMemcpyAsync(&cnt, list_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+                unsigned cnt[2] = {0, 0};
+                cudaMemcpyAsync(cnt, list_count, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, s);
                 cudaStreamSynchronize(s);
-                std::vector<uint32_t> h(cnt);
-                cudaMemcpy(h.data(), list, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-                size_t nn = 0;
-                for (uint32_t e : h) nn += (e >> 31);
-                fprintf(stderr, "[dkdn] r=%g n=%lld refined=%u (%.2f%%) of which need_n=%zu (%.2f%%)\n", r, (long long)g->n, cnt,
-                        100.0 * cnt / (double)g->n, nn, 100.0 * nn / (double)g->n);
+                fprintf(stderr, "[dkdn] r=%g n=%lld refined: dk only %u (%.2f%%), whole expression %u (%.3f%%)\n", r,
+                        (long long)g->n, cnt[0], 100.0 * cnt[0] / (double)g->n, cnt[1], 100.0 * cnt[1] / (double)g->n);
             }
         } else if (split) {
             dkdn_kernel<false, true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err);
