@@ -75,7 +75,7 @@ __device__ __forceinline__ void st_feat(FeatRec* __restrict__ f, int64_t n, int6
 // One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
 // query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
 template <int MODE, bool TALL>
-__global__ void __launch_bounds__(WALK_THREADS, 3) moments_kernel(GridView g, CurvParams prm,
+__global__ void __launch_bounds__(WALK_THREADS, 4) moments_kernel(GridView g, CurvParams prm,
                                                                double* __restrict__ normals,
                                                                double* __restrict__ lam_ratio,
                                                                float* __restrict__ Kout,
@@ -398,20 +398,24 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
 // { x float32 : |fl64(Kp - x)| <= T } as a closed float32 interval [lo, hi] (the fp64 difference is monotone in x).
 // ok = false if the few-ulp search did not pin both ends (the point is then refined unconditionally).
 __device__ __forceinline__ bool dk_pred(double Kp, float x, double T) { return fabs(__dsub_rn(Kp, (double)x)) <= T; }
+// next float32 above / below a finite x (bit arithmetic; nextafterf costs a branchy library call per use)
+__device__ __forceinline__ float f32_up(float x) {
+    const int b = __float_as_int(x);
+    return (x == 0.0f) ? __int_as_float(1) : __int_as_float(b >= 0 ? b + 1 : b - 1);
+}
+__device__ __forceinline__ float f32_down(float x) {
+    const int b = __float_as_int(x);
+    return (x == 0.0f) ? __int_as_float((int)0x80000001u) : __int_as_float(b >= 0 ? b - 1 : b + 1);
+}
 __device__ __forceinline__ bool dk_interval(double Kp, double T, float& lo, float& hi) {
-    const float inf = __int_as_float(0x7f800000);
+    // the ends lie within one float32 of Kp -+ T rounded outwards: one corrective step each, then the defining
+    // property of both ends is verified (a failed verification only sends the point to the refinement pass)
     float l = __double2float_rd(Kp - T), h = __double2float_ru(Kp + T);
-#pragma unroll 1
-    for (int k = 0; k < 4 && !dk_pred(Kp, l, T); ++k) l = nextafterf(l, inf);
-#pragma unroll 1
-    for (int k = 0; k < 4 && dk_pred(Kp, nextafterf(l, -inf), T); ++k) l = nextafterf(l, -inf);
-#pragma unroll 1
-    for (int k = 0; k < 4 && !dk_pred(Kp, h, T); ++k) h = nextafterf(h, -inf);
-#pragma unroll 1
-    for (int k = 0; k < 4 && dk_pred(Kp, nextafterf(h, inf), T); ++k) h = nextafterf(h, inf);
+    if (!dk_pred(Kp, l, T)) l = f32_up(l);
+    if (!dk_pred(Kp, h, T)) h = f32_down(h);
     lo = l; hi = h;
-    return dk_pred(Kp, l, T) && !dk_pred(Kp, nextafterf(l, -inf), T) && dk_pred(Kp, h, T) &&
-           !dk_pred(Kp, nextafterf(h, inf), T) && l <= h && isfinite(l) && isfinite(h);
+    return dk_pred(Kp, l, T) && !dk_pred(Kp, f32_down(l), T) && dk_pred(Kp, h, T) && !dk_pred(Kp, f32_up(h), T) &&
+           l <= h && isfinite(l) && isfinite(h);
 }
 
 struct ScreenAcc {
@@ -580,10 +584,12 @@ struct DkAcc {
         Kp = kword_K(__double_as_longlong(pa.w));
         s1k = s2k = wk = wsum = 0.0;
     }
-    __device__ __forceinline__ void add(const D4& qa, const DkDnParams& prm) {
+    // valid = false: the record is a clamped re-read past the end of the candidate list and adds nothing (the loop
+    // around this has no branches: every lane of a group executes the same steps)
+    __device__ __forceinline__ void add(const D4& qa, bool valid, const DkDnParams& prm) {
         const double d2 = dist2_rule(px - qa.x, py - qa.y, pz - qa.z);
         const long long kb = __double_as_longlong(qa.w);
-        const bool in = d2 <= prm.r2;
+        const bool in = valid & (d2 <= prm.r2);
         const bool u = in & !((int)kb & 1);
         double dk = Kp - kword_K(kb);
         dk = u ? dk : 0.0;
@@ -688,25 +694,25 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) dk_refine_kernel(GridView g, 
         pa_next = ld_d4<true>(feat, g.n, (int64_t)ent_next, 0);
         DkAcc dk;
         dk.init(pa);
-        {
-            const uint32_t total = rr.total;
+        if (rr.total) {
+            const uint32_t total = rr.total, last = total - 1;
             uint32_t t = gl;
-            D4 c0, c1, n0, n1;
-            c0 = c1 = n0 = n1 = pa;
-            if (t < total) c0 = ld_d4<true>(feat, g.n, rr.locate(t), 0);
-            if (t + G < total) c1 = ld_d4<true>(feat, g.n, rr.locate(t + G), 0);
-            while (t < total) {
-                if (t + 2 * G < total) n0 = ld_d4<true>(feat, g.n, rr.locate(t + 2 * G), 0);
-                if (t + 3 * G < total) n1 = ld_d4<true>(feat, g.n, rr.locate(t + 3 * G), 0);
-                dk.add(c0, prm);
-                if (t + G < total) dk.add(c1, prm);
+            // two records in flight while two are consumed; reads past the end are clamped to the last candidate and masked
+            auto fetch = [&](uint32_t tt) { return ld_d4<true>(feat, g.n, rr.locate(min(tt, last)), 0); };
+            D4 c0 = fetch(t), c1 = fetch(t + G), n0, n1;
+            while (true) {
+                n0 = fetch(t + 2 * G);
+                n1 = fetch(t + 3 * G);
+                dk.add(c0, t < total, prm);
+                dk.add(c1, t + G < total, prm);
                 t += 2 * G;
                 if (t >= total) break;
-                if (t + 2 * G < total) c0 = ld_d4<true>(feat, g.n, rr.locate(t + 2 * G), 0);
-                if (t + 3 * G < total) c1 = ld_d4<true>(feat, g.n, rr.locate(t + 3 * G), 0);
-                dk.add(n0, prm);
-                if (t + G < total) dk.add(n1, prm);
+                c0 = fetch(t + 2 * G);
+                c1 = fetch(t + 3 * G);
+                dk.add(n0, t < total, prm);
+                dk.add(n1, t + G < total, prm);
                 t += 2 * G;
+                if (t >= total) break;
             }
         }
         __syncwarp();
