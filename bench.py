@@ -276,10 +276,18 @@ def run_ours(args, rank, world, local_rank):
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms_per_step"])
     achieved = kern[dom]["algorithmic_GBs"]
     tr = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    names = {"dkdn": "dk/dn pass: dkdn_screen_kernel + dk_refine_kernel + dkdn_refine_kernel", "moments": "moments_kernel"}
+    calls = len(RADII)
+    traffic = (tr or {}).get(dom)
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": (tr or {}).get(dom), "algorithmic_bytes_per_step": alg[dom],
-                "kernel_share_of_step": kern[dom]["ms_per_step"] / (ms / args.steps)}
+                "traffic": traffic, "algorithmic_bytes_per_step": alg[dom], "calls_per_step": calls,
+                "kernel_share_of_step": kern[dom]["ms_per_step"] / (ms / args.steps),
+                # what the memory system really moves: ncu DRAM bytes per call (profiles/traffic.json) over the live time
+                "dram_GBs": (traffic * calls / (kern[dom]["ms_per_step"] * 1e-3) / 1e9) if traffic else None,
+                "note": ("achieved = SURVEY 8d pair-gather bytes (N*40 + 32*sum m per radius) / CUDA-event time of the group; "
+                         "the gather is served by L1/L2 (DRAM traffic = `traffic` per call), so this HBM-equivalent rate can "
+                         "exceed the HBM peak: the binding limits are issue slots and the FP64 pipe (profiles/README.md)")}
 
     # ---- configs[4]: strong scaling of ONE 500 M-point tile (r = 0.5), the same global cloud for every N ----
     strong = None
@@ -289,6 +297,8 @@ def run_ours(args, rank, world, local_rank):
         else:
             del resident, host, out_host
         import gc
+        from more3d_b200.pipeline import release_staging_buffers
+        release_staging_buffers()
         gc.collect()
         torch.cuda.empty_cache()
         strong = strong_leg(args, rank, world, dev)

@@ -42,6 +42,13 @@ int more3d_profile_reset(void);
 int more3d_profile_get(const char* name, double* ms_h, int64_t* count_h);
 int more3d_profile_names(char* buf_h, int len);
 
+/* Kernel variant of the dk/dn pass (more3d_dk_dn*), for A/B measurements and the equivalence tests; grids built
+ * afterwards follow it (the feature-record layout is chosen per grid).  0 = two passes: a screening walk that settles
+ * every point whose outputs the count rules of Saliency_Kernel.process (DM_saliency.py:286-316) force to zero, then a
+ * refinement of the listed rest (default); 1 = shared-memory staged one-pass walk; 2 = global-memory one-pass walk.
+ * The environment variable MORE3D_DKDN_VARIANT sets the initial value. */
+int more3d_set_dkdn_variant(int variant);
+
 /* ---- spatial index --------------------------------------------------------------------------
  * Replaces BallTreePointSet.__init__ -> sklearn BallTree build (Downsampling/BallTreePointSet.py:19-53).
  * Uniform xy-column grid: fp64 cell keys -> LSD radix sort -> column-start table -> sorted

@@ -540,29 +540,37 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_screen_kernel(GridView g, c
         }
         owned = all_owned || (orig >= prm.own_lo && orig < prm.own_hi);
     }
-    // work lists: one atomic per warp and list, entries of a warp stay in sorted order.  Points whose dn is settled (dk
-    // only) fill the buffer from the front, the rare ones that need the whole expression from the back.
+    // work lists: the entries of one CTA (256 consecutive sorted points) are appended as ONE contiguous chunk per list
+    // -- shared-memory atomics order the warps inside the chunk, one global atomic per CTA and list places it -- so that
+    // the refinement pass, which takes consecutive entries per CTA, works on spatially compact sets (L1 reuse).
+    // Points whose dn is settled (dk only) fill the buffer from the front, the rare ones that need the whole expression
+    // from the back.
+    __shared__ unsigned s_cnt[2], s_base[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned vote_k = __ballot_sync(0xffffffffu, refine && !need_n);
     const unsigned vote_n = __ballot_sync(0xffffffffu, refine && need_n);
+    unsigned off_k = 0, off_n = 0;
     if (vote_k) {
         const int leader = __ffs(vote_k) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(list_count, (unsigned)__popc(vote_k));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (refine && !need_n) {
-            const unsigned pos = base + __popc(vote_k & ((1u << lane) - 1u));
-            list[pos] = (uint32_t)i;
-            aux[pos] = counts;
-        }
+        if (lane == leader) off_k = atomicAdd(&s_cnt[0], (unsigned)__popc(vote_k));
+        off_k = __shfl_sync(0xffffffffu, off_k, leader) + __popc(vote_k & ((1u << lane) - 1u));
     }
     if (vote_n) {
         const int leader = __ffs(vote_n) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(list_count + 1, (unsigned)__popc(vote_n));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (refine && need_n) list[(size_t)g.n - 1 - (base + __popc(vote_n & ((1u << lane) - 1u)))] = (uint32_t)i;
+        if (lane == leader) off_n = atomicAdd(&s_cnt[1], (unsigned)__popc(vote_n));
+        off_n = __shfl_sync(0xffffffffu, off_n, leader) + __popc(vote_n & ((1u << lane) - 1u));
     }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(list_count + threadIdx.x, s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (refine && !need_n) {
+        const unsigned pos = s_base[0] + off_k;
+        list[pos] = (uint32_t)i;
+        aux[pos] = counts;
+    }
+    if (refine && need_n) list[(size_t)g.n - 1 - (s_base[1] + off_n)] = (uint32_t)i;
     if (mm) {
         const bool c0 = live && owned && !refine;       // refined points enter the extrema in pass 2
         const unsigned z = f32_ordered(0.0f);
@@ -606,7 +614,7 @@ struct DkAcc {
 // table, shuffle tree, finish) is shared by the 32 / G points a warp handles at once, and that many independent
 // dependency chains are in flight per warp.  The G lanes stride over the point's concatenated stencil rows:
 // rows: s_off[k] = first flattened index of row k (s_off[nrows] = total), s_b[k] = its first record.
-constexpr int REFINE_G = 8;
+constexpr int REFINE_G = 4;
 constexpr int REFINE_ROWS = 32;        // stencil rows per point (2 sy + 1 <= 31, checked by the host)
 
 struct RefineRows {
@@ -750,6 +758,54 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) dk_refine_kernel(GridView g, 
                 any = true;
                 if (!isnan(dkf)) { const unsigned u = f32_ordered(dkf); lo_k = min(lo_k, u); hi_k = max(hi_k, u); }
             }
+        }
+    }
+    if (mm && hi_k >= lo_k) { atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k); }
+    if (mm && any) { const unsigned z = f32_ordered(0.0f); atomicMin(mm + 2, z); atomicMax(mm + 3, z); }
+}
+
+// pass 2a, one THREAD per listed point (the row walk of the one-pass kernels over the compacted list)
+__global__ void __launch_bounds__(WALK_THREADS) dk_refine_thread_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                               DkDnParams prm, const double* __restrict__ chi2_table,
+                                                               float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                               unsigned* __restrict__ mm,
+                                                               const uint32_t* __restrict__ list,
+                                                               const unsigned long long* __restrict__ aux,
+                                                               const unsigned* __restrict__ list_count) {
+    const unsigned count = list_count[0];
+    const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
+    unsigned lo_k = 0xffffffffu, hi_k = 0u;
+    bool any = false;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const int64_t i = (int64_t)__ldg(list + e);
+        DkAcc dk;
+        dk.init(ld_d4<true>(feat, g.n, i, 0));
+        walk_candidates_pipelined<false>(g, dk.px, dk.py, dk.pz, prm.r, prm.s, [&](int64_t j) {
+            return ld_d4<true>(feat, g.n, j, 0);
+        }, [&](const D4& c) { dk.add(c, true, prm); });
+        const unsigned long long cw = __ldg(aux + e);
+        const int m = (int)(cw & 0xffffu), mu = (int)((cw >> 16) & 0xffffu), nact = (int)((cw >> 32) & 0xffffu),
+                  zk = (int)(cw >> 48);
+        const double chi_t = chi2_table[nact];
+        const double imu = 1.0 / (double)mu;
+        const double mk = dk.s1k * imu;
+        const double std_k = sqrt(fmax(dk.s2k * imu - mk * mk, 0.0));
+        const double sdk = isnan(dk.s1k) ? dk.s1k : std_k;
+        const double chi_k = (double)(m - 1) * sdk / prm.sigma_k;
+        const double lim = 0.6 * (double)nact;
+        double v;
+        if (chi_k < chi_t) v = 0.0;
+        else if ((double)zk > lim) v = 0.0;
+        else v = fabs(dk.wk / dk.wsum);
+        const float dkf = (float)v;
+        const int64_t orig = (prm.grid_order && all_owned)
+                                 ? 0 : __double_as_longlong(__ldg(reinterpret_cast<const double*>(g.rec + i) + 3));
+        const int64_t o = prm.grid_order ? i : orig;
+        dk_out[o] = dkf;
+        dn_out[o] = 0.0f;
+        if (all_owned || (orig >= prm.own_lo && orig < prm.own_hi)) {
+            any = true;
+            if (!isnan(dkf)) { const unsigned u = f32_ordered(dkf); lo_k = min(lo_k, u); hi_k = max(hi_k, u); }
         }
     }
     if (mm && hi_k >= lo_k) { atomicMin(mm + 0, lo_k); atomicMax(mm + 1, hi_k); }
@@ -1006,12 +1062,17 @@ extern "C" int more3d_normals_curvature(const more3d_grid* g, double r, double e
 // 1 = shared-memory staged one-pass walk, 2 = global-memory one-pass walk (always used on tall grids).
 // MORE3D_DKDN_VARIANT / MORE3D_SMEM_CAP in the environment select it for A/B measurements (read once).
 namespace m3d {
+static int g_dkdn_variant = -1;
 int dkdn_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("MORE3D_DKDN_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
+    if (g_dkdn_variant < 0) { const char* e = getenv("MORE3D_DKDN_VARIANT"); g_dkdn_variant = e ? atoi(e) : 0; }
+    return g_dkdn_variant;
 }
 }  // namespace m3d
+extern "C" int more3d_set_dkdn_variant(int variant) {
+    M3D_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0 (two passes), 1 (shared-memory staged) or 2 (one pass)");
+    m3d::g_dkdn_variant = variant;
+    return MORE3D_OK;
+}
 // persistent grids of the refinement passes: every SM filled once (queried once per device)
 template <typename K>
 static int persistent_grid(K kernel, int fallback_per_sm) {
@@ -1118,8 +1179,20 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
             }
             {
                 ProfScope p2("dkdn_refine", s);
-                dk_refine_kernel<REFINE_G><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                          minmax ? mm : nullptr, err, list, aux, list_count);
+                static int refine_g = -1;
+                if (refine_g < 0) { const char* e = getenv("MORE3D_REFINE_G"); refine_g = e ? atoi(e) : REFINE_G; }
+                if (refine_g == 1)
+                    dk_refine_thread_kernel<<<148 * 8, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                             minmax ? mm : nullptr, list, aux, list_count);
+                else if (refine_g == 2)
+                    dk_refine_kernel<2><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                        minmax ? mm : nullptr, err, list, aux, list_count);
+                else if (refine_g == 4)
+                    dk_refine_kernel<4><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                        minmax ? mm : nullptr, err, list, aux, list_count);
+                else
+                    dk_refine_kernel<8><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
+                                                                        minmax ? mm : nullptr, err, list, aux, list_count);
                 dkdn_refine_kernel<REFINE_G><<<grid_n, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
                                                                             minmax ? mm : nullptr, err, list, list_count);
             }

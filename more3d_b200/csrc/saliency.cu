@@ -46,10 +46,16 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ dk
     const double min_n = (double)minmax[2], max_n = (double)minmax[3];
     const double diff_k = __dsub_rn(max_k, min_k), diff_n = __dsub_rn(max_n, min_n);   // :570-571
     unsigned lo = 0xffffffffu, hi = 0u;
+    // most dk and nearly all dn are exactly 0 (the count rules of Saliency_Kernel.process): their normalised value is
+    // one constant, evaluated once with the same expression, and the fp64 division is skipped for them
+    const float ndk0 = (float)__dadd_rn(__ddiv_rn(__dsub_rn(0.0, min_k), diff_k), min_k);
+    const float ndn0 = (float)__dadd_rn(__ddiv_rn(__dsub_rn(0.0, min_n), diff_n), min_n);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const float ndk = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)dk[i], min_k), diff_k), min_k);  // :577
-        const float ndn = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)dn[i], min_n), diff_n), min_n);  // :578
+        const float vk = dk[i], vn = dn[i];
+        float ndk = ndk0, ndn = ndn0;
+        if (vk != 0.0f) ndk = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)vk, min_k), diff_k), min_k);  // :577
+        if (vn != 0.0f) ndn = (float)__dadd_rn(__ddiv_rn(__dsub_rn((double)vn, min_n), diff_n), min_n);  // :578
         const float sv = (float)__dadd_rn(__dmul_rn(nw, (double)ndn), __dmul_rn(cw, (double)ndk));      // :579-580
         sal[i] = sv;
         // grid-order columns of a strip: only the rows of its OWN points (original index in [own_lo, own_hi)) count

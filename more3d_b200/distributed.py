@@ -511,7 +511,9 @@ class StripSaliency:
         up = torch.cuda.Stream(device=self.dev)
         down = torch.cuda.Stream(device=self.dev)
         # two staging buffers filled alternately (no allocation between the strips, see pipeline.multiscale_saliency_tiles)
-        bufs = [torch.empty_like(self.resident) for _ in range(min(2, max(k, 1)))]
+        if getattr(self, "_staging", None) is None:
+            self._staging = [torch.empty_like(self.resident) for _ in range(2)]     # kept between calls
+        bufs = self._staging[:min(2, max(k, 1))]
         freed = [None] * len(bufs)
 
         def upload(i):

@@ -72,6 +72,24 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
     return out
 
 
+_STAGING = {}
+
+
+def _staging_buffers(dev, nmax):
+    """The two device staging buffers of the tile stream, kept between calls (a stream of equally sized tiles then
+    allocates nothing); they are replaced when a larger tile arrives."""
+    key = (dev.type, dev.index)
+    cur = _STAGING.get(key)
+    if cur is None or cur[0].shape[0] < nmax:
+        _STAGING[key] = cur = [torch.empty((nmax, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+    return cur
+
+
+def release_staging_buffers():
+    """Free the tile stream's cached staging buffers (2 x 24 B x the largest tile seen)."""
+    _STAGING.clear()
+
+
 def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, device=None, keep_results=True,
                               **params):
     """The pipeline over a sequence of host-resident tiles (pinned (N,3) float64 tensors), tile after tile on one
@@ -92,7 +110,7 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
     # two device staging buffers, filled alternately: no allocation (and no allocator-induced synchronisation)
     # happens between the tiles, and a buffer is overwritten only after the kernels that read it were issued
     nmax = max(int(t.shape[0]) for t in tiles)
-    bufs = [torch.empty((nmax, 3), dtype=torch.float64, device=dev) for _ in range(min(2, len(tiles)))]
+    bufs = _staging_buffers(dev, nmax)[:min(2, len(tiles))]
     freed = [None] * len(bufs)
 
     def upload(k):

@@ -172,6 +172,47 @@ def test_dk_dn_and_saliency(golden_dir, name):
         assert np.array_equal(dm.get("_saliency_minmax"), np.array([want.min(), want.max()], np.float32))
 
 
+@pytest.mark.parametrize("params", [dict(sigma_normal=0.01, sigma_curvature=0.01, noise=0.02, boulders=0),
+                                    dict(sigma_normal=1e-3, sigma_curvature=0.01, noise=0.05, boulders=3),
+                                    dict(sigma_normal=0.05, sigma_curvature=0.1, noise=0.1, boulders=2)])
+def test_two_pass_dkdn_equals_one_pass(params):
+    """The default dk/dn (screening walk + refinement of the listed points) against the one-pass kernel on the same
+    cloud, with coincident points, rough relief (the refinement's whole-expression path) and three radii on one grid:
+    identical zero / NaN patterns and neighbour counts (integer decisions), values equal up to the rounding of fp64 sums
+    that are added in another order."""
+    import torch
+    from more3d_b200 import synthetic, _lib
+    from more3d_b200.pipeline import multiscale_saliency
+    rng = np.random.Generator(np.random.PCG64(31))
+    pts = synthetic.terrain(150000, seed=41, noise=params["noise"], boulders=params["boulders"])
+    pts = np.vstack([pts, pts[rng.choice(len(pts), 3000, replace=False)]])           # coincident copies
+    pts = pts[rng.permutation(len(pts))]
+    d = torch.from_numpy(pts).cuda()
+    kw = dict(roughness=0.02, alpha=0.05, sigma_normal=params["sigma_normal"], sigma_curvature=params["sigma_curvature"],
+              min_points=4, keep=True)
+    out = {}
+    try:
+        for variant in (2, 0):
+            _lib.set_dkdn_variant(variant)
+            res = multiscale_saliency(d, (0.5, 0.75, 1.0), **kw)
+            out[variant] = {r: {k: v.cpu().numpy() for k, v in res[r].items() if k in ("_dk", "_dn", "_pcount", "_saliency")}
+                            for r in res}
+    finally:
+        _lib.set_dkdn_variant(0)
+    for r in (0.5, 0.75, 1.0):
+        a, b = out[2][r], out[0][r]
+        assert np.array_equal(a["_pcount"], b["_pcount"])
+        for k in ("_dk", "_dn"):
+            assert np.array_equal(a[k] == 0, b[k] == 0), (r, k)
+            assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])), (r, k)
+            nz = (a[k] != 0) & ~np.isnan(a[k])
+            assert np.allclose(a[k][nz], b[k][nz], rtol=1e-6, atol=0), (r, k)
+        fin = np.isfinite(a["_saliency"])
+        assert np.array_equal(fin, np.isfinite(b["_saliency"]))
+        assert np.allclose(a["_saliency"][fin], b["_saliency"][fin], rtol=1e-5, atol=1e-7)
+        print(r, params, "nonzero dk %.3f dn %.4f" % ((b["_dk"] != 0).mean(), (b["_dn"] != 0).mean()))
+
+
 def test_histogram_matches_numpy():
     import torch
     import ctypes as C

@@ -16,7 +16,11 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread",
            "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
-           "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size"]
+           "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "launch__grid_size", "launch__block_size"]
 
 
 def launches(path, out_md):
@@ -48,7 +52,7 @@ def full(path, out_csv, out_json):
     rows = list(csv.reader(raw.splitlines()))
     H, units = rows[0], rows[1]
     idx = [(m, H.index(m)) for m in ["Kernel Name"] + METRICS if m in H]
-    traffic = {}
+    traffic, calls = {}, {}
     with open(out_csv, "w") as f:
         w = csv.writer(f)
         w.writerow([m for m, _ in idx])
@@ -56,13 +60,17 @@ def full(path, out_csv, out_json):
         for r in rows[2:]:
             w.writerow([r[i].split("(")[0] if m == "Kernel Name" else r[i] for m, i in idx])
             name = r[H.index("Kernel Name")]
-            key = "dkdn" if "dkdn" in name else ("moments" if "moments" in name else None)
+            # one dk/dn CALL is three kernels (screening walk + the two refinement passes): their DRAM bytes are added
+            # up and divided by the number of calls (= screening launches); the one-pass kernel is a call of its own
+            key = "dkdn" if ("dkdn" in name or "dk_refine" in name) else ("moments" if "moments" in name else None)
             if key:
                 def tobytes(col):
                     v, u = float(r[H.index(col)].replace(",", "")), units[H.index(col)]
                     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                 traffic.setdefault(key, []).append(tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"))
-    json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(out_json, "w"))
+                if key == "moments" or "dkdn_screen" in name or "dkdn_kernel" in name:
+                    calls[key] = calls.get(key, 0) + 1
+    json.dump({k: sum(v) / max(calls.get(k, 1), 1) for k, v in traffic.items()}, open(out_json, "w"))
 
 
 if __name__ == "__main__":
