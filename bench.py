@@ -255,6 +255,26 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t.item())
         return ms
 
+    # what this box's host <-> device path delivers from the SAME pinned buffers (outside the timed region): the e2e leg
+    # overlaps the copies with the kernels, so a step costs max(kernels, copies) and a slow path shows up here first
+    # (with several GPUs every rank probes at the same time, as in the e2e leg; rank 0 reports what it saw)
+    def copy_rate(dst, src, nbytes):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        a.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        return 3 * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
+    p_host = job.host if distributed else host
+    p_out = job.out_host if distributed else out_host
+    tmp = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    col = torch.zeros(n, dtype=torch.float32, device=dev)
+    copy_probe = {"h2d_GBs": copy_rate(tmp, p_host, h2d), "d2h_GBs": copy_rate(p_out[RADII[0]], col, 4 * n)}
+    del tmp, col
+
     ms_e2e_warm = timed_batch(steps_e2e, 1)
     ms_e2e = timed_batch(steps_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -313,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(n, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "copy_probe": copy_probe},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern}
     if not distributed:
         line["nonzero_fraction_dk_dn"] = {str(r): nonzero[r] for r in RADII}

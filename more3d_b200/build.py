@@ -10,6 +10,8 @@ LIB = os.path.join(HERE, "libmore3d_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
+# experiments: extra nvcc flags (e.g. MORE3D_NVCC_FLAGS="-DM3D_PREFETCH_DEPTH=2"); rebuild with --force
+FLAGS += os.environ.get("MORE3D_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -2,6 +2,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef M3D_PREFETCH_DEPTH
+#define M3D_PREFETCH_DEPTH 1
+#endif
+
 namespace m3d {
 
 struct GridView {
@@ -182,6 +186,25 @@ __device__ __forceinline__ void for_each_candidate_tall(const GridView& g, doubl
 template <typename L, typename P>
 __device__ __forceinline__ void run_range_pipelined(uint32_t b, uint32_t e, L&& load, P&& process) {
     if (b >= e) return;
+#if M3D_PREFETCH_DEPTH == 2
+    // two records in flight: candidate j + 2 is requested before candidate j is processed (reads past the end of the
+    // range are clamped to its last record and dropped); the three buffers rotate by unrolling, not by moves
+    const uint32_t last = e - 1;
+    auto r0 = load((int64_t)b);
+    auto r1 = load((int64_t)min(b + 1, last));
+    uint32_t j = b;
+    while (true) {
+        auto r2 = load((int64_t)min(j + 2, last));
+        process(r0);
+        if (++j >= e) break;
+        r0 = load((int64_t)min(j + 2, last));
+        process(r1);
+        if (++j >= e) break;
+        r1 = load((int64_t)min(j + 2, last));
+        process(r2);
+        if (++j >= e) break;
+    }
+#else
     auto cur = load((int64_t)b);
 #pragma unroll 2
     for (uint32_t j = b + 1; j < e; ++j) {
@@ -190,6 +213,7 @@ __device__ __forceinline__ void run_range_pipelined(uint32_t b, uint32_t e, L&& 
         cur = nxt;
     }
     process(cur);
+#endif
 }
 
 template <bool TALL, typename L, typename P>

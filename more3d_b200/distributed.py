@@ -388,10 +388,10 @@ class StripSaliency:
     One step = pack both halo bands + bounding box (one kernel) -> ONE all-gather of 8 doubles per rank (global
     bounding box = the shared column lattice, and the neighbours' halo sizes; the step's only host read before the
     grid build) -> point-to-point halo exchange -> StripStep: grid over [left ghosts, own, right ghosts] on the
-    tile's lattice, 3 radii of normals / curvature / dk / dn -> ONE all-reduce of all radii's dk/dn extrema ->
-    blend -> ONE all-reduce of the saliency extrema -> histograms -> ONE all-reduce of the 256-bin histograms (the
-    global Otsu input, Downsample.py:54).  Three small collectives per step instead of five per radius; the Otsu
-    thresholds are read lazily (`otsu`)."""
+    tile's lattice, 3 radii of normals / curvature / dk / dn -> ONE all-reduce of all radii's dk/dn extrema (the
+    Histo pass of DM_saliency.py:562-568 over the whole tile) -> blend.  Two small collectives per step.  The global
+    Otsu threshold of the downsampling stage (Downsample.py:54: saliency extrema, 256-bin histograms, two more
+    all-reduces) is computed on demand by `otsu`, as on a single GPU where it is not part of the saliency step."""
 
     def __init__(self, n, rank, world, device, radii, params, curvature_weight, seed=2, cloud=None, x_range=None,
                  host_buffers=True):
@@ -478,10 +478,12 @@ class StripSaliency:
             out[r] = step.saliency(r)
             if out_host is not None:
                 _copy_out(out[r], out_host[r], copy_stream, self.dev)
-        allreduce_minmax_rows(step.owned_minmax())
-        dist.all_reduce(step.histograms(), op=dist.ReduceOp.SUM)
         pc = step.pcount
-        res = step.result()
+        # the global Otsu threshold (Downsample.py:54) is NOT part of the saliency step (the single-GPU step has none
+        # either): the step keeps its owned saliency columns and their local extrema, `otsu` runs the two collectives
+        self._otsu_in = (dict(out), step.sal_minmax, step.radii)
+        self._otsu = None
+        res = _StepResult(step.radii, step.status, step.table_len, None, None)
         step.close()
         if self._last is not None:
             # the previous step's overflow words: read now, one step late, so that no step waits for its own
@@ -493,8 +495,22 @@ class StripSaliency:
 
     @property
     def otsu(self):
-        """{radius: global Otsu threshold of the saliency column} of the last step (host read)."""
-        return self._last.otsu()
+        """{radius: global Otsu threshold of the saliency column} of the last step.  COLLECTIVE: every rank must read it
+        (one all-reduce of the saliency extrema, 256-bin histograms over the global range, one all-reduce of the
+        histograms, then the host scan)."""
+        if self._otsu is None:
+            lib = _lib.load()
+            sal, smm, radii = self._otsu_in
+            smm = smm.clone()
+            allreduce_minmax_rows(smm)
+            with torch.cuda.device(self.dev):
+                hist = torch.empty((len(radii), 256), dtype=torch.int64, device=self.dev)
+                for i, r in enumerate(radii):
+                    v = sal[r].contiguous()
+                    check(lib.more3d_histogram256_range(ptr(v), 4, int(v.numel()), ptr(smm[i]), 4, ptr(hist[i]), stream_ptr()))
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+            self._otsu = _StepResult(radii, None, 0, smm, hist).otsu()
+        return self._otsu
 
     def step_resident(self):
         return self._run(self.resident, None)[0]
