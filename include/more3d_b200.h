@@ -48,6 +48,10 @@ int more3d_profile_names(char* buf_h, int len);
  * refinement of the listed rest (default); 1 = shared-memory staged one-pass walk; 2 = global-memory one-pass walk.
  * The environment variable MORE3D_DKDN_VARIANT sets the initial value. */
 int more3d_set_dkdn_variant(int variant);
+/* Two-pass dk/dn only: when the screening pass lists more than `fraction` * n points for refinement (a whole-expression
+ * entry counts three times) the one-pass kernel is run over the whole cloud instead -- decided on the device, both
+ * alternatives are launched.  Default 0.45; a value >= 4 never falls back, 0 always does (tests). */
+int more3d_set_dkdn_gate(double fraction);
 
 /* ---- spatial index --------------------------------------------------------------------------
  * Replaces BallTreePointSet.__init__ -> sklearn BallTree build (Downsampling/BallTreePointSet.py:19-53).

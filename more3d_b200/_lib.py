@@ -20,6 +20,7 @@ SIGNATURES = {
     "more3d_profile_get": [C.c_char_p, C.POINTER(_f64), C.POINTER(_i64)],
     "more3d_profile_names": [C.c_char_p, _i32],
     "more3d_set_dkdn_variant": [_i32],
+    "more3d_set_dkdn_gate": [_f64],
     "more3d_grid_create": [_vp, _i64, _f64, _vp, C.POINTER(_vp)],
     "more3d_grid_create_segments": [C.POINTER(_vp), C.POINTER(_i64), _i32, _f64, _i32, C.POINTER(_f64), C.POINTER(_f64),
                                     _vp, C.POINTER(_vp)],
@@ -153,6 +154,11 @@ def profile_enable(on=True):
 def set_dkdn_variant(variant):
     """0 = two-pass dk/dn (default), 1 = shared-memory staged walk, 2 = one-pass walk; applies to grids built afterwards."""
     check(load().more3d_set_dkdn_variant(int(variant)))
+
+
+def set_dkdn_gate(fraction):
+    """Listed fraction of the cloud above which the two-pass dk/dn falls back to the one-pass kernel (default 0.45)."""
+    check(load().more3d_set_dkdn_gate(float(fraction)))
 
 
 def profile_reset():

@@ -341,12 +341,24 @@ __device__ __forceinline__ void dkdn_minmax(unsigned lo_k, unsigned hi_k, unsign
     }
 }
 
+// Two-pass dk/dn: the refinement costs about as much per listed point as the one-pass kernel costs per point (a whole-
+// expression entry about three times that), so when the screening pass lists more than ~45 % of the cloud (very rough
+// surfaces, tiny sigmas) the one-pass kernel is run over everything instead.  The decision is taken on the device from
+// the list counters: both alternatives are launched, one of them returns at once.
+__device__ __forceinline__ bool refine_gate_open(const unsigned* __restrict__ counts, unsigned above) {
+    return (unsigned long long)__ldg(counts) + 3ull * (unsigned long long)__ldg(counts + 1) > (unsigned long long)above;
+}
+
 template <bool TALL, bool SPLIT>
 __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
                                                    DkDnParams prm, const double* __restrict__ chi2_table,
                                                    float* __restrict__ dk_out, float* __restrict__ dn_out,
                                                    unsigned* __restrict__ mm /* ordered min/max x4 */,
-                                                   int* __restrict__ err) {
+                                                   int* __restrict__ err,
+                                                   const unsigned* __restrict__ gate = nullptr, unsigned gate_above = 0) {
+    // gate: the work-list counters of the two-pass path -- this kernel then runs only if the screening pass left more
+    // than `gate_above` weighted entries (refine_gate), i.e. as the fallback on clouds where screening does not pay
+    if (gate && !refine_gate_open(gate, gate_above)) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float dkf = 0.0f, dnf = 0.0f;
     const bool live = i < g.n;
@@ -680,9 +692,10 @@ __global__ void __launch_bounds__(WALK_THREADS, 3) dk_refine_kernel(GridView g, 
                                                            unsigned* __restrict__ mm, int* __restrict__ err,
                                                            const uint32_t* __restrict__ list,
                                                            const unsigned long long* __restrict__ aux,
-                                                           const unsigned* __restrict__ list_count) {
+                                                           const unsigned* __restrict__ list_count, unsigned gate_above) {
     constexpr int GP = 32 / G;
     __shared__ uint32_t s_b[REFINE_WARPS][GP][REFINE_ROWS], s_off[REFINE_WARPS][GP][REFINE_ROWS + 1];
+    if (refine_gate_open(list_count, gate_above)) return;      // the one-pass kernel takes over
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, grp = lane / G, gl = lane % G;
     const unsigned count = list_count[0];
     const unsigned stride = gridDim.x * REFINE_WARPS * GP;
@@ -771,7 +784,8 @@ __global__ void __launch_bounds__(WALK_THREADS) dk_refine_thread_kernel(GridView
                                                                unsigned* __restrict__ mm,
                                                                const uint32_t* __restrict__ list,
                                                                const unsigned long long* __restrict__ aux,
-                                                               const unsigned* __restrict__ list_count) {
+                                                               const unsigned* __restrict__ list_count, unsigned gate_above) {
+    if (refine_gate_open(list_count, gate_above)) return;
     const unsigned count = list_count[0];
     const bool all_owned = prm.own_lo <= 0 && prm.own_hi >= g.n;
     unsigned lo_k = 0xffffffffu, hi_k = 0u;
@@ -819,9 +833,10 @@ __global__ void __launch_bounds__(WALK_THREADS, 2) dkdn_refine_kernel(GridView g
                                                           float* __restrict__ dk_out, float* __restrict__ dn_out,
                                                           unsigned* __restrict__ mm, int* __restrict__ err,
                                                           const uint32_t* __restrict__ list,
-                                                          const unsigned* __restrict__ list_count) {
+                                                          const unsigned* __restrict__ list_count, unsigned gate_above) {
     constexpr int GP = 32 / G;
     __shared__ uint32_t s_b[REFINE_WARPS][GP][REFINE_ROWS], s_off[REFINE_WARPS][GP][REFINE_ROWS + 1];
+    if (refine_gate_open(list_count, gate_above)) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, grp = lane / G, gl = lane % G;
     const unsigned count = list_count[1];
     const unsigned stride = gridDim.x * REFINE_WARPS * GP;
@@ -1068,6 +1083,12 @@ int dkdn_variant() {
     return g_dkdn_variant;
 }
 }  // namespace m3d
+static double g_dkdn_gate = 0.45;
+extern "C" int more3d_set_dkdn_gate(double fraction) {
+    M3D_REQUIRE(fraction >= 0.0 && isfinite(fraction), "fraction must be finite and >= 0");
+    g_dkdn_gate = fraction;
+    return MORE3D_OK;
+}
 extern "C" int more3d_set_dkdn_variant(int variant) {
     M3D_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0 (two passes), 1 (shared-memory staged) or 2 (one pass)");
     m3d::g_dkdn_variant = variant;
@@ -1169,6 +1190,7 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
             M3D_TRY(sc.alloc(&aux, (size_t)g->n));
             M3D_TRY(sc.alloc(&list_count, 2));
             M3D_CUDA(cudaMemsetAsync(list_count, 0, 2 * sizeof(unsigned), s));
+            const unsigned gate_above = (unsigned)fmin(g_dkdn_gate * (double)g->n, 4.0e9);
             static int grid_k = 0, grid_n = 0;
             if (!grid_k) grid_k = persistent_grid(dk_refine_kernel<REFINE_G>, 3);
             if (!grid_n) grid_n = persistent_grid(dkdn_refine_kernel<REFINE_G>, 2);
@@ -1183,20 +1205,23 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
                 if (refine_g < 0) { const char* e = getenv("MORE3D_REFINE_G"); refine_g = e ? atoi(e) : REFINE_G; }
                 if (refine_g == 1)
                     dk_refine_thread_kernel<<<148 * 8, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                             minmax ? mm : nullptr, list, aux, list_count);
+                                                                             minmax ? mm : nullptr, list, aux, list_count, gate_above);
                 else if (refine_g == 2)
                     dk_refine_kernel<2><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                        minmax ? mm : nullptr, err, list, aux, list_count);
+                                                                        minmax ? mm : nullptr, err, list, aux, list_count, gate_above);
                 else if (refine_g == 4)
                     dk_refine_kernel<4><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                        minmax ? mm : nullptr, err, list, aux, list_count);
+                                                                        minmax ? mm : nullptr, err, list, aux, list_count, gate_above);
                 else
                     dk_refine_kernel<8><<<grid_k, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                        minmax ? mm : nullptr, err, list, aux, list_count);
+                                                                        minmax ? mm : nullptr, err, list, aux, list_count, gate_above);
                 dkdn_refine_kernel<REFINE_G><<<grid_n, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
-                                                                            minmax ? mm : nullptr, err, list, list_count);
+                                                                            minmax ? mm : nullptr, err, list, list_count, gate_above);
+                // the fallback (returns at once unless the lists are long): every point through the one-pass kernel
+                dkdn_kernel<false, true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err,
+                                                            list_count, gate_above);
             }
-            count_launches(2);
+            count_launches(3);
             if (getenv("MORE3D_DKDN_STATS")) {       // debugging aid: synchronises
                 unsigned cnt[2] = {0, 0};
                 cudaMemcpyAsync(cnt, list_count, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, s);

@@ -192,15 +192,19 @@ def test_two_pass_dkdn_equals_one_pass(params):
               min_points=4, keep=True)
     out = {}
     try:
-        for variant in (2, 0):
+        # 2: one pass; 0 with the fallback gate wide open (every listed point goes through the refinement kernels, also
+        # where most of the cloud is listed) and with the default gate (rough clouds fall back to the one-pass kernel)
+        for key, variant, gate in (("one", 2, 0.45), ("two", 0, 100.0), ("two_gated", 0, 0.45)):
             _lib.set_dkdn_variant(variant)
+            _lib.set_dkdn_gate(gate)
             res = multiscale_saliency(d, (0.5, 0.75, 1.0), **kw)
-            out[variant] = {r: {k: v.cpu().numpy() for k, v in res[r].items() if k in ("_dk", "_dn", "_pcount", "_saliency")}
-                            for r in res}
+            out[key] = {r: {k: v.cpu().numpy() for k, v in res[r].items() if k in ("_dk", "_dn", "_pcount", "_saliency")}
+                        for r in res}
     finally:
         _lib.set_dkdn_variant(0)
-    for r in (0.5, 0.75, 1.0):
-        a, b = out[2][r], out[0][r]
+        _lib.set_dkdn_gate(0.45)
+    for r, key in [(r, key) for r in (0.5, 0.75, 1.0) for key in ("two", "two_gated")]:
+        a, b = out["one"][r], out[key][r]
         assert np.array_equal(a["_pcount"], b["_pcount"])
         for k in ("_dk", "_dn"):
             assert np.array_equal(a[k] == 0, b[k] == 0), (r, k)
