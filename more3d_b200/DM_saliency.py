@@ -45,6 +45,21 @@ def _status_words(device, count):
     return t
 
 
+_PINNED = [None, 0]
+
+
+def _pinned_words(count):
+    """`count` pinned int32 words from a ring that is allocated once (64 rows of 16; a row is read one tile after it was
+    handed out, long before the ring comes round) -- a pinned allocation per tile costs a cudaHostAlloc now and then."""
+    if count > 16:
+        return torch.empty(count, dtype=torch.int32).pin_memory()
+    if _PINNED[0] is None:
+        _PINNED[0] = torch.zeros((64, 16), dtype=torch.int32).pin_memory()
+    row = _PINNED[0][_PINNED[1] % 64]
+    _PINNED[1] += 1
+    return row[:count]
+
+
 def _status_ring_poisoned(device):
     _STATUS_RING.pop(str(device), None)      # an overflow left a non-zero word: start a fresh ring
 
@@ -203,7 +218,7 @@ class PointCloudDM:
         ev = torch.cuda.Event()
         ev.record(cur)
         words = self._status[:len(self._pending)]
-        host = torch.empty(len(self._pending), dtype=torch.int32).pin_memory()
+        host = _pinned_words(len(self._pending))
         with torch.cuda.stream(side_stream):
             side_stream.wait_event(ev)
             host.copy_(words, non_blocking=True)
@@ -211,9 +226,21 @@ class PointCloudDM:
             done = torch.cuda.Event()
             done.record(side_stream)
 
+        # the closure must not keep `self` (and with it every column of this cloud) alive until it is called: it gets the
+        # few values it needs, the cloud's own bookkeeping is reset now
+        pending, device = list(self._pending), self.device
+        self._pending = []
+        self._status = None
+
         def result():
             done.synchronize()
-            return self._need(host.tolist())
+            need = 0
+            for v, length in zip(host.tolist(), pending):
+                if int(v) != 0:
+                    _status_ring_poisoned(device)
+                if int(v) > length:
+                    need = max(need, int(v))
+            return need
         return result
 
     def drop_grids(self):

@@ -349,17 +349,12 @@ __device__ __forceinline__ bool refine_gate_open(const unsigned* __restrict__ co
     return (unsigned long long)__ldg(counts) + 3ull * (unsigned long long)__ldg(counts + 1) > (unsigned long long)above;
 }
 
+// one sorted point of the one-pass dk/dn: walk, finish, write, fused extrema (all 32 lanes of a warp must call it)
 template <bool TALL, bool SPLIT>
-__global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
-                                                   DkDnParams prm, const double* __restrict__ chi2_table,
-                                                   float* __restrict__ dk_out, float* __restrict__ dn_out,
-                                                   unsigned* __restrict__ mm /* ordered min/max x4 */,
-                                                   int* __restrict__ err,
-                                                   const unsigned* __restrict__ gate = nullptr, unsigned gate_above = 0) {
-    // gate: the work-list counters of the two-pass path -- this kernel then runs only if the screening pass left more
-    // than `gate_above` weighted entries (refine_gate), i.e. as the fallback on clouds where screening does not pay
-    if (gate && !refine_gate_open(gate, gate_above)) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void dkdn_point(const GridView& g, const FeatRec* __restrict__ feat, const DkDnParams& prm,
+                                           const double* __restrict__ chi2_table, float* __restrict__ dk_out,
+                                           float* __restrict__ dn_out, unsigned* __restrict__ mm, int* __restrict__ err,
+                                           int64_t i) {
     float dkf = 0.0f, dnf = 0.0f;
     const bool live = i < g.n;
     bool owned = false;
@@ -386,6 +381,29 @@ __global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const Fe
         dkdn_minmax(ck ? f32_ordered(dkf) : 0xffffffffu, ck ? f32_ordered(dkf) : 0u,
                     cn ? f32_ordered(dnf) : 0xffffffffu, cn ? f32_ordered(dnf) : 0u, mm);
     }
+}
+
+template <bool TALL, bool SPLIT>
+__global__ void __launch_bounds__(WALK_THREADS) dkdn_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                   DkDnParams prm, const double* __restrict__ chi2_table,
+                                                   float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                   unsigned* __restrict__ mm /* ordered min/max x4 */,
+                                                   int* __restrict__ err) {
+    dkdn_point<TALL, SPLIT>(g, feat, prm, chi2_table, dk_out, dn_out, mm, err,
+                            (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// The fallback of the two-pass path: the one-pass expression over the whole cloud, as a small persistent grid that
+// returns at once unless the screening pass listed more than `gate_above` weighted entries (refine_gate_open).
+__global__ void __launch_bounds__(WALK_THREADS) dkdn_fallback_kernel(GridView g, const FeatRec* __restrict__ feat,
+                                                            DkDnParams prm, const double* __restrict__ chi2_table,
+                                                            float* __restrict__ dk_out, float* __restrict__ dn_out,
+                                                            unsigned* __restrict__ mm, int* __restrict__ err,
+                                                            const unsigned* __restrict__ gate, unsigned gate_above) {
+    if (!refine_gate_open(gate, gate_above)) return;
+    const int64_t tiles = (g.n + WALK_THREADS - 1) / WALK_THREADS;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x)
+        dkdn_point<false, true>(g, feat, prm, chi2_table, dk_out, dn_out, mm, err, t * WALK_THREADS + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1218,8 +1236,8 @@ static int run_dk_dn(const more3d_grid* g, double r, const double* normals, cons
                 dkdn_refine_kernel<REFINE_G><<<grid_n, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn,
                                                                             minmax ? mm : nullptr, err, list, list_count, gate_above);
                 // the fallback (returns at once unless the lists are long): every point through the one-pass kernel
-                dkdn_kernel<false, true><<<nb, 256, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr, err,
-                                                            list_count, gate_above);
+                dkdn_fallback_kernel<<<148 * 6, WALK_THREADS, 0, s>>>(v, feat, prm, chi2_table, dk, dn, minmax ? mm : nullptr,
+                                                                      err, list_count, gate_above);
             }
             count_launches(3);
             if (getenv("MORE3D_DKDN_STATS")) {       // debugging aid: synchronises

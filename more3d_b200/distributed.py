@@ -379,7 +379,8 @@ def _copy_out(sal, host, copy_stream, dev):
     with torch.cuda.stream(copy_stream):
         copy_stream.wait_event(ev)
         host.copy_(sal, non_blocking=True)
-        sal.record_stream(copy_stream)
+    from .pipeline import hold_until_copied
+    hold_until_copied(sal, copy_stream)
 
 
 class StripSaliency:

@@ -51,7 +51,7 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(ev)
                 out_host[r].copy_(sal, non_blocking=True)
-                sal.record_stream(copy_stream)
+            hold_until_copied(sal, copy_stream)
         if keep:
             out[r] = {k: v for k, v in dm.attrs.items()}
             out[r]["normals"] = dm.normals
@@ -73,6 +73,20 @@ def multiscale_saliency(xyz, radii=DEFAULT_RADII, roughness=0.02, alpha=0.05, si
 
 
 _STAGING = {}
+_IN_FLIGHT = []
+
+
+def hold_until_copied(tensor, copy_stream):
+    """Keep `tensor` alive until the copy just queued on `copy_stream` has read it.  (Tensor.record_stream does the
+    same job but hands the block back to the caching allocator at an unpredictable time: in a tile stream the
+    allocator then keeps growing with cudaMalloc calls of 10-300 ms in the middle of the stream.)  Finished copies
+    are dropped here, so the allocator sees one free per column and reaches a steady state after two tiles."""
+    done = torch.cuda.Event()
+    done.record(copy_stream)
+    _IN_FLIGHT[:] = [(e, t) for e, t in _IN_FLIGHT if not e.query()]
+    _IN_FLIGHT.append((done, tensor))
+
+
 
 
 def _staging_buffers(dev, nmax):
@@ -134,6 +148,7 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
         # the overflow word of tile j is read while a later tile computes; a tile whose chi2 table was too short (rare:
         # > 1023 active neighbours in one neighbourhood) is repeated at the end with the reported length
         need = checks[j]()
+        checks[j] = None
         if need:
             redo.append((j, need))
 

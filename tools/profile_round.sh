@@ -10,8 +10,8 @@ python bench.py $FAST > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py $FAST > gpurun_out/${TAG}_ncu1.log 2>&1
 # skip the warm-up launches (4 pipelines x 12 hot launches), capture the 3 radii of one timed step of the hot kernels:
-# moments, screening walk and the two refinement passes of dk/dn
+# moments, screening walk and the two refinement passes of dk/dn (the gated fallback returns at once: not captured)
 python bench.py $FAST > gpurun_out/${TAG}_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"moments_kernel|dkdn_screen_kernel|dk_refine_kernel|dkdn_refine_kernel|dkdn_kernel" -s 48 -c 12 \
+ncu --set full --clock-control none --import-source on -k regex:"moments_kernel|dkdn_screen_kernel|dk_refine_kernel|dkdn_refine_kernel" -s 48 -c 12 \
     -o gpurun_out/${TAG}_prof -f python bench.py $FAST > gpurun_out/${TAG}_ncu2.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu2.log
