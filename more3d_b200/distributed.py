@@ -558,6 +558,8 @@ class StripSaliency:
             freed[i % len(bufs)] = done
         cur.wait_stream(down)
         cur.synchronize()
+        from .pipeline import release_copied
+        release_copied()
         return res
 
 

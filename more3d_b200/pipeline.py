@@ -99,6 +99,11 @@ def _staging_buffers(dev, nmax):
     return cur
 
 
+def release_copied():
+    """Drop the tensors held for device->host copies that have finished (called when a stream of tiles has ended)."""
+    _IN_FLIGHT[:] = [(e, t) for e, t in _IN_FLIGHT if not e.query()]
+
+
 def release_staging_buffers():
     """Free the tile stream's cached staging buffers (2 x 24 B x the largest tile seen)."""
     _STAGING.clear()
@@ -172,6 +177,7 @@ def multiscale_saliency_tiles(host_tiles, radii=DEFAULT_RADII, out_hosts=None, d
     settle(len(tiles) - 1)
     cur.wait_stream(down)
     cur.synchronize()
+    release_copied()
     for j, need in redo:
         res = multiscale_saliency(tiles[j].to(dev), radii, out_host=None if out_hosts is None else out_hosts[j],
                                   chi2_table_len=need, **params)
