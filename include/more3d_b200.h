@@ -52,6 +52,12 @@ int more3d_set_dkdn_variant(int variant);
  * entry counts three times) the one-pass kernel is run over the whole cloud instead -- decided on the device, both
  * alternatives are launched.  Default 0.45; a value >= 4 never falls back, 0 always does (tests). */
 int more3d_set_dkdn_gate(double fraction);
+/* Host-only helper behind the screening pass: the reference calls a neighbour ACTIVE when its ring weight
+ * w = d2/rho^2 (d2 < rho^2) or 2 - d2/rho^2 (d2 > rho^2) exceeds 0.01 (DM_saliency.py:272-279).  Both branches are
+ * monotone roundings of d2, so the test equals act_lo <= d2 <= act_hi, d2 != rho^2 for two doubles found with the same
+ * arithmetic: *act_lo_h = smallest d2 with fl(d2 / rho^2) > 0.01, *act_hi_h = largest d2 with fl(2 - fl(d2 / rho^2)) > 0.01.
+ * Needs no device. */
+int more3d_dkdn_act_interval(double rho, double* act_lo_h, double* act_hi_h);
 
 /* ---- spatial index --------------------------------------------------------------------------
  * Replaces BallTreePointSet.__init__ -> sklearn BallTree build (Downsampling/BallTreePointSet.py:19-53).

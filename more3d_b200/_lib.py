@@ -21,6 +21,7 @@ SIGNATURES = {
     "more3d_profile_names": [C.c_char_p, _i32],
     "more3d_set_dkdn_variant": [_i32],
     "more3d_set_dkdn_gate": [_f64],
+    "more3d_dkdn_act_interval": [_f64, C.POINTER(_f64), C.POINTER(_f64)],
     "more3d_grid_create": [_vp, _i64, _f64, _vp, C.POINTER(_vp)],
     "more3d_grid_create_segments": [C.POINTER(_vp), C.POINTER(_i64), _i32, _f64, _i32, C.POINTER(_f64), C.POINTER(_f64),
                                     _vp, C.POINTER(_vp)],

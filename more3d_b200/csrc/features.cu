@@ -1101,6 +1101,14 @@ int dkdn_variant() {
     return g_dkdn_variant;
 }
 }  // namespace m3d
+// host-only: the two thresholds of the screening pass's active test for a given rho (no device needed; the CPU tests
+// check them against the reference's expression evaluated in numpy)
+extern "C" int more3d_dkdn_act_interval(double rho, double* act_lo_h, double* act_hi_h) {
+    M3D_REQUIRE(act_lo_h && act_hi_h, "NULL argument");
+    const double rho2 = rho * rho;
+    M3D_REQUIRE(act_interval(rho2, 1.0 / rho2, act_lo_h, act_hi_h), "rho is degenerate: no screening thresholds");
+    return MORE3D_OK;
+}
 static double g_dkdn_gate = 0.45;
 extern "C" int more3d_set_dkdn_gate(double fraction) {
     M3D_REQUIRE(fraction >= 0.0 && isfinite(fraction), "fraction must be finite and >= 0");

@@ -141,3 +141,35 @@ def test_ls_state_struct_matches_the_ctypes_mirror():
     got = [(n, "ptr" if t is ctypes.c_void_p else {ctypes.c_int64: "int64_t", ctypes.c_double: "double",
                                                      ctypes.c_int: "int"}[t]) for n, t in _State._fields_]
     assert got == list(zip(names, kinds))
+
+
+def test_screening_thresholds_reproduce_the_reference_active_test():
+    """The screening pass of dk/dn replaces `w > 0.01` (DM_saliency.py:272-279) by two thresholds on the squared distance
+    (more3d_dkdn_act_interval, host only).  Against the reference's own expression in numpy float64: each threshold sits
+    exactly at the edge of its branch, and random distances agree with the expression on both sides."""
+    import numpy as np
+    from more3d_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.Generator(np.random.PCG64(5))
+    for rho in [0.5 / np.sqrt(2), 0.75 / np.sqrt(2), 1.0 / np.sqrt(2), 0.3, 1.234567, 1e-3, 37.5]:
+        lo, hi = ctypes.c_double(0), ctypes.c_double(0)
+        _lib.check(lib.more3d_dkdn_act_interval(float(rho), ctypes.byref(lo), ctypes.byref(hi)))
+        lo, hi = lo.value, hi.value
+        rho2 = np.float64(rho) ** 2
+
+        def active(d):                           # the reference's expression, element by element
+            d = np.asarray(d, np.float64)
+            w = np.zeros_like(d)
+            a, b = d < rho2, d > rho2
+            w[a] = 1 / rho2 * d[a]
+            w[b] = -1 / rho2 * d[b] + 2
+            w[w < 0] = 0
+            return w > 0.01
+
+        assert lo < rho2 < hi
+        assert active([lo])[0] and not active([np.nextafter(lo, 0.0)])[0]
+        assert active([hi])[0] and not active([np.nextafter(hi, np.inf)])[0]
+        d = np.concatenate([rng.random(20000) * 2.2 * rho2, lo * (1 + (rng.random(2000) - 0.5) * 1e-13),
+                            hi * (1 + (rng.random(2000) - 0.5) * 1e-13), [rho2, 0.0, 2 * rho2]])
+        assert np.array_equal(active(d), (d >= lo) & (d <= hi) & (d != rho2))
+    assert lib.more3d_dkdn_act_interval(0.0, ctypes.byref(ctypes.c_double()), ctypes.byref(ctypes.c_double())) == -1
