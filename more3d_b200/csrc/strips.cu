@@ -45,21 +45,21 @@ __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t wbase = (int64_t)tile * SP_TILE + (int64_t)warp * (32 * SP_ITEMS);
-    double px[SP_ITEMS], py[SP_ITEMS], pz[SP_ITEMS];
     unsigned ml[SP_ITEMS], mr[SP_ITEMS];              // ballots of round j: lanes in the left / right band
     unsigned cl = 0, cr = 0;                          // warp totals
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // the coordinates are NOT kept in registers across the scan (24 doubles per thread cost two thirds of the resident
+    // CTAs): the band members -- under 1 % of the points -- re-read theirs from L1 / L2 when they are written out
 #pragma unroll
     for (int j = 0; j < SP_ITEMS; ++j) {
         const int64_t i = wbase + j * 32 + lane;
         bool fl = false, fr = false;
-        px[j] = py[j] = pz[j] = 0.0;
         if (i < n) {
-            px[j] = xyz[3 * i]; py[j] = xyz[3 * i + 1]; pz[j] = xyz[3 * i + 2];
-            fl = px[j] < left_below;
-            fr = px[j] >= right_from;
-            lo[0] = fmin(lo[0], px[j]); lo[1] = fmin(lo[1], py[j]); lo[2] = fmin(lo[2], pz[j]);
-            hi[0] = fmax(hi[0], px[j]); hi[1] = fmax(hi[1], py[j]); hi[2] = fmax(hi[2], pz[j]);
+            const double x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+            fl = x < left_below;
+            fr = x >= right_from;
+            lo[0] = fmin(lo[0], x); lo[1] = fmin(lo[1], y); lo[2] = fmin(lo[2], z);
+            hi[0] = fmax(hi[0], x); hi[1] = fmax(hi[1], y); hi[2] = fmax(hi[2], z);
         }
         ml[j] = __ballot_sync(0xffffffffu, fl);
         mr[j] = __ballot_sync(0xffffffffu, fr);
@@ -89,13 +89,14 @@ __global__ void __launch_bounds__(SP_THREADS) strip_pack_kernel(const double* __
     int64_t l = (int64_t)(ex & 0x7fffffffull), r = (int64_t)(ex >> 31);
 #pragma unroll
     for (int j = 0; j < SP_ITEMS; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
         if (ml[j] & (1u << lane)) {
             const int64_t o = l + __popc(ml[j] & lt);
-            if (o < cap) { left_out[3 * o] = px[j]; left_out[3 * o + 1] = py[j]; left_out[3 * o + 2] = pz[j]; }
+            if (o < cap) { left_out[3 * o] = __ldg(xyz + 3 * i); left_out[3 * o + 1] = __ldg(xyz + 3 * i + 1); left_out[3 * o + 2] = __ldg(xyz + 3 * i + 2); }
         }
         if (mr[j] & (1u << lane)) {
             const int64_t o = r + __popc(mr[j] & lt);
-            if (o < cap) { right_out[3 * o] = px[j]; right_out[3 * o + 1] = py[j]; right_out[3 * o + 2] = pz[j]; }
+            if (o < cap) { right_out[3 * o] = __ldg(xyz + 3 * i); right_out[3 * o + 1] = __ldg(xyz + 3 * i + 1); right_out[3 * o + 2] = __ldg(xyz + 3 * i + 2); }
         }
         l += __popc(ml[j]);
         r += __popc(mr[j]);
