@@ -41,6 +41,10 @@ int more3d_profile_enable(int on);
 int more3d_profile_reset(void);
 int more3d_profile_get(const char* name, double* ms_h, int64_t* count_h);
 int more3d_profile_names(char* buf_h, int len);
+/* Read `bytes` (<= 4096 for the fast path) of device memory into host memory, ordered behind everything queued on
+ * `stream`, WITHOUT the device-to-host copy engine: a one-warp kernel stores into a pinned mapped slot and the host
+ * waits for an event.  A small cudaMemcpy would queue behind any large download in flight (tile streaming). */
+int more3d_read_back(const void* src_dev, void* dst_h, int64_t bytes, void* stream);
 
 /* Kernel variant of the dk/dn pass (more3d_dk_dn*), for A/B measurements and the equivalence tests; grids built
  * afterwards follow it (the feature-record layout is chosen per grid).  0 = two passes: a screening walk that settles

@@ -19,6 +19,7 @@ SIGNATURES = {
     "more3d_profile_reset": [],
     "more3d_profile_get": [C.c_char_p, C.POINTER(_f64), C.POINTER(_i64)],
     "more3d_profile_names": [C.c_char_p, _i32],
+    "more3d_read_back": [_vp, _vp, _i64, _vp],
     "more3d_set_dkdn_variant": [_i32],
     "more3d_set_dkdn_gate": [_f64],
     "more3d_dkdn_act_interval": [_f64, C.POINTER(_f64), C.POINTER(_f64)],
@@ -150,6 +151,18 @@ def require_cuda():
 
 def profile_enable(on=True):
     check(load().more3d_profile_enable(1 if on else 0))
+
+
+def read_back(t):
+    """Small CUDA tensor -> numpy array on the host, ordered behind the current stream's work, without the copy engine
+    (more3d_read_back): a `.cpu()` of a few bytes waits for any large download that is in flight."""
+    import numpy as np
+    import torch
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    with torch.cuda.device(t.device):
+        check(load().more3d_read_back(ptr(t), out.ctypes.data_as(C.c_void_p), int(t.numel() * t.element_size()), stream_ptr()))
+    return out
 
 
 def set_dkdn_variant(variant):

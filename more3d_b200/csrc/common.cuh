@@ -42,6 +42,13 @@ void count_launches(int n);
         }                                              \
     } while (0)
 
+// Small device -> host read-back that does NOT go through a copy engine: a one-warp kernel stores the bytes into a
+// pinned, device-mapped staging slot and the host waits for an event behind it.  A cudaMemcpyAsync of a few bytes is
+// queued in the device-to-host copy engine behind whatever large download is in flight (the previous tile's saliency
+// columns: 40-120 MB, 1-6 ms); the kernel's posted writes are not.  bytes <= 4096; returns after dst_h holds the data
+// (everything queued earlier on `s` has then completed, like cudaStreamSynchronize would guarantee for that stream).
+int read_back(void* dst_h, const void* src_dev, size_t bytes, cudaStream_t s);
+
 // one-time per-device setup: keep stream-ordered pool memory cached instead of returning it to the
 // driver at every synchronisation (otherwise each call pays cudaMalloc-class latencies)
 void init_device_pool();

@@ -276,8 +276,7 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
         count_launches(2);
         M3D_CHECK_LAUNCH();
-        M3D_CUDA(cudaMemcpyAsync(b6, part + 6 * nparts, sizeof(b6), cudaMemcpyDeviceToHost, s));
-        M3D_CUDA(cudaStreamSynchronize(s));
+        M3D_TRY(read_back(b6, part + 6 * nparts, sizeof(b6), s));
         dev_free(part, s);
     }
     const double bb[4] = {b6[0], b6[1], b6[3], b6[4]};   // min x, min y, max x, max y
@@ -373,8 +372,7 @@ extern "C" int more3d_grid_create_segments(const double* const* seg_xyz_h, const
         G_TRY(dev_alloc(&d_max, 1, s));
         G_CUDA(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), s));
         col_max_pop<<<592, 256, 0, s>>>(g->col_start, ncols, d_max);
-        G_CUDA(cudaMemcpyAsync(&g->max_col_pop, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        G_CUDA(cudaStreamSynchronize(s));
+        G_TRY(read_back(&g->max_col_pop, d_max, sizeof(uint32_t), s));
         dev_free(d_max, s);
         g->tall = g->max_col_pop > M3D_TALL_COLUMN ? 1 : 0;
         // thin grids: the two-pass dk/dn reads only the first halves of the feature records in its screening pass, so the
@@ -436,8 +434,7 @@ int m3d::cloud_bbox(const double* xyz, int64_t n, double box_h[6], cudaStream_t 
     bbox_final<<<1, 32, 0, s>>>(part, nparts, part + 6 * nparts);
     count_launches(2);
     M3D_CHECK_LAUNCH();
-    M3D_CUDA(cudaMemcpyAsync(box_h, part + 6 * nparts, 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    M3D_CUDA(cudaStreamSynchronize(s));
+    M3D_TRY(read_back(box_h, part + 6 * nparts, 6 * sizeof(double), s));
     dev_free(part, s);
     return MORE3D_OK;
 }

@@ -39,6 +39,40 @@ void init_device_pool() {
     done[dev] = true;
 }
 
+// ---- small read-backs without the copy engine ---------------------------------------------------
+__global__ void store_to_host_kernel(const unsigned char* __restrict__ src, unsigned char* dst_mapped, unsigned bytes) {
+    for (unsigned i = threadIdx.x; i < bytes; i += blockDim.x) dst_mapped[i] = src[i];
+    __threadfence_system();
+}
+
+int read_back(void* dst_h, const void* src_dev, size_t bytes, cudaStream_t s) {
+    constexpr size_t CAP = 4096;
+    struct Slot { void* host = nullptr; void* dev = nullptr; cudaEvent_t ev = nullptr; int device = -1; };
+    static thread_local Slot slot;
+    if (bytes == 0) return MORE3D_OK;
+    int dev = 0;
+    M3D_CUDA(cudaGetDevice(&dev));
+    if (bytes > CAP) {          // not a "small" read: the ordinary path
+        M3D_CUDA(cudaMemcpyAsync(dst_h, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+        M3D_CUDA(cudaStreamSynchronize(s));
+        return MORE3D_OK;
+    }
+    if (slot.host == nullptr || slot.device != dev) {
+        if (slot.host) { cudaFreeHost(slot.host); cudaEventDestroy(slot.ev); slot.host = nullptr; }
+        M3D_CUDA(cudaHostAlloc(&slot.host, CAP, cudaHostAllocMapped | cudaHostAllocPortable));
+        M3D_CUDA(cudaHostGetDevicePointer(&slot.dev, slot.host, 0));
+        M3D_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+        slot.device = dev;
+    }
+    store_to_host_kernel<<<1, 128, 0, s>>>((const unsigned char*)src_dev, (unsigned char*)slot.dev, (unsigned)bytes);
+    count_launches(1);
+    M3D_CHECK_LAUNCH();
+    M3D_CUDA(cudaEventRecord(slot.ev, s));
+    M3D_CUDA(cudaEventSynchronize(slot.ev));
+    memcpy(dst_h, slot.host, bytes);
+    return MORE3D_OK;
+}
+
 // ---- profiler ---------------------------------------------------------------------------------
 struct ProfRec { int name; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
@@ -366,6 +400,10 @@ int radix_sort_pairs_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_alt, uin
 }  // namespace m3d
 
 extern "C" int64_t more3d_launch_count(void) { return (int64_t)m3d::get_launches(); }
+extern "C" int more3d_read_back(const void* src_dev, void* dst_h, int64_t bytes, void* stream) {
+    M3D_REQUIRE(src_dev && dst_h && bytes >= 0, "NULL argument");
+    return m3d::read_back(dst_h, src_dev, (size_t)bytes, (cudaStream_t)stream);
+}
 extern "C" int more3d_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(m3d::g_prof_mu);
     m3d::g_prof_on = on != 0;

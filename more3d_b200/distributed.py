@@ -315,7 +315,7 @@ class _StepResult:
 
     def overflow(self):
         """0, or the chi2-table length that would have sufficed (reads the status words: synchronises)."""
-        need = int(self.status.cpu().numpy().max())
+        need = int(_lib.read_back(self.status).max())
         if need:
             from .DM_saliency import _status_ring_poisoned
             _status_ring_poisoned(self.status.device)
@@ -441,7 +441,9 @@ class StripSaliency:
         send_l, send_r, info = strip_pack(own, left_below, right_from, self.cap)
         allinfo = torch.empty((world, 8), dtype=torch.float64, device=self.dev)
         dist.all_gather_into_tensor(allinfo, info)
-        ai = allinfo.cpu().numpy()                       # the step's host read: global box + every halo size
+        # the step's host read: global box + every halo size.  Not `.cpu()`: a small copy would queue in the download
+        # engine behind the previous step's saliency columns (120 MB) and stall the whole step for milliseconds
+        ai = _lib.read_back(allinfo)
         cnt = ai[:, 6:8].astype(np.int64)
         if cnt.max() > self.cap:
             raise _lib.More3DError("halo band holds %d points, capacity %d" % (int(cnt.max()), self.cap), _lib.E_RANGE)
