@@ -237,42 +237,54 @@ class StripStep:
         self.hist = None
         self.grid = None
 
-    def features(self):
+    def build_grid(self):
         from .DM_saliency import Curvature_Kernel, _chi2_table
         p = self.params
         ck = Curvature_Kernel()
         ck.setArgs(alpha=p["alpha"], roughness=p["roughness"], min_points=p["min_points"])
-        eps = ck.epsilon()
-        self.grid = g = UniformGrid(self.own, cell_for_radius(self.radii[0]), left=self.left, right=self.right,
-                                    lattice=self.lattice, bounds=self.bounds, x_split=X_SPLIT)
-        table = _chi2_table(p["alpha"], self.table_len, self.dev)
-        self.dk, self.dn, self.pcount = {}, {}, {}
-        for i, r in enumerate(self.radii):
-            if cell_for_radius(r) / g.requested_cell > 2.05:
-                raise ValueError("radii of one strip step must lie within a factor 2 (one shared grid)")
-            rho = r / np.sqrt(2.0)
-            _, _, _, pcount = g.normals_curvature_gridorder(r, eps, p["min_points"])
-            dk, dn, _ = g.dk_dn_gridorder(r, rho, p["sigma_normal"], p["sigma_curvature"], table, p["min_points"],
-                                          own_lo=self.n_left, n_owned=self.n_own, status=self.status[i:i + 1],
-                                          minmax=self.minmax[i])
-            self.dk[r], self.dn[r] = dk, dn
-            self.pcount[r] = _OwnedRows(pcount, self.n_left, self.n_own)
+        self._eps = ck.epsilon()
+        self.grid = UniformGrid(self.own, cell_for_radius(self.radii[0]), left=self.left, right=self.right,
+                                lattice=self.lattice, bounds=self.bounds, x_split=X_SPLIT)
+        self._table = _chi2_table(p["alpha"], self.table_len, self.dev)
+        self.dk, self.dn, self.pcount, self.sal_grid = {}, {}, {}, {}
+
+    def features_radius(self, i):
+        """normals / curvature -> dk / dn of radius i (grid order); fills self.minmax[i] with the owned rows' extrema."""
+        p, g, r = self.params, self.grid, self.radii[i]
+        if cell_for_radius(r) / g.requested_cell > 2.05:
+            raise ValueError("radii of one strip step must lie within a factor 2 (one shared grid)")
+        rho = r / np.sqrt(2.0)
+        _, _, _, pcount = g.normals_curvature_gridorder(r, self._eps, p["min_points"])
+        dk, dn, _ = g.dk_dn_gridorder(r, rho, p["sigma_normal"], p["sigma_curvature"], self._table, p["min_points"],
+                                      own_lo=self.n_left, n_owned=self.n_own, status=self.status[i:i + 1],
+                                      minmax=self.minmax[i])
+        self.dk[r], self.dn[r] = dk, dn
+        self.pcount[r] = _OwnedRows(pcount, self.n_left, self.n_own)
+
+    def features(self):
+        self.build_grid()
+        for i in range(len(self.radii)):
+            self.features_radius(i)
         return self.minmax
+
+    def blend_radius(self, i, curvature_weight):
+        """normalise + blend radius i with the (global) extrema in self.minmax[i]; fills self.sal_minmax[i] with the
+        extrema of the OWNED rows."""
+        lib = _lib.load()
+        r, n = self.radii[i], self.grid.n
+        with torch.cuda.device(self.dev):
+            sal = torch.empty(n, dtype=torch.float32, device=self.dev)      # blend is elementwise: grid order
+            # ghosts are other strips' points (and near the halo's outer edge their neighbourhoods are incomplete)
+            check(lib.more3d_saliency_blend_owned(self.grid._h, ptr(self.dk[r].data), ptr(self.dn[r].data),
+                                                  ptr(self.minmax[i]), float(curvature_weight), self.n_left,
+                                                  self.n_own, ptr(sal), ptr(self.sal_minmax[i]), stream_ptr()))
+            self.sal_grid[r] = GridColumn(self.dk[r], sal)
 
     def blend(self, curvature_weight):
         """normalise + blend every radius with the (global) extrema in self.minmax; fills self.sal_minmax with the
         extrema of the OWNED rows (rows {min, max}: ready for the MIN all-reduce)."""
-        lib = _lib.load()
-        self.sal_grid = {}
-        n = self.grid.n
-        with torch.cuda.device(self.dev):
-            for i, r in enumerate(self.radii):
-                sal = torch.empty(n, dtype=torch.float32, device=self.dev)      # blend is elementwise: grid order
-                # ghosts are other strips' points (and near the halo's outer edge their neighbourhoods are incomplete)
-                check(lib.more3d_saliency_blend_owned(self.grid._h, ptr(self.dk[r].data), ptr(self.dn[r].data),
-                                                      ptr(self.minmax[i]), float(curvature_weight), self.n_left,
-                                                      self.n_own, ptr(sal), ptr(self.sal_minmax[i]), stream_ptr()))
-                self.sal_grid[r] = GridColumn(self.dk[r], sal)
+        for i in range(len(self.radii)):
+            self.blend_radius(i, curvature_weight)
         return self.sal_minmax
 
     def saliency(self, r):
@@ -474,12 +486,22 @@ class StripSaliency:
                   min(max(float(ai[rank, 3]), self.x_hi) + self.halo, float(gmax[0])), float(gmax[1]), float(gmax[2]))
         step = StripStep(own, from_l if n_from_l else None, from_r if n_from_r else None, self.radii, self.params,
                          lattice=lattice, bounds=bounds)
-        allreduce_minmax_rows(step.features())
-        step.blend(self.cw)
         out = {}
-        for r in self.radii:
-            out[r] = step.saliency(r)
-            if out_host is not None:
+        if out_host is None:
+            allreduce_minmax_rows(step.features())           # ONE collective for all radii
+            step.blend(self.cw)
+            for r in self.radii:
+                out[r] = step.saliency(r)
+        else:
+            # host buffers: one collective PER radius, so that every saliency column starts its way to the host as soon
+            # as its radius is done -- the downloads spread over the step instead of piling up behind its end (with
+            # eight ranks on one host a column takes 3-4 ms)
+            step.build_grid()
+            for i, r in enumerate(self.radii):
+                step.features_radius(i)
+                allreduce_minmax_rows(step.minmax[i:i + 1])
+                step.blend_radius(i, self.cw)
+                out[r] = step.saliency(r)
                 _copy_out(out[r], out_host[r], copy_stream, self.dev)
         pc = step.pcount
         # the global Otsu threshold (Downsample.py:54) is NOT part of the saliency step (the single-GPU step has none

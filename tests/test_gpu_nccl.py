@@ -42,7 +42,15 @@ def _worker(rank, world, port, ret):
         job = StripSaliency(per, rank, world, dev, RADII, PARAMS, 0.5, cloud=own, x_range=(x_lo, x_lo + lx / world),
                             host_buffers=False)
         out = job.step_resident()
-        ret[rank] = ({r: out[r].cpu().numpy() for r in RADII}, job.checksum, job.otsu)
+        res = {r: out[r].cpu().numpy() for r in RADII}
+        otsu = job.otsu
+        # the host-buffer path (one collective per radius, columns downloaded as soon as their radius is done): two
+        # strips streamed from pinned memory must land in the host buffers bit-identical to the resident step
+        job.host = own.cpu().pin_memory()
+        job.out_host = {r: torch.empty(per, dtype=torch.float32).pin_memory() for r in RADII}
+        job.steps_e2e(2)
+        e2e_same = all(np.array_equal(job.out_host[r].numpy(), res[r], equal_nan=True) for r in RADII)
+        ret[rank] = (res, job.checksum, otsu, e2e_same)
     finally:
         dist.destroy_process_group()
 
@@ -71,3 +79,4 @@ def test_two_ranks_over_nccl_bit_identical_to_untiled():
             assert np.array_equal(ret[k][0][r], sal[k * per:(k + 1) * per], equal_nan=True)    # bit-identical
             assert ret[k][1][r][0] == int(pc[k * per:(k + 1) * per].sum())
         assert ret[0][2][r] == ret[1][2][r] == rp.otsu_threshold(sal[~np.isnan(sal)])          # global Otsu
+    assert ret[0][3] and ret[1][3]                                                             # host-buffer path
