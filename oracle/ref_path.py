@@ -233,7 +233,8 @@ def saliency_stats(sal):
 
 
 # --------------------------------------------------------------------------------------------
-# H8  Downsample.py:44-83 (declared repair) + threshold_otsu -- parity unpinned
+# H8  Downsample.py:44-83 (declared repair) + threshold_otsu -- parity unpinned (skimage absent; the Otsu criterion is
+#     cross-checked against OpenCV on 8-bit data, tests/test_oracle_golden.py::test_otsu_restatement_against_opencv)
 # --------------------------------------------------------------------------------------------
 def otsu_histogram(values, nbins=256):
     v = np.asarray(values, np.float64).ravel()

@@ -244,3 +244,24 @@ def test_cpu_bench_kinds_agree():
     if "reference" in outs:
         np.testing.assert_allclose(outs["port"][0], outs["reference"][0], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(outs["port"][1], outs["reference"][1], rtol=1e-4, atol=1e-7)
+
+
+def test_otsu_restatement_against_opencv():
+    """skimage (the reference's `threshold_otsu`, Downsample.py:54) is absent offline, so the restatement in
+    oracle/ref_path.py cannot be pinned on skimage itself.  An INDEPENDENT implementation of the same criterion is here:
+    OpenCV's THRESH_OTSU on 8-bit data.  On integer-valued data with both ends present every value has its own bin in the
+    float path (256 bins over [0, 255]), the returned bin centre identifies the split 'bins <= idx | bins > idx', and that
+    split must be OpenCV's 'v <= T | v > T' (maximum between-class variance, first maximum)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ref_path as rp
+    rng = np.random.Generator(np.random.PCG64(1))
+    for trial in range(120):
+        n = 20000
+        a = rng.normal(rng.uniform(30, 120), rng.uniform(5, 30), n // 2)
+        b = rng.normal(rng.uniform(130, 230), rng.uniform(5, 30), n - n // 2)
+        img = np.clip(np.rint(np.concatenate([a, b])), 0, 255).astype(np.uint8)
+        img[0], img[1] = 0, 255
+        T, _ = cv2.threshold(img.reshape(1, -1), 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        t = rp.otsu_threshold(img.astype(np.float64))
+        idx = int(round(t * 256 / 255 - 0.5))              # bin centre (idx + 0.5) * 255 / 256 -> idx
+        assert idx == int(T), (trial, T, idx, t)
