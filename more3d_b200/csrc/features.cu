@@ -74,27 +74,15 @@ __device__ __forceinline__ void st_feat(FeatRec* __restrict__ f, int64_t n, int6
 
 // One thread per sorted point.  Accumulates m, sum(d), sum(d d^T) with d = q - p (fp64, shifted to the
 // query so there is no cancellation against the ~1e3 m coordinates), then finishes in registers.
-template <int MODE, bool TALL>
-__global__ void __launch_bounds__(WALK_THREADS, 4) moments_kernel(GridView g, CurvParams prm,
-                                                               double* __restrict__ normals,
-                                                               double* __restrict__ lam_ratio,
-                                                               float* __restrict__ Kout,
-                                                               int32_t* __restrict__ pcount,
-                                                               FeatRec* __restrict__ feat_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n) return;
-    const PointRec p = load_rec(g.rec, i);
-    const int64_t o = prm.grid_order ? i : p.idx;
-    int m = 0;
-    double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    // The fp64 differences serve both the exact accept rule and the moments, so an fp32 pre-filter
-    // (used by the count/fill kernels) does not pay here: measured 2x slower (conditional fp64 loads
-    // lose the unrolled loop's memory-level parallelism).
-    walk_candidates_pipelined<TALL>(g, p.x, p.y, p.z, prm.r, prm.s, [&](int64_t j) {
-        return load_rec(g.rec, j);
-    }, [&](const PointRec& c) {
+// neighbourhood sums of one query point: count, sum(d), sum(d d^T), d = q - p
+struct Moments {
+    int m;
+    double sx, sy, sz, sxx, sxy, sxz, syy, syz, szz;
+    __device__ __forceinline__ void clear() { m = 0; sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0.0; }
+    template <int MODE>
+    __device__ __forceinline__ void add(const PointRec& c, const PointRec& p, double r2) {
         const double dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
-        if (dist2_rule(dx, dy, dz) <= prm.r2) {
+        if (dist2_rule(dx, dy, dz) <= r2) {
             ++m;
             sx += dx; sy += dy; sz += dz;
             if (MODE != MODE_CURV) {
@@ -102,8 +90,18 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) moments_kernel(GridView g, Cu
                 syy += dy * dy; syz += dy * dz; szz += dz * dz;
             }
         }
-    });
+    }
+};
 
+// everything after the walk for sorted point i: PCA normal / surface variation, Curvature_Kernel.process, outputs
+template <int MODE>
+__device__ __forceinline__ void moments_finish(const GridView& g, const CurvParams& prm, int64_t i, const PointRec& p,
+                                               const Moments& s, double* __restrict__ normals,
+                                               double* __restrict__ lam_ratio, float* __restrict__ Kout,
+                                               int32_t* __restrict__ pcount, FeatRec* __restrict__ feat_out) {
+    const int64_t o = prm.grid_order ? i : p.idx;
+    const int m = s.m;
+    const double sx = s.sx, sy = s.sy, sz = s.sz;
     double nx, ny, nz;
     if (MODE == MODE_CURV) {
         nx = normals[3 * o]; ny = normals[3 * o + 1]; nz = normals[3 * o + 2];
@@ -112,8 +110,8 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) moments_kernel(GridView g, Cu
         if (m >= 3) {
             const double im = 1.0 / (double)m;
             const double cx = sx * im, cy = sy * im, cz = sz * im;
-            const double a00 = sxx * im - cx * cx, a01 = sxy * im - cx * cy, a02 = sxz * im - cx * cz;
-            const double a11 = syy * im - cy * cy, a12 = syz * im - cy * cz, a22 = szz * im - cz * cz;
+            const double a00 = s.sxx * im - cx * cx, a01 = s.sxy * im - cx * cy, a02 = s.sxz * im - cx * cz;
+            const double a11 = s.syy * im - cy * cy, a12 = s.syz * im - cy * cz, a22 = s.szz * im - cz * cz;
             double lmin, v[3];
             sym3_min_eig(a00, a01, a02, a11, a12, a22, lmin, v);
             nx = v[0]; ny = v[1]; nz = v[2];
@@ -158,6 +156,27 @@ __global__ void __launch_bounds__(WALK_THREADS, 4) moments_kernel(GridView g, Cu
         // from the original-order columns by build_feat_kernel; same arithmetic as there
         st_feat(feat_out, g.feat_n, i, p.x, p.y, p.z, K, g.dup[i] != 0, nx, ny, nz);
     }
+}
+
+template <int MODE, bool TALL>
+__global__ void __launch_bounds__(WALK_THREADS, 4) moments_kernel(GridView g, CurvParams prm,
+                                                               double* __restrict__ normals,
+                                                               double* __restrict__ lam_ratio,
+                                                               float* __restrict__ Kout,
+                                                               int32_t* __restrict__ pcount,
+                                                               FeatRec* __restrict__ feat_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const PointRec p = load_rec(g.rec, i);
+    Moments s;
+    s.clear();
+    // The fp64 differences serve both the exact accept rule and the moments, so an fp32 pre-filter
+    // (used by the count/fill kernels) does not pay here: measured 2x slower (conditional fp64 loads
+    // lose the unrolled loop's memory-level parallelism).
+    walk_candidates_pipelined<TALL>(g, p.x, p.y, p.z, prm.r, prm.s, [&](int64_t j) {
+        return load_rec(g.rec, j);
+    }, [&](const PointRec& c) { s.add<MODE>(c, p, prm.r2); });
+    moments_finish<MODE>(g, prm, i, p, s, normals, lam_ratio, Kout, pcount, feat_out);
 }
 
 // ------------------------------------------------------------------------------------------
