@@ -310,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
                 # the same figure for both hot groups (moments = one kernel, three launches)
                 "per_group": {k: {"achieved": kern[k]["algorithmic_GBs"], "frac": kern[k]["algorithmic_GBs"] / peak,
                                   "ms_per_step": kern[k]["ms_per_step"], "algorithmic_bytes_per_step": alg[k]}
-                              for k in kern if k in alg},
+                              for k in kern if k in alg and "algorithmic_GBs" in kern[k]},
                 "note": ("achieved = SURVEY 8d pair-gather bytes (N*40 + 32*sum m per radius) / CUDA-event time of the group; "
                          "the gather is served by L1/L2 (DRAM traffic = `traffic` per call), so this HBM-equivalent rate can "
                          "exceed the HBM peak: the binding limits are issue slots and the FP64 pipe (profiles/README.md)")}
