@@ -103,15 +103,16 @@ struct __align__(32) PointRec {
     long long idx;  // original index
 };
 
-// sorted feature record for the dk/dn pass: 64 B per point, STORED AS TWO ARRAYS OF 32-BYTE HALVES (first (x, y, z, K)
+// sorted feature record for the dk/dn pass: 64 B per point, STORED AS TWO ARRAYS OF 32-BYTE HALVES (first (x, y, z, kw)
 // of all points, then (nx, ny, nz, pad) of all points; see ld_d4 / st_feat in features.cu) -- the struct only sizes it
 struct __align__(32) FeatRec {
     double x, y, z;
-    double K;        // _nonparam_K (f32 value widened: 29 zero mantissa bits) with two flags in bits 0-1:
-                     // bit 0 = coincident with an earlier point (np.unique drop), bit 1 = raw normal was NaN.
-                     // Keeping the flags in the FIRST 32-B half lets the accept/dedup decision be taken
-                     // before the second half (the normal) is requested: one dependent load, not two.
-    double nx, ny, nz;  // unit normal (n / ||n||), NaN if the point has no normal
+    double K;        // the word `kw` (features.cu, feat_kword): [63..32] float32 bits of _nonparam_K, [31..2] the unit
+                     // normal quantised to 3 x 10 bits (screening pass of dk/dn only), [1..0] flags: bit 0 = coincident
+                     // with an earlier point (np.unique drop), bit 1 = raw normal was NaN.  Everything the screening
+                     // pass needs sits in this FIRST 32-B half: one load per candidate.
+    double nx, ny, nz;  // unit normal (n / ||n||), NaN if the point has no normal; read by the refinement of the few points
+                        // whose dn the screening pass cannot settle, and by the one-pass kernels
     double pad;
 };
 
@@ -141,7 +142,7 @@ struct more3d_grid {
     uint32_t* col_start;    // nx*ny + 1
     uint8_t* dup;           // n (sorted order): 1 if coincident with an earlier sorted point
     m3d::FeatRec* feat;     // n sorted feature records cached by the last more3d_normals_curvature (or NULL)
-    int feat_split;         // 1: stored as two arrays of 32-B halves (fine grids), 0: interleaved 64-B records
+    int feat_split;         // 1: stored as two arrays of 32-B halves (every thin grid, fine tall grids), 0: interleaved 64-B records
 };
 
 namespace m3d {

@@ -27,14 +27,15 @@ constexpr int WALK_THREADS = 256;
 
 struct D4 { double x, y, z, w; };
 struct D4x2 { D4 a, b; };
-// The feature records live as TWO arrays of 32-byte halves -- half 0 = (x, y, z, K | flags) of all n points, then half 1
-// = (nx, ny, nz, pad) of all n points -- not as n 64-byte structs: at every candidate step the 32 lanes of a warp read
-// ~13 distinct records out of a window of ~32 consecutive ones, and with 32-byte elements that window is 8 cache lines
-// per load instead of 16 (the L1 data pipe, this kernel's highest bound, charges a wavefront per line touched).
-// That pays on fine grids (a 9x9 stencil of quarter-radius columns: 14.83 -> 14.41 ms over the three radii of
-// configs[1]); on a coarse grid (>= 4 points per column: the lanes of a warp sit in ~3 columns and both halves of their
-// few records share cache lines) the interleaved 64-byte layout is 8-12 % faster, so the layout follows the grid's
-// mean column population (feat_split, decided when the grid is built).  n == 0 selects the interleaved layout.
+// The feature records live as TWO arrays of 32-byte halves -- half 0 = (x, y, z, kw) of all n points, then half 1
+// = (nx, ny, nz, pad) of all n points -- not as n 64-byte structs.  The screening pass of the two-pass dk/dn reads half 0
+// only, so every thin grid uses this layout.  For the one-pass kernel (tall grids, MORE3D_DKDN_VARIANT=2), which reads
+// both halves of every candidate, the layout follows the grid's mean column population (feat_split, decided when the
+// grid is built): at every candidate step the 32 lanes of a warp read ~13 distinct records out of a window of ~32
+// consecutive ones, and with 32-byte elements that window is 8 cache lines per load instead of 16 (14.83 -> 14.41 ms
+// over the three radii of configs[1] on fine grids); on a coarse grid (>= 4 points per column: the lanes sit in ~3
+// columns and both halves of their few records share cache lines) the interleaved 64-byte layout is 8-12 % faster.
+// n == 0 selects the interleaved layout.
 template <bool SPLIT>
 __device__ __forceinline__ D4 ld_d4(const FeatRec* __restrict__ f, int64_t n, int64_t j, int h) {
     D4 r;      // the layout is a template parameter: one more select + multiply per load costs 7 % in this issue-bound loop
