@@ -35,7 +35,8 @@ const char* more3d_last_error(void);
 /* ---- optional per-kernel timing (CUDA events on the launching stream; used by bench.py) ----------
  * enable(1) makes every library kernel group record an event pair; get() synchronises the recorded
  * events and returns the accumulated milliseconds / launch count of one named group, e.g.
- * "moments", "dkdn", "grid_build", "build_feat".  names() writes a comma-separated list. */
+ * "moments", "dkdn" (with its parts "dkdn_screen" and "dkdn_refine"), "grid_build", "build_feat".  names() writes a
+ * comma-separated list. */
 int64_t more3d_launch_count(void); /* kernels launched by this library since it was loaded */
 int more3d_profile_enable(int on);
 int more3d_profile_reset(void);
