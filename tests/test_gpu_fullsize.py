@@ -145,6 +145,37 @@ def _canon(idx_array, starts, n):
     return idx_array[np.lexsort((idx_array, seg))]
 
 
+def test_config1_two_pass_dkdn_equals_one_pass_10m():
+    """configs[1] at full size: the default dk/dn (screening walk + refinement) against the one-pass
+    kernel on all 3 x 10 M points -- identical neighbour counts and zero / NaN patterns (the integer decisions), values
+    equal to the rounding of fp64 sums added in another order (observed: bit-identical float32 columns)."""
+    import torch
+    from more3d_b200 import synthetic, _lib
+    from more3d_b200.pipeline import multiscale_saliency
+    n = sized(10_000_000)
+    d = synthetic.hash_terrain_device(2, 0, n, n)
+    cols = {}
+    try:
+        for key, variant in (("one", 2), ("two", 0)):
+            _lib.set_dkdn_variant(variant)
+            res = multiscale_saliency(d, (0.5, 0.75, 1.0), curvature_weight=0.5, keep=True, **PARAMS)
+            cols[key] = {r: {k: res[r][k].cpu().numpy() for k in ("_dk", "_dn", "_pcount", "_saliency")} for r in res}
+            del res
+    finally:
+        _lib.set_dkdn_variant(0)
+    for r in (0.5, 0.75, 1.0):
+        a, b = cols["one"][r], cols["two"][r]
+        assert np.array_equal(a["_pcount"], b["_pcount"])
+        for k in ("_dk", "_dn"):
+            assert np.array_equal(a[k] == 0, b[k] == 0) and np.array_equal(np.isnan(a[k]), np.isnan(b[k])), (r, k)
+            nz = (a[k] != 0) & ~np.isnan(a[k])
+            assert np.allclose(a[k][nz], b[k][nz], rtol=1e-6, atol=0), (r, k)
+        fin = np.isfinite(a["_saliency"])
+        assert np.array_equal(fin, np.isfinite(b["_saliency"]))
+        assert np.allclose(a["_saliency"][fin], b["_saliency"][fin], rtol=1e-5, atol=1e-7)
+        assert 0.02 < (b["_dk"] != 0).mean() < 0.5          # the refinement really ran on a share of the points
+
+
 def test_config2_hierarchy_and_selection_10m_vs_sklearn():
     """configs[2]: the LOD tree of a 10 M-point cloud against sklearn's BallTree (node ranges, leaf membership,
     radii), the cell lists of every LOD and one saliency-driven selection against the oracle loop."""
